@@ -1,0 +1,464 @@
+// api.cu -- extern "C" entry points of librecode_b200.so (see include/recode_b200.h).
+#include "common.cuh"
+#include "kernels.cuh"
+#include "deflate_chunk.cuh"
+
+// ---- helpers -----------------------------------------------------------------------------------
+static int check_cfg(rc_ctx *ctx, const rc_config *c)
+{
+    if (!c) RC_FAIL(ctx, -1, "config is null");
+    if (c->ny < 1 || c->nx < 1 || c->ny > 65535 || c->nx > 65535)
+        RC_FAIL(ctx, -1, "ny/nx out of range [1, 65535]: %d x %d", c->ny, c->nx);
+    if ((size_t)c->ny * (size_t)c->nx > 0x7fffffffu - TILE_PX)
+        RC_FAIL(ctx, -1, "frame has too many pixels for 32-bit indexing");
+    if (c->itemsize != 1 && c->itemsize != 2) RC_FAIL(ctx, -1, "itemsize must be 1 or 2 (got %d)", c->itemsize);
+    if (c->bit_depth < 1 || c->bit_depth > 8 * c->itemsize)
+        RC_FAIL(ctx, -1, "bit_depth %d does not fit itemsize %d", c->bit_depth, c->itemsize);
+    if (c->reduction_level < 1 || c->reduction_level > 4) RC_FAIL(ctx, -1, "reduction_level must be 1..4");
+    if (c->rc_operation_mode != 0 && c->rc_operation_mode != 1) RC_FAIL(ctx, -1, "rc_operation_mode must be 0 or 1");
+    if (c->compression_level < 0 || c->compression_level > 9) RC_FAIL(ctx, -1, "compression_level must be 0..9");
+    if (c->l2_statistics < 0 || c->l2_statistics > 2) RC_FAIL(ctx, -1, "l2_statistics must be 0..2");
+    if (c->l4_centroiding < 0 || c->l4_centroiding > 3) RC_FAIL(ctx, -1, "l4_centroiding must be 0..3");
+    if (c->max_frames < 1) RC_FAIL(ctx, -1, "max_frames must be >= 1");
+    return 0;
+}
+
+// bytes per frame of the packed value stream, worst case (every pixel foreground), 16-byte multiple + slack
+static size_t packed_stride_of(const rc_config *c)
+{
+    const size_t P = (size_t)c->ny * c->nx;
+    if (c->reduction_level == 3 || c->reduction_level == 4) return 16;
+    return round_up((P * (size_t)c->bit_depth + 7) / 8, 16) + 16;
+}
+
+struct ReduceWs {
+    uint32_t *tilecnt, *tilepre, *rootcnt, *rootpre;
+    uint16_t *segpre;
+    void *vals;
+    uint32_t *parent, *acc, *bbox, *ord;
+    uint16_t *stats16;
+    uint64_t *cent, *cent_tiles;
+    uint32_t *map1;
+};
+
+// what: 0 = rc_reduce, 1 = rc_ccl_label, 2 = rc_l4_centroids
+static ReduceWs carve_reduce(Carver &c, const rc_config *cfg, const Geom &g, int what)
+{
+    ReduceWs w;
+    memset(&w, 0, sizeof(w));
+    const size_t F = (size_t)cfg->max_frames;
+    const int level = cfg->reduction_level;
+    w.tilecnt = c.take<uint32_t>(F * g.NT);
+    w.tilepre = c.take<uint32_t>(F * (g.NT + 1));
+    w.segpre = c.take<uint16_t>(F * g.NT * SEGS_PER_TILE);
+    const bool ccl = what != 0 || level == 2 || level == 4;
+    if (what == 0 && level != 3) w.vals = c.take<uint8_t>(F * g.slots * cfg->itemsize);
+    if (what == 2) w.vals = c.take<uint8_t>(F * g.slots * cfg->itemsize);
+    if (ccl) {
+        w.parent = c.take<uint32_t>(F * g.slots);
+        w.rootcnt = c.take<uint32_t>(F * g.NT);
+        w.rootpre = c.take<uint32_t>(F * (g.NT + 1));
+    }
+    if (what == 0 && level == 2) {
+        w.acc = c.take<uint32_t>(F * g.slots);
+        w.stats16 = c.take<uint16_t>(F * g.slots);
+    }
+    if ((what == 0 && level == 4) || what == 2) {
+        w.bbox = c.take<uint32_t>(F * g.slots * 4);
+        w.map1 = c.take<uint32_t>(F * g.MS + 16);
+    }
+    if (what == 1) w.ord = c.take<uint32_t>(F * g.slots);
+    if (what == 2) {
+        w.cent = c.take<uint64_t>(F * g.slots);
+        w.cent_tiles = c.take<uint64_t>(F * g.slots);
+    }
+    return w;
+}
+
+struct CompressWs {
+    uint32_t *maps;
+    uint8_t *packed;
+    uint32_t *packed_bytes;
+    uint64_t *in_off;
+    uint32_t *in_bytes;
+    DeflateWs d;
+    size_t packed_stride;
+    int spf;
+};
+
+static size_t max_stream_bytes(const rc_config *cfg, const Geom &g)
+{
+    const size_t ps = packed_stride_of(cfg);
+    return g.map_bytes > ps ? g.map_bytes : ps;
+}
+
+static CompressWs carve_compress(Carver &c, const rc_config *cfg, const Geom &g)
+{
+    CompressWs w;
+    const size_t F = (size_t)cfg->max_frames;
+    w.spf = (cfg->reduction_level <= 2) ? 2 : 1;
+    w.packed_stride = packed_stride_of(cfg);
+    w.maps = c.take<uint32_t>(F * g.MS + 16);
+    w.packed = c.take<uint8_t>(F * w.packed_stride + 16);
+    w.packed_bytes = c.take<uint32_t>(F + 1);
+    w.in_off = c.take<uint64_t>(F * 2 + 1);
+    w.in_bytes = c.take<uint32_t>(F * 2 + 1);
+    const size_t chunks = F * ((g.map_bytes + DF_CHUNK - 1) / DF_CHUNK) +
+                          (w.spf == 2 ? F * ((w.packed_stride + DF_CHUNK - 1) / DF_CHUNK) : 0);
+    w.d = carve_deflate_ws(c, (int)F * w.spf, chunks, cfg->rc_operation_mode == 1);
+    return w;
+}
+
+__global__ void k_stream_desc(const uint8_t *base, const uint32_t *maps, size_t MS, uint32_t map_bytes,
+                              const uint8_t *packed, size_t packed_stride, const uint32_t *packed_bytes, int F, int spf,
+                              uint64_t *in_off, uint32_t *in_bytes)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    in_off[f * spf] = (uint64_t)((const uint8_t *)(maps + (size_t)f * MS) - base);
+    in_bytes[f * spf] = map_bytes;
+    if (spf == 2) {
+        in_off[f * spf + 1] = (uint64_t)(packed + (size_t)f * packed_stride - base);
+        in_bytes[f * spf + 1] = packed_bytes[f];
+    }
+}
+
+// ---- lifecycle ---------------------------------------------------------------------------------
+extern "C" int rc_create(rc_ctx **out, int device)
+{
+    if (!out) return -1;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return -2;     // no CUDA device: there is no fallback
+    if (device < 0 || device >= n) return -1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -2;
+    if (prop.major < 10) return -4;                                      // built for sm_100a only
+    rc_ctx *c = (rc_ctx *)calloc(1, sizeof(rc_ctx));
+    if (!c) return -5;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return 0;
+}
+
+extern "C" void rc_destroy(rc_ctx *ctx) { free(ctx); }
+extern "C" const char *rc_last_error(const rc_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" int rc_version(void) { return RC_VERSION; }
+extern "C" int rc_sm_count(const rc_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+// ---- sizes -------------------------------------------------------------------------------------
+extern "C" size_t rc_map_stride_words(size_t n_pixels)
+{
+    return (n_pixels + TILE_PX - 1) / TILE_PX * TILE_WORDS;
+}
+
+extern "C" size_t rc_packed_stride_bytes(const rc_config *cfg) { return packed_stride_of(cfg); }
+
+extern "C" size_t rc_deflate_bound(size_t in_bytes)
+{
+    return in_bytes + 10 * ((in_bytes + DF_CHUNK - 1) / DF_CHUNK) + 8;
+}
+
+extern "C" size_t rc_workspace_bytes(const rc_config *cfg)
+{
+    const Geom g = make_geom(cfg->ny, cfg->nx);
+    rc_config c2 = *cfg;
+    // the stage APIs share one workspace: size it for the largest user
+    size_t best = 0;
+    for (int what = 0; what < 3; what++) {
+        Carver cc(nullptr);
+        carve_reduce(cc, &c2, g, what);
+        if (what == 0) carve_compress(cc, &c2, g);
+        if (cc.used() > best) best = cc.used();
+    }
+    return best + 256;
+}
+
+extern "C" size_t rc_records_capacity(const rc_config *cfg)
+{
+    const Geom g = make_geom(cfg->ny, cfg->nx);
+    size_t per = 16 + rc_deflate_bound(g.map_bytes);
+    if (cfg->reduction_level <= 2) per += rc_deflate_bound(packed_stride_of(cfg));
+    return per * (size_t)cfg->max_frames + 64;
+}
+
+extern "C" size_t rc_deflate_workspace_bytes(int n_streams, size_t max_in_bytes)
+{
+    Carver c(nullptr);
+    carve_deflate_ws(c, n_streams, deflate_max_chunks(n_streams, max_in_bytes), true);
+    return c.used() + 256;
+}
+
+extern "C" size_t rc_read_workspace_bytes(const rc_config *cfg)
+{
+    const Geom g = make_geom(cfg->ny, cfg->nx);
+    const size_t F = (size_t)cfg->max_frames;
+    Carver c(nullptr);
+    c.take<uint32_t>(F * g.NT);
+    c.take<uint32_t>(F * (g.NT + 1));
+    c.take<uint16_t>(F * g.NT * SEGS_PER_TILE);
+    return c.used() + 256;
+}
+
+// ---- write side --------------------------------------------------------------------------------
+extern "C" int rc_make_threshold(rc_ctx *ctx, const rc_config *cfg, const void *d_dark, uint64_t eps, void *d_thr,
+                                 void *stream)
+{
+    if (!ctx) return -1;
+    if (check_cfg(ctx, cfg)) return -1;
+    return launch_make_threshold(ctx, cfg->itemsize, d_dark, eps, d_thr, (size_t)cfg->ny * cfg->nx, (cudaStream_t)stream);
+}
+
+// shared body of rc_reduce / rc_reduce_compress
+static int run_reduce(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const ReduceWs &w, const void *frames, int F,
+                      const void *thr, uint32_t *maps, uint8_t *packed, size_t packed_stride, uint32_t *packed_bytes,
+                      uint32_t *counts, cudaStream_t st)
+{
+    const int level = cfg->reduction_level, b = cfg->bit_depth, isz = cfg->itemsize;
+    int rc;
+    if (level == 1) {
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 1, 0, frames, thr, F, maps, w.tilecnt, w.segpre, w.vals, nullptr,
+                                      nullptr, st))) return rc;
+        if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, packed_bytes, b, st))) return rc;
+        return launch_bitpack(ctx, g, isz, w.vals, w.tilepre, F, b, packed, packed_stride, st);
+    }
+    if (level == 3) {
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 0, 0, frames, thr, F, maps, w.tilecnt, w.segpre, nullptr, nullptr,
+                                      nullptr, st))) return rc;
+        return launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, nullptr, 0, st);
+    }
+    if (level == 2) {
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 1, frames, thr, F, maps, w.tilecnt, w.segpre, w.vals, w.parent,
+                                      w.acc, st))) return rc;
+        if ((rc = launch_ccl_union(ctx, g, maps, w.segpre, w.parent, F, st))) return rc;
+        if ((rc = launch_ccl_flatten(ctx, g, cfg->l2_statistics == 2 ? 2 : 1, maps, w.segpre, w.parent, w.acc, nullptr,
+                                     F, st))) return rc;
+        if ((rc = launch_ccl_roots(ctx, g, 1, w.tilecnt, w.parent, w.acc, nullptr, w.rootcnt, nullptr, w.stats16,
+                                   nullptr, F, st))) return rc;
+        if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, packed_bytes, b, st))) return rc;
+        return launch_bitpack(ctx, g, 2, w.stats16, w.rootpre, F, b, packed, packed_stride, st);
+    }
+    // level 4: threshold map -> map1, centroid map -> maps
+    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, frames, thr, F, w.map1, w.tilecnt, w.segpre, w.vals, w.parent,
+                                  nullptr, st))) return rc;
+    if ((rc = launch_ccl_union(ctx, g, w.map1, w.segpre, w.parent, F, st))) return rc;
+    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.segpre, w.parent, nullptr, w.bbox, F, st))) return rc;
+    RC_CUDA(ctx, cudaMemsetAsync(maps, 0, (size_t)F * g.MS * sizeof(uint32_t), st));
+    if ((rc = launch_l4_centroids(ctx, g, isz, cfg->l4_centroiding, w.map1, w.segpre, w.parent, w.bbox, w.vals, maps,
+                                  nullptr, F, st))) return rc;
+    // puddle count = number of roots
+    if ((rc = launch_ccl_roots(ctx, g, 3, w.tilecnt, w.parent, nullptr, nullptr, w.rootcnt, nullptr, nullptr, nullptr,
+                               F, st))) return rc;
+    return launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, nullptr, 0, st);
+}
+
+extern "C" int rc_reduce(rc_ctx *ctx, const rc_config *cfg, const void *d_frames, int n_frames, const void *d_thr,
+                         void *d_workspace, size_t workspace_bytes, uint32_t *d_maps, uint8_t *d_packed,
+                         uint32_t *d_packed_bytes, uint32_t *d_counts, void *stream)
+{
+    if (!ctx) return -1;
+    if (check_cfg(ctx, cfg)) return -1;
+    if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames %d exceeds max_frames %d", n_frames, cfg->max_frames);
+    if (workspace_bytes < rc_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
+    const Geom g = make_geom(cfg->ny, cfg->nx);
+    Carver c(d_workspace);
+    const ReduceWs w = carve_reduce(c, cfg, g, 0);
+    return run_reduce(ctx, cfg, g, w, d_frames, n_frames, d_thr, d_maps, d_packed, packed_stride_of(cfg), d_packed_bytes,
+                      d_counts, (cudaStream_t)stream);
+}
+
+extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void *d_frames, int n_frames,
+                                  const void *d_thr, uint32_t first_frame_id, void *d_workspace, size_t workspace_bytes,
+                                  uint8_t *d_records, size_t records_capacity, uint64_t *d_record_offsets,
+                                  uint32_t *d_counts, uint32_t *d_status, void *stream)
+{
+    if (!ctx) return -1;
+    if (check_cfg(ctx, cfg)) return -1;
+    if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames %d exceeds max_frames %d", n_frames, cfg->max_frames);
+    if (workspace_bytes < rc_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom g = make_geom(cfg->ny, cfg->nx);
+    Carver c(d_workspace);
+    const ReduceWs w = carve_reduce(c, cfg, g, 0);
+    const CompressWs cw = carve_compress(c, cfg, g);
+    const int F = n_frames;
+    int rc;
+    RC_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
+    if (F == 0) {
+        RC_CUDA(ctx, cudaMemsetAsync(d_record_offsets, 0, sizeof(uint64_t), st));
+        return 0;
+    }
+    if ((rc = run_reduce(ctx, cfg, g, w, d_frames, F, d_thr, cw.maps, cw.packed, cw.packed_stride, cw.packed_bytes,
+                         d_counts, st))) return rc;
+    const int S = F * cw.spf;
+    const uint8_t *base = (const uint8_t *)d_workspace;
+    k_stream_desc<<<(F + 127) / 128, 128, 0, st>>>(base, cw.maps, g.MS, (uint32_t)g.map_bytes, cw.packed, cw.packed_stride,
+                                                  cw.packed_bytes, F, cw.spf, cw.in_off, cw.in_bytes);
+    RC_LAUNCH_CHECK(ctx, "k_stream_desc");
+    const int wrap = cfg->rc_operation_mode == 1;
+    if ((rc = launch_deflate_streams(ctx, cfg->compression_level, wrap, base, cw.in_off, cw.in_bytes, S, cw.d, st))) return rc;
+    if ((rc = launch_layout_records(ctx, cw.d, cw.packed_bytes, F, cw.spf, cfg->rc_operation_mode, first_frame_id,
+                                    d_records, records_capacity, d_record_offsets, d_status, st))) return rc;
+    return launch_copy_pieces(ctx, cw.d, wrap, base, cw.in_off, cw.in_bytes, S, d_records, records_capacity, d_status, st);
+}
+
+extern "C" int rc_ccl_label(rc_ctx *ctx, const rc_config *cfg, const uint32_t *d_maps, int n_frames, void *d_workspace,
+                            size_t workspace_bytes, int32_t *d_labels, uint32_t *d_counts, void *stream)
+{
+    if (!ctx) return -1;
+    if (check_cfg(ctx, cfg)) return -1;
+    if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames exceeds max_frames");
+    if (workspace_bytes < rc_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom g = make_geom(cfg->ny, cfg->nx);
+    Carver c(d_workspace);
+    const ReduceWs w = carve_reduce(c, cfg, g, 1);
+    const int F = n_frames;
+    int rc;
+    if ((rc = launch_map_counts(ctx, g, d_maps, F, w.tilecnt, w.segpre, st))) return rc;
+    if ((rc = launch_ccl_init(ctx, g, w.tilecnt, w.parent, F, st))) return rc;
+    if ((rc = launch_ccl_union(ctx, g, d_maps, w.segpre, w.parent, F, st))) return rc;
+    if ((rc = launch_ccl_flatten(ctx, g, 0, d_maps, w.segpre, w.parent, nullptr, nullptr, F, st))) return rc;
+    if ((rc = launch_ccl_roots(ctx, g, 0, w.tilecnt, w.parent, nullptr, nullptr, w.rootcnt, w.ord, nullptr, nullptr, F, st))) return rc;
+    if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, d_counts, nullptr, 0, st))) return rc;
+    return launch_ccl_label_image(ctx, g, d_maps, w.segpre, w.parent, w.ord, w.rootpre, d_labels, F, st);
+}
+
+extern "C" int rc_l4_centroids(rc_ctx *ctx, const rc_config *cfg, const void *d_frames, int n_frames, const void *d_thr,
+                               void *d_workspace, size_t workspace_bytes, float *d_centroids, size_t centroid_capacity,
+                               uint32_t *d_counts, void *stream)
+{
+    if (!ctx) return -1;
+    if (check_cfg(ctx, cfg)) return -1;
+    if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames exceeds max_frames");
+    if (workspace_bytes < rc_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom g = make_geom(cfg->ny, cfg->nx);
+    Carver c(d_workspace);
+    const ReduceWs w = carve_reduce(c, cfg, g, 2);
+    const int F = n_frames, isz = cfg->itemsize;
+    int rc;
+    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, d_frames, d_thr, F, w.map1, w.tilecnt, w.segpre, w.vals, w.parent,
+                                  nullptr, st))) return rc;
+    if ((rc = launch_ccl_union(ctx, g, w.map1, w.segpre, w.parent, F, st))) return rc;
+    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.segpre, w.parent, nullptr, w.bbox, F, st))) return rc;
+    if ((rc = launch_l4_centroids(ctx, g, isz, cfg->l4_centroiding, w.map1, w.segpre, w.parent, w.bbox, w.vals, nullptr,
+                                  w.cent, F, st))) return rc;
+    if ((rc = launch_ccl_roots(ctx, g, 2, w.tilecnt, w.parent, nullptr, w.cent, w.rootcnt, nullptr, nullptr, w.cent_tiles,
+                               F, st))) return rc;
+    if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, d_counts, nullptr, 0, st))) return rc;
+    return launch_gather_centroids(ctx, g, w.cent_tiles, w.rootpre, F, d_centroids, centroid_capacity, st);
+}
+
+extern "C" int rc_deflate_zlib(rc_ctx *ctx, int compression_level, const uint8_t *d_in, const uint64_t *d_in_offsets,
+                               const uint32_t *d_in_bytes, int n_streams, size_t max_in_bytes, void *d_workspace,
+                               size_t workspace_bytes, uint8_t *d_out, size_t out_stride, uint32_t *d_out_bytes,
+                               void *stream)
+{
+    if (!ctx) return -1;
+    if (compression_level < 0 || compression_level > 9) RC_FAIL(ctx, -1, "compression_level must be 0..9");
+    if (n_streams <= 0) return 0;
+    if (out_stride < rc_deflate_bound(max_in_bytes)) RC_FAIL(ctx, -1, "out_stride smaller than rc_deflate_bound");
+    if (workspace_bytes < rc_deflate_workspace_bytes(n_streams, max_in_bytes)) RC_FAIL(ctx, -1, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver c(d_workspace);
+    DeflateWs w = carve_deflate_ws(c, n_streams, deflate_max_chunks(n_streams, max_in_bytes), true);
+    uint32_t *status = w.counters + 4;
+    int rc;
+    if ((rc = launch_deflate_streams(ctx, compression_level, 1, d_in, d_in_offsets, d_in_bytes, n_streams, w, st))) return rc;
+    if ((rc = launch_layout_strided(ctx, w, n_streams, out_stride, d_out_bytes, st))) return rc;
+    return launch_copy_pieces(ctx, w, 1, d_in, d_in_offsets, d_in_bytes, n_streams, d_out, (size_t)n_streams * out_stride,
+                              status, st);
+}
+
+// ---- read side ---------------------------------------------------------------------------------
+extern "C" size_t rc_inflate_workspace_bytes(int n_streams, size_t out_stride)
+{
+    return inflate_workspace_bytes(n_streams, out_stride) + 256;
+}
+
+extern "C" int rc_inflate_zlib(rc_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_offsets, const uint32_t *d_in_bytes,
+                               int n_streams, void *d_workspace, size_t workspace_bytes, uint8_t *d_out,
+                               size_t out_stride, uint32_t *d_out_bytes, uint32_t *d_status, void *stream)
+{
+    if (!ctx) return -1;
+    if (n_streams <= 0) return 0;
+    if (out_stride % 16) RC_FAIL(ctx, -1, "out_stride must be a multiple of 16");
+    if (workspace_bytes < rc_inflate_workspace_bytes(n_streams, out_stride)) RC_FAIL(ctx, -1, "workspace too small");
+    return launch_inflate(ctx, d_in, d_in_offsets, d_in_bytes, n_streams, d_workspace, d_out, out_stride, d_out_bytes,
+                          d_status, (cudaStream_t)stream);
+}
+
+struct ReadWs {
+    uint32_t *tilecnt, *tilepre;
+    uint16_t *segpre;
+};
+
+static ReadWs carve_read(Carver &c, const rc_config *cfg, const Geom &g)
+{
+    ReadWs w;
+    const size_t F = (size_t)cfg->max_frames;
+    w.tilecnt = c.take<uint32_t>(F * g.NT);
+    w.tilepre = c.take<uint32_t>(F * (g.NT + 1));
+    w.segpre = c.take<uint16_t>(F * g.NT * SEGS_PER_TILE);
+    return w;
+}
+
+extern "C" int rc_unpack_sparse(rc_ctx *ctx, const rc_config *cfg, const uint32_t *d_maps, const uint8_t *d_packed,
+                                size_t packed_stride, int n_frames, void *d_workspace, size_t workspace_bytes,
+                                uint64_t *d_triples, size_t triple_capacity, uint32_t *d_counts, void *stream)
+{
+    if (!ctx) return -1;
+    if (check_cfg(ctx, cfg)) return -1;
+    if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames exceeds max_frames");
+    if (workspace_bytes < rc_read_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
+    if (packed_stride % 4) RC_FAIL(ctx, -1, "packed_stride must be a multiple of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom g = make_geom(cfg->ny, cfg->nx);
+    Carver c(d_workspace);
+    const ReadWs w = carve_read(c, cfg, g);
+    int rc;
+    if ((rc = launch_map_counts(ctx, g, d_maps, n_frames, w.tilecnt, w.segpre, st))) return rc;
+    if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, n_frames, w.tilepre, d_counts, nullptr, 0, st))) return rc;
+    return launch_unpack_sparse(ctx, g, cfg->reduction_level, cfg->bit_depth, d_maps, d_packed, packed_stride, w.segpre,
+                                w.tilepre, n_frames, d_triples, triple_capacity, st);
+}
+
+extern "C" int rc_unpack_dense(rc_ctx *ctx, const rc_config *cfg, const uint32_t *d_maps, const uint8_t *d_packed,
+                               size_t packed_stride, int n_frames, void *d_workspace, size_t workspace_bytes,
+                               void *d_dense, uint32_t *d_sum, uint32_t *d_counts, void *stream)
+{
+    if (!ctx) return -1;
+    if (check_cfg(ctx, cfg)) return -1;
+    if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames exceeds max_frames");
+    if (workspace_bytes < rc_read_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
+    if (packed_stride % 4) RC_FAIL(ctx, -1, "packed_stride must be a multiple of 4");
+    if (!d_dense && !d_sum) RC_FAIL(ctx, -1, "need d_dense and/or d_sum");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom g = make_geom(cfg->ny, cfg->nx);
+    Carver c(d_workspace);
+    const ReadWs w = carve_read(c, cfg, g);
+    int rc;
+    if ((rc = launch_map_counts(ctx, g, d_maps, n_frames, w.tilecnt, w.segpre, st))) return rc;
+    if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, n_frames, w.tilepre, d_counts, nullptr, 0, st))) return rc;
+    return launch_unpack_dense(ctx, g, cfg->itemsize, cfg->reduction_level, cfg->bit_depth, d_maps, d_packed,
+                               packed_stride, w.segpre, w.tilepre, n_frames, d_dense, d_sum, st);
+}
+
+extern "C" int rc_bit_unpack(rc_ctx *ctx, int bit_depth, const uint8_t *d_packed, uint64_t n_values, uint64_t *d_out,
+                             void *stream)
+{
+    if (!ctx) return -1;
+    if (bit_depth < 1 || bit_depth > 16) RC_FAIL(ctx, -1, "bit_depth must be 1..16");
+    return launch_bitunpack_flat(ctx, bit_depth, d_packed, n_values, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int rc_bit_pack(rc_ctx *ctx, int bit_depth, const uint16_t *d_vals, uint64_t n_values, uint8_t *d_packed,
+                           void *stream)
+{
+    if (!ctx) return -1;
+    if (bit_depth < 1 || bit_depth > 16) RC_FAIL(ctx, -1, "bit_depth must be 1..16");
+    if ((uintptr_t)d_packed % 4) RC_FAIL(ctx, -1, "d_packed must be 4-byte aligned");
+    return launch_bitpack_flat(ctx, bit_depth, d_vals, n_values, d_packed, (cudaStream_t)stream);
+}

@@ -1,0 +1,443 @@
+// ccl.cu -- 8-connected puddle labelling on the bit-packed binary map and the per-puddle reductions
+// of reduction levels 2 and 4.
+//
+// Replaces scipy.ndimage.label(binary, 3x3) (recode_writer.py:443), get_summary_stats_nb
+// (pyrecode/utils/converters.py:262-297), get_centroids_2D_nb (:157-259) and make_binary_map (:300-309).
+//
+// Representation: union-find over foreground SLOTS (common.cuh).  parent[slot] <= slot always, so the root
+// of a puddle is its first pixel in raster order -- exactly scipy's label order (labels numbered by the
+// raster order of each component's first pixel).  Only foreground pixels are ever touched: the kernels
+// walk the set bits of the map words, so the work is O(foreground), not O(pixels).
+//
+//   k_ccl_union     one thread per map word; links each foreground pixel to its W / NW / N / NE neighbours
+//                   with atomicMin unions.
+//   k_ccl_flatten   parent[slot] = root; L2: folds each member's value into acc[root] (max or sum);
+//                   L4: grows the root's bounding box (row extent, left / right column extents).
+//   k_ccl_roots     per tile: compacts per-root payloads (L2 statistics, centroids, ordinals) in slot order
+//                   == label order.
+//   k_l4_centroids  one thread per root: replays the puddle's pixels in raster order inside its bounding
+//                   box with the reference's float32-after-every-add accumulation, divides, rounds half to
+//                   even and sets the centroid bit.  Single-pixel puddles are their own centroid.
+#include "common.cuh"
+#include "kernels.cuh"
+
+__device__ __forceinline__ uint32_t uf_find_ro(const uint32_t *parent, uint32_t x)
+{
+    // volatile: other threads lower parents concurrently; any value read is a valid ancestor
+    uint32_t p = ((const volatile uint32_t *)parent)[x];
+    while (p != x) {
+        x = p;
+        p = ((const volatile uint32_t *)parent)[x];
+    }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b)
+{
+    while (true) {
+        a = uf_find_ro(parent, a);
+        b = uf_find_ro(parent, b);
+        if (a == b) return;
+        if (a > b) { uint32_t t = a; a = b; b = t; }
+        const uint32_t old = atomicMin(&parent[b], a);   // link the larger root under the smaller
+        if (old == b) return;
+        b = old;                                         // b was linked elsewhere meanwhile: merge with that
+    }
+}
+
+__device__ __forceinline__ uint32_t get_bit(const uint32_t *__restrict__ map, uint32_t q)
+{
+    return (map[q >> 5] >> (q & 31)) & 1u;
+}
+
+// slot of the first pixel of word w (whether or not it is set)
+__device__ __forceinline__ uint32_t word_slot_base(const uint32_t *__restrict__ map,
+                                                   const uint16_t *__restrict__ segpre, uint32_t w)
+{
+    const uint32_t seg = w >> 3;
+    uint32_t s = ((w >> 8) << 13) + segpre[seg];
+    for (uint32_t i = seg << 3; i < w; i++) s += __popc(map[i]);
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_union(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ segpre_all, int NT,
+            uint32_t *__restrict__ parent_all, int nx, uint32_t MW)
+{
+    const int f = blockIdx.y;
+    const uint32_t w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= MW) return;
+    const uint32_t *map = maps + (size_t)f * MS;
+    uint32_t bits = map[w];
+    if (!bits) return;
+    const uint16_t *segpre = segpre_all + (size_t)f * NT * SEGS_PER_TILE;
+    uint32_t *parent = parent_all + (size_t)f * ((size_t)NT * TILE_PX);
+    uint32_t s = word_slot_base(map, segpre, w);
+    uint32_t p0 = w << 5;
+    uint32_t r = p0 / (uint32_t)nx, c = p0 - r * (uint32_t)nx;   // of bit 0; advanced incrementally
+    uint32_t prev_k = 0;
+    while (bits) {
+        const uint32_t k = __ffs(bits) - 1;
+        bits &= bits - 1;
+        c += k - prev_k;
+        prev_k = k;
+        while (c >= (uint32_t)nx) { c -= nx; r++; }
+        const uint32_t p = p0 + k;
+        if (c > 0 && get_bit(map, p - 1)) uf_union(parent, s, slot_of(map, segpre, p - 1));
+        if (r > 0) {
+            const uint32_t up = p - nx;
+            if (get_bit(map, up)) {
+                // N is set: NW and NE are horizontally adjacent to N, their own W-links connect them
+                uf_union(parent, s, slot_of(map, segpre, up));
+            } else {
+                if (c > 0 && get_bit(map, up - 1)) uf_union(parent, s, slot_of(map, segpre, up - 1));
+                if (c + 1 < (uint32_t)nx && get_bit(map, up + 1)) uf_union(parent, s, slot_of(map, segpre, up + 1));
+            }
+        }
+        s++;
+    }
+}
+
+// MODE 0: labels only.  MODE 1: L2 max.  MODE 2: L2 sum.  MODE 3: L4 bounding boxes.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_ccl_flatten(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ segpre_all, int NT,
+              uint32_t *__restrict__ parent_all, uint32_t *__restrict__ acc_all, uint32_t *__restrict__ bbox_all,
+              int nx, uint32_t MW)
+{
+    const int f = blockIdx.y;
+    const uint32_t w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= MW) return;
+    const uint32_t *map = maps + (size_t)f * MS;
+    uint32_t bits = map[w];
+    if (!bits) return;
+    const size_t slots = (size_t)NT * TILE_PX;
+    const uint16_t *segpre = segpre_all + (size_t)f * NT * SEGS_PER_TILE;
+    uint32_t *parent = parent_all + (size_t)f * slots;
+    uint32_t s = word_slot_base(map, segpre, w);
+    const uint32_t p0 = w << 5;
+    while (bits) {
+        const uint32_t k = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint32_t root = uf_find_ro(parent, s);
+        if (root != s) {
+            parent[s] = root;
+            if (MODE == 1) atomicMax(&acc_all[(size_t)f * slots + root], acc_all[(size_t)f * slots + s]);
+            if (MODE == 2) atomicAdd(&acc_all[(size_t)f * slots + root], acc_all[(size_t)f * slots + s]);
+            if (MODE == 3) {
+                // pixel of the root: invert the slot -> pixel map by rank select inside the root's tile
+                // is expensive; instead the root's pixel index is kept in bbox[3] by k_l4_root_pixels.
+                const uint32_t p = p0 + k;
+                const uint32_t rp = bbox_all[((size_t)f * slots + root) * 4 + 3];
+                const uint32_t r = p / (uint32_t)nx, c = p - r * (uint32_t)nx;
+                const uint32_t rr = rp / (uint32_t)nx, rc = rp - rr * (uint32_t)nx;
+                uint32_t *bb = bbox_all + ((size_t)f * slots + root) * 4;
+                atomicMax(&bb[0], r - rr);                       // rows below the root (root is the top row)
+                if (c < rc) atomicMax(&bb[1], rc - c);           // columns left of the root
+                if (c > rc) atomicMax(&bb[2], c - rc);           // columns right of the root
+            }
+        }
+        s++;
+    }
+}
+
+// L4: bbox[slot] = {0, 0, 0, pixel index} for every foreground slot (must precede k_ccl_flatten<3>)
+__global__ void __launch_bounds__(256)
+k_l4_init_bbox(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ segpre_all, int NT,
+               uint32_t *__restrict__ bbox_all, uint32_t MW)
+{
+    const int f = blockIdx.y;
+    const uint32_t w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= MW) return;
+    const uint32_t *map = maps + (size_t)f * MS;
+    uint32_t bits = map[w];
+    if (!bits) return;
+    const size_t slots = (size_t)NT * TILE_PX;
+    uint32_t s = word_slot_base(map, segpre_all + (size_t)f * NT * SEGS_PER_TILE, w);
+    while (bits) {
+        const uint32_t k = __ffs(bits) - 1;
+        bits &= bits - 1;
+        reinterpret_cast<uint4 *>(bbox_all)[(size_t)f * slots + s] = make_uint4(0, 0, 0, (w << 5) + k);
+        s++;
+    }
+}
+
+// ---- root compaction ---------------------------------------------------------------------------
+// For tile (f, tile): roots in slot order get local ordinals 0..; rootcnt[f][tile] = number of roots.
+// PAYLOAD 0: ord[slot] = local ordinal (for label images)
+// PAYLOAD 1: out16[tile-compacted] = (uint16) acc[slot]                (L2 statistics)
+// PAYLOAD 2: out64[tile-compacted] = cent[slot] (float2 as uint64)     (L4 centroid lists)
+// PAYLOAD 3: count only
+template <int PAYLOAD>
+__global__ void __launch_bounds__(256)
+k_ccl_roots(const uint32_t *__restrict__ tilecnt, int NT, const uint32_t *__restrict__ parent_all,
+            const uint32_t *__restrict__ acc_all, const uint64_t *__restrict__ cent_all,
+            uint32_t *__restrict__ rootcnt, uint32_t *__restrict__ ord_all, uint16_t *__restrict__ out16,
+            uint64_t *__restrict__ out64)
+{
+    __shared__ uint32_t s_warp[9];
+    const int f = blockIdx.x, tile = blockIdx.y, t = threadIdx.x;
+    const size_t slots = (size_t)NT * TILE_PX;
+    const size_t fs = (size_t)f * slots;
+    const uint32_t tb = (uint32_t)tile * TILE_PX;
+    const uint32_t cnt = tilecnt[(size_t)f * NT + tile];
+    uint32_t carry = 0;
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 256) {
+        const uint32_t i = i0 + t;
+        const uint32_t s = tb + i;
+        const bool is_root = i < cnt && parent_all[fs + s] == s;
+        uint32_t total;
+        const uint32_t e = block_excl_scan<8>(is_root ? 1u : 0u, s_warp, &total);
+        if (is_root) {
+            const uint32_t j = carry + e;
+            if (PAYLOAD == 0) ord_all[fs + s] = j;
+            if (PAYLOAD == 1) out16[fs + tb + j] = (uint16_t)acc_all[fs + s];
+            if (PAYLOAD == 2) out64[fs + tb + j] = cent_all[fs + s];
+        }
+        carry += total;
+        __syncthreads();
+    }
+    if (t == 0) rootcnt[(size_t)f * NT + tile] = carry;
+}
+
+// dense label image: label = global ordinal of the root + 1 (scipy numbering), 0 = background
+__global__ void __launch_bounds__(256)
+k_ccl_label_image(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ segpre_all, int NT,
+                  const uint32_t *__restrict__ parent_all, const uint32_t *__restrict__ ord_all,
+                  const uint32_t *__restrict__ rootpre_all, int32_t *__restrict__ labels, size_t P, uint32_t MW)
+{
+    const int f = blockIdx.y;
+    const uint32_t w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= MW) return;
+    const uint32_t *map = maps + (size_t)f * MS;
+    const uint32_t bits = map[w];
+    const size_t slots = (size_t)NT * TILE_PX;
+    const uint32_t *parent = parent_all + (size_t)f * slots;
+    const uint32_t *ord = ord_all + (size_t)f * slots;
+    const uint32_t *rootpre = rootpre_all + (size_t)f * (NT + 1);
+    uint32_t s = bits ? word_slot_base(map, segpre_all + (size_t)f * NT * SEGS_PER_TILE, w) : 0;
+    int32_t *out = labels + (size_t)f * P;
+    const size_t p0 = (size_t)w << 5;
+    for (int k = 0; k < 32; k++) {
+        if (p0 + k >= P) break;
+        int32_t L = 0;
+        if (bits & (1u << k)) {
+            const uint32_t root = parent[s];
+            L = (int32_t)(rootpre[root >> 13] + ord[root]) + 1;
+            s++;
+        }
+        out[p0 + k] = L;
+    }
+}
+
+// ---- L4 centroids ------------------------------------------------------------------------------
+// One thread per root.  mode: 0/1 weighted (converters.py:167-197), 2 max pixel (:229-259), 3 unweighted (:200-226).
+// Each += of the reference is float64 arithmetic rounded to float32 (numba: float32 element += float64 value).
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ segpre_all, int NT,
+               const uint32_t *__restrict__ parent_all, const uint32_t *__restrict__ bbox_all,
+               const T *__restrict__ vals_all, int ny, int nx, uint32_t MW, int mode,
+               uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all)
+{
+    const int f = blockIdx.y;
+    const uint32_t w = blockIdx.x * 128 + threadIdx.x;
+    if (w >= MW) return;
+    const uint32_t *map = maps + (size_t)f * MS;
+    uint32_t bits = map[w];
+    if (!bits) return;
+    const size_t slots = (size_t)NT * TILE_PX;
+    const uint16_t *segpre = segpre_all + (size_t)f * NT * SEGS_PER_TILE;
+    const uint32_t *parent = parent_all + (size_t)f * slots;
+    const T *vals = vals_all + (size_t)f * slots;
+    uint32_t *map2 = map2_all + (size_t)f * MS;
+    uint32_t s = word_slot_base(map, segpre, w);
+    const uint32_t p0 = w << 5;
+    for (; bits; s++) {
+        const uint32_t k = __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (parent[s] != s) continue;
+        const uint32_t p = p0 + k;
+        const uint32_t r0 = p / (uint32_t)nx, c0 = p - r0 * (uint32_t)nx;
+        const uint4 bb = reinterpret_cast<const uint4 *>(bbox_all)[(size_t)f * slots + s];
+        float fr, fc;
+        if ((bb.x | bb.y | bb.z) == 0) {
+            // single-pixel puddle: RN32(v*r)/v rounds back to r (|error| <= r * 2^-23 << 0.5); same for c
+            const float v = (float)vals[s];
+            if (mode == 2 || mode == 3) { fr = (float)r0; fc = (float)c0; }
+            else {
+                fr = __fdiv_rn((float)((double)v * (double)r0), v);
+                fc = __fdiv_rn((float)((double)v * (double)c0), v);
+            }
+        } else {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            bool first = true;
+            const uint32_t cl = c0 - bb.y, cr = c0 + bb.z;
+            for (uint32_t r = r0; r <= r0 + bb.x; r++) {
+                const uint32_t q0 = r * (uint32_t)nx + cl, q1 = r * (uint32_t)nx + cr;   // inclusive pixel range
+                for (uint32_t ww = q0 >> 5; ww <= (q1 >> 5); ww++) {
+                    uint32_t mb = map[ww];
+                    if (ww == (q0 >> 5)) mb &= 0xffffffffu << (q0 & 31);
+                    if (ww == (q1 >> 5)) mb &= 0xffffffffu >> (31 - (q1 & 31));
+                    while (mb) {
+                        const uint32_t kk = __ffs(mb) - 1;
+                        mb &= mb - 1;
+                        const uint32_t q = (ww << 5) + kk;
+                        const uint32_t sq = slot_of(map, segpre, q);
+                        if (parent[sq] != s) continue;
+                        const double v = (double)vals[sq];
+                        const uint32_t c = q - r * (uint32_t)nx;
+                        if (mode == 2) {
+                            if (first || v > (double)a2) { a0 = (float)r; a1 = (float)c; a2 = (float)v; }
+                        } else if (mode == 3) {
+                            a0 = (float)((double)a0 + (double)r);
+                            a1 = (float)((double)a1 + (double)c);
+                            a2 = (float)((double)a2 + 1.0);
+                        } else {
+                            a0 = (float)((double)a0 + v * (double)r);
+                            a1 = (float)((double)a1 + v * (double)c);
+                            a2 = (float)((double)a2 + v);
+                        }
+                        first = false;
+                    }
+                }
+            }
+            if (mode == 2) { fr = a0; fc = a1; }
+            else { fr = __fdiv_rn(a0, a2); fc = __fdiv_rn(a1, a2); }
+        }
+        if (cent_all) {
+            const uint64_t pk = (uint64_t)__float_as_uint(fr) | ((uint64_t)__float_as_uint(fc) << 32);
+            cent_all[(size_t)f * slots + s] = pk;
+        }
+        if (map2_all) {
+            const long rr = (long)rintf(fr), cc = (long)rintf(fc);     // round half to even (np.round)
+            if (rr >= 0 && rr < ny && cc >= 0 && cc < nx) {
+                const uint32_t q = (uint32_t)rr * (uint32_t)nx + (uint32_t)cc;
+                atomicOr(&map2[q >> 5], 1u << (q & 31));
+            }
+        }
+    }
+}
+
+
+// parent[slot] = slot for every foreground slot (when the map did not come from k_reduce_tiles)
+__global__ void __launch_bounds__(256)
+k_ccl_init(const uint32_t *__restrict__ tilecnt, int NT, uint32_t *__restrict__ parent_all)
+{
+    const int f = blockIdx.x, tile = blockIdx.y;
+    const uint32_t cnt = tilecnt[(size_t)f * NT + tile];
+    const uint32_t tb = (uint32_t)tile * TILE_PX;
+    uint32_t *parent = parent_all + (size_t)f * ((size_t)NT * TILE_PX);
+    for (uint32_t i = threadIdx.x; i < cnt; i += 256) parent[tb + i] = tb + i;
+}
+
+// centroid lists in label order from the tile-compacted per-root payloads
+__global__ void __launch_bounds__(256)
+k_gather_centroids(const uint64_t *__restrict__ cent_tiles, const uint32_t *__restrict__ rootpre_all, int NT,
+                   float *__restrict__ out, size_t capacity)
+{
+    const int f = blockIdx.x, tile = blockIdx.y;
+    const uint32_t *rootpre = rootpre_all + (size_t)f * (NT + 1);
+    const uint32_t r0 = rootpre[tile], r1 = rootpre[tile + 1];
+    const uint64_t *src = cent_tiles + (size_t)f * ((size_t)NT * TILE_PX) + (size_t)tile * TILE_PX;
+    for (uint32_t j = threadIdx.x; j < r1 - r0; j += 256) {
+        if ((size_t)(r0 + j) >= capacity) break;
+        const uint64_t pk = src[j];
+        float *o = out + ((size_t)f * capacity + r0 + j) * 2;
+        o[0] = __uint_as_float((uint32_t)pk);
+        o[1] = __uint_as_float((uint32_t)(pk >> 32));
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+int launch_ccl_init(rc_ctx *ctx, const Geom &g, const uint32_t *tilecnt, uint32_t *parent, int F, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    k_ccl_init<<<dim3(F, g.NT), 256, 0, st>>>(tilecnt, g.NT, parent);
+    RC_LAUNCH_CHECK(ctx, "k_ccl_init");
+    return 0;
+}
+
+int launch_gather_centroids(rc_ctx *ctx, const Geom &g, const uint64_t *cent_tiles, const uint32_t *rootpre, int F,
+                            float *out, size_t capacity, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    k_gather_centroids<<<dim3(F, g.NT), 256, 0, st>>>(cent_tiles, rootpre, g.NT, out, capacity);
+    RC_LAUNCH_CHECK(ctx, "k_gather_centroids");
+    return 0;
+}
+int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *segpre, uint32_t *parent,
+                     int F, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    dim3 grid((unsigned)((g.MW + 255) / 256), F);
+    k_ccl_union<<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, g.nx, (uint32_t)g.MW);
+    RC_LAUNCH_CHECK(ctx, "k_ccl_union");
+    return 0;
+}
+
+int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *segpre,
+                       uint32_t *parent, uint32_t *acc, uint32_t *bbox, int F, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    dim3 grid((unsigned)((g.MW + 255) / 256), F);
+    const uint32_t MW = (uint32_t)g.MW;
+    if (mode == 3) {
+        k_l4_init_bbox<<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, bbox, MW);
+        RC_LAUNCH_CHECK(ctx, "k_l4_init_bbox");
+    }
+    switch (mode) {
+    case 0: k_ccl_flatten<0><<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, acc, bbox, g.nx, MW); break;
+    case 1: k_ccl_flatten<1><<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, acc, bbox, g.nx, MW); break;
+    case 2: k_ccl_flatten<2><<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, acc, bbox, g.nx, MW); break;
+    default: k_ccl_flatten<3><<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, acc, bbox, g.nx, MW); break;
+    }
+    RC_LAUNCH_CHECK(ctx, "k_ccl_flatten");
+    return 0;
+}
+
+int launch_ccl_roots(rc_ctx *ctx, const Geom &g, int payload, const uint32_t *tilecnt, const uint32_t *parent,
+                     const uint32_t *acc, const uint64_t *cent, uint32_t *rootcnt, uint32_t *ord, uint16_t *out16,
+                     uint64_t *out64, int F, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    dim3 grid(F, g.NT);
+    if (payload == 0)
+        k_ccl_roots<0><<<grid, 256, 0, st>>>(tilecnt, g.NT, parent, acc, cent, rootcnt, ord, out16, out64);
+    else if (payload == 1)
+        k_ccl_roots<1><<<grid, 256, 0, st>>>(tilecnt, g.NT, parent, acc, cent, rootcnt, ord, out16, out64);
+    else if (payload == 2)
+        k_ccl_roots<2><<<grid, 256, 0, st>>>(tilecnt, g.NT, parent, acc, cent, rootcnt, ord, out16, out64);
+    else
+        k_ccl_roots<3><<<grid, 256, 0, st>>>(tilecnt, g.NT, parent, acc, cent, rootcnt, ord, out16, out64);
+    RC_LAUNCH_CHECK(ctx, "k_ccl_roots");
+    return 0;
+}
+
+int launch_ccl_label_image(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *segpre,
+                           const uint32_t *parent, const uint32_t *ord, const uint32_t *rootpre, int32_t *labels,
+                           int F, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    dim3 grid((unsigned)((g.MW + 255) / 256), F);
+    k_ccl_label_image<<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, ord, rootpre, labels, g.P,
+                                            (uint32_t)g.MW);
+    RC_LAUNCH_CHECK(ctx, "k_ccl_label_image");
+    return 0;
+}
+
+int launch_l4_centroids(rc_ctx *ctx, const Geom &g, int itemsize, int mode, const uint32_t *maps,
+                        const uint16_t *segpre, const uint32_t *parent, const uint32_t *bbox, const void *vals,
+                        uint32_t *map2, uint64_t *cent, int F, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    dim3 grid((unsigned)((g.MW + 127) / 128), F);
+    if (itemsize == 2)
+        k_l4_centroids<uint16_t><<<grid, 128, 0, st>>>(maps, g.MS, segpre, g.NT, parent, bbox, (const uint16_t *)vals,
+                                                       g.ny, g.nx, (uint32_t)g.MW, mode, map2, cent);
+    else
+        k_l4_centroids<uint8_t><<<grid, 128, 0, st>>>(maps, g.MS, segpre, g.NT, parent, bbox, (const uint8_t *)vals,
+                                                      g.ny, g.nx, (uint32_t)g.MW, mode, map2, cent);
+    RC_LAUNCH_CHECK(ctx, "k_l4_centroids");
+    return 0;
+}

@@ -1,0 +1,162 @@
+// common.cuh -- shared definitions of librecode_b200 (sm_100a only).
+//
+// Device data layout (all per batch of F frames; P = ny*nx pixels per frame):
+//   map      uint32 [F][MS]        binary map words, pixel i -> word i>>5, bit i&31 (== byte i>>3, bit i&7
+//                                  on a little-endian host: recode_writer.py:622-634).  MS = MW rounded up to 8.
+//   tile     8192 consecutive pixels (256 map words) in linear (raster) order; NT tiles per frame.
+//   segment  256 consecutive pixels (8 map words = one 32-byte sector); 32 segments per tile.
+//   slot     index of a foreground pixel in the "tile-compacted" space: tile*8192 + rank of the pixel
+//            among the foreground pixels of its tile.  Monotone in raster order.  All per-foreground
+//            arrays (vals, parent, acc ...) are indexed by slot, so a tile never needs another tile's
+//            prefix to place its data, and only tilecnt[tile] entries per tile are ever touched.
+//   tilecnt  uint32 [F][NT]        foreground pixels per tile
+//   tilepre  uint32 [F][NT+1]      exclusive scan of tilecnt (tilepre[NT] = n foreground pixels of the frame)
+//   segpre   uint16 [F][NT*32]     foreground pixels of the tile before each segment
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/recode_b200.h"
+
+#define RC_VERSION 100
+
+constexpr int TILE_PX = 8192;
+constexpr int TILE_WORDS = TILE_PX / 32;     // 256
+constexpr int SEG_PX = 256;
+constexpr int SEG_WORDS = SEG_PX / 32;       // 8
+constexpr int SEGS_PER_TILE = TILE_PX / SEG_PX;  // 32
+
+struct rc_ctx {
+    int device;
+    int sm_count;
+    char err[512];
+};
+
+#define RC_FAIL(ctx, code, ...)                                   \
+    do {                                                          \
+        snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);    \
+        return (code);                                            \
+    } while (0)
+
+#define RC_CUDA(ctx, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            RC_FAIL(ctx, -2, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                \
+                    cudaGetErrorString(e__));                                                     \
+    } while (0)
+
+#define RC_LAUNCH_CHECK(ctx, name)                                                                \
+    do {                                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess)                                                                   \
+            RC_FAIL(ctx, -3, "launch of %s failed: %s", name, cudaGetErrorString(e__));          \
+    } while (0)
+
+// ---- geometry ------------------------------------------------------------------------------
+struct Geom {
+    int ny, nx;
+    size_t P;        // pixels per frame
+    size_t MW;       // map words actually holding pixels: ceil(P/32)
+    size_t MS;       // map stride in words (multiple of 8 -> 32-byte aligned frames)
+    int NT;          // tiles per frame
+    size_t slots;    // NT * TILE_PX
+    size_t map_bytes;  // ceil(P/8): the on-disk size of a map
+};
+
+static inline __host__ __device__ size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+static inline Geom make_geom(int ny, int nx)
+{
+    Geom g;
+    g.ny = ny; g.nx = nx;
+    g.P = (size_t)ny * (size_t)nx;
+    g.MW = (g.P + 31) / 32;
+    g.NT = (int)((g.P + TILE_PX - 1) / TILE_PX);
+    g.MS = (size_t)g.NT * TILE_WORDS;   // whole tiles: kernels may write full tile rows of words
+    g.slots = (size_t)g.NT * TILE_PX;
+    g.map_bytes = (g.P + 7) / 8;
+    return g;
+}
+
+// ---- bump allocator over the caller-supplied workspace ---------------------------------------
+struct Carver {
+    uint8_t *base;
+    size_t off;
+    explicit Carver(void *p) : base((uint8_t *)p), off(0) {}
+    template <typename T>
+    T *take(size_t n)
+    {
+        off = round_up(off, 256);
+        T *r = base ? (T *)(base + off) : nullptr;
+        off += n * sizeof(T);
+        return r;
+    }
+    size_t used() const { return round_up(off, 256); }
+};
+
+// ---- warp / block primitives -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += n;
+    }
+    return v;
+}
+
+// exclusive scan over a block of NW warps; returns exclusive prefix, total in *total.
+// s_warp must hold NW+1 uint32.  Contains two __syncthreads().
+template <int NW>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = warp_incl_scan(v);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < NW ? s_warp[lane] : 0;
+        uint32_t wi = warp_incl_scan(w);
+        if (lane < NW) s_warp[lane] = wi - w;
+        if (lane == NW - 1) s_warp[NW] = wi;
+    }
+    __syncthreads();
+    *total = s_warp[NW];
+    return incl - v + s_warp[warp];
+}
+
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t *p)
+{
+    return __ldg(p);
+}
+
+// streaming 128-bit load: read-only path, do not allocate in L1 (frames are read exactly once)
+__device__ __forceinline__ uint4 ld_stream_u4(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream_u2(const void *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+// slot of pixel q (which must be foreground) of one frame.  map/segpre point at the frame's arrays.
+__device__ __forceinline__ uint32_t slot_of(const uint32_t *__restrict__ map, const uint16_t *__restrict__ segpre,
+                                            uint32_t q)
+{
+    const uint32_t w = q >> 5, seg = q >> 8;
+    uint32_t r = (q & ~(uint32_t)(TILE_PX - 1)) + segpre[seg];
+    const uint32_t w0 = seg << 3;
+    for (uint32_t i = w0; i < w; i++) r += __popc(map[i]);
+    r += __popc(map[w] & ((1u << (q & 31)) - 1u));
+    return r;
+}

@@ -1,0 +1,458 @@
+// deflate.cu -- batched zlib-format deflate on the GPU and assembly of the ReCoDe frame records.
+//
+// Replaces zlib.compress (pyrecode/recode_compressors.py:84-85) and the record assembly of
+// ReCoDeWriter._reduce_compress / _write_to_frame_buffer (pyrecode/recode_writer.py:482-574).
+//
+// Pipeline over S input streams (for the writer: 2 per frame, map and packed values):
+//   k_deflate_plan      1 CTA    chunks per stream (16 KiB each), exclusive scan -> chunk_base, total
+//   k_deflate_chunks    persistent CTAs pull chunk tickets; each chunk is an independent, byte-aligned
+//                       piece (deflate_chunk.cuh) written to its scratch slot, plus its Adler-32 partials
+//   k_stream_finalize   1 CTA per stream: prefix of piece sizes, Adler-32 combine, total stream size
+//   k_layout_*          destination offset of every stream (fixed stride, or ReCoDe records incl. the
+//                       [frame_id][sizes...] header and the exclusive scan of record sizes)
+//   k_copy_pieces       persistent CTAs copy pieces to their final byte offsets (funnel-shifted 32-bit
+//                       words) and write the zlib header / final block / Adler-32 trailer
+// Only compact records cross PCIe afterwards.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "deflate_chunk.cuh"
+
+__global__ void __launch_bounds__(256)
+k_deflate_plan(const uint32_t *__restrict__ in_bytes, int n_streams, uint32_t *__restrict__ chunk_base,
+               uint32_t *__restrict__ counters)
+{
+    __shared__ uint32_t s_warp[9];
+    uint32_t carry = 0;
+    for (int s0 = 0; s0 < n_streams; s0 += 256) {
+        const int s = s0 + threadIdx.x;
+        const uint32_t nc = s < n_streams ? (in_bytes[s] + DF_CHUNK - 1) / DF_CHUNK : 0;
+        uint32_t total;
+        const uint32_t e = block_excl_scan<8>(nc, s_warp, &total);
+        if (s < n_streams) chunk_base[s] = carry + e;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        chunk_base[n_streams] = carry;
+        counters[0] = 0;      // deflate ticket
+        counters[1] = 0;      // copy ticket
+    }
+}
+
+__device__ __forceinline__ int find_stream(const uint32_t *__restrict__ chunk_base, int n_streams, uint32_t gci)
+{
+    int lo = 0, hi = n_streams;         // chunk_base[lo] <= gci < chunk_base[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_base[mid] <= gci) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(DF_THREADS)
+k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                 const uint32_t *__restrict__ in_bytes, int n_streams, const uint32_t *__restrict__ chunk_base,
+                 uint32_t *__restrict__ counters, int level, uint8_t *__restrict__ scratch,
+                 uint32_t *__restrict__ chunk_bytes, uint2 *__restrict__ chunk_adler)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    DeflateShared &S = *reinterpret_cast<DeflateShared *>(smem_raw);
+    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_warp[9];
+    const int t = threadIdx.x;
+    const uint32_t total_chunks = chunk_base[n_streams];
+
+    while (true) {
+        if (t == 0) s_ticket = atomicAdd(&counters[0], 1u);
+        __syncthreads();
+        const uint32_t gci = s_ticket;
+        if (gci >= total_chunks) break;
+        const int s = find_stream(chunk_base, n_streams, gci);
+        const uint32_t ci = gci - chunk_base[s];
+        const uint32_t slen = in_bytes[s];
+        const int clen = (int)min((uint32_t)DF_CHUNK, slen - ci * DF_CHUNK);
+        const uint8_t *src = in + in_off[s] + (size_t)ci * DF_CHUNK;
+
+        // ---- phase 0: zero state, stage the chunk (coalesced 128-bit loads -> transposed, swizzled smem)
+        for (int i = t; i < DF_OUT_WORDS; i += DF_THREADS) S.out[i] = 0;
+        for (int i = t; i < DF_NSYM; i += DF_THREADS) S.hist[i] = 0;
+        if (t == 0) { S.n_match = 0; S.adler_a = 0; S.adler_b = 0; S.stored = 0; }
+        const bool aligned = ((uintptr_t)src & 15) == 0;
+        for (int u = t; u < DF_CHUNK / 16; u += DF_THREADS) {
+            const int o = u * 16;
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (aligned && o + 16 <= clen) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(src + o);
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            } else if (o < clen) {
+                for (int b = 0; b < 16 && o + b < clen; b++) w[b >> 2] |= (uint32_t)src[o + b] << (8 * (b & 3));
+            }
+            const int tt = u >> 2, k0 = (u & 3) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; i++) S.in32[df_in_index(tt, k0 + i)] = w[i];
+        }
+        __syncthreads();
+
+        // ---- phase 1: histogram + adler
+        if (level > 0) df_phase_hist(S, t, clen);
+        else {
+            // stored-only: still need adler partials
+            int nbytes = clen - t * DF_SEG;
+            if (nbytes > DF_SEG) nbytes = DF_SEG;
+            uint32_t a = 0, b = 0;
+            for (int i = 0; i < nbytes; i++) {
+                const uint32_t c = (S.in32[df_in_index(t, i >> 2)] >> (8 * (i & 3))) & 0xffu;
+                a += c;
+                b += (uint32_t)(clen - (t * DF_SEG + i)) * c;
+            }
+            if (nbytes > 0) { atomicAdd(&S.adler_a, a % 65521u); atomicAdd(&S.adler_b, b % 65521u); }
+        }
+        __syncthreads();
+
+        uint32_t body_bits = 0;
+        bool stored = level == 0;
+        if (!stored) {
+            // ---- phase 2: sort symbols by count (bitonic, 512 keys), build codes + header
+            if (t == 0) S.hist[256] = 1;
+            __syncthreads();
+            for (int i = t; i < 512; i += DF_THREADS) {
+                const uint32_t c = i < DF_NSYM ? S.hist[i] : 0;
+                S.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
+            }
+            __syncthreads();
+            for (int k = 2; k <= 512; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = t; i < 512; i += DF_THREADS) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const uint32_t a = S.keys[i], b = S.keys[ixj];
+                            const bool up = (i & k) == 0;
+                            if ((a > b) == up) { S.keys[i] = b; S.keys[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            // number of used symbols = first index holding the sentinel
+            if (t == 0) {
+                int lo = 0, hi = 512;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (S.keys[mid] != 0xffffffffu) lo = mid + 1; else hi = mid; }
+                df_phase_build(S, lo);
+            }
+            __syncthreads();
+
+            // ---- phase 3: sizes + exclusive scan
+            df_phase_size(S, t, clen);
+            uint32_t tok_bits;
+            const uint32_t e = block_excl_scan<8>(S.tbits[t], s_warp, &tok_bits);
+            S.tbits[t] = e;
+            body_bits = S.header_bits + tok_bits;
+            stored = df_dynamic_bytes(S, body_bits) >= (uint32_t)clen + 10u;
+            __syncthreads();
+        }
+
+        if (!stored) {
+            df_phase_emit(S, t, clen);
+            __syncthreads();
+            if (t == 0) df_phase_finish(S, body_bits);
+        } else {
+            // stored block: 00 | LEN | ~LEN | data | sync marker (00 0000 FFFF)
+            uint8_t *ob = reinterpret_cast<uint8_t *>(S.out);
+            if (t == 0) {
+                ob[0] = 0;
+                ob[1] = (uint8_t)(clen & 0xff); ob[2] = (uint8_t)(clen >> 8);
+                ob[3] = (uint8_t)(~clen & 0xff); ob[4] = (uint8_t)((~clen >> 8) & 0xff);
+                ob[5 + clen] = 0; ob[6 + clen] = 0; ob[7 + clen] = 0; ob[8 + clen] = 0xff; ob[9 + clen] = 0xff;
+                S.out_bytes = (uint32_t)clen + 10u;
+            }
+            // word 1 holds header byte 4 and data bytes 0..2: written bytewise, so no ordering issue
+            for (int i = t; i < clen; i += DF_THREADS) {
+                const int tt = i / DF_SEG, bi = i % DF_SEG;
+                ob[5 + i] = (uint8_t)(S.in32[df_in_index(tt, bi >> 2)] >> (8 * (bi & 3)));
+            }
+        }
+        __syncthreads();
+
+        // ---- store the piece
+        const uint32_t nb = S.out_bytes;
+        uint4 *dst = reinterpret_cast<uint4 *>(scratch + (size_t)gci * DF_SLOT_BYTES);
+        const uint4 *so = reinterpret_cast<const uint4 *>(S.out);
+        for (uint32_t i = t; i < (nb + 15) / 16; i += DF_THREADS) dst[i] = so[i];
+        if (t == 0) {
+            chunk_bytes[gci] = nb;
+            chunk_adler[gci] = make_uint2(S.adler_a % 65521u, S.adler_b % 65521u);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- per-stream totals ---------------------------------------------------------------------------
+// wrap = 1: zlib wrapper (2-byte header, final empty fixed block 03 00, Adler-32): stream = 2 + pieces + 6
+// wrap = 0: raw concatenation (mode 0: chunk_bytes must already hold the raw chunk lengths)
+__global__ void __launch_bounds__(256)
+k_stream_finalize(const uint32_t *__restrict__ in_bytes, const uint32_t *__restrict__ chunk_base,
+                  const uint32_t *__restrict__ chunk_bytes, const uint2 *__restrict__ chunk_adler, int wrap,
+                  uint32_t *__restrict__ chunk_rel, uint32_t *__restrict__ stream_bytes,
+                  uint32_t *__restrict__ stream_adler)
+{
+    __shared__ uint32_t s_warp[9];
+    const int s = blockIdx.x, t = threadIdx.x;
+    const uint32_t c0 = chunk_base[s], c1 = chunk_base[s + 1];
+    uint32_t carry = 0;
+    for (uint32_t i0 = c0; i0 < c1; i0 += 256) {
+        const uint32_t i = i0 + t;
+        const uint32_t v = i < c1 ? chunk_bytes[i] : 0;
+        uint32_t total;
+        const uint32_t e = block_excl_scan<8>(v, s_warp, &total);
+        if (i < c1) chunk_rel[i] = carry + e;
+        carry += total;
+        __syncthreads();
+    }
+    if (t == 0) {
+        stream_bytes[s] = wrap ? carry + 8u : carry;
+        if (wrap) {
+            // Adler-32 over the concatenated chunks from (A_c, B_c, len_c) partials
+            uint32_t s1 = 1, s2 = 0;
+            const uint32_t slen = in_bytes[s];
+            for (uint32_t i = c0; i < c1; i++) {
+                const uint32_t clen = min((uint32_t)DF_CHUNK, slen - (i - c0) * DF_CHUNK);
+                const uint2 ab = chunk_adler[i];
+                s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)clen * s1 + ab.y) % 65521u);
+                s1 = (s1 + ab.x) % 65521u;
+            }
+            stream_adler[s] = (s2 << 16) | s1;
+        }
+    }
+}
+
+// ---- layouts ---------------------------------------------------------------------------------------
+__global__ void k_layout_strided(const uint32_t *__restrict__ stream_bytes, int n_streams, size_t stride,
+                                 uint64_t *__restrict__ stream_dst, uint32_t *__restrict__ out_bytes)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    stream_dst[s] = (uint64_t)s * stride;
+    out_bytes[s] = stream_bytes[s];
+}
+
+__device__ __forceinline__ void put_u32le(uint8_t *p, uint32_t v)
+{
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+
+// ReCoDe records.  streams_per_frame = 2 (L1/L2: map, vals) or 1 (L3/L4: map); stream index = f*spf + j.
+// mode 1 header: [frame_id][n_comp_map]([n_comp_vals][n_packed]); mode 0 header: [frame_id]([n_packed]).
+__global__ void __launch_bounds__(256)
+k_layout_records(const uint32_t *__restrict__ stream_bytes, const uint32_t *__restrict__ packed_bytes, int n_frames,
+                 int spf, int mode, uint32_t first_frame_id, size_t capacity, uint8_t *__restrict__ records,
+                 uint64_t *__restrict__ record_off, uint64_t *__restrict__ stream_dst, uint32_t *__restrict__ status)
+{
+    __shared__ uint32_t s_warp[9];
+    __shared__ uint64_t s_carry;
+    const int t = threadIdx.x;
+    if (t == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t hdr = mode == 1 ? (spf == 2 ? 16u : 8u) : (spf == 2 ? 8u : 4u);
+    for (int f0 = 0; f0 < n_frames; f0 += 256) {
+        const int f = f0 + t;
+        uint32_t len = 0, l0 = 0, l1 = 0;
+        if (f < n_frames) {
+            l0 = stream_bytes[f * spf];
+            l1 = spf == 2 ? stream_bytes[f * spf + 1] : 0;
+            len = hdr + l0 + l1;        // < 2^32: bounded by the records capacity check below
+        }
+        uint32_t total;
+        const uint32_t e = block_excl_scan<8>(len, s_warp, &total);
+        const uint64_t off = s_carry + e;
+        if (f < n_frames) {
+            record_off[f] = off;
+            stream_dst[f * spf] = off + hdr;
+            if (spf == 2) stream_dst[f * spf + 1] = off + hdr + l0;
+            if (off + len <= capacity) {
+                uint8_t *r = records + off;
+                put_u32le(r, first_frame_id + (uint32_t)f);
+                if (mode == 1) {
+                    put_u32le(r + 4, l0);
+                    if (spf == 2) { put_u32le(r + 8, l1); put_u32le(r + 12, packed_bytes[f]); }
+                } else if (spf == 2) {
+                    put_u32le(r + 4, packed_bytes[f]);
+                }
+            } else {
+                atomicOr(status, RC_STATUS_RECORDS_OVERFLOW);
+            }
+        }
+        __syncthreads();
+        if (t == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (t == 0) record_off[n_frames] = s_carry;
+}
+
+// ---- piece copy ------------------------------------------------------------------------------------
+// src is 4-byte aligned (scratch slot or a 16-byte aligned raw stream + multiple of 16 KiB); dst arbitrary.
+__device__ __forceinline__ void copy_bytes_shifted(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
+                                                   uint32_t n, int t, int nt)
+{
+    // head bytes up to the first 4-byte aligned destination address
+    uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
+    if (head > n) head = n;
+    if ((uint32_t)t < head) dst[t] = src[t];
+    const uint32_t nw = (n - head) >> 2;
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
+    const uint32_t sh = head * 8;     // source byte offset of the first aligned destination word is `head`
+    if (sh == 0) {
+        for (uint32_t i = t; i < nw; i += nt) d32[i] = s32[i];
+    } else {
+        for (uint32_t i = t; i < nw; i += nt) d32[i] = __funnelshift_r(s32[i], s32[i + 1], sh);
+    }
+    const uint32_t done = head + nw * 4;
+    if (done + (uint32_t)t < n) dst[done + t] = src[done + t];      // tail: at most 3 bytes
+}
+
+__global__ void __launch_bounds__(256)
+k_copy_pieces(const uint8_t *__restrict__ raw_in, const uint64_t *__restrict__ in_off,
+              const uint32_t *__restrict__ in_bytes, int n_streams, const uint32_t *__restrict__ chunk_base,
+              const uint8_t *__restrict__ scratch, const uint32_t *__restrict__ chunk_bytes,
+              const uint32_t *__restrict__ chunk_rel, const uint32_t *__restrict__ stream_bytes,
+              const uint32_t *__restrict__ stream_adler, const uint64_t *__restrict__ stream_dst, int wrap,
+              uint8_t *__restrict__ out, size_t capacity, uint32_t *__restrict__ counters,
+              uint32_t *__restrict__ status)
+{
+    __shared__ uint32_t s_ticket;
+    const int t = threadIdx.x;
+    const uint32_t total_chunks = chunk_base[n_streams];
+    // empty streams have no chunk: their wrapper is written by the first CTA
+    if (wrap && blockIdx.x == 0) {
+        for (int s = t; s < n_streams; s += 256) {
+            if (chunk_base[s + 1] == chunk_base[s] && stream_dst[s] + 8 <= capacity) {
+                uint8_t *d = out + stream_dst[s];
+                d[0] = 0x78; d[1] = 0x01; d[2] = 0x03; d[3] = 0x00; d[4] = 0; d[5] = 0; d[6] = 0; d[7] = 1;
+            }
+        }
+    }
+    while (true) {
+        if (t == 0) s_ticket = atomicAdd(&counters[1], 1u);
+        __syncthreads();
+        const uint32_t gci = s_ticket;
+        __syncthreads();
+        if (gci >= total_chunks) break;
+        const int s = find_stream(chunk_base, n_streams, gci);
+        const uint32_t ci = gci - chunk_base[s];
+        const uint64_t sd = stream_dst[s];
+        const uint32_t sb = stream_bytes[s];
+        if (sd + sb > capacity) {
+            if (t == 0) atomicOr(status, RC_STATUS_RECORDS_OVERFLOW);
+            continue;
+        }
+        const uint32_t nb = chunk_bytes[gci];
+        uint8_t *dst = out + sd + (wrap ? 2 : 0) + chunk_rel[gci];
+        const uint8_t *src = wrap ? scratch + (size_t)gci * DF_SLOT_BYTES
+                                  : raw_in + in_off[s] + (size_t)ci * DF_CHUNK;
+        copy_bytes_shifted(dst, src, nb, t, 256);
+        if (wrap && t == 0) {
+            if (ci == 0) { out[sd] = 0x78; out[sd + 1] = 0x01; }
+            if (gci + 1 == chunk_base[s + 1]) {
+                uint8_t *tr = out + sd + sb - 6;
+                const uint32_t ad = stream_adler[s];
+                tr[0] = 0x03; tr[1] = 0x00;          // BFINAL=1, BTYPE=01, end-of-block: the final empty block
+                tr[2] = (uint8_t)(ad >> 24); tr[3] = (uint8_t)(ad >> 16); tr[4] = (uint8_t)(ad >> 8); tr[5] = (uint8_t)ad;
+            }
+        }
+    }
+}
+
+// mode 0: chunk_bytes = raw chunk lengths
+__global__ void k_raw_chunk_bytes(const uint32_t *__restrict__ in_bytes, const uint32_t *__restrict__ chunk_base,
+                                  int n_streams, uint32_t *__restrict__ chunk_bytes)
+{
+    const int s = blockIdx.x;
+    const uint32_t c0 = chunk_base[s], c1 = chunk_base[s + 1], slen = in_bytes[s];
+    for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x)
+        chunk_bytes[i] = min((uint32_t)DF_CHUNK, slen - (i - c0) * DF_CHUNK);
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+size_t deflate_max_chunks(int n_streams, size_t max_in_bytes)
+{
+    return (size_t)n_streams * ((max_in_bytes + DF_CHUNK - 1) / DF_CHUNK);
+}
+
+DeflateWs carve_deflate_ws(Carver &c, int n_streams, size_t max_chunks, bool need_scratch)
+{
+    DeflateWs w;
+    w.chunk_base = c.take<uint32_t>((size_t)n_streams + 1);
+    w.counters = c.take<uint32_t>(8);
+    w.chunk_bytes = c.take<uint32_t>(max_chunks + 1);
+    w.chunk_rel = c.take<uint32_t>(max_chunks + 1);
+    w.chunk_adler = c.take<uint2>(max_chunks + 1);
+    w.stream_bytes = c.take<uint32_t>((size_t)n_streams + 1);
+    w.stream_adler = c.take<uint32_t>((size_t)n_streams + 1);
+    w.stream_dst = c.take<uint64_t>((size_t)n_streams + 1);
+    w.scratch = need_scratch ? c.take<uint8_t>(max_chunks * DF_SLOT_BYTES + 64) : nullptr;
+    w.max_chunks = max_chunks;
+    return w;
+}
+
+static int deflate_smem_bytes() { return (int)sizeof(DeflateShared); }
+
+// encodes (mode 1) or sizes (mode 0) the chunks and finalizes per-stream totals
+int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, const uint8_t *in, const uint64_t *in_off,
+                           const uint32_t *in_bytes, int n_streams, const DeflateWs &w, cudaStream_t st)
+{
+    if (n_streams <= 0) return 0;
+    k_deflate_plan<<<1, 256, 0, st>>>(in_bytes, n_streams, w.chunk_base, w.counters);
+    RC_LAUNCH_CHECK(ctx, "k_deflate_plan");
+    if (wrap) {
+        static bool attr_set[64] = {false};
+        const int smem = deflate_smem_bytes();
+        if (!attr_set[ctx->device & 63]) {
+            RC_CUDA(ctx, cudaFuncSetAttribute(k_deflate_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set[ctx->device & 63] = true;
+        }
+        size_t want = w.max_chunks < (size_t)ctx->sm_count * 5 ? w.max_chunks : (size_t)ctx->sm_count * 5;
+        if (want < 1) want = 1;
+        k_deflate_chunks<<<(unsigned)want, DF_THREADS, smem, st>>>(in, in_off, in_bytes, n_streams, w.chunk_base,
+                                                                   w.counters, level, w.scratch, w.chunk_bytes,
+                                                                   w.chunk_adler);
+        RC_LAUNCH_CHECK(ctx, "k_deflate_chunks");
+    } else {
+        k_raw_chunk_bytes<<<n_streams, 128, 0, st>>>(in_bytes, w.chunk_base, n_streams, w.chunk_bytes);
+        RC_LAUNCH_CHECK(ctx, "k_raw_chunk_bytes");
+    }
+    k_stream_finalize<<<n_streams, 256, 0, st>>>(in_bytes, w.chunk_base, w.chunk_bytes, w.chunk_adler, wrap,
+                                                 w.chunk_rel, w.stream_bytes, w.stream_adler);
+    RC_LAUNCH_CHECK(ctx, "k_stream_finalize");
+    return 0;
+}
+
+int launch_layout_strided(rc_ctx *ctx, const DeflateWs &w, int n_streams, size_t stride, uint32_t *out_bytes,
+                          cudaStream_t st)
+{
+    k_layout_strided<<<(n_streams + 255) / 256, 256, 0, st>>>(w.stream_bytes, n_streams, stride, w.stream_dst, out_bytes);
+    RC_LAUNCH_CHECK(ctx, "k_layout_strided");
+    return 0;
+}
+
+int launch_layout_records(rc_ctx *ctx, const DeflateWs &w, const uint32_t *packed_bytes, int n_frames, int spf,
+                          int mode, uint32_t first_frame_id, uint8_t *records, size_t capacity,
+                          uint64_t *record_off, uint32_t *status, cudaStream_t st)
+{
+    k_layout_records<<<1, 256, 0, st>>>(w.stream_bytes, packed_bytes, n_frames, spf, mode, first_frame_id, capacity,
+                                        records, record_off, w.stream_dst, status);
+    RC_LAUNCH_CHECK(ctx, "k_layout_records");
+    return 0;
+}
+
+int launch_copy_pieces(rc_ctx *ctx, const DeflateWs &w, int wrap, const uint8_t *raw_in, const uint64_t *in_off,
+                       const uint32_t *in_bytes, int n_streams, uint8_t *out, size_t capacity, uint32_t *status,
+                       cudaStream_t st)
+{
+    size_t want = w.max_chunks < (size_t)ctx->sm_count * 8 ? w.max_chunks : (size_t)ctx->sm_count * 8;
+    if (want < 1) want = 1;
+    k_copy_pieces<<<(unsigned)want, 256, 0, st>>>(raw_in, in_off, in_bytes, n_streams, w.chunk_base, w.scratch,
+                                                  w.chunk_bytes, w.chunk_rel, w.stream_bytes, w.stream_adler,
+                                                  w.stream_dst, wrap, out, capacity, w.counters, status);
+    RC_LAUNCH_CHECK(ctx, "k_copy_pieces");
+    return 0;
+}

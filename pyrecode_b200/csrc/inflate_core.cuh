@@ -1,0 +1,262 @@
+// inflate_core.cuh -- sequential deflate decoder used by one lane of a warp.
+//
+// Replaces zlib.decompress on the read path (reference: pyrecode/recode_compressors.py:42-43, called from
+// recode_reader.py:397-400,428-431,454).  Accepts every deflate block type (stored, fixed, dynamic) because
+// reference-written files are ordinary multi-block dynamic streams.
+//
+// The decoder works on a [start, ...) bit range of a compressed buffer and can stop at the first empty
+// stored block (the sync-flush marker our encoder puts after every chunk), which is what makes streams
+// written by deflate.cu decodable chunk-parallel.  __host__ __device__ so tests/csrc can run the same code
+// against stock zlib output on the CPU (test infrastructure only).
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define IF_HD __host__ __device__ __forceinline__
+#else
+#define IF_HD inline
+#endif
+
+constexpr int IF_LUT_BITS = 9;
+constexpr int IF_LUT_SIZE = 1 << IF_LUT_BITS;
+
+// decoding tables of one Huffman code: fast LUT + canonical (count/symbol) fallback for longer codes
+struct IfTable {
+    uint16_t lut[IF_LUT_SIZE];     // (len << 12) | symbol, len = 0 -> not in LUT
+    uint16_t count[16];            // codes per length
+    uint16_t symbol[288];          // symbols ordered by (length, value)
+};
+
+struct IfTables {
+    IfTable ll;    // literal / length
+    IfTable d;     // distance (only the first 32 symbol slots used)
+};
+
+enum { IF_OK = 0, IF_END_SYNC = 1, IF_END_FINAL = 2, IF_ERR_DATA = -1, IF_ERR_OUT = -2, IF_ERR_IN = -3 };
+
+struct IfBits {
+    const uint8_t *in;
+    uint64_t nbytes;     // bytes available
+    uint64_t pos;        // next byte to load
+    uint64_t buf;
+    int cnt;             // valid bits in buf
+    IF_HD void init(const uint8_t *p, uint64_t n, uint64_t start_byte)
+    {
+        in = p; nbytes = n; pos = start_byte; buf = 0; cnt = 0;
+    }
+    IF_HD void refill()
+    {
+        while (cnt <= 56) {
+            const uint64_t b = pos < nbytes ? in[pos] : 0;    // zeros past the end; overrun is checked by callers
+            pos++;
+            buf |= b << cnt;
+            cnt += 8;
+        }
+    }
+    IF_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
+    IF_HD void drop(int n) { buf >>= n; cnt -= n; }
+    IF_HD uint32_t get(int n)
+    {
+        if (cnt < n) refill();
+        const uint32_t v = peek(n);
+        drop(n);
+        return v;
+    }
+    // position (in bits) of the next unread bit
+    IF_HD uint64_t bitpos() const { return pos * 8 - (uint64_t)cnt; }
+    IF_HD bool overrun() const { return bitpos() > nbytes * 8; }
+    IF_HD void align_byte() { drop(cnt & 7); }
+};
+
+IF_HD uint32_t if_bitrev(uint32_t c, int n)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < n; i++) { r = (r << 1) | (c & 1); c >>= 1; }
+    return r;
+}
+
+// builds a table from code lengths; returns 0 ok, <0 over-subscribed / incomplete (incomplete is accepted only
+// for a single one-bit code, like zlib's inflate_table)
+IF_HD int if_build(IfTable &T, const uint8_t *len, int n)
+{
+    for (int i = 0; i < 16; i++) T.count[i] = 0;
+    for (int s = 0; s < n; s++) T.count[len[s]]++;
+    for (int i = 0; i < IF_LUT_SIZE; i++) T.lut[i] = 0;
+    if (T.count[0] == n) return 0;                 // no codes at all (legal for distances)
+    int left = 1;
+    for (int l = 1; l <= 15; l++) {
+        left <<= 1;
+        left -= T.count[l];
+        if (left < 0) return -1;                   // over-subscribed
+    }
+    uint16_t offs[16];
+    offs[1] = 0;
+    for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + T.count[l];
+    for (int s = 0; s < n; s++) if (len[s]) T.symbol[offs[len[s]]++] = (uint16_t)s;
+    // fast LUT for codes up to IF_LUT_BITS
+    uint32_t code = 0;
+    int idx = 0;
+    for (int l = 1; l <= 15; l++) {
+        for (int c = 0; c < T.count[l]; c++, idx++, code++) {
+            if (l <= IF_LUT_BITS) {
+                const uint32_t r = if_bitrev(code, l);
+                const uint16_t e = (uint16_t)((l << 12) | T.symbol[idx]);
+                for (uint32_t x = r; x < (uint32_t)IF_LUT_SIZE; x += 1u << l) T.lut[x] = e;
+            }
+        }
+        code <<= 1;
+    }
+    if (left > 0) {
+        // incomplete: only tolerated when there is exactly one code, of length 1
+        int total = 0;
+        for (int l = 1; l <= 15; l++) total += T.count[l];
+        if (!(total == 1 && T.count[1] == 1)) return -2;
+    }
+    return 0;
+}
+
+// decode one symbol; returns -1 on invalid code
+IF_HD int if_decode(IfBits &B, const IfTable &T)
+{
+    if (B.cnt < 15) B.refill();
+    const uint16_t e = T.lut[B.peek(IF_LUT_BITS)];
+    if (e) {
+        B.drop(e >> 12);
+        return e & 0xfff;
+    }
+    // canonical walk (puff-style), MSB-first code
+    int code = 0, first = 0, index = 0;
+    uint64_t bits = B.buf;
+    for (int l = 1; l <= 15; l++) {
+        code |= (int)(bits & 1);
+        bits >>= 1;
+        const int count = T.count[l];
+        if (code - count < first) {
+            B.drop(l);
+            return T.symbol[index + (code - first)];
+        }
+        index += count;
+        first += count;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+struct IfOut {
+    uint8_t *out;
+    uint64_t cap;
+    uint64_t n;          // bytes produced
+    uint32_t s1, s2;     // Adler-32 partials of the produced bytes, started from (0, 0)
+    IF_HD void put(uint8_t c)
+    {
+        out[n++] = c;
+        s1 += c; s2 += s1;
+        if ((n & 2047) == 0) { s1 %= 65521u; s2 %= 65521u; }
+    }
+};
+
+// Decodes blocks starting at byte `start` of in[0..nbytes).  Stops after the final block (IF_END_FINAL) or,
+// if stop_at_sync, right after an empty stored block (IF_END_SYNC).  *end_byte receives the byte offset
+// following the consumed data (only meaningful for the two END codes: both end byte aligned... the final
+// block does not: it is rounded up).  Window = everything written to O.out so far (O.n); a distance reaching
+// before O.out[0] is an error, i.e. independent chunks only.
+IF_HD int if_inflate(const uint8_t *in, uint64_t nbytes, uint64_t start, IfOut &O, IfTables &T, bool stop_at_sync,
+                     uint64_t *end_byte)
+{
+    const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+    IfBits B;
+    B.init(in, nbytes, start);
+    while (true) {
+        const uint32_t bfinal = B.get(1);
+        const uint32_t btype = B.get(2);
+        if (btype == 0) {
+            B.align_byte();
+            const uint32_t len = B.get(16), nlen = B.get(16);
+            if ((len ^ 0xffffu) != nlen) return IF_ERR_DATA;
+            if (B.overrun()) return IF_ERR_IN;
+            if (O.n + len > O.cap) return IF_ERR_OUT;
+            // the bit buffer holds whole bytes here
+            for (uint32_t i = 0; i < len; i++) O.put((uint8_t)B.get(8));
+            if (B.overrun()) return IF_ERR_IN;
+            if (len == 0 && !bfinal && stop_at_sync) { *end_byte = B.bitpos() >> 3; return IF_END_SYNC; }
+        } else if (btype == 1 || btype == 2) {
+            uint8_t lens[320];
+            int nlen_codes, ndist_codes;
+            if (btype == 1) {
+                for (int i = 0; i < 144; i++) lens[i] = 8;
+                for (int i = 144; i < 256; i++) lens[i] = 9;
+                for (int i = 256; i < 280; i++) lens[i] = 7;
+                for (int i = 280; i < 288; i++) lens[i] = 8;
+                for (int i = 0; i < 32; i++) lens[288 + i] = 5;     // 30 and 31 never occur in valid data
+                nlen_codes = 288; ndist_codes = 32;
+            } else {
+                nlen_codes = (int)B.get(5) + 257;
+                ndist_codes = (int)B.get(5) + 1;
+                const int ncl = (int)B.get(4) + 4;
+                if (nlen_codes > 286 || ndist_codes > 30) return IF_ERR_DATA;
+                uint8_t cl[19];
+                for (int i = 0; i < 19; i++) cl[i] = 0;
+                for (int i = 0; i < ncl; i++) cl[order[i]] = (uint8_t)B.get(3);
+                if (if_build(T.d, cl, 19) != 0) return IF_ERR_DATA;     // T.d reused as the code-length table
+                int idx = 0;
+                while (idx < nlen_codes + ndist_codes) {
+                    const int sym = if_decode(B, T.d);
+                    if (sym < 0) return IF_ERR_DATA;
+                    if (sym < 16) lens[idx++] = (uint8_t)sym;
+                    else {
+                        int rep, val = 0;
+                        if (sym == 16) {
+                            if (idx == 0) return IF_ERR_DATA;
+                            val = lens[idx - 1];
+                            rep = 3 + (int)B.get(2);
+                        } else if (sym == 17) rep = 3 + (int)B.get(3);
+                        else rep = 11 + (int)B.get(7);
+                        if (idx + rep > nlen_codes + ndist_codes) return IF_ERR_DATA;
+                        while (rep--) lens[idx++] = (uint8_t)val;
+                    }
+                }
+                if (lens[256] == 0) return IF_ERR_DATA;
+                // move distance lengths to a fixed place
+                uint8_t dl[30];
+                for (int i = 0; i < ndist_codes; i++) dl[i] = lens[nlen_codes + i];
+                for (int i = 0; i < ndist_codes; i++) lens[288 + i] = dl[i];
+            }
+            if (B.overrun()) return IF_ERR_IN;
+            if (if_build(T.ll, lens, nlen_codes) != 0) return IF_ERR_DATA;
+            if (if_build(T.d, lens + 288, ndist_codes) != 0) return IF_ERR_DATA;
+            while (true) {
+                const int sym = if_decode(B, T.ll);
+                if (sym < 0) return IF_ERR_DATA;
+                if (sym < 256) {
+                    if (O.n >= O.cap) return IF_ERR_OUT;
+                    O.put((uint8_t)sym);
+                } else if (sym == 256) {
+                    break;
+                } else {
+                    const int li = sym - 257;
+                    if (li >= 29) return IF_ERR_DATA;
+                    const uint32_t len = lbase[li] + B.get(lext[li]);
+                    const int ds = if_decode(B, T.d);
+                    if (ds < 0 || ds >= 30) return IF_ERR_DATA;
+                    const uint32_t dist = dbase[ds] + B.get(dext[ds]);
+                    if (dist > O.n) return IF_ERR_DATA;          // reaches before this range's own output
+                    if (O.n + len > O.cap) return IF_ERR_OUT;
+                    for (uint32_t i = 0; i < len; i++) O.put(O.out[O.n - dist]);
+                }
+                if (B.overrun()) return IF_ERR_IN;
+            }
+        } else {
+            return IF_ERR_DATA;
+        }
+        if (bfinal) {
+            *end_byte = (B.bitpos() + 7) >> 3;
+            return B.overrun() ? IF_ERR_IN : IF_END_FINAL;
+        }
+    }
+}

@@ -1,0 +1,395 @@
+// reduce.cu -- streaming reduction kernels of the write path.
+//
+//   k_reduce_tiles   fused dark-threshold compare + binary-map bit packing + per-tile compaction of the
+//                    foreground values (reference: recode_writer.py:437 compare, :440 gather/subtract,
+//                    :456 + :622-634 _pack_binary_frame).  One CTA per (frame, tile of 8192 pixels); the
+//                    frame is read exactly once with 128-bit streaming loads.  HBM-bound:
+//                    algorithmic bytes per tile = 8192 * itemsize (frame) [+ the same for the threshold
+//                    tile, which stays L2-resident across the frames of a batch].
+//   k_scan_tiles     per-frame exclusive scan of the tile counts (tiny).
+//   k_bitpack        variable-bit-depth packing of tile-compacted values into the LSB-first bit stream
+//                    (reference: recode_writer.py:637-652 _bit_pack == reader.h:105-140); owner-computes
+//                    per 32-bit output word, no atomics.
+#include "common.cuh"
+#include "kernels.cuh"
+
+// ---- pixel-type helpers --------------------------------------------------------------------
+template <typename T> struct Px;
+
+template <> struct Px<uint16_t> {
+    static constexpr int W = 4;   // 32-bit words per group of 8 pixels
+    static __device__ __forceinline__ void load_stream(const uint16_t *p, uint32_t (&w)[4])
+    {
+        uint4 v = ld_stream_u4(p);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+    static __device__ __forceinline__ void load_cached(const uint16_t *p, uint32_t (&w)[4])
+    {
+        uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+    static __device__ __forceinline__ uint32_t get(const uint32_t (&w)[4], int k)
+    {
+        return (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+    }
+    static __device__ __forceinline__ void set(uint32_t (&w)[4], int k, uint32_t v)
+    {
+        w[k >> 1] |= v << ((k & 1) * 16);
+    }
+    // bit k = frame pixel k > threshold pixel k.  VIMNMX.U16x2 gives both halfword predicates of
+    // (t >= f) in one instruction; foreground is its complement.
+    static __device__ __forceinline__ uint32_t gt_mask(const uint32_t (&f)[4], const uint32_t (&t)[4])
+    {
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            bool ge_hi, ge_lo;
+            (void)__vibmax_u16x2(t[i], f[i], &ge_hi, &ge_lo);
+            m |= (ge_lo ? 0u : 1u) << (2 * i);
+            m |= (ge_hi ? 0u : 2u) << (2 * i);
+        }
+        return m;
+    }
+};
+
+template <> struct Px<uint8_t> {
+    static constexpr int W = 2;
+    static __device__ __forceinline__ void load_stream(const uint8_t *p, uint32_t (&w)[2])
+    {
+        uint2 v = ld_stream_u2(p);
+        w[0] = v.x; w[1] = v.y;
+    }
+    static __device__ __forceinline__ void load_cached(const uint8_t *p, uint32_t (&w)[2])
+    {
+        uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        w[0] = v.x; w[1] = v.y;
+    }
+    static __device__ __forceinline__ uint32_t get(const uint32_t (&w)[2], int k)
+    {
+        return (w[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+    }
+    static __device__ __forceinline__ void set(uint32_t (&w)[2], int k, uint32_t v)
+    {
+        w[k >> 2] |= v << ((k & 3) * 8);
+    }
+    static __device__ __forceinline__ uint32_t gt_mask(const uint32_t (&f)[2], const uint32_t (&t)[2])
+    {
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            uint32_t r = __vcmpgtu4(f[i], t[i]) & 0x01010101u;    // bit 0 of each byte
+            r = (r | (r >> 7) | (r >> 14) | (r >> 21)) & 0xfu;
+            m |= r << (4 * i);
+        }
+        return m;
+    }
+};
+
+// ---- K1 ------------------------------------------------------------------------------------
+// VALMODE: 0 = no value stream (L3), 1 = frame - thr (L1), 2 = raw frame value (L2 / L4)
+// CCL:     0 = none, 1 = parent[slot] = slot and acc[slot] = value (L2), 2 = parent only (L4)
+template <typename T, int VALMODE, int CCL>
+__global__ void __launch_bounds__(256)
+k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P, int NT, size_t MS,
+               uint32_t *__restrict__ maps, uint32_t *__restrict__ tilecnt, uint16_t *__restrict__ segpre,
+               T *__restrict__ vals, uint32_t *__restrict__ parent, uint32_t *__restrict__ acc, int vec_ok)
+{
+    constexpr int W = Px<T>::W;
+    const int t = threadIdx.x;
+    const int f = blockIdx.x;                 // frame fastest: CTAs running together share the threshold tile
+    const int tile = blockIdx.y;
+    const size_t base = (size_t)tile * TILE_PX;
+    const size_t left = P - base;
+    const int npx = left < (size_t)TILE_PX ? (int)left : TILE_PX;
+    const T *fr = frames + (size_t)f * P + base;
+    const T *th = thr + base;
+
+    __shared__ uint32_t s_mask[TILE_WORDS];
+    __shared__ uint16_t s_wpre[TILE_WORDS];
+    __shared__ uint32_t s_warp[9];
+    __shared__ T s_vals[VALMODE ? TILE_PX : 1];
+
+    uint32_t fw[4][W], tw[4][W];
+    uint32_t m = 0;
+    const bool fast = vec_ok && npx == TILE_PX;
+    if (fast) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) Px<T>::load_stream(fr + j * 2048 + t * 8, fw[j]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) Px<T>::load_cached(th + j * 2048 + t * 8, tw[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int i = 0; i < W; i++) { fw[j][i] = 0; tw[j][i] = 0; }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int q = j * 2048 + t * 8 + k;
+                if (q < npx) {
+                    Px<T>::set(fw[j], k, fr[q]);
+                    Px<T>::set(tw[j], k, th[q]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t mj = Px<T>::gt_mask(fw[j], tw[j]);
+        m |= mj << (8 * j);
+        reinterpret_cast<uint8_t *>(s_mask)[j * 256 + t] = (uint8_t)mj;
+    }
+    __syncthreads();
+
+    const uint32_t word = s_mask[t];          // pixels [32t, 32t+32) of the tile
+    maps[(size_t)f * MS + (size_t)tile * TILE_WORDS + t] = word;
+    const uint32_t pc = __popc(word);
+    uint32_t total;
+    const uint32_t excl = block_excl_scan<8>(pc, s_warp, &total);
+    s_wpre[t] = (uint16_t)excl;
+    if ((t & 7) == 0) segpre[((size_t)f * NT + tile) * SEGS_PER_TILE + (t >> 3)] = (uint16_t)excl;
+    if (t == 0) tilecnt[(size_t)f * NT + tile] = total;
+
+    if (VALMODE) {
+        __syncthreads();
+        if (m) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t wq = j * 64 + (t >> 2);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (m & (1u << (8 * j + k))) {
+                        const uint32_t bp = ((t & 3) << 3) + k;
+                        const uint32_t rank = s_wpre[wq] + __popc(s_mask[wq] & ((1u << bp) - 1u));
+                        uint32_t v = Px<T>::get(fw[j], k);
+                        if (VALMODE == 1) v -= Px<T>::get(tw[j], k);
+                        s_vals[rank] = (T)v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const size_t sbase = (size_t)f * ((size_t)NT * TILE_PX) + base;
+        for (uint32_t i = t; i < total; i += 256) {
+            const T v = s_vals[i];
+            vals[sbase + i] = v;
+            if (CCL) parent[sbase + i] = (uint32_t)(base + i);
+            if (CCL == 1) acc[sbase + i] = (uint32_t)v;
+        }
+    }
+}
+
+template <typename T>
+static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, int ccl, const void *frames,
+                                 const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *segpre,
+                                 void *vals, uint32_t *parent, uint32_t *acc, cudaStream_t st)
+{
+    const int vec_ok = ((g.P * sizeof(T)) % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)thr % 16 == 0);
+    dim3 grid(F, g.NT), block(256);
+#define RC_K1(VM, C)                                                                                          \
+    k_reduce_tiles<T, VM, C><<<grid, block, 0, st>>>((const T *)frames, (const T *)thr, g.P, g.NT, g.MS, maps, \
+                                                     tilecnt, segpre, (T *)vals, parent, acc, vec_ok)
+    if (valmode == 0) RC_K1(0, 0);
+    else if (valmode == 1) RC_K1(1, 0);
+    else if (ccl == 1) RC_K1(2, 1);
+    else if (ccl == 2) RC_K1(2, 2);
+    else RC_K1(2, 0);
+#undef RC_K1
+    RC_LAUNCH_CHECK(ctx, "k_reduce_tiles");
+    return 0;
+}
+
+int launch_reduce_tiles(rc_ctx *ctx, const Geom &g, int itemsize, int valmode, int ccl, const void *frames,
+                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *segpre, void *vals,
+                        uint32_t *parent, uint32_t *acc, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    if (itemsize == 2)
+        return launch_reduce_tiles_t<uint16_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, segpre, vals,
+                                               parent, acc, st);
+    return launch_reduce_tiles_t<uint8_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, segpre, vals, parent,
+                                          acc, st);
+}
+
+// ---- map-only tile counts (read side: a map came out of inflate) ------------------------------
+// Computes tilecnt / segpre from existing maps so the unpack kernels can rank pixels.
+__global__ void __launch_bounds__(256)
+k_map_counts(const uint32_t *__restrict__ maps, size_t MS, int NT, uint32_t *__restrict__ tilecnt,
+             uint16_t *__restrict__ segpre)
+{
+    __shared__ uint32_t s_warp[9];
+    const int t = threadIdx.x, f = blockIdx.x, tile = blockIdx.y;
+    const uint32_t word = maps[(size_t)f * MS + (size_t)tile * TILE_WORDS + t];
+    const uint32_t pc = __popc(word);
+    uint32_t total;
+    const uint32_t excl = block_excl_scan<8>(pc, s_warp, &total);
+    if ((t & 7) == 0) segpre[((size_t)f * NT + tile) * SEGS_PER_TILE + (t >> 3)] = (uint16_t)excl;
+    if (t == 0) tilecnt[(size_t)f * NT + tile] = total;
+}
+
+int launch_map_counts(rc_ctx *ctx, const Geom &g, const uint32_t *maps, int F, uint32_t *tilecnt, uint16_t *segpre,
+                      cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    k_map_counts<<<dim3(F, g.NT), 256, 0, st>>>(maps, g.MS, g.NT, tilecnt, segpre);
+    RC_LAUNCH_CHECK(ctx, "k_map_counts");
+    return 0;
+}
+
+// ---- K2: per-frame exclusive scan of tile counts ----------------------------------------------
+// counts[f] = n; packed_bytes[f] = ceil(n*b/8) when b > 0 (either may be null).
+__global__ void __launch_bounds__(256)
+k_scan_tiles(const uint32_t *__restrict__ tilecnt, int NT, uint32_t *__restrict__ tilepre,
+             uint32_t *__restrict__ counts, uint32_t *__restrict__ packed_bytes, int b)
+{
+    __shared__ uint32_t s_warp[9];
+    const int f = blockIdx.x, t = threadIdx.x;
+    const uint32_t *c = tilecnt + (size_t)f * NT;
+    uint32_t *p = tilepre + (size_t)f * (NT + 1);
+    uint32_t carry = 0;
+    for (int i0 = 0; i0 < NT; i0 += 256) {
+        const int i = i0 + t;
+        const uint32_t v = i < NT ? c[i] : 0;
+        uint32_t total;
+        const uint32_t e = block_excl_scan<8>(v, s_warp, &total);
+        if (i < NT) p[i] = carry + e;
+        carry += total;
+        __syncthreads();
+    }
+    if (t == 0) {
+        p[NT] = carry;
+        if (counts) counts[f] = carry;
+        if (packed_bytes) packed_bytes[f] = (uint32_t)(((uint64_t)carry * (uint32_t)b + 7) / 8);
+    }
+}
+
+int launch_scan_tiles(rc_ctx *ctx, const Geom &g, const uint32_t *tilecnt, int F, uint32_t *tilepre,
+                      uint32_t *counts, uint32_t *packed_bytes, int b, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    k_scan_tiles<<<F, 256, 0, st>>>(tilecnt, g.NT, tilepre, counts, packed_bytes, b);
+    RC_LAUNCH_CHECK(ctx, "k_scan_tiles");
+    return 0;
+}
+
+// ---- K3: bit packing -------------------------------------------------------------------------
+// Output word w of frame f gathers every value whose bit range [j*b, (j+1)*b) overlaps [32w, 32w+32).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bitpack(const T *__restrict__ vals, const uint32_t *__restrict__ tilepre, int NT, int b,
+          uint8_t *__restrict__ packed, size_t packed_stride)
+{
+    const int f = blockIdx.y;
+    const uint32_t *pre = tilepre + (size_t)f * (NT + 1);
+    const T *v = vals + (size_t)f * ((size_t)NT * TILE_PX);
+    uint32_t *out = reinterpret_cast<uint32_t *>(packed + (size_t)f * packed_stride);
+    const uint64_t n = pre[NT];
+    const uint64_t nbits = n * (uint64_t)b;
+    const uint64_t nwords = (nbits + 31) / 32;
+    const uint32_t vmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+    for (uint64_t w = (uint64_t)blockIdx.x * 256 + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * 256) {
+        const uint64_t bit0 = w * 32;
+        uint64_t j = bit0 / (uint32_t)b;
+        uint64_t jl = (bit0 + 31) / (uint32_t)b;
+        if (jl >= n) jl = n - 1;
+        // tile holding rank j: largest tt with pre[tt] <= j
+        int lo = 0, hi = NT;                    // invariant: pre[lo] <= j < pre[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pre[mid] <= j) lo = mid; else hi = mid;
+        }
+        int tt = lo;
+        uint32_t acc = 0;
+        for (; j <= jl; j++) {
+            while (pre[tt + 1] <= j) tt++;
+            const uint32_t val = (uint32_t)v[(size_t)tt * TILE_PX + (size_t)(j - pre[tt])] & vmask;
+            const int64_t sh = (int64_t)(j * (uint32_t)b) - (int64_t)bit0;
+            acc |= sh >= 0 ? (val << sh) : (val >> (-sh));
+        }
+        out[w] = acc;
+    }
+}
+
+int launch_bitpack(rc_ctx *ctx, const Geom &g, int val_itemsize, const void *vals, const uint32_t *tilepre, int F,
+                   int b, uint8_t *packed, size_t packed_stride, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    dim3 grid(64, F);
+    if (val_itemsize == 2)
+        k_bitpack<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)vals, tilepre, g.NT, b, packed, packed_stride);
+    else
+        k_bitpack<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)vals, tilepre, g.NT, b, packed, packed_stride);
+    RC_LAUNCH_CHECK(ctx, "k_bitpack");
+    return 0;
+}
+
+// ---- plain-array packers (c_recode.Reader.bit_pack / bit_unpack replacements) --------------------
+__global__ void k_bitpack_flat(const uint16_t *__restrict__ v, uint64_t n, int b, uint32_t *__restrict__ out)
+{
+    const uint64_t nwords = (n * (uint64_t)b + 31) / 32;
+    const uint32_t vmask = (1u << b) - 1u;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t bit0 = w * 32;
+        uint64_t j = bit0 / (uint32_t)b, jl = (bit0 + 31) / (uint32_t)b;
+        if (jl >= n) jl = n - 1;
+        uint32_t acc = 0;
+        for (; j <= jl; j++) {
+            const uint32_t val = (uint32_t)v[j] & vmask;
+            const int64_t sh = (int64_t)(j * (uint32_t)b) - (int64_t)bit0;
+            acc |= sh >= 0 ? (val << sh) : (val >> (-sh));
+        }
+        out[w] = acc;
+    }
+}
+
+__global__ void k_bitunpack_flat(const uint8_t *__restrict__ packed, uint64_t n, int b, uint64_t *__restrict__ out)
+{
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t bit = j * (uint32_t)b;
+        const uint64_t by = bit >> 3;
+        const int sh = (int)(bit & 7);
+        // b <= 16 and sh <= 7 -> at most 3 bytes
+        uint32_t x = packed[by];
+        if (sh + b > 8) x |= (uint32_t)packed[by + 1] << 8;
+        if (sh + b > 16) x |= (uint32_t)packed[by + 2] << 16;
+        out[j] = (x >> sh) & ((1u << b) - 1u);
+    }
+}
+
+int launch_bitpack_flat(rc_ctx *ctx, int b, const uint16_t *vals, uint64_t n, uint8_t *packed, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    const uint64_t nwords = (n * (uint64_t)b + 31) / 32;
+    const int blocks = (int)((nwords + 255) / 256 > 4096 ? 4096 : (nwords + 255) / 256);
+    k_bitpack_flat<<<blocks, 256, 0, st>>>(vals, n, b, reinterpret_cast<uint32_t *>(packed));
+    RC_LAUNCH_CHECK(ctx, "k_bitpack_flat");
+    return 0;
+}
+
+int launch_bitunpack_flat(rc_ctx *ctx, int b, const uint8_t *packed, uint64_t n, uint64_t *out, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    const int blocks = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+    k_bitunpack_flat<<<blocks, 256, 0, st>>>(packed, n, b, out);
+    RC_LAUNCH_CHECK(ctx, "k_bitunpack_flat");
+    return 0;
+}
+
+// ---- threshold frame -------------------------------------------------------------------------
+template <typename T>
+__global__ void k_make_threshold(const T *__restrict__ dark, T eps, T *__restrict__ thr, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        thr[i] = (T)(dark[i] + eps);
+}
+
+int launch_make_threshold(rc_ctx *ctx, int itemsize, const void *dark, uint64_t eps, void *thr, size_t n,
+                          cudaStream_t st)
+{
+    const int blocks = (int)((n + 255) / 256 > 2048 ? 2048 : (n + 255) / 256);
+    if (itemsize == 2)
+        k_make_threshold<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t *)dark, (uint16_t)eps, (uint16_t *)thr, n);
+    else
+        k_make_threshold<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t *)dark, (uint8_t)eps, (uint8_t *)thr, n);
+    RC_LAUNCH_CHECK(ctx, "k_make_threshold");
+    return 0;
+}

@@ -1,0 +1,136 @@
+// unpack.cu -- read-side unpack kernels.
+//
+// Replaces c_recode.Reader.get_frame_sparse (pyrecode/pyrecode.cpp:95-119 -> c_extensions/reader.h:10-68) and the
+// scipy COO -> dense step user code performs (recode_reader.py:464-471, tests/minimal_read_write_test.py:91),
+// plus the live-view accumulation of examples/ReCoDe_Live_View_MT.ipynb cell 1.
+//
+// The reference walks all ny*nx pixels with a per-bit inner loop.  Here a foreground pixel's rank comes from
+// popcounts (tile prefix + segment prefix + in-segment popc), its value is one funnel-shifted load at bit
+// rank*b, and the dense frame is written with full 128-bit coalesced stores (one warp = one 256-pixel
+// segment = 512 contiguous output bytes for uint16).  HBM-bound on the dense write: ny*nx*itemsize bytes/frame.
+#include "common.cuh"
+#include "kernels.cuh"
+
+__device__ __forceinline__ uint32_t fetch_bits(const uint32_t *__restrict__ packed32, uint64_t bit, int b)
+{
+    const uint64_t w = bit >> 5;
+    const uint32_t sh = (uint32_t)(bit & 31);
+    const uint32_t lo = packed32[w];
+    const uint32_t hi = (sh + b > 32) ? packed32[w + 1] : 0;
+    return __funnelshift_r(lo, hi, sh) & ((1u << b) - 1u);
+}
+
+__global__ void __launch_bounds__(256)
+k_unpack_sparse(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__restrict__ packed, size_t packed_stride,
+                const uint16_t *__restrict__ segpre_all, const uint32_t *__restrict__ tilepre_all, int NT, int nx,
+                uint32_t MW, int level, int b, uint64_t *__restrict__ triples, size_t capacity)
+{
+    const int f = blockIdx.y;
+    const uint32_t w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= MW) return;
+    const uint32_t *map = maps + (size_t)f * MS;
+    uint32_t bits = map[w];
+    if (!bits) return;
+    const uint16_t *segpre = segpre_all + (size_t)f * NT * SEGS_PER_TILE;
+    const uint32_t *tilepre = tilepre_all + (size_t)f * (NT + 1);
+    const uint32_t *pk = reinterpret_cast<const uint32_t *>(packed + (size_t)f * packed_stride);
+    // global rank of the first set bit of this word
+    const uint32_t seg = w >> 3;
+    uint64_t rank = (uint64_t)tilepre[w >> 8] + segpre[seg];
+    for (uint32_t i = seg << 3; i < w; i++) rank += __popc(map[i]);
+    uint64_t *out = triples + (size_t)f * capacity * 3;
+    const uint32_t p0 = w << 5;
+    while (bits) {
+        const uint32_t k = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint32_t p = p0 + k;
+        if (rank < capacity) {
+            const uint32_t r = p / (uint32_t)nx;
+            out[rank * 3 + 0] = r;
+            out[rank * 3 + 1] = p - r * (uint32_t)nx;
+            out[rank * 3 + 2] = level == 1 ? fetch_bits(pk, rank * (uint32_t)b, b) : 1u;
+        }
+        rank++;
+    }
+}
+
+// One warp per 256-pixel segment, lane l owns pixels [8l, 8l+8) of the segment.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_unpack_dense(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__restrict__ packed, size_t packed_stride,
+               const uint16_t *__restrict__ segpre_all, const uint32_t *__restrict__ tilepre_all, int NT, size_t P,
+               int level, int b, T *__restrict__ dense, uint32_t *__restrict__ sum, int vec_ok)
+{
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const uint32_t seg = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint32_t nseg = (uint32_t)NT * SEGS_PER_TILE;
+    if (seg >= nseg) return;
+    const size_t p_base = (size_t)seg * SEG_PX + (size_t)lane * 8;
+    if ((size_t)seg * SEG_PX >= P) return;
+    const uint8_t *mapb = reinterpret_cast<const uint8_t *>(maps + (size_t)f * MS);
+    const uint32_t m = mapb[(size_t)seg * 32 + lane];
+    const uint32_t pc = __popc(m);
+    const uint32_t incl = warp_incl_scan(pc);
+    uint64_t rank = (uint64_t)tilepre_all[(size_t)f * (NT + 1) + (seg >> 5)] +
+                    segpre_all[(size_t)f * nseg + seg] + (incl - pc);
+    const uint32_t *pk = reinterpret_cast<const uint32_t *>(packed + (size_t)f * packed_stride);
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v[k] = 0;
+        if (m & (1u << k)) {
+            v[k] = level == 1 ? fetch_bits(pk, rank * (uint32_t)b, b) : 1u;
+            rank++;
+            if (sum) atomicAdd(&sum[p_base + k], v[k]);
+        }
+    }
+    if (dense) {
+        T *o = dense + (size_t)f * P + p_base;
+        if (vec_ok && p_base + 8 <= P) {
+            if (sizeof(T) == 2) {
+                uint4 q;
+                q.x = v[0] | (v[1] << 16); q.y = v[2] | (v[3] << 16); q.z = v[4] | (v[5] << 16); q.w = v[6] | (v[7] << 16);
+                *reinterpret_cast<uint4 *>(o) = q;
+            } else {
+                uint2 q;
+                q.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+                q.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+                *reinterpret_cast<uint2 *>(o) = q;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (p_base + k < P) o[k] = (T)v[k];
+        }
+    }
+}
+
+int launch_unpack_sparse(rc_ctx *ctx, const Geom &g, int level, int b, const uint32_t *maps, const uint8_t *packed,
+                         size_t packed_stride, const uint16_t *segpre, const uint32_t *tilepre, int F,
+                         uint64_t *triples, size_t capacity, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    dim3 grid((unsigned)((g.MW + 255) / 256), F);
+    k_unpack_sparse<<<grid, 256, 0, st>>>(maps, g.MS, packed, packed_stride, segpre, tilepre, g.NT, g.nx,
+                                          (uint32_t)g.MW, level, b, triples, capacity);
+    RC_LAUNCH_CHECK(ctx, "k_unpack_sparse");
+    return 0;
+}
+
+int launch_unpack_dense(rc_ctx *ctx, const Geom &g, int itemsize, int level, int b, const uint32_t *maps,
+                        const uint8_t *packed, size_t packed_stride, const uint16_t *segpre, const uint32_t *tilepre,
+                        int F, void *dense, uint32_t *sum, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    const uint32_t nseg = (uint32_t)g.NT * SEGS_PER_TILE;
+    dim3 grid((nseg + 7) / 8, F);
+    const int vec_ok = dense && ((g.P * itemsize) % 16 == 0) && ((uintptr_t)dense % 16 == 0);
+    if (itemsize == 2)
+        k_unpack_dense<uint16_t><<<grid, 256, 0, st>>>(maps, g.MS, packed, packed_stride, segpre, tilepre, g.NT, g.P,
+                                                       level, b, (uint16_t *)dense, sum, vec_ok);
+    else
+        k_unpack_dense<uint8_t><<<grid, 256, 0, st>>>(maps, g.MS, packed, packed_stride, segpre, tilepre, g.NT, g.P,
+                                                      level, b, (uint8_t *)dense, sum, vec_ok);
+    RC_LAUNCH_CHECK(ctx, "k_unpack_dense");
+    return 0;
+}

@@ -1,0 +1,147 @@
+// codec_host_test.cpp -- TEST INFRASTRUCTURE: runs the __host__ __device__ phases of the GPU deflate encoder
+// (pyrecode_b200/csrc/deflate_chunk.cuh) and the inflate core (inflate_core.cuh) on the CPU, one simulated
+// thread at a time, in exactly the order the kernels in deflate.cu / inflate.cu run them.  Lets the non-GPU
+// test suite check the codec logic against stock zlib.  Never linked into the product library.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "../../pyrecode_b200/csrc/deflate_chunk.cuh"
+#include "../../pyrecode_b200/csrc/inflate_core.cuh"
+
+static uint32_t encode_chunk(DeflateShared &S, const uint8_t *src, int clen, int level, uint8_t *dst,
+                             uint32_t *adler_a, uint32_t *adler_b)
+{
+    memset(&S, 0, sizeof(S));
+    for (int o = 0; o < DF_CHUNK; o += 4) {
+        uint32_t w = 0;
+        for (int b = 0; b < 4; b++) if (o + b < clen) w |= (uint32_t)src[o + b] << (8 * b);
+        df_store_word(S, o, w);
+    }
+    uint32_t body_bits = 0;
+    bool stored = level == 0;
+    if (!stored) {
+        for (int t = 0; t < DF_THREADS; t++) df_phase_hist(S, t, clen);
+        S.hist[256] = 1;
+        for (int i = 0; i < 512; i++) {
+            const uint32_t c = i < DF_NSYM ? S.hist[i] : 0;
+            S.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
+        }
+        std::sort(S.keys, S.keys + 512);
+        int n_used = 0;
+        while (n_used < 512 && S.keys[n_used] != 0xffffffffu) n_used++;
+        df_phase_build(S, n_used);
+        for (int t = 0; t < DF_THREADS; t++) df_phase_size(S, t, clen);
+        uint32_t run = 0;
+        for (int t = 0; t < DF_THREADS; t++) { const uint32_t v = S.tbits[t]; S.tbits[t] = run; run += v; }
+        body_bits = S.header_bits + run;
+        stored = df_dynamic_bytes(S, body_bits) >= (uint32_t)clen + 10u;
+    } else {
+        // adler partials only
+        uint32_t a = 0, b = 0;
+        for (int i = 0; i < clen; i++) { a = (a + src[i]) % 65521u; b = (b + (uint64_t)(clen - i) * src[i]) % 65521u; }
+        S.adler_a = a; S.adler_b = b;
+    }
+    if (!stored) {
+        for (int t = 0; t < DF_THREADS; t++) df_phase_emit(S, t, clen);
+        df_phase_finish(S, body_bits);
+    } else {
+        uint8_t *ob = reinterpret_cast<uint8_t *>(S.out);
+        ob[0] = 0; ob[1] = clen & 0xff; ob[2] = clen >> 8; ob[3] = ~clen & 0xff; ob[4] = (~clen >> 8) & 0xff;
+        memcpy(ob + 5, src, clen);
+        ob[5 + clen] = 0; ob[6 + clen] = 0; ob[7 + clen] = 0; ob[8 + clen] = 0xff; ob[9 + clen] = 0xff;
+        S.out_bytes = clen + 10;
+    }
+    memcpy(dst, S.out, S.out_bytes);
+    *adler_a = S.adler_a % 65521u;
+    *adler_b = S.adler_b % 65521u;
+    return S.out_bytes;
+}
+
+extern "C" long host_deflate_stream(const uint8_t *in, uint32_t n, int level, uint8_t *out, uint32_t cap)
+{
+    static DeflateShared S;
+    std::vector<uint8_t> piece(DF_SLOT_BYTES);
+    uint32_t pos = 0;
+    if (cap < 8) return -1;
+    out[pos++] = 0x78; out[pos++] = 0x01;
+    uint32_t s1 = 1, s2 = 0;
+    for (uint32_t off = 0; off < n; off += DF_CHUNK) {
+        const int clen = (int)std::min<uint32_t>(DF_CHUNK, n - off);
+        uint32_t a, b;
+        const uint32_t nb = encode_chunk(S, in + off, clen, level, piece.data(), &a, &b);
+        if (pos + nb + 6 > cap) return -1;
+        memcpy(out + pos, piece.data(), nb);
+        pos += nb;
+        s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)clen * s1 + b) % 65521u);
+        s1 = (s1 + a) % 65521u;
+    }
+    out[pos++] = 0x03; out[pos++] = 0x00;
+    const uint32_t ad = (s2 << 16) | s1;
+    out[pos++] = ad >> 24; out[pos++] = ad >> 16; out[pos++] = ad >> 8; out[pos++] = ad;
+    return pos;
+}
+
+// serial = 1: k_inflate_serial path.  serial = 0: scan / chunks / validate path; returns -100 if the validator
+// would fall back to the serial path.
+extern "C" long host_inflate_stream(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t cap, int serial)
+{
+    static IfTables T;
+    if (n < 8) return -1;
+    if ((in[0] & 0x0f) != 8 || ((in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) return -1;
+    if (serial) {
+        IfOut O{out, cap, 0, 0, 0};
+        uint64_t end = 0;
+        const int code = if_inflate(in, n, 2, O, T, false, &end);
+        if (code != IF_END_FINAL || end + 4 > n) return code == IF_ERR_OUT ? -2 : -1;
+        const uint32_t a = (1u + O.s1 % 65521u) % 65521u;
+        const uint32_t b = (uint32_t)(((uint64_t)O.n + O.s2) % 65521u);
+        const uint32_t want = ((uint32_t)in[end] << 24) | (in[end + 1] << 16) | (in[end + 2] << 8) | in[end + 3];
+        if (want != ((b << 16) | a)) return -3;
+        return (long)O.n;
+    }
+    std::vector<uint32_t> cand{2};
+    const uint32_t last = n - 6;
+    for (uint32_t q = 2; q + 4 <= last; q++)
+        if (in[q] == 0 && in[q + 1] == 0 && in[q + 2] == 0xff && in[q + 3] == 0xff) cand.push_back(q + 4);
+    uint32_t pos = 2, total = 0, s1 = 1, s2 = 0;
+    bool finished = false;
+    for (size_t j = 0; j < cand.size(); j++) {
+        const uint64_t ooff = (uint64_t)j * 16384;
+        IfOut O{out + ooff, ooff < cap ? cap - ooff : 0, 0, 0, 0};
+        uint64_t end = 0;
+        const int code = if_inflate(in, n, cand[j], O, T, true, &end);
+        if (cand[j] != pos) return -100;
+        if (code != IF_END_SYNC && code != IF_END_FINAL) return -100;
+        if (O.n && total != j * 16384u) return -100;
+        s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)O.n * s1 + O.s2 % 65521u) % 65521u);
+        s1 = (s1 + O.s1 % 65521u) % 65521u;
+        total += (uint32_t)O.n;
+        pos = (uint32_t)end;
+        if (code == IF_END_FINAL) { finished = j + 1 == cand.size(); break; }
+    }
+    if (!finished || pos + 4 > n) return -100;
+    const uint32_t want = ((uint32_t)in[pos] << 24) | (in[pos + 1] << 16) | (in[pos + 2] << 8) | in[pos + 3];
+    if (want != ((s2 << 16) | s1)) return -100;
+    return total;
+}
+
+// Huffman builder stress: returns 0 if the produced lengths form a complete prefix code within maxbits
+extern "C" int host_huffman_check(const uint32_t *freq, int n, int maxbits)
+{
+    std::vector<uint32_t> keys;
+    for (int i = 0; i < n; i++) if (freq[i]) keys.push_back((freq[i] << 9) | (uint32_t)i);
+    std::sort(keys.begin(), keys.end());
+    std::vector<uint8_t> len(n);
+    std::vector<uint32_t> nw(DF_NSYM);
+    std::vector<uint16_t> np(2 * DF_NSYM);
+    std::vector<uint8_t> nd(DF_NSYM);
+    df_build_lengths(keys.data(), (int)keys.size(), maxbits, len.data(), n, nw.data(), np.data(), nd.data());
+    if (keys.size() < 2) return 0;
+    uint64_t kraft = 0;
+    for (int i = 0; i < n; i++) {
+        if ((freq[i] != 0) != (len[i] != 0)) return -1;
+        if (len[i] > maxbits) return -2;
+        if (len[i]) kraft += 1ull << (maxbits - len[i]);
+    }
+    return kraft == (1ull << maxbits) ? 0 : -3;
+}
