@@ -58,6 +58,12 @@ const char  *rc_last_error(const rc_ctx *ctx);
 int          rc_version(void);
 int          rc_sm_count(const rc_ctx *ctx);
 
+/* instrumentation (replaces the datetime.now() stage timers of recode_writer.py:433-555): CUDA-event stage
+ * timing of the last rc_reduce_compress call and a count of kernels launched through the context */
+int                 rc_profile_enable(rc_ctx *ctx, int on);
+int                 rc_profile_read(rc_ctx *ctx, float *ms, int capacity);   /* returns number of stages (4) */
+unsigned long long  rc_launch_count(const rc_ctx *ctx);
+
 /* ---- sizes ----------------------------------------------------------------------------- */
 size_t rc_map_stride_words(size_t n_pixels);                 /* uint32 words per frame map on device      */
 size_t rc_packed_stride_bytes(const rc_config *cfg);         /* bytes per frame of packed values (worst)  */

@@ -32,7 +32,8 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        dbg = ['-DRC_DEBUG'] if os.environ.get('RC_DEBUG') else []
+        cmd = [nvcc] + NVCC_FLAGS + dbg + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

@@ -142,7 +142,41 @@ extern "C" int rc_create(rc_ctx **out, int device)
     return 0;
 }
 
-extern "C" void rc_destroy(rc_ctx *ctx) { free(ctx); }
+extern "C" void rc_destroy(rc_ctx *ctx)
+{
+    if (!ctx) return;
+    if (ctx->profile) for (int i = 0; i < RC_MAX_MARKS; i++) cudaEventDestroy(ctx->marks[i]);
+    free(ctx);
+}
+
+// stage timing of rc_reduce_compress: marks = start | threshold+map+compaction | rest of the reduction
+// (scan, CCL, bit packing) | deflate | record assembly.  rc_profile_read synchronizes on the last mark and
+// returns the elapsed milliseconds between consecutive marks of the most recent call.
+extern "C" int rc_profile_enable(rc_ctx *ctx, int on)
+{
+    if (!ctx) return -1;
+    if (on && !ctx->profile) {
+        for (int i = 0; i < RC_MAX_MARKS; i++) RC_CUDA(ctx, cudaEventCreate(&ctx->marks[i]));
+        ctx->profile = 1;
+        ctx->n_marks = 0;
+    } else if (!on && ctx->profile) {
+        for (int i = 0; i < RC_MAX_MARKS; i++) cudaEventDestroy(ctx->marks[i]);
+        ctx->profile = 0;
+    }
+    return 0;
+}
+
+extern "C" int rc_profile_read(rc_ctx *ctx, float *ms, int capacity)
+{
+    if (!ctx || !ctx->profile || ctx->n_marks < 2) return 0;
+    RC_CUDA(ctx, cudaEventSynchronize(ctx->marks[ctx->n_marks - 1]));
+    int n = 0;
+    for (int i = 0; i + 1 < ctx->n_marks && n < capacity; i++, n++)
+        RC_CUDA(ctx, cudaEventElapsedTime(&ms[n], ctx->marks[i], ctx->marks[i + 1]));
+    return n;
+}
+
+extern "C" unsigned long long rc_launch_count(const rc_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" const char *rc_last_error(const rc_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" int rc_version(void) { return RC_VERSION; }
 extern "C" int rc_sm_count(const rc_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
@@ -220,17 +254,20 @@ static int run_reduce(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const Re
     if (level == 1) {
         if ((rc = launch_reduce_tiles(ctx, g, isz, 1, 0, frames, thr, F, maps, w.tilecnt, w.segpre, w.vals, nullptr,
                                       nullptr, st))) return rc;
+        rc_mark(ctx, 1, st);
         if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, packed_bytes, b, st))) return rc;
         return launch_bitpack(ctx, g, isz, w.vals, w.tilepre, F, b, packed, packed_stride, st);
     }
     if (level == 3) {
         if ((rc = launch_reduce_tiles(ctx, g, isz, 0, 0, frames, thr, F, maps, w.tilecnt, w.segpre, nullptr, nullptr,
                                       nullptr, st))) return rc;
+        rc_mark(ctx, 1, st);
         return launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, nullptr, 0, st);
     }
     if (level == 2) {
         if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 1, frames, thr, F, maps, w.tilecnt, w.segpre, w.vals, w.parent,
                                       w.acc, st))) return rc;
+        rc_mark(ctx, 1, st);
         if ((rc = launch_ccl_union(ctx, g, maps, w.segpre, w.parent, F, st))) return rc;
         if ((rc = launch_ccl_flatten(ctx, g, cfg->l2_statistics == 2 ? 2 : 1, maps, w.segpre, w.parent, w.acc, nullptr,
                                      F, st))) return rc;
@@ -242,6 +279,7 @@ static int run_reduce(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const Re
     // level 4: threshold map -> map1, centroid map -> maps
     if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, frames, thr, F, w.map1, w.tilecnt, w.segpre, w.vals, w.parent,
                                   nullptr, st))) return rc;
+    rc_mark(ctx, 1, st);
     if ((rc = launch_ccl_union(ctx, g, w.map1, w.segpre, w.parent, F, st))) return rc;
     if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.segpre, w.parent, nullptr, w.bbox, F, st))) return rc;
     RC_CUDA(ctx, cudaMemsetAsync(maps, 0, (size_t)F * g.MS * sizeof(uint32_t), st));
@@ -289,8 +327,10 @@ extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void 
         RC_CUDA(ctx, cudaMemsetAsync(d_record_offsets, 0, sizeof(uint64_t), st));
         return 0;
     }
+    rc_mark(ctx, 0, st);
     if ((rc = run_reduce(ctx, cfg, g, w, d_frames, F, d_thr, cw.maps, cw.packed, cw.packed_stride, cw.packed_bytes,
                          d_counts, st))) return rc;
+    rc_mark(ctx, 2, st);
     const int S = F * cw.spf;
     const uint8_t *base = (const uint8_t *)d_workspace;
     k_stream_desc<<<(F + 127) / 128, 128, 0, st>>>(base, cw.maps, g.MS, (uint32_t)g.map_bytes, cw.packed, cw.packed_stride,
@@ -298,9 +338,12 @@ extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void 
     RC_LAUNCH_CHECK(ctx, "k_stream_desc");
     const int wrap = cfg->rc_operation_mode == 1;
     if ((rc = launch_deflate_streams(ctx, cfg->compression_level, wrap, base, cw.in_off, cw.in_bytes, S, cw.d, st))) return rc;
+    rc_mark(ctx, 3, st);
     if ((rc = launch_layout_records(ctx, cw.d, cw.packed_bytes, F, cw.spf, cfg->rc_operation_mode, first_frame_id,
                                     d_records, records_capacity, d_record_offsets, d_status, st))) return rc;
-    return launch_copy_pieces(ctx, cw.d, wrap, base, cw.in_off, cw.in_bytes, S, d_records, records_capacity, d_status, st);
+    rc = launch_copy_pieces(ctx, cw.d, wrap, base, cw.in_off, cw.in_bytes, S, d_records, records_capacity, d_status, st);
+    rc_mark(ctx, 4, st);
+    return rc;
 }
 
 extern "C" int rc_ccl_label(rc_ctx *ctx, const rc_config *cfg, const uint32_t *d_maps, int n_frames, void *d_workspace,

@@ -27,11 +27,26 @@ constexpr int SEG_PX = 256;
 constexpr int SEG_WORDS = SEG_PX / 32;       // 8
 constexpr int SEGS_PER_TILE = TILE_PX / SEG_PX;  // 32
 
+constexpr int RC_MAX_MARKS = 8;
+
 struct rc_ctx {
     int device;
     int sm_count;
     char err[512];
+    unsigned long long launches;       // kernels launched through this context (bench.py's gpu_launches)
+    int profile;                       // when set, stage boundaries of rc_reduce_compress record events
+    int n_marks;
+    cudaEvent_t marks[RC_MAX_MARKS];
+    bool deflate_attr_set;
 };
+
+static inline void rc_mark(rc_ctx *ctx, int idx, cudaStream_t st)
+{
+    if (ctx->profile && idx < RC_MAX_MARKS) {
+        cudaEventRecord(ctx->marks[idx], st);
+        if (idx + 1 > ctx->n_marks) ctx->n_marks = idx + 1;
+    }
+}
 
 #define RC_FAIL(ctx, code, ...)                                   \
     do {                                                          \
@@ -52,6 +67,7 @@ struct rc_ctx {
         cudaError_t e__ = cudaGetLastError();                                                     \
         if (e__ != cudaSuccess)                                                                   \
             RC_FAIL(ctx, -3, "launch of %s failed: %s", name, cudaGetErrorString(e__));          \
+        (ctx)->launches++;                                                                        \
     } while (0)
 
 // ---- geometry ------------------------------------------------------------------------------

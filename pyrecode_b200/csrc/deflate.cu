@@ -404,11 +404,10 @@ int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, const uint8_t *in, 
     k_deflate_plan<<<1, 256, 0, st>>>(in_bytes, n_streams, w.chunk_base, w.counters);
     RC_LAUNCH_CHECK(ctx, "k_deflate_plan");
     if (wrap) {
-        static bool attr_set[64] = {false};
         const int smem = deflate_smem_bytes();
-        if (!attr_set[ctx->device & 63]) {
+        if (!ctx->deflate_attr_set) {
             RC_CUDA(ctx, cudaFuncSetAttribute(k_deflate_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set[ctx->device & 63] = true;
+            ctx->deflate_attr_set = true;
         }
         size_t want = w.max_chunks < (size_t)ctx->sm_count * 5 ? w.max_chunks : (size_t)ctx->sm_count * 5;
         if (want < 1) want = 1;

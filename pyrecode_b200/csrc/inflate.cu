@@ -115,6 +115,9 @@ k_inflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
             InfTask r;
             r.end = (uint32_t)end; r.out_len = (uint32_t)O.n; r.s1 = O.s1 % 65521u; r.s2 = O.s2 % 65521u; r.code = code;
             tasks[ti] = r;
+#ifdef RC_DEBUG
+            printf("[chunks] ti=%u s=%d j=%u start=%u code=%d end=%u out=%u\n", ti, s, j, cand[(size_t)s * cmax + j], code, r.end, r.out_len);
+#endif
         }
         __syncwarp();
     }
@@ -151,6 +154,9 @@ __global__ void k_inflate_validate(const uint8_t *__restrict__ in, const uint64_
         const uint32_t want = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | tr[3];
         if (want == ((s2 << 16) | s1)) { out_bytes[s] = total; return; }
     }
+#ifdef RC_DEBUG
+    printf("[validate] s=%d nc=%u ok=%d finished=%d pos=%u total=%u in_bytes=%u\n", s, nc, (int)ok, (int)finished, pos, total, in_bytes[s]);
+#endif
     need_serial[s] = 1;
 }
 
@@ -178,6 +184,9 @@ k_inflate_serial(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
         const uint32_t want = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | tr[3];
         if (want != ((b << 16) | a)) st = RC_STATUS_BAD_STREAM;
     }
+#ifdef RC_DEBUG
+    printf("[serial] s=%d code=%d end=%llu n=%llu st=%u\n", s, code, (unsigned long long)end, (unsigned long long)O.n, st);
+#endif
     out_bytes[s] = (uint32_t)O.n;
     status[s] = st;
 }

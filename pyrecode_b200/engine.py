@@ -1,0 +1,340 @@
+"""Batch engines over the C ABI: device buffers (torch), pinned staging, launches, D2H of compact results.
+
+WriteEngine  = the per-frame hot path of ReCoDeWriter._reduce_compress (reference: pyrecode/recode_writer.py:430-557)
+               for a batch of frames.
+ReadEngine   = ReCoDeReader._get_frame_sparse (reference: pyrecode/recode_reader.py:379-462) for a batch of frames:
+               inflate -> unpack to triples / dense frames / summed live-view image.
+
+PyTorch only owns memory and streams here; all arithmetic is in librecode_b200.so.
+"""
+import numpy as np
+import torch
+
+from . import _native
+from ._native import Context, make_config
+
+
+class WriteEngine:
+    def __init__(self, ny, nx, itemsize, bit_depth, reduction_level, rc_operation_mode=1, l2_statistics=0,
+                 l4_centroiding=0, compression_level=1, max_frames=16, device=None, records_capacity=None):
+        self.ctx = Context(device)
+        self.dev = self.ctx.device
+        self.ny, self.nx, self.itemsize, self.bit_depth = int(ny), int(nx), int(itemsize), int(bit_depth)
+        self.level, self.mode = int(reduction_level), int(rc_operation_mode)
+        self.max_frames = int(max_frames)
+        self.cfg = make_config(ny, nx, itemsize, bit_depth, reduction_level, rc_operation_mode, l2_statistics,
+                               l4_centroiding, compression_level, max_frames)
+        self.P = self.ny * self.nx
+        self.np_dtype = _native.numpy_dtype(itemsize)
+        self.t_dtype = _native.torch_dtype(itemsize)
+        with torch.cuda.device(self.dev):
+            self.ws = self.ctx.empty(self.ctx.workspace_bytes(self.cfg))
+            cap = self.ctx.records_capacity(self.cfg) if records_capacity is None else int(records_capacity)
+            self.records = self.ctx.empty(cap)
+            self.offsets = self.ctx.zeros(self.max_frames + 1, torch.int64)
+            self.counts = self.ctx.zeros(self.max_frames, torch.int32)
+            self.status = self.ctx.zeros(1, torch.int32)
+            self.frames_dev = None
+        self.thr = None
+        self._pin_in = None
+        self._pin_meta = torch.empty(self.max_frames + 1, dtype=torch.int64).pin_memory()
+        self._pin_rec = None
+
+    # ---- calibration -----------------------------------------------------------------------------
+    def set_threshold(self, dark, eps):
+        """thr = dark + eps in the source dtype (recode_writer.py:126-137), computed on the device."""
+        d = torch.from_numpy(np.ascontiguousarray(dark, dtype=self.np_dtype)).to(self.dev)
+        with torch.cuda.device(self.dev):
+            self.thr = self.ctx.make_threshold(self.cfg, d, eps)
+        return self.thr
+
+    # ---- input staging ----------------------------------------------------------------------------
+    def _to_device(self, frames):
+        """frames: numpy [n, ny, nx], pinned/pageable torch CPU tensor, or CUDA tensor of the source dtype."""
+        if isinstance(frames, torch.Tensor) and frames.is_cuda:
+            assert frames.dtype == self.t_dtype and frames.is_contiguous()
+            return frames, 0
+        if isinstance(frames, np.ndarray):
+            a = np.ascontiguousarray(frames, dtype=self.np_dtype)
+            n = a.shape[0]
+            if self._pin_in is None:
+                self._pin_in = torch.empty((self.max_frames, self.ny, self.nx), dtype=self.t_dtype).pin_memory()
+            self._pin_in[:n].numpy()[...] = a
+            src = self._pin_in[:n]
+        else:
+            src = frames
+            n = src.shape[0]
+        if self.frames_dev is None:
+            self.frames_dev = torch.empty((self.max_frames, self.ny, self.nx), dtype=self.t_dtype, device=self.dev)
+        dst = self.frames_dev[:n]
+        dst.copy_(src, non_blocking=True)
+        return dst, src.numel() * src.element_size()
+
+    # ---- the hot path ------------------------------------------------------------------------------
+    def launch(self, frames_dev, n, first_frame_id):
+        """Asynchronous: all kernels of one batch on the current stream."""
+        if self.thr is None:
+            raise RuntimeError('set_threshold() must be called first')
+        self.ctx.reduce_compress(self.cfg, frames_dev, n, self.thr, int(first_frame_id), self.ws, self.records,
+                                 self.offsets, self.counts, self.status)
+
+    def reduce_compress(self, frames, first_frame_id=0):
+        """-> (records: np.uint8 [total], offsets: np.int64 [n+1], counts: np.int32 [n], h2d_bytes, d2h_bytes)."""
+        n = int(frames.shape[0])
+        if n > self.max_frames:
+            raise ValueError('batch larger than max_frames')
+        with torch.cuda.device(self.dev):
+            fd, h2d = self._to_device(frames)
+            self.launch(fd, n, first_frame_id)
+            meta = self._pin_meta
+            meta[:n + 1].copy_(self.offsets[:n + 1], non_blocking=True)
+            st = self.status.cpu()          # synchronizes the stream
+            counts = self.counts[:n].cpu().numpy()
+            offs = meta[:n + 1].numpy().copy()
+            total = int(offs[n])
+            if int(st[0]) & _native.RC_STATUS_RECORDS_OVERFLOW:
+                raise ValueError('Buffer size smaller than compressed data size')
+            if self._pin_rec is None or self._pin_rec.numel() < total:
+                self._pin_rec = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
+            self._pin_rec[:total].copy_(self.records[:total], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return self._pin_rec[:total].numpy(), offs, counts, h2d, total + (n + 1) * 8 + n * 4 + 4
+
+    # ---- stage access (parity tests, c_recode shim) --------------------------------------------------
+    def reduce(self, frames):
+        """-> (maps: [bytes], packed: [bytes], counts) through rc_reduce."""
+        n = int(frames.shape[0])
+        with torch.cuda.device(self.dev):
+            fd, _ = self._to_device(frames)
+            ms = self.ctx.map_stride_words(self.P)
+            ps = self.ctx.packed_stride_bytes(self.cfg)
+            maps = self.ctx.zeros(n * ms + 16, torch.int32)
+            packed = self.ctx.zeros(n * ps + 16)
+            pbytes = self.ctx.zeros(n, torch.int32)
+            counts = self.ctx.zeros(n, torch.int32)
+            self.ctx.reduce(self.cfg, fd, n, self.thr, self.ws, maps, packed, pbytes, counts)
+            torch.cuda.synchronize()
+            mh = maps.cpu().numpy().view(np.uint8)
+            ph = packed.cpu().numpy()
+            pb = pbytes.cpu().numpy()
+            mb = (self.P + 7) // 8
+            out_m = [mh[f * ms * 4:f * ms * 4 + mb].tobytes() for f in range(n)]
+            out_p = [ph[f * ps:f * ps + int(pb[f])].tobytes() for f in range(n)]
+            return out_m, out_p, counts.cpu().numpy()
+
+    def labels(self, maps_bytes):
+        """8-connected labels of packed binary maps -> (int32 [n, ny, nx], k[n]) through rc_ccl_label."""
+        n = len(maps_bytes)
+        ms = self.ctx.map_stride_words(self.P)
+        host = np.zeros((n, ms * 4), dtype=np.uint8)
+        for f, m in enumerate(maps_bytes):
+            host[f, :len(m)] = np.frombuffer(m, dtype=np.uint8)
+        with torch.cuda.device(self.dev):
+            maps = torch.from_numpy(host.view(np.int32).reshape(-1)).to(self.dev)
+            labels = self.ctx.empty(n * self.P, torch.int32)
+            counts = self.ctx.zeros(n, torch.int32)
+            self.ctx.ccl_label(self.cfg, maps, n, self.ws, labels, counts)
+            torch.cuda.synchronize()
+            return labels.cpu().numpy().reshape(n, self.ny, self.nx), counts.cpu().numpy()
+
+    def centroids(self, frames):
+        """L4 centroid lists -> [float32 [k, 2]] through rc_l4_centroids."""
+        n = int(frames.shape[0])
+        cap = (self.ny + 1) // 2 * ((self.nx + 1) // 2) + 1
+        with torch.cuda.device(self.dev):
+            fd, _ = self._to_device(frames)
+            cent = self.ctx.zeros(n * cap * 2, torch.float32)
+            counts = self.ctx.zeros(n, torch.int32)
+            self.ctx.l4_centroids(self.cfg, fd, n, self.thr, self.ws, cent, cap, counts)
+            torch.cuda.synchronize()
+            c = cent.cpu().numpy().reshape(n, cap, 2)
+            k = counts.cpu().numpy()
+            return [c[f, :int(k[f])].copy() for f in range(n)]
+
+
+def deflate_batch(ctx, payloads, level=1):
+    """zlib-format deflate of a list of byte strings on the GPU -> list of bytes (rc_deflate_zlib)."""
+    n = len(payloads)
+    if n == 0:
+        return []
+    sizes = np.array([len(p) for p in payloads], dtype=np.uint32)
+    offs = np.zeros(n, dtype=np.uint64)
+    pos = 0
+    for i, s in enumerate(sizes):
+        offs[i] = pos
+        pos += (int(s) + 15) // 16 * 16
+    blob = np.zeros(pos + 64, dtype=np.uint8)
+    for i, p in enumerate(payloads):
+        blob[int(offs[i]):int(offs[i]) + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    mx = int(sizes.max())
+    stride = (ctx.deflate_bound(mx) + 15) // 16 * 16
+    with torch.cuda.device(ctx.device):
+        d_in = torch.from_numpy(blob).to(ctx.device)
+        d_off = torch.from_numpy(offs.view(np.int64)).to(ctx.device)
+        d_sz = torch.from_numpy(sizes.view(np.int32)).to(ctx.device)
+        out = ctx.empty(n * stride + 64)
+        out_bytes = ctx.zeros(n, torch.int32)
+        ws = ctx.deflate_zlib(level, d_in, d_off, d_sz, n, mx, out, stride, out_bytes)
+        torch.cuda.synchronize()
+        del ws
+        ob = out_bytes.cpu().numpy()
+        oh = out.cpu().numpy()
+    return [oh[i * stride:i * stride + int(ob[i])].tobytes() for i in range(n)]
+
+
+def _stage_streams(ctx, streams):
+    n = len(streams)
+    sizes = np.array([len(p) for p in streams], dtype=np.uint32)
+    offs = np.zeros(n, dtype=np.uint64)
+    pos = 0
+    for i, s in enumerate(sizes):
+        offs[i] = pos
+        pos += (int(s) + 15) // 16 * 16
+    blob = np.zeros(pos + 64, dtype=np.uint8)
+    for i, p in enumerate(streams):
+        blob[int(offs[i]):int(offs[i]) + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    d_in = torch.from_numpy(blob).to(ctx.device, non_blocking=False)
+    d_off = torch.from_numpy(offs.view(np.int64)).to(ctx.device)
+    d_sz = torch.from_numpy(sizes.view(np.int32)).to(ctx.device)
+    return d_in, d_off, d_sz, int(pos)
+
+
+def inflate_batch(ctx, streams, out_capacity):
+    """zlib-format inflate of a list of byte strings on the GPU -> (list of bytes, status[n]) (rc_inflate_zlib)."""
+    n = len(streams)
+    if n == 0:
+        return [], np.zeros(0, np.uint32)
+    stride = (int(out_capacity) + 15) // 16 * 16 + 16
+    with torch.cuda.device(ctx.device):
+        d_in, d_off, d_sz, _ = _stage_streams(ctx, streams)
+        out = ctx.empty(n * stride + 64)
+        out_bytes = ctx.zeros(n, torch.int32)
+        status = ctx.zeros(n, torch.int32)
+        ws = ctx.inflate_zlib(d_in, d_off, d_sz, n, out, stride, out_bytes, status)
+        torch.cuda.synchronize()
+        ob = out_bytes.cpu().numpy()
+        st = status.cpu().numpy().astype(np.uint32)
+        del ws
+        oh = out.cpu().numpy()
+    return [oh[i * stride:i * stride + int(ob[i])].tobytes() for i in range(n)], st
+
+
+class ReadEngine:
+    def __init__(self, ny, nx, itemsize, bit_depth, reduction_level, rc_operation_mode=1, max_frames=16, device=None):
+        self.ctx = Context(device)
+        self.dev = self.ctx.device
+        self.ny, self.nx, self.itemsize, self.bit_depth = int(ny), int(nx), int(itemsize), int(bit_depth)
+        self.level, self.mode = int(reduction_level), int(rc_operation_mode)
+        self.max_frames = int(max_frames)
+        self.P = self.ny * self.nx
+        self.cfg = make_config(ny, nx, itemsize, bit_depth, reduction_level, rc_operation_mode, 0, 0, 1, max_frames)
+        self.np_dtype = _native.numpy_dtype(itemsize)
+        self.t_dtype = _native.torch_dtype(itemsize)
+        self.map_bytes = (self.P + 7) // 8
+        self.ms = self.ctx.map_stride_words(self.P)
+        # one stride for both stream kinds so a single inflate call handles [maps..., vals...]
+        need = max(self.ms * 4, (self.P * self.bit_depth + 7) // 8 if self.level <= 2 else 0)
+        self.stride = (need + 15) // 16 * 16 + 16
+        F = self.max_frames
+        with torch.cuda.device(self.dev):
+            self.ws = self.ctx.empty(self.ctx.read_workspace_bytes(self.cfg))
+            self.inflated = self.ctx.zeros(2 * F * self.stride + 64)
+            self.out_bytes = self.ctx.zeros(2 * F, torch.int32)
+            self.status = self.ctx.zeros(2 * F, torch.int32)
+            self.counts = self.ctx.zeros(F, torch.int32)
+            self._inf_ws = None
+
+    def load(self, map_streams, val_streams):
+        """Stage n frames' streams (compressed when mode 1, raw when mode 0) -> device maps / packed values."""
+        n = len(map_streams)
+        if n > self.max_frames:
+            raise ValueError('batch larger than max_frames')
+        has_vals = val_streams is not None and self.level <= 2
+        F = self.max_frames
+        with torch.cuda.device(self.dev):
+            if self.mode == 1:
+                streams = list(map_streams) + (list(val_streams) if has_vals else [])
+                d_in, d_off, d_sz, staged = _stage_streams(self.ctx, streams)
+                ns = len(streams)
+                # maps occupy stream slots [0, n), values [F, F + n): issue as two calls so strides line up
+                self._inf_ws = self.ctx.inflate_zlib(d_in, d_off, d_sz, n, self.inflated, self.stride,
+                                                     self.out_bytes, self.status, self._inf_ws)
+                if has_vals:
+                    self._inf_ws = self.ctx.inflate_zlib(d_in, d_off[n:], d_sz[n:], n,
+                                                         self.inflated[F * self.stride:], self.stride,
+                                                         self.out_bytes[F:], self.status[F:], self._inf_ws)
+                self._keep = (d_in, d_off, d_sz)
+                h2d = staged + ns * 12
+            else:
+                host = np.zeros((2 * F, self.stride), dtype=np.uint8)
+                for f in range(n):
+                    host[f, :len(map_streams[f])] = np.frombuffer(map_streams[f], dtype=np.uint8)
+                    if has_vals:
+                        host[F + f, :len(val_streams[f])] = np.frombuffer(val_streams[f], dtype=np.uint8)
+                self.inflated[:2 * F * self.stride].copy_(torch.from_numpy(host.reshape(-1)))
+                self.status.zero_()
+                ob = np.zeros(2 * F, dtype=np.int32)
+                ob[:n] = [len(m) for m in map_streams]
+                if has_vals:
+                    ob[F:F + n] = [len(v) for v in val_streams]
+                self.out_bytes.copy_(torch.from_numpy(ob))
+                h2d = host.nbytes
+        self.n = n
+        self.has_vals = has_vals
+        return h2d
+
+    def _views(self):
+        F = self.max_frames
+        maps = self.inflated[:F * self.stride]
+        packed = self.inflated[F * self.stride:]
+        return maps, packed
+
+    def check(self):
+        """Host-side validation after load(): stream status and sizes (raises ValueError like zlib.error would)."""
+        F, n = self.max_frames, self.n
+        st = self.status.cpu().numpy()
+        ob = self.out_bytes.cpu().numpy()
+        for f in range(n):
+            if st[f] or (self.has_vals and st[F + f]):
+                raise ValueError('corrupt compressed stream in frame %d (status %d/%d)' % (f, st[f], st[F + f]))
+            if ob[f] != self.map_bytes:
+                raise ValueError('binary map of frame %d inflates to %d bytes, expected %d' % (f, ob[f], self.map_bytes))
+        return ob
+
+    def sparse(self):
+        """-> list of uint64 [n_fg, 3] (row, col, value) arrays, the c_recode.get_frame_sparse result."""
+        n = self.n
+        maps, packed = self._views()
+        with torch.cuda.device(self.dev):
+            # the map is strided by self.stride bytes here, not by the library's map stride: repack
+            m2 = self._maps_contig()
+            cap = self.P
+            tri = self.ctx.empty(n * cap * 3, torch.int64)
+            self.ctx.unpack_sparse(self.cfg, m2, packed, self.stride, n, self.ws, tri, cap, self.counts)
+            torch.cuda.synchronize()
+            k = self.counts[:n].cpu().numpy()
+            out = []
+            for f in range(n):
+                t = tri[f * cap * 3:f * cap * 3 + int(k[f]) * 3].cpu().numpy().view(np.uint64).reshape(-1, 3)
+                out.append(t)
+            return out
+
+    def _maps_contig(self):
+        F, n = self.max_frames, self.n
+        maps, _ = self._views()
+        v = maps.view(F, self.stride)[:n, :self.ms * 4]
+        m = v.contiguous().view(-1)
+        # zero the padding bits/bytes beyond the map (inflate wrote exactly map_bytes)
+        if self.ms * 4 > self.map_bytes:
+            m.view(n, self.ms * 4)[:, self.map_bytes:] = 0
+        return torch.cat([m, torch.zeros(64, dtype=torch.uint8, device=self.dev)])
+
+    def dense(self, total=None, want_dense=True):
+        """-> dense frames tensor [n, ny, nx] on the device (and/or accumulates into `total`, uint32 [ny*nx])."""
+        n = self.n
+        _, packed = self._views()
+        with torch.cuda.device(self.dev):
+            m2 = self._maps_contig()
+            dense = torch.empty((n, self.ny, self.nx), dtype=self.t_dtype, device=self.dev) if want_dense else None
+            self.ctx.unpack_dense(self.cfg, m2, packed, self.stride, n, self.ws, dense, total, self.counts)
+        return dense
