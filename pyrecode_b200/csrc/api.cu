@@ -33,7 +33,7 @@ static size_t packed_stride_of(const rc_config *c)
 
 struct ReduceWs {
     uint32_t *tilecnt, *tilepre, *rootcnt, *rootpre;
-    uint16_t *segpre;
+    uint16_t *wordpre;
     void *vals;
     uint32_t *parent, *acc, *bbox, *ord;
     uint16_t *stats16;
@@ -50,9 +50,9 @@ static ReduceWs carve_reduce(Carver &c, const rc_config *cfg, const Geom &g, int
     const int level = cfg->reduction_level;
     w.tilecnt = c.take<uint32_t>(F * g.NT);
     w.tilepre = c.take<uint32_t>(F * (g.NT + 1));
-    w.segpre = c.take<uint16_t>(F * g.NT * SEGS_PER_TILE);
+    w.wordpre = c.take<uint16_t>(F * g.MS);
     const bool ccl = what != 0 || level == 2 || level == 4;
-    if (what == 0 && level != 3) w.vals = c.take<uint8_t>(F * g.slots * cfg->itemsize);
+    if (what == 0 && (level == 1 || level == 4)) w.vals = c.take<uint8_t>(F * g.slots * cfg->itemsize);
     if (what == 2) w.vals = c.take<uint8_t>(F * g.slots * cfg->itemsize);
     if (ccl) {
         w.parent = c.take<uint32_t>(F * g.slots);
@@ -231,7 +231,7 @@ extern "C" size_t rc_read_workspace_bytes(const rc_config *cfg)
     Carver c(nullptr);
     c.take<uint32_t>(F * g.NT);
     c.take<uint32_t>(F * (g.NT + 1));
-    c.take<uint16_t>(F * g.NT * SEGS_PER_TILE);
+    c.take<uint16_t>(F * g.MS);
     return c.used() + 256;
 }
 
@@ -252,24 +252,24 @@ static int run_reduce(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const Re
     const int level = cfg->reduction_level, b = cfg->bit_depth, isz = cfg->itemsize;
     int rc;
     if (level == 1) {
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 1, 0, frames, thr, F, maps, w.tilecnt, w.segpre, w.vals, nullptr,
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 1, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, w.vals, nullptr,
                                       nullptr, st))) return rc;
         rc_mark(ctx, 1, st);
         if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, packed_bytes, b, st))) return rc;
         return launch_bitpack(ctx, g, isz, w.vals, w.tilepre, F, b, packed, packed_stride, st);
     }
     if (level == 3) {
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 0, 0, frames, thr, F, maps, w.tilecnt, w.segpre, nullptr, nullptr,
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 0, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, nullptr, nullptr,
                                       nullptr, st))) return rc;
         rc_mark(ctx, 1, st);
         return launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, nullptr, 0, st);
     }
     if (level == 2) {
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 1, frames, thr, F, maps, w.tilecnt, w.segpre, w.vals, w.parent,
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 1, frames, thr, F, maps, w.tilecnt, w.wordpre, w.vals, w.parent,
                                       w.acc, st))) return rc;
         rc_mark(ctx, 1, st);
-        if ((rc = launch_ccl_union(ctx, g, maps, w.segpre, w.parent, F, st))) return rc;
-        if ((rc = launch_ccl_flatten(ctx, g, cfg->l2_statistics == 2 ? 2 : 1, maps, w.segpre, w.parent, w.acc, nullptr,
+        if ((rc = launch_ccl_union(ctx, g, maps, w.wordpre, w.parent, F, st))) return rc;
+        if ((rc = launch_ccl_flatten(ctx, g, cfg->l2_statistics == 2 ? 2 : 1, maps, w.wordpre, w.parent, w.acc, nullptr,
                                      F, st))) return rc;
         if ((rc = launch_ccl_roots(ctx, g, 1, w.tilecnt, w.parent, w.acc, nullptr, w.rootcnt, nullptr, w.stats16,
                                    nullptr, F, st))) return rc;
@@ -277,13 +277,13 @@ static int run_reduce(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const Re
         return launch_bitpack(ctx, g, 2, w.stats16, w.rootpre, F, b, packed, packed_stride, st);
     }
     // level 4: threshold map -> map1, centroid map -> maps
-    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, frames, thr, F, w.map1, w.tilecnt, w.segpre, w.vals, w.parent,
+    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, frames, thr, F, w.map1, w.tilecnt, w.wordpre, w.vals, w.parent,
                                   nullptr, st))) return rc;
     rc_mark(ctx, 1, st);
-    if ((rc = launch_ccl_union(ctx, g, w.map1, w.segpre, w.parent, F, st))) return rc;
-    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.segpre, w.parent, nullptr, w.bbox, F, st))) return rc;
+    if ((rc = launch_ccl_union(ctx, g, w.map1, w.wordpre, w.parent, F, st))) return rc;
+    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, nullptr, w.bbox, F, st))) return rc;
     RC_CUDA(ctx, cudaMemsetAsync(maps, 0, (size_t)F * g.MS * sizeof(uint32_t), st));
-    if ((rc = launch_l4_centroids(ctx, g, isz, cfg->l4_centroiding, w.map1, w.segpre, w.parent, w.bbox, w.vals, maps,
+    if ((rc = launch_l4_centroids(ctx, g, isz, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox, w.vals, maps,
                                   nullptr, F, st))) return rc;
     // puddle count = number of roots
     if ((rc = launch_ccl_roots(ctx, g, 3, w.tilecnt, w.parent, nullptr, nullptr, w.rootcnt, nullptr, nullptr, nullptr,
@@ -359,13 +359,13 @@ extern "C" int rc_ccl_label(rc_ctx *ctx, const rc_config *cfg, const uint32_t *d
     const ReduceWs w = carve_reduce(c, cfg, g, 1);
     const int F = n_frames;
     int rc;
-    if ((rc = launch_map_counts(ctx, g, d_maps, F, w.tilecnt, w.segpre, st))) return rc;
+    if ((rc = launch_map_counts(ctx, g, d_maps, F, w.tilecnt, w.wordpre, st))) return rc;
     if ((rc = launch_ccl_init(ctx, g, w.tilecnt, w.parent, F, st))) return rc;
-    if ((rc = launch_ccl_union(ctx, g, d_maps, w.segpre, w.parent, F, st))) return rc;
-    if ((rc = launch_ccl_flatten(ctx, g, 0, d_maps, w.segpre, w.parent, nullptr, nullptr, F, st))) return rc;
+    if ((rc = launch_ccl_union(ctx, g, d_maps, w.wordpre, w.parent, F, st))) return rc;
+    if ((rc = launch_ccl_flatten(ctx, g, 0, d_maps, w.wordpre, w.parent, nullptr, nullptr, F, st))) return rc;
     if ((rc = launch_ccl_roots(ctx, g, 0, w.tilecnt, w.parent, nullptr, nullptr, w.rootcnt, w.ord, nullptr, nullptr, F, st))) return rc;
     if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, d_counts, nullptr, 0, st))) return rc;
-    return launch_ccl_label_image(ctx, g, d_maps, w.segpre, w.parent, w.ord, w.rootpre, d_labels, F, st);
+    return launch_ccl_label_image(ctx, g, d_maps, w.wordpre, w.parent, w.ord, w.rootpre, d_labels, F, st);
 }
 
 extern "C" int rc_l4_centroids(rc_ctx *ctx, const rc_config *cfg, const void *d_frames, int n_frames, const void *d_thr,
@@ -382,11 +382,11 @@ extern "C" int rc_l4_centroids(rc_ctx *ctx, const rc_config *cfg, const void *d_
     const ReduceWs w = carve_reduce(c, cfg, g, 2);
     const int F = n_frames, isz = cfg->itemsize;
     int rc;
-    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, d_frames, d_thr, F, w.map1, w.tilecnt, w.segpre, w.vals, w.parent,
+    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, d_frames, d_thr, F, w.map1, w.tilecnt, w.wordpre, w.vals, w.parent,
                                   nullptr, st))) return rc;
-    if ((rc = launch_ccl_union(ctx, g, w.map1, w.segpre, w.parent, F, st))) return rc;
-    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.segpre, w.parent, nullptr, w.bbox, F, st))) return rc;
-    if ((rc = launch_l4_centroids(ctx, g, isz, cfg->l4_centroiding, w.map1, w.segpre, w.parent, w.bbox, w.vals, nullptr,
+    if ((rc = launch_ccl_union(ctx, g, w.map1, w.wordpre, w.parent, F, st))) return rc;
+    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, nullptr, w.bbox, F, st))) return rc;
+    if ((rc = launch_l4_centroids(ctx, g, isz, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox, w.vals, nullptr,
                                   w.cent, F, st))) return rc;
     if ((rc = launch_ccl_roots(ctx, g, 2, w.tilecnt, w.parent, nullptr, w.cent, w.rootcnt, nullptr, nullptr, w.cent_tiles,
                                F, st))) return rc;
@@ -435,7 +435,7 @@ extern "C" int rc_inflate_zlib(rc_ctx *ctx, const uint8_t *d_in, const uint64_t 
 
 struct ReadWs {
     uint32_t *tilecnt, *tilepre;
-    uint16_t *segpre;
+    uint16_t *wordpre;
 };
 
 static ReadWs carve_read(Carver &c, const rc_config *cfg, const Geom &g)
@@ -444,7 +444,7 @@ static ReadWs carve_read(Carver &c, const rc_config *cfg, const Geom &g)
     const size_t F = (size_t)cfg->max_frames;
     w.tilecnt = c.take<uint32_t>(F * g.NT);
     w.tilepre = c.take<uint32_t>(F * (g.NT + 1));
-    w.segpre = c.take<uint16_t>(F * g.NT * SEGS_PER_TILE);
+    w.wordpre = c.take<uint16_t>(F * g.MS);
     return w;
 }
 
@@ -462,9 +462,9 @@ extern "C" int rc_unpack_sparse(rc_ctx *ctx, const rc_config *cfg, const uint32_
     Carver c(d_workspace);
     const ReadWs w = carve_read(c, cfg, g);
     int rc;
-    if ((rc = launch_map_counts(ctx, g, d_maps, n_frames, w.tilecnt, w.segpre, st))) return rc;
+    if ((rc = launch_map_counts(ctx, g, d_maps, n_frames, w.tilecnt, w.wordpre, st))) return rc;
     if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, n_frames, w.tilepre, d_counts, nullptr, 0, st))) return rc;
-    return launch_unpack_sparse(ctx, g, cfg->reduction_level, cfg->bit_depth, d_maps, d_packed, packed_stride, w.segpre,
+    return launch_unpack_sparse(ctx, g, cfg->reduction_level, cfg->bit_depth, d_maps, d_packed, packed_stride, w.wordpre,
                                 w.tilepre, n_frames, d_triples, triple_capacity, st);
 }
 
@@ -483,10 +483,10 @@ extern "C" int rc_unpack_dense(rc_ctx *ctx, const rc_config *cfg, const uint32_t
     Carver c(d_workspace);
     const ReadWs w = carve_read(c, cfg, g);
     int rc;
-    if ((rc = launch_map_counts(ctx, g, d_maps, n_frames, w.tilecnt, w.segpre, st))) return rc;
+    if ((rc = launch_map_counts(ctx, g, d_maps, n_frames, w.tilecnt, w.wordpre, st))) return rc;
     if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, n_frames, w.tilepre, d_counts, nullptr, 0, st))) return rc;
     return launch_unpack_dense(ctx, g, cfg->itemsize, cfg->reduction_level, cfg->bit_depth, d_maps, d_packed,
-                               packed_stride, w.segpre, w.tilepre, n_frames, d_dense, d_sum, st);
+                               packed_stride, w.wordpre, w.tilepre, n_frames, d_dense, d_sum, st);
 }
 
 extern "C" int rc_bit_unpack(rc_ctx *ctx, int bit_depth, const uint8_t *d_packed, uint64_t n_values, uint64_t *d_out,

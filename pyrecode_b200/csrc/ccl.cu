@@ -6,15 +6,18 @@
 //
 // Representation: union-find over foreground SLOTS (common.cuh).  parent[slot] <= slot always, so the root
 // of a puddle is its first pixel in raster order -- exactly scipy's label order (labels numbered by the
-// raster order of each component's first pixel).  Only foreground pixels are ever touched: the kernels
-// walk the set bits of the map words, so the work is O(foreground), not O(pixels).
+// raster order of each component's first pixel).  Only foreground pixels are ever touched.
 //
-//   k_ccl_union     one thread per map word; links each foreground pixel to its W / NW / N / NE neighbours
-//                   with atomicMin unions.
+// All kernels run one thread per 32-pixel map word.  When nx is a multiple of 32 (every shipped geometry)
+// the neighbourhood of the 32 pixels is evaluated bit-parallel from the 3 x 3 surrounding words, so a word
+// whose pixels have no neighbour at all (the common case in electron-counting frames) costs a handful of
+// coalesced loads and logic ops and exits; other geometries take a per-pixel path with the same results.
+//
+//   k_ccl_union     links each foreground pixel to its W / NW / N / NE neighbours with atomicMin unions.
 //   k_ccl_flatten   parent[slot] = root; L2: folds each member's value into acc[root] (max or sum);
 //                   L4: grows the root's bounding box (row extent, left / right column extents).
-//   k_ccl_roots     per tile: compacts per-root payloads (L2 statistics, centroids, ordinals) in slot order
-//                   == label order.
+//   k_ccl_roots     one warp per tile: compacts per-root payloads (L2 statistics, centroids, ordinals) in
+//                   slot order == label order.
 //   k_l4_centroids  one thread per root: replays the puddle's pixels in raster order inside its bounding
 //                   box with the reference's float32-after-every-add accumulation, divides, rounds half to
 //                   even and sets the centroid bit.  Single-pixel puddles are their own centroid.
@@ -50,48 +53,98 @@ __device__ __forceinline__ uint32_t get_bit(const uint32_t *__restrict__ map, ui
     return (map[q >> 5] >> (q & 31)) & 1u;
 }
 
-// slot of the first pixel of word w (whether or not it is set)
-__device__ __forceinline__ uint32_t word_slot_base(const uint32_t *__restrict__ map,
-                                                   const uint16_t *__restrict__ segpre, uint32_t w)
+// Neighbour masks of the 32 pixels of word w for nx % 32 == 0.  Bit k of `west` is set when pixel k's west
+// neighbour is foreground, etc.  Rows above / below the frame and columns outside it contribute zeros.
+struct Nbr {
+    uint32_t west, east, n, nw, ne, s, sw, se;
+};
+
+template <bool WITH_SOUTH>
+__device__ __forceinline__ Nbr neighbour_masks(const uint32_t *__restrict__ map, uint32_t w, uint32_t bits,
+                                               uint32_t wpr, uint32_t ny)
 {
-    const uint32_t seg = w >> 3;
-    uint32_t s = ((w >> 8) << 13) + segpre[seg];
-    for (uint32_t i = seg << 3; i < w; i++) s += __popc(map[i]);
-    return s;
+    Nbr m;
+    const uint32_t row = w / wpr, wc = w - row * wpr;
+    const bool has_l = wc > 0, has_r = wc + 1 < wpr;
+    const uint32_t cl = has_l ? map[w - 1] : 0, cr = has_r ? map[w + 1] : 0;
+    m.west = (bits << 1) | (cl >> 31);
+    m.east = (bits >> 1) | (cr << 31);
+    if (row > 0) {
+        const uint32_t u = map[w - wpr];
+        const uint32_t ul = has_l ? map[w - wpr - 1] : 0, ur = has_r ? map[w - wpr + 1] : 0;
+        m.n = u;
+        m.nw = (u << 1) | (ul >> 31);
+        m.ne = (u >> 1) | (ur << 31);
+    } else {
+        m.n = m.nw = m.ne = 0;
+    }
+    if (WITH_SOUTH && row + 1 < ny) {
+        const uint32_t d = map[w + wpr];
+        const uint32_t dl = has_l ? map[w + wpr - 1] : 0, dr = has_r ? map[w + wpr + 1] : 0;
+        m.s = d;
+        m.sw = (d << 1) | (dl >> 31);
+        m.se = (d >> 1) | (dr << 31);
+    } else {
+        m.s = m.sw = m.se = 0;
+    }
+    return m;
 }
 
 __global__ void __launch_bounds__(256)
-k_ccl_union(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ segpre_all, int NT,
-            uint32_t *__restrict__ parent_all, int nx, uint32_t MW)
+k_ccl_union(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
+            uint32_t *__restrict__ parent_all, int ny, int nx, uint32_t MW)
 {
     const int f = blockIdx.y;
     const uint32_t w = blockIdx.x * 256 + threadIdx.x;
     if (w >= MW) return;
     const uint32_t *map = maps + (size_t)f * MS;
-    uint32_t bits = map[w];
+    const uint32_t bits = map[w];
     if (!bits) return;
-    const uint16_t *segpre = segpre_all + (size_t)f * NT * SEGS_PER_TILE;
+    const uint16_t *wordpre = wordpre_all + (size_t)f * MS;
     uint32_t *parent = parent_all + (size_t)f * ((size_t)NT * TILE_PX);
-    uint32_t s = word_slot_base(map, segpre, w);
-    uint32_t p0 = w << 5;
+    const uint32_t p0 = w << 5;
+    if ((nx & 31) == 0) {
+        const uint32_t wpr = (uint32_t)nx >> 5;
+        const Nbr m = neighbour_masks<false>(map, w, bits, wpr, (uint32_t)ny);
+        uint32_t need = bits & (m.west | m.n | m.nw | m.ne);
+        if (!need) return;
+        const uint32_t sb = word_slot_base(wordpre, w);
+        while (need) {
+            const uint32_t k = __ffs(need) - 1;
+            need &= need - 1;
+            const uint32_t bk = 1u << k;
+            const uint32_t s = sb + __popc(bits & (bk - 1u));
+            const uint32_t p = p0 + k;
+            if (m.west & bk) uf_union(parent, s, k ? s - 1 : slot_of(map, wordpre, p - 1));
+            if (m.n & bk) {
+                // N is set: NW and NE are horizontally adjacent to N, their own W-links connect them
+                uf_union(parent, s, slot_of(map, wordpre, p - nx));
+            } else {
+                if (m.nw & bk) uf_union(parent, s, slot_of(map, wordpre, p - nx - 1));
+                if (m.ne & bk) uf_union(parent, s, slot_of(map, wordpre, p - nx + 1));
+            }
+        }
+        return;
+    }
+    // generic geometry: per-pixel neighbour tests
+    uint32_t s = word_slot_base(wordpre, w);
     uint32_t r = p0 / (uint32_t)nx, c = p0 - r * (uint32_t)nx;   // of bit 0; advanced incrementally
-    uint32_t prev_k = 0;
-    while (bits) {
-        const uint32_t k = __ffs(bits) - 1;
-        bits &= bits - 1;
+    uint32_t prev_k = 0, rest = bits;
+    while (rest) {
+        const uint32_t k = __ffs(rest) - 1;
+        rest &= rest - 1;
         c += k - prev_k;
         prev_k = k;
         while (c >= (uint32_t)nx) { c -= nx; r++; }
         const uint32_t p = p0 + k;
-        if (c > 0 && get_bit(map, p - 1)) uf_union(parent, s, slot_of(map, segpre, p - 1));
+        if (c > 0 && get_bit(map, p - 1)) uf_union(parent, s, slot_of(map, wordpre, p - 1));
         if (r > 0) {
             const uint32_t up = p - nx;
             if (get_bit(map, up)) {
-                // N is set: NW and NE are horizontally adjacent to N, their own W-links connect them
-                uf_union(parent, s, slot_of(map, segpre, up));
+                uf_union(parent, s, slot_of(map, wordpre, up));
             } else {
-                if (c > 0 && get_bit(map, up - 1)) uf_union(parent, s, slot_of(map, segpre, up - 1));
-                if (c + 1 < (uint32_t)nx && get_bit(map, up + 1)) uf_union(parent, s, slot_of(map, segpre, up + 1));
+                if (c > 0 && get_bit(map, up - 1)) uf_union(parent, s, slot_of(map, wordpre, up - 1));
+                if (c + 1 < (uint32_t)nx && get_bit(map, up + 1)) uf_union(parent, s, slot_of(map, wordpre, up + 1));
             }
         }
         s++;
@@ -101,59 +154,63 @@ k_ccl_union(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
 // MODE 0: labels only.  MODE 1: L2 max.  MODE 2: L2 sum.  MODE 3: L4 bounding boxes.
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_ccl_flatten(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ segpre_all, int NT,
+k_ccl_flatten(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
               uint32_t *__restrict__ parent_all, uint32_t *__restrict__ acc_all, uint32_t *__restrict__ bbox_all,
-              int nx, uint32_t MW)
+              int ny, int nx, uint32_t MW)
 {
     const int f = blockIdx.y;
     const uint32_t w = blockIdx.x * 256 + threadIdx.x;
     if (w >= MW) return;
     const uint32_t *map = maps + (size_t)f * MS;
-    uint32_t bits = map[w];
+    const uint32_t bits = map[w];
     if (!bits) return;
+    uint32_t todo = bits;
+    if ((nx & 31) == 0) {
+        // a pixel without any of its 8 neighbours set is a single-pixel puddle: already its own root
+        const Nbr m = neighbour_masks<true>(map, w, bits, (uint32_t)nx >> 5, (uint32_t)ny);
+        todo = bits & (m.west | m.east | m.n | m.nw | m.ne | m.s | m.sw | m.se);
+        if (!todo) return;
+    }
     const size_t slots = (size_t)NT * TILE_PX;
-    const uint16_t *segpre = segpre_all + (size_t)f * NT * SEGS_PER_TILE;
     uint32_t *parent = parent_all + (size_t)f * slots;
-    uint32_t s = word_slot_base(map, segpre, w);
+    const uint32_t sb = word_slot_base(wordpre_all + (size_t)f * MS, w);
     const uint32_t p0 = w << 5;
-    while (bits) {
-        const uint32_t k = __ffs(bits) - 1;
-        bits &= bits - 1;
+    while (todo) {
+        const uint32_t k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t s = sb + __popc(bits & ((1u << k) - 1u));
         const uint32_t root = uf_find_ro(parent, s);
         if (root != s) {
             parent[s] = root;
             if (MODE == 1) atomicMax(&acc_all[(size_t)f * slots + root], acc_all[(size_t)f * slots + s]);
             if (MODE == 2) atomicAdd(&acc_all[(size_t)f * slots + root], acc_all[(size_t)f * slots + s]);
             if (MODE == 3) {
-                // pixel of the root: invert the slot -> pixel map by rank select inside the root's tile
-                // is expensive; instead the root's pixel index is kept in bbox[3] by k_l4_root_pixels.
+                // the root's pixel index was stored in bbox[3] by k_l4_init_bbox
                 const uint32_t p = p0 + k;
-                const uint32_t rp = bbox_all[((size_t)f * slots + root) * 4 + 3];
+                uint32_t *bb = bbox_all + ((size_t)f * slots + root) * 4;
+                const uint32_t rp = bb[3];
                 const uint32_t r = p / (uint32_t)nx, c = p - r * (uint32_t)nx;
                 const uint32_t rr = rp / (uint32_t)nx, rc = rp - rr * (uint32_t)nx;
-                uint32_t *bb = bbox_all + ((size_t)f * slots + root) * 4;
                 atomicMax(&bb[0], r - rr);                       // rows below the root (root is the top row)
                 if (c < rc) atomicMax(&bb[1], rc - c);           // columns left of the root
                 if (c > rc) atomicMax(&bb[2], c - rc);           // columns right of the root
             }
         }
-        s++;
     }
 }
 
 // L4: bbox[slot] = {0, 0, 0, pixel index} for every foreground slot (must precede k_ccl_flatten<3>)
 __global__ void __launch_bounds__(256)
-k_l4_init_bbox(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ segpre_all, int NT,
+k_l4_init_bbox(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
                uint32_t *__restrict__ bbox_all, uint32_t MW)
 {
     const int f = blockIdx.y;
     const uint32_t w = blockIdx.x * 256 + threadIdx.x;
     if (w >= MW) return;
-    const uint32_t *map = maps + (size_t)f * MS;
-    uint32_t bits = map[w];
+    uint32_t bits = maps[(size_t)f * MS + w];
     if (!bits) return;
     const size_t slots = (size_t)NT * TILE_PX;
-    uint32_t s = word_slot_base(map, segpre_all + (size_t)f * NT * SEGS_PER_TILE, w);
+    uint32_t s = word_slot_base(wordpre_all + (size_t)f * MS, w);
     while (bits) {
         const uint32_t k = __ffs(bits) - 1;
         bits &= bits - 1;
@@ -162,60 +219,69 @@ k_l4_init_bbox(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__r
     }
 }
 
+// parent[slot] = slot for every foreground slot (when the map did not come from k_reduce_tiles)
+__global__ void __launch_bounds__(256)
+k_ccl_init(const uint32_t *__restrict__ tilecnt, int NT, uint32_t *__restrict__ parent_all)
+{
+    const int f = blockIdx.x, tile = blockIdx.y;
+    const uint32_t cnt = tilecnt[(size_t)f * NT + tile];
+    const uint32_t tb = (uint32_t)tile * TILE_PX;
+    uint32_t *parent = parent_all + (size_t)f * ((size_t)NT * TILE_PX);
+    for (uint32_t i = threadIdx.x; i < cnt; i += 256) parent[tb + i] = tb + i;
+}
+
 // ---- root compaction ---------------------------------------------------------------------------
-// For tile (f, tile): roots in slot order get local ordinals 0..; rootcnt[f][tile] = number of roots.
+// One warp per tile: roots in slot order get local ordinals 0..; rootcnt[f][tile] = number of roots.
 // PAYLOAD 0: ord[slot] = local ordinal (for label images)
 // PAYLOAD 1: out16[tile-compacted] = (uint16) acc[slot]                (L2 statistics)
 // PAYLOAD 2: out64[tile-compacted] = cent[slot] (float2 as uint64)     (L4 centroid lists)
 // PAYLOAD 3: count only
 template <int PAYLOAD>
 __global__ void __launch_bounds__(256)
-k_ccl_roots(const uint32_t *__restrict__ tilecnt, int NT, const uint32_t *__restrict__ parent_all,
+k_ccl_roots(const uint32_t *__restrict__ tilecnt, int NT, int n_tiles_total, const uint32_t *__restrict__ parent_all,
             const uint32_t *__restrict__ acc_all, const uint64_t *__restrict__ cent_all,
             uint32_t *__restrict__ rootcnt, uint32_t *__restrict__ ord_all, uint16_t *__restrict__ out16,
             uint64_t *__restrict__ out64)
 {
-    __shared__ uint32_t s_warp[9];
-    const int f = blockIdx.x, tile = blockIdx.y, t = threadIdx.x;
-    const size_t slots = (size_t)NT * TILE_PX;
-    const size_t fs = (size_t)f * slots;
+    const int gt = blockIdx.x * 8 + (threadIdx.x >> 5);       // global tile index = f * NT + tile
+    if (gt >= n_tiles_total) return;
+    const int lane = threadIdx.x & 31;
+    const int f = gt / NT, tile = gt - f * NT;
+    const size_t fs = (size_t)f * ((size_t)NT * TILE_PX);
     const uint32_t tb = (uint32_t)tile * TILE_PX;
-    const uint32_t cnt = tilecnt[(size_t)f * NT + tile];
+    const uint32_t cnt = tilecnt[gt];
     uint32_t carry = 0;
-    for (uint32_t i0 = 0; i0 < cnt; i0 += 256) {
-        const uint32_t i = i0 + t;
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+        const uint32_t i = i0 + lane;
         const uint32_t s = tb + i;
         const bool is_root = i < cnt && parent_all[fs + s] == s;
-        uint32_t total;
-        const uint32_t e = block_excl_scan<8>(is_root ? 1u : 0u, s_warp, &total);
+        const uint32_t b = __ballot_sync(0xffffffffu, is_root);
         if (is_root) {
-            const uint32_t j = carry + e;
+            const uint32_t j = carry + __popc(b & ((1u << lane) - 1u));
             if (PAYLOAD == 0) ord_all[fs + s] = j;
             if (PAYLOAD == 1) out16[fs + tb + j] = (uint16_t)acc_all[fs + s];
             if (PAYLOAD == 2) out64[fs + tb + j] = cent_all[fs + s];
         }
-        carry += total;
-        __syncthreads();
+        carry += __popc(b);
     }
-    if (t == 0) rootcnt[(size_t)f * NT + tile] = carry;
+    if (lane == 0) rootcnt[gt] = carry;
 }
 
 // dense label image: label = global ordinal of the root + 1 (scipy numbering), 0 = background
 __global__ void __launch_bounds__(256)
-k_ccl_label_image(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ segpre_all, int NT,
+k_ccl_label_image(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
                   const uint32_t *__restrict__ parent_all, const uint32_t *__restrict__ ord_all,
                   const uint32_t *__restrict__ rootpre_all, int32_t *__restrict__ labels, size_t P, uint32_t MW)
 {
     const int f = blockIdx.y;
     const uint32_t w = blockIdx.x * 256 + threadIdx.x;
     if (w >= MW) return;
-    const uint32_t *map = maps + (size_t)f * MS;
-    const uint32_t bits = map[w];
+    const uint32_t bits = maps[(size_t)f * MS + w];
     const size_t slots = (size_t)NT * TILE_PX;
     const uint32_t *parent = parent_all + (size_t)f * slots;
     const uint32_t *ord = ord_all + (size_t)f * slots;
     const uint32_t *rootpre = rootpre_all + (size_t)f * (NT + 1);
-    uint32_t s = bits ? word_slot_base(map, segpre_all + (size_t)f * NT * SEGS_PER_TILE, w) : 0;
+    uint32_t s = bits ? word_slot_base(wordpre_all + (size_t)f * MS, w) : 0;
     int32_t *out = labels + (size_t)f * P;
     const size_t p0 = (size_t)w << 5;
     for (int k = 0; k < 32; k++) {
@@ -230,12 +296,30 @@ k_ccl_label_image(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *
     }
 }
 
+// centroid lists in label order from the tile-compacted per-root payloads
+__global__ void __launch_bounds__(256)
+k_gather_centroids(const uint64_t *__restrict__ cent_tiles, const uint32_t *__restrict__ rootpre_all, int NT,
+                   float *__restrict__ out, size_t capacity)
+{
+    const int f = blockIdx.x, tile = blockIdx.y;
+    const uint32_t *rootpre = rootpre_all + (size_t)f * (NT + 1);
+    const uint32_t r0 = rootpre[tile], r1 = rootpre[tile + 1];
+    const uint64_t *src = cent_tiles + (size_t)f * ((size_t)NT * TILE_PX) + (size_t)tile * TILE_PX;
+    for (uint32_t j = threadIdx.x; j < r1 - r0; j += 256) {
+        if ((size_t)(r0 + j) >= capacity) break;
+        const uint64_t pk = src[j];
+        float *o = out + ((size_t)f * capacity + r0 + j) * 2;
+        o[0] = __uint_as_float((uint32_t)pk);
+        o[1] = __uint_as_float((uint32_t)(pk >> 32));
+    }
+}
+
 // ---- L4 centroids ------------------------------------------------------------------------------
 // One thread per root.  mode: 0/1 weighted (converters.py:167-197), 2 max pixel (:229-259), 3 unweighted (:200-226).
 // Each += of the reference is float64 arithmetic rounded to float32 (numba: float32 element += float64 value).
 template <typename T>
 __global__ void __launch_bounds__(128)
-k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ segpre_all, int NT,
+k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
                const uint32_t *__restrict__ parent_all, const uint32_t *__restrict__ bbox_all,
                const T *__restrict__ vals_all, int ny, int nx, uint32_t MW, int mode,
                uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all)
@@ -247,11 +331,11 @@ k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__r
     uint32_t bits = map[w];
     if (!bits) return;
     const size_t slots = (size_t)NT * TILE_PX;
-    const uint16_t *segpre = segpre_all + (size_t)f * NT * SEGS_PER_TILE;
+    const uint16_t *wordpre = wordpre_all + (size_t)f * MS;
     const uint32_t *parent = parent_all + (size_t)f * slots;
     const T *vals = vals_all + (size_t)f * slots;
     uint32_t *map2 = map2_all + (size_t)f * MS;
-    uint32_t s = word_slot_base(map, segpre, w);
+    uint32_t s = word_slot_base(wordpre, w);
     const uint32_t p0 = w << 5;
     for (; bits; s++) {
         const uint32_t k = __ffs(bits) - 1;
@@ -262,7 +346,7 @@ k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__r
         const uint4 bb = reinterpret_cast<const uint4 *>(bbox_all)[(size_t)f * slots + s];
         float fr, fc;
         if ((bb.x | bb.y | bb.z) == 0) {
-            // single-pixel puddle: RN32(v*r)/v rounds back to r (|error| <= r * 2^-23 << 0.5); same for c
+            // single-pixel puddle: the reference computes RN32(v*r) / RN32(v)
             const float v = (float)vals[s];
             if (mode == 2 || mode == 3) { fr = (float)r0; fc = (float)c0; }
             else {
@@ -283,7 +367,7 @@ k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__r
                         const uint32_t kk = __ffs(mb) - 1;
                         mb &= mb - 1;
                         const uint32_t q = (ww << 5) + kk;
-                        const uint32_t sq = slot_of(map, segpre, q);
+                        const uint32_t sq = slot_of(map, wordpre, q);
                         if (parent[sq] != s) continue;
                         const double v = (double)vals[sq];
                         const uint32_t c = q - r * (uint32_t)nx;
@@ -319,36 +403,6 @@ k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__r
     }
 }
 
-
-// parent[slot] = slot for every foreground slot (when the map did not come from k_reduce_tiles)
-__global__ void __launch_bounds__(256)
-k_ccl_init(const uint32_t *__restrict__ tilecnt, int NT, uint32_t *__restrict__ parent_all)
-{
-    const int f = blockIdx.x, tile = blockIdx.y;
-    const uint32_t cnt = tilecnt[(size_t)f * NT + tile];
-    const uint32_t tb = (uint32_t)tile * TILE_PX;
-    uint32_t *parent = parent_all + (size_t)f * ((size_t)NT * TILE_PX);
-    for (uint32_t i = threadIdx.x; i < cnt; i += 256) parent[tb + i] = tb + i;
-}
-
-// centroid lists in label order from the tile-compacted per-root payloads
-__global__ void __launch_bounds__(256)
-k_gather_centroids(const uint64_t *__restrict__ cent_tiles, const uint32_t *__restrict__ rootpre_all, int NT,
-                   float *__restrict__ out, size_t capacity)
-{
-    const int f = blockIdx.x, tile = blockIdx.y;
-    const uint32_t *rootpre = rootpre_all + (size_t)f * (NT + 1);
-    const uint32_t r0 = rootpre[tile], r1 = rootpre[tile + 1];
-    const uint64_t *src = cent_tiles + (size_t)f * ((size_t)NT * TILE_PX) + (size_t)tile * TILE_PX;
-    for (uint32_t j = threadIdx.x; j < r1 - r0; j += 256) {
-        if ((size_t)(r0 + j) >= capacity) break;
-        const uint64_t pk = src[j];
-        float *o = out + ((size_t)f * capacity + r0 + j) * 2;
-        o[0] = __uint_as_float((uint32_t)pk);
-        o[1] = __uint_as_float((uint32_t)(pk >> 32));
-    }
-}
-
 // ---- launchers ---------------------------------------------------------------------------------
 int launch_ccl_init(rc_ctx *ctx, const Geom &g, const uint32_t *tilecnt, uint32_t *parent, int F, cudaStream_t st)
 {
@@ -366,31 +420,32 @@ int launch_gather_centroids(rc_ctx *ctx, const Geom &g, const uint64_t *cent_til
     RC_LAUNCH_CHECK(ctx, "k_gather_centroids");
     return 0;
 }
-int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *segpre, uint32_t *parent,
+
+int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre, uint32_t *parent,
                      int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
     dim3 grid((unsigned)((g.MW + 255) / 256), F);
-    k_ccl_union<<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, g.nx, (uint32_t)g.MW);
+    k_ccl_union<<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, g.ny, g.nx, (uint32_t)g.MW);
     RC_LAUNCH_CHECK(ctx, "k_ccl_union");
     return 0;
 }
 
-int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *segpre,
+int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
                        uint32_t *parent, uint32_t *acc, uint32_t *bbox, int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
     dim3 grid((unsigned)((g.MW + 255) / 256), F);
     const uint32_t MW = (uint32_t)g.MW;
     if (mode == 3) {
-        k_l4_init_bbox<<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, bbox, MW);
+        k_l4_init_bbox<<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, bbox, MW);
         RC_LAUNCH_CHECK(ctx, "k_l4_init_bbox");
     }
     switch (mode) {
-    case 0: k_ccl_flatten<0><<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, acc, bbox, g.nx, MW); break;
-    case 1: k_ccl_flatten<1><<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, acc, bbox, g.nx, MW); break;
-    case 2: k_ccl_flatten<2><<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, acc, bbox, g.nx, MW); break;
-    default: k_ccl_flatten<3><<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, acc, bbox, g.nx, MW); break;
+    case 0: k_ccl_flatten<0><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, acc, bbox, g.ny, g.nx, MW); break;
+    case 1: k_ccl_flatten<1><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, acc, bbox, g.ny, g.nx, MW); break;
+    case 2: k_ccl_flatten<2><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, acc, bbox, g.ny, g.nx, MW); break;
+    default: k_ccl_flatten<3><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, acc, bbox, g.ny, g.nx, MW); break;
     }
     RC_LAUNCH_CHECK(ctx, "k_ccl_flatten");
     return 0;
@@ -401,42 +456,43 @@ int launch_ccl_roots(rc_ctx *ctx, const Geom &g, int payload, const uint32_t *ti
                      uint64_t *out64, int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
-    dim3 grid(F, g.NT);
+    const int nt = F * g.NT;
+    const unsigned grid = (unsigned)((nt + 7) / 8);
     if (payload == 0)
-        k_ccl_roots<0><<<grid, 256, 0, st>>>(tilecnt, g.NT, parent, acc, cent, rootcnt, ord, out16, out64);
+        k_ccl_roots<0><<<grid, 256, 0, st>>>(tilecnt, g.NT, nt, parent, acc, cent, rootcnt, ord, out16, out64);
     else if (payload == 1)
-        k_ccl_roots<1><<<grid, 256, 0, st>>>(tilecnt, g.NT, parent, acc, cent, rootcnt, ord, out16, out64);
+        k_ccl_roots<1><<<grid, 256, 0, st>>>(tilecnt, g.NT, nt, parent, acc, cent, rootcnt, ord, out16, out64);
     else if (payload == 2)
-        k_ccl_roots<2><<<grid, 256, 0, st>>>(tilecnt, g.NT, parent, acc, cent, rootcnt, ord, out16, out64);
+        k_ccl_roots<2><<<grid, 256, 0, st>>>(tilecnt, g.NT, nt, parent, acc, cent, rootcnt, ord, out16, out64);
     else
-        k_ccl_roots<3><<<grid, 256, 0, st>>>(tilecnt, g.NT, parent, acc, cent, rootcnt, ord, out16, out64);
+        k_ccl_roots<3><<<grid, 256, 0, st>>>(tilecnt, g.NT, nt, parent, acc, cent, rootcnt, ord, out16, out64);
     RC_LAUNCH_CHECK(ctx, "k_ccl_roots");
     return 0;
 }
 
-int launch_ccl_label_image(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *segpre,
+int launch_ccl_label_image(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre,
                            const uint32_t *parent, const uint32_t *ord, const uint32_t *rootpre, int32_t *labels,
                            int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
     dim3 grid((unsigned)((g.MW + 255) / 256), F);
-    k_ccl_label_image<<<grid, 256, 0, st>>>(maps, g.MS, segpre, g.NT, parent, ord, rootpre, labels, g.P,
+    k_ccl_label_image<<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, ord, rootpre, labels, g.P,
                                             (uint32_t)g.MW);
     RC_LAUNCH_CHECK(ctx, "k_ccl_label_image");
     return 0;
 }
 
 int launch_l4_centroids(rc_ctx *ctx, const Geom &g, int itemsize, int mode, const uint32_t *maps,
-                        const uint16_t *segpre, const uint32_t *parent, const uint32_t *bbox, const void *vals,
+                        const uint16_t *wordpre, const uint32_t *parent, const uint32_t *bbox, const void *vals,
                         uint32_t *map2, uint64_t *cent, int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
     dim3 grid((unsigned)((g.MW + 127) / 128), F);
     if (itemsize == 2)
-        k_l4_centroids<uint16_t><<<grid, 128, 0, st>>>(maps, g.MS, segpre, g.NT, parent, bbox, (const uint16_t *)vals,
+        k_l4_centroids<uint16_t><<<grid, 128, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, bbox, (const uint16_t *)vals,
                                                        g.ny, g.nx, (uint32_t)g.MW, mode, map2, cent);
     else
-        k_l4_centroids<uint8_t><<<grid, 128, 0, st>>>(maps, g.MS, segpre, g.NT, parent, bbox, (const uint8_t *)vals,
+        k_l4_centroids<uint8_t><<<grid, 128, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, bbox, (const uint8_t *)vals,
                                                       g.ny, g.nx, (uint32_t)g.MW, mode, map2, cent);
     RC_LAUNCH_CHECK(ctx, "k_l4_centroids");
     return 0;

@@ -11,7 +11,7 @@
 //            prefix to place its data, and only tilecnt[tile] entries per tile are ever touched.
 //   tilecnt  uint32 [F][NT]        foreground pixels per tile
 //   tilepre  uint32 [F][NT+1]      exclusive scan of tilecnt (tilepre[NT] = n foreground pixels of the frame)
-//   segpre   uint16 [F][NT*32]     foreground pixels of the tile before each segment
+//   wordpre  uint16 [F][MS]        foreground pixels of the tile before each map word (exclusive, per tile)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -165,14 +165,16 @@ __device__ __forceinline__ uint2 ld_stream_u2(const void *p)
     return r;
 }
 
-// slot of pixel q (which must be foreground) of one frame.  map/segpre point at the frame's arrays.
-__device__ __forceinline__ uint32_t slot_of(const uint32_t *__restrict__ map, const uint16_t *__restrict__ segpre,
+// slot of pixel q (which must be foreground) of one frame.  map/wordpre point at the frame's arrays.
+__device__ __forceinline__ uint32_t slot_of(const uint32_t *__restrict__ map, const uint16_t *__restrict__ wordpre,
                                             uint32_t q)
 {
-    const uint32_t w = q >> 5, seg = q >> 8;
-    uint32_t r = (q & ~(uint32_t)(TILE_PX - 1)) + segpre[seg];
-    const uint32_t w0 = seg << 3;
-    for (uint32_t i = w0; i < w; i++) r += __popc(map[i]);
-    r += __popc(map[w] & ((1u << (q & 31)) - 1u));
-    return r;
+    const uint32_t w = q >> 5;
+    return (q & ~(uint32_t)(TILE_PX - 1)) + wordpre[w] + __popc(map[w] & ((1u << (q & 31)) - 1u));
+}
+
+// slot of the first pixel of word w (whether or not it is set)
+__device__ __forceinline__ uint32_t word_slot_base(const uint16_t *__restrict__ wordpre, uint32_t w)
+{
+    return ((w >> 8) << 13) + wordpre[w];
 }

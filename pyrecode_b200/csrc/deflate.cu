@@ -19,7 +19,7 @@
 
 __global__ void __launch_bounds__(256)
 k_deflate_plan(const uint32_t *__restrict__ in_bytes, int n_streams, uint32_t *__restrict__ chunk_base,
-               uint32_t *__restrict__ counters)
+               uint32_t *__restrict__ counters, uint32_t *__restrict__ ghist)
 {
     __shared__ uint32_t s_warp[9];
     uint32_t carry = 0;
@@ -32,10 +32,13 @@ k_deflate_plan(const uint32_t *__restrict__ in_bytes, int n_streams, uint32_t *_
         carry += total;
         __syncthreads();
     }
+    if (ghist)
+        for (int i = threadIdx.x; i < n_streams * DF_NSYM; i += 256) ghist[i] = 0;
     if (threadIdx.x == 0) {
         chunk_base[n_streams] = carry;
-        counters[0] = 0;      // deflate ticket
+        counters[0] = 0;      // histogram ticket
         counters[1] = 0;      // copy ticket
+        counters[2] = 0;      // emit ticket
     }
 }
 
@@ -49,19 +52,38 @@ __device__ __forceinline__ int find_stream(const uint32_t *__restrict__ chunk_ba
     return lo;
 }
 
-__global__ void __launch_bounds__(DF_THREADS)
-k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
-                 const uint32_t *__restrict__ in_bytes, int n_streams, const uint32_t *__restrict__ chunk_base,
-                 uint32_t *__restrict__ counters, int level, uint8_t *__restrict__ scratch,
-                 uint32_t *__restrict__ chunk_bytes, uint2 *__restrict__ chunk_adler)
+// coalesced 128-bit loads of one chunk -> transposed, swizzled shared staging (zero padded past clen)
+__device__ __forceinline__ void stage_chunk(uint32_t *in32, const uint8_t *__restrict__ src, int clen, int t)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    DeflateShared &S = *reinterpret_cast<DeflateShared *>(smem_raw);
+    const bool aligned = ((uintptr_t)src & 15) == 0;
+    for (int u = t; u < DF_CHUNK / 16; u += DF_THREADS) {
+        const int o = u * 16;
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (aligned && o + 16 <= clen) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(src + o);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else if (o < clen) {
+            for (int b = 0; b < 16 && o + b < clen; b++) w[b >> 2] |= (uint32_t)src[o + b] << (8 * (b & 3));
+        }
+        const int tt = u >> 2, k0 = (u & 3) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; i++) in32[df_in_index(tt, k0 + i)] = w[i];
+    }
+}
+
+// pass 1 over every chunk: token histogram summed per stream + per-chunk Adler-32 partials
+__global__ void __launch_bounds__(DF_THREADS)
+k_deflate_hist(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+               const uint32_t *__restrict__ in_bytes, int n_streams, const uint32_t *__restrict__ chunk_base,
+               uint32_t *__restrict__ counters, int level, uint32_t *__restrict__ ghist,
+               uint2 *__restrict__ chunk_adler)
+{
+    __shared__ uint32_t s_in[DF_CHUNK / 4];
+    __shared__ uint32_t s_hist[DF_NSYM];
+    __shared__ uint32_t s_adler[2];
     __shared__ uint32_t s_ticket;
-    __shared__ uint32_t s_warp[9];
     const int t = threadIdx.x;
     const uint32_t total_chunks = chunk_base[n_streams];
-
     while (true) {
         if (t == 0) s_ticket = atomicAdd(&counters[0], 1u);
         __syncthreads();
@@ -69,85 +91,139 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
         if (gci >= total_chunks) break;
         const int s = find_stream(chunk_base, n_streams, gci);
         const uint32_t ci = gci - chunk_base[s];
-        const uint32_t slen = in_bytes[s];
-        const int clen = (int)min((uint32_t)DF_CHUNK, slen - ci * DF_CHUNK);
-        const uint8_t *src = in + in_off[s] + (size_t)ci * DF_CHUNK;
-
-        // ---- phase 0: zero state, stage the chunk (coalesced 128-bit loads -> transposed, swizzled smem)
-        for (int i = t; i < DF_OUT_WORDS; i += DF_THREADS) S.out[i] = 0;
-        for (int i = t; i < DF_NSYM; i += DF_THREADS) S.hist[i] = 0;
-        if (t == 0) { S.n_match = 0; S.adler_a = 0; S.adler_b = 0; S.stored = 0; }
-        const bool aligned = ((uintptr_t)src & 15) == 0;
-        for (int u = t; u < DF_CHUNK / 16; u += DF_THREADS) {
-            const int o = u * 16;
-            uint32_t w[4] = {0, 0, 0, 0};
-            if (aligned && o + 16 <= clen) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(src + o);
-                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            } else if (o < clen) {
-                for (int b = 0; b < 16 && o + b < clen; b++) w[b >> 2] |= (uint32_t)src[o + b] << (8 * (b & 3));
+        const int clen = (int)min((uint32_t)DF_CHUNK, in_bytes[s] - ci * DF_CHUNK);
+        for (int i = t; i < DF_NSYM; i += DF_THREADS) s_hist[i] = 0;
+        if (t < 2) s_adler[t] = 0;
+        stage_chunk(s_in, in + in_off[s] + (size_t)ci * DF_CHUNK, clen, t);
+        __syncthreads();
+        df_phase_hist(s_in, s_hist, s_adler, t, clen, level > 0);
+        __syncthreads();
+        if (level > 0)
+            for (int i = t; i < DF_NSYM; i += DF_THREADS) {
+                const uint32_t h = s_hist[i];
+                if (h) atomicAdd(&ghist[(size_t)s * DF_NSYM + i], h);
             }
-            const int tt = u >> 2, k0 = (u & 3) * 4;
-#pragma unroll
-            for (int i = 0; i < 4; i++) S.in32[df_in_index(tt, k0 + i)] = w[i];
+        if (t == 0) chunk_adler[gci] = make_uint2(s_adler[0] % 65521u, s_adler[1] % 65521u);
+        __syncthreads();
+    }
+}
+
+// one CTA per stream: sort the symbols by count (bitonic, 512 keys), build the code and its header
+__global__ void __launch_bounds__(DF_THREADS)
+k_deflate_tables(const uint32_t *__restrict__ ghist, const uint32_t *__restrict__ chunk_base,
+                 const uint32_t *__restrict__ in_bytes, DeflateTable *__restrict__ tables)
+{
+    __shared__ DfBuildShared B;
+    __shared__ float s_bits[DF_THREADS];
+    __shared__ uint32_t s_tok[DF_THREADS];
+    __shared__ int s_skip;
+    const int s = blockIdx.x, t = threadIdx.x;
+    if (chunk_base[s + 1] == chunk_base[s]) return;          // empty stream: no chunk will ask for a table
+    // Entropy estimate of the token stream: a stream that would shrink by < 3 % (bit-packed intensities are
+    // close to random bytes) is emitted as stored blocks, which skips the code construction and both
+    // tokenizer passes for all of its chunks.
+    {
+        uint32_t tok = 0;
+        for (int i = t; i < DF_NSYM; i += DF_THREADS) tok += ghist[(size_t)s * DF_NSYM + i];
+        s_tok[t] = tok;
+        __syncthreads();
+        if (t == 0) { uint32_t n = 0; for (int i = 0; i < DF_THREADS; i++) n += s_tok[i]; s_tok[0] = n; }
+        __syncthreads();
+        const float n = (float)s_tok[0];
+        float bits = 0.f;
+        for (int i = t; i < DF_NSYM; i += DF_THREADS) {
+            const uint32_t h = ghist[(size_t)s * DF_NSYM + i];
+            if (h) bits += (float)h * (log2f(n / (float)h) + (i > 264 ? 2.f : (i > 256 ? 1.f : 0.f)));
+        }
+        s_bits[t] = bits;
+        __syncthreads();
+        if (t == 0) {
+            float b = 0.f;
+            for (int i = 0; i < DF_THREADS; i++) b += s_bits[i];
+            s_skip = b * 0.125f + 128.f >= 0.97f * (float)in_bytes[s];
         }
         __syncthreads();
-
-        // ---- phase 1: histogram + adler
-        if (level > 0) df_phase_hist(S, t, clen);
-        else {
-            // stored-only: still need adler partials
-            int nbytes = clen - t * DF_SEG;
-            if (nbytes > DF_SEG) nbytes = DF_SEG;
-            uint32_t a = 0, b = 0;
-            for (int i = 0; i < nbytes; i++) {
-                const uint32_t c = (S.in32[df_in_index(t, i >> 2)] >> (8 * (i & 3))) & 0xffu;
-                a += c;
-                b += (uint32_t)(clen - (t * DF_SEG + i)) * c;
-            }
-            if (nbytes > 0) { atomicAdd(&S.adler_a, a % 65521u); atomicAdd(&S.adler_b, b % 65521u); }
+        if (s_skip) {
+            if (t == 0) tables[s].header_bits = 0xffffffffu;    // sentinel: store every chunk of this stream
+            return;
         }
-        __syncthreads();
+    }
+    for (int i = t; i < 512; i += DF_THREADS) {
+        uint32_t c = i < DF_NSYM ? ghist[(size_t)s * DF_NSYM + i] : 0;
+        if (i == 256) c = 1;                                  // end-of-block is used once per chunk; any count > 0 works
+        B.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
+    }
+    __syncthreads();
+    for (int k = 2; k <= 512; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < 512; i += DF_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint32_t a = B.keys[i], b = B.keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { B.keys[i] = b; B.keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (t == 0) {
+        int lo = 0, hi = 512;                                 // used symbols = index of the first sentinel
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (B.keys[mid] != 0xffffffffu) lo = mid + 1; else hi = mid; }
+        df_phase_build(B, lo);
+    }
+    __syncthreads();
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&B.tab);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&tables[s]);
+    for (int i = t; i < (int)(sizeof(DeflateTable) / 4); i += DF_THREADS) dst[i] = src[i];
+}
 
+// pass 2 over every chunk: encode with the stream's code
+__global__ void __launch_bounds__(DF_THREADS)
+k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                 const uint32_t *__restrict__ in_bytes, int n_streams, const uint32_t *__restrict__ chunk_base,
+                 uint32_t *__restrict__ counters, int level, const DeflateTable *__restrict__ tables,
+                 uint8_t *__restrict__ scratch, uint32_t *__restrict__ chunk_bytes)
+{
+    __shared__ DfEmitShared S;
+    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_warp[9];
+    const int t = threadIdx.x;
+    const uint32_t total_chunks = chunk_base[n_streams];
+
+    while (true) {
+        if (t == 0) s_ticket = atomicAdd(&counters[2], 1u);
+        __syncthreads();
+        const uint32_t gci = s_ticket;
+        if (gci >= total_chunks) break;
+        const int s = find_stream(chunk_base, n_streams, gci);
+        const uint32_t ci = gci - chunk_base[s];
+        const int clen = (int)min((uint32_t)DF_CHUNK, in_bytes[s] - ci * DF_CHUNK);
+
+        stage_chunk(S.in32, in + in_off[s] + (size_t)ci * DF_CHUNK, clen, t);
         uint32_t body_bits = 0;
         bool stored = level == 0;
         if (!stored) {
-            // ---- phase 2: sort symbols by count (bitonic, 512 keys), build codes + header
-            if (t == 0) S.hist[256] = 1;
+            const DeflateTable &T = tables[s];
+            const uint32_t hb = T.header_bits;
+            stored = hb == 0xffffffffu;
+        }
+        if (!stored) {
+            const DeflateTable &T = tables[s];
+            const uint32_t hb = T.header_bits;
+            const int hw = (int)((hb + 31) >> 5);
+            for (int i = t; i < DF_OUT_WORDS; i += DF_THREADS) S.out[i] = i < hw ? T.header[i] : 0;
+            df_load_table(S, T, t, DF_THREADS);
+            if (t == 0) S.header_bits = hb;
             __syncthreads();
-            for (int i = t; i < 512; i += DF_THREADS) {
-                const uint32_t c = i < DF_NSYM ? S.hist[i] : 0;
-                S.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
-            }
-            __syncthreads();
-            for (int k = 2; k <= 512; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = t; i < 512; i += DF_THREADS) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const uint32_t a = S.keys[i], b = S.keys[ixj];
-                            const bool up = (i & k) == 0;
-                            if ((a > b) == up) { S.keys[i] = b; S.keys[ixj] = a; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            // number of used symbols = first index holding the sentinel
-            if (t == 0) {
-                int lo = 0, hi = 512;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (S.keys[mid] != 0xffffffffu) lo = mid + 1; else hi = mid; }
-                df_phase_build(S, lo);
-            }
-            __syncthreads();
-
-            // ---- phase 3: sizes + exclusive scan
             df_phase_size(S, t, clen);
             uint32_t tok_bits;
             const uint32_t e = block_excl_scan<8>(S.tbits[t], s_warp, &tok_bits);
             S.tbits[t] = e;
-            body_bits = S.header_bits + tok_bits;
-            stored = df_dynamic_bytes(S, body_bits) >= (uint32_t)clen + 10u;
+            body_bits = hb + tok_bits;
+            stored = df_dynamic_bytes(body_bits, (int)(S.cl[256] >> 16)) >= (uint32_t)clen + 10u;
+            __syncthreads();
+        } else {
             __syncthreads();
         }
 
@@ -156,7 +232,7 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
             __syncthreads();
             if (t == 0) df_phase_finish(S, body_bits);
         } else {
-            // stored block: 00 | LEN | ~LEN | data | sync marker (00 0000 FFFF)
+            // stored block: 00 | LEN | ~LEN | data | sync marker (00 0000 FFFF); every byte below is overwritten
             uint8_t *ob = reinterpret_cast<uint8_t *>(S.out);
             if (t == 0) {
                 ob[0] = 0;
@@ -165,7 +241,6 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
                 ob[5 + clen] = 0; ob[6 + clen] = 0; ob[7 + clen] = 0; ob[8 + clen] = 0xff; ob[9 + clen] = 0xff;
                 S.out_bytes = (uint32_t)clen + 10u;
             }
-            // word 1 holds header byte 4 and data bytes 0..2: written bytewise, so no ordering issue
             for (int i = t; i < clen; i += DF_THREADS) {
                 const int tt = i / DF_SEG, bi = i % DF_SEG;
                 ob[5 + i] = (uint8_t)(S.in32[df_in_index(tt, bi >> 2)] >> (8 * (bi & 3)));
@@ -173,15 +248,11 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
         }
         __syncthreads();
 
-        // ---- store the piece
         const uint32_t nb = S.out_bytes;
         uint4 *dst = reinterpret_cast<uint4 *>(scratch + (size_t)gci * DF_SLOT_BYTES);
         const uint4 *so = reinterpret_cast<const uint4 *>(S.out);
         for (uint32_t i = t; i < (nb + 15) / 16; i += DF_THREADS) dst[i] = so[i];
-        if (t == 0) {
-            chunk_bytes[gci] = nb;
-            chunk_adler[gci] = make_uint2(S.adler_a % 65521u, S.adler_b % 65521u);
-        }
+        if (t == 0) chunk_bytes[gci] = nb;
         __syncthreads();
     }
 }
@@ -389,31 +460,35 @@ DeflateWs carve_deflate_ws(Carver &c, int n_streams, size_t max_chunks, bool nee
     w.stream_bytes = c.take<uint32_t>((size_t)n_streams + 1);
     w.stream_adler = c.take<uint32_t>((size_t)n_streams + 1);
     w.stream_dst = c.take<uint64_t>((size_t)n_streams + 1);
+    w.ghist = need_scratch ? c.take<uint32_t>((size_t)n_streams * DF_NSYM) : nullptr;
+    w.tables = need_scratch ? c.take<DeflateTable>((size_t)n_streams) : nullptr;
     w.scratch = need_scratch ? c.take<uint8_t>(max_chunks * DF_SLOT_BYTES + 64) : nullptr;
     w.max_chunks = max_chunks;
     return w;
 }
 
-static int deflate_smem_bytes() { return (int)sizeof(DeflateShared); }
-
-// encodes (mode 1) or sizes (mode 0) the chunks and finalizes per-stream totals
+// encodes (wrap = 1) or sizes (wrap = 0, reduce-only mode) the chunks and finalizes per-stream totals
 int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, const uint8_t *in, const uint64_t *in_off,
                            const uint32_t *in_bytes, int n_streams, const DeflateWs &w, cudaStream_t st)
 {
     if (n_streams <= 0) return 0;
-    k_deflate_plan<<<1, 256, 0, st>>>(in_bytes, n_streams, w.chunk_base, w.counters);
+    k_deflate_plan<<<1, 256, 0, st>>>(in_bytes, n_streams, w.chunk_base, w.counters, wrap ? w.ghist : nullptr);
     RC_LAUNCH_CHECK(ctx, "k_deflate_plan");
     if (wrap) {
-        const int smem = deflate_smem_bytes();
-        if (!ctx->deflate_attr_set) {
-            RC_CUDA(ctx, cudaFuncSetAttribute(k_deflate_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            ctx->deflate_attr_set = true;
-        }
-        size_t want = w.max_chunks < (size_t)ctx->sm_count * 5 ? w.max_chunks : (size_t)ctx->sm_count * 5;
+        size_t want = w.max_chunks < (size_t)ctx->sm_count * 8 ? w.max_chunks : (size_t)ctx->sm_count * 8;
         if (want < 1) want = 1;
-        k_deflate_chunks<<<(unsigned)want, DF_THREADS, smem, st>>>(in, in_off, in_bytes, n_streams, w.chunk_base,
-                                                                   w.counters, level, w.scratch, w.chunk_bytes,
-                                                                   w.chunk_adler);
+        k_deflate_hist<<<(unsigned)want, DF_THREADS, 0, st>>>(in, in_off, in_bytes, n_streams, w.chunk_base, w.counters,
+                                                               level, w.ghist, w.chunk_adler);
+        RC_LAUNCH_CHECK(ctx, "k_deflate_hist");
+        if (level > 0) {
+            k_deflate_tables<<<n_streams, DF_THREADS, 0, st>>>(w.ghist, w.chunk_base, in_bytes, (DeflateTable *)w.tables);
+            RC_LAUNCH_CHECK(ctx, "k_deflate_tables");
+        }
+        want = w.max_chunks < (size_t)ctx->sm_count * 6 ? w.max_chunks : (size_t)ctx->sm_count * 6;
+        if (want < 1) want = 1;
+        k_deflate_chunks<<<(unsigned)want, DF_THREADS, 0, st>>>(in, in_off, in_bytes, n_streams, w.chunk_base,
+                                                                 w.counters, level, (const DeflateTable *)w.tables,
+                                                                 w.scratch, w.chunk_bytes);
         RC_LAUNCH_CHECK(ctx, "k_deflate_chunks");
     } else {
         k_raw_chunk_bytes<<<n_streams, 128, 0, st>>>(in_bytes, w.chunk_base, n_streams, w.chunk_bytes);

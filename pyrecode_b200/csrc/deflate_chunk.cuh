@@ -1,22 +1,26 @@
-// deflate_chunk.cuh -- one deflate chunk (<= 16 KiB of input) encoded by one CTA of 256 threads.
+// deflate_chunk.cuh -- the GPU deflate encoder, written as per-thread phases.
 //
 // Replaces zlib.compress on the hot path (reference: pyrecode/recode_compressors.py:84-85, called from
 // recode_writer.py:503-511,538-540).  Only the INFLATED payload has to match the reference, not the
 // compressed bytes, so the encoder is designed for the GPU and for this data:
 //
-//   * LZ77 restricted to distance-1 matches (byte runs): binary maps are 85-99 % 0x00 bytes, and a run is
-//     found with one compare per byte, in lock step across the 256 threads (64 input bytes per thread).
-//   * one dynamic-Huffman block per chunk: 286-symbol histogram in shared memory, CTA-wide bitonic sort,
-//     two-queue Huffman merge + zlib-style 15-bit length limiting + canonical codes by one thread.
-//   * every chunk starts byte aligned and ends with an empty stored block (the Z_SYNC_FLUSH marker
-//     00 00 FF FF), and never references bytes before its own start.  Chunks of a stream are therefore
-//     independent: they are encoded by different CTAs, concatenated by byte copies, and can be found and
-//     inflated in parallel again on the read side.  Stock zlib inflates the result (verified in tests).
+//   * input streams are cut into 16 KiB chunks; a chunk is encoded by one CTA of 256 threads, 64 input
+//     bytes per thread, all threads in lock step.
+//   * LZ77 restricted to distance-1 matches (byte runs): binary maps are 85-99 % 0x00 bytes; a run costs one
+//     compare per byte, or one compare per 4 bytes on the all-equal-word fast path.
+//   * ONE dynamic-Huffman code per stream: k_deflate_hist sums the token histogram of all chunks of a
+//     stream, k_deflate_tables builds the code once (two-queue Huffman merge, zlib-style 15-bit length
+//     limiting, canonical codes, RFC 1951 code-length header) and every chunk of the stream re-uses the
+//     prebuilt header bits.  That removes all serial work from the per-chunk kernel.
+//   * every chunk is its own deflate block, starts byte aligned, ends with an empty stored block (the
+//     Z_SYNC_FLUSH marker 00 00 FF FF) and never references bytes before its own start.  Chunks are therefore
+//     independent: encoded by different CTAs, concatenated by byte copies, and found and inflated in parallel
+//     again on the read side.  Stock zlib inflates the result (verified in tests).
 //   * a chunk that would not shrink is emitted as a stored block.
 //
-// The per-thread phases are __host__ __device__ so that tests/csrc/deflate_host_test.cpp can run the very
-// same code on the CPU (threads simulated by a loop per phase) against stock zlib.  The CPU build is test
-// infrastructure only; the product calls the CUDA kernel in deflate.cu.
+// The phases are __host__ __device__ so that tests/csrc/codec_host_test.cpp can run the very same code on the
+// CPU (threads simulated by a loop per phase) against stock zlib.  The CPU build is test infrastructure only;
+// the product calls the CUDA kernels in deflate.cu.
 #pragma once
 #include <stdint.h>
 
@@ -39,30 +43,28 @@ constexpr int DF_SEG = 64;                          // input bytes per thread
 constexpr int DF_CHUNK = DF_THREADS * DF_SEG;       // 16384
 constexpr int DF_SEG_WORDS = DF_SEG / 4;            // 16
 constexpr int DF_NSYM = 288;                        // literal/length alphabet (286 used)
-constexpr int DF_OUT_WORDS = DF_CHUNK / 4 + 64;     // compressed chunk never exceeds the stored form
+constexpr int DF_OUT_WORDS = DF_CHUNK / 4 + 64;     // a compressed chunk never exceeds the stored form
 constexpr int DF_SLOT_BYTES = DF_CHUNK + 64;        // scratch slot per chunk (multiple of 16)
-constexpr int DF_MAX_HEADER_BITS = 17 + 19 * 3 + (286 + 2) * (7 + 7);   // loose bound
+constexpr int DF_HDR_WORDS = 136;                   // 17 + 57 + 288 * 14 bits worst case
 
-struct DeflateShared {
-    uint32_t in32[DF_CHUNK / 4];      // transposed + swizzled: word k of thread t at [k*256 + (t ^ ((k>>2)<<3))]
-    uint32_t out[DF_OUT_WORDS];       // bit stream, zero initialised
-    uint32_t hist[DF_NSYM];           // symbol counts; reused as sort keys (count << 9 | symbol)
-    uint32_t keys[512];               // sort buffer
+// per-stream code, built once by k_deflate_tables and read by every chunk of the stream
+struct DeflateTable {
     uint16_t code[DF_NSYM];           // bit-reversed canonical codes
     uint8_t len[DF_NSYM];             // code lengths
-    uint32_t tbits[DF_THREADS];       // per-thread bit counts -> exclusive bit offsets
-    uint32_t node_w[DF_NSYM];         // Huffman internal node weights
-    uint16_t node_parent[2 * DF_NSYM];  // [0,288) leaves (sorted order), [288, 576) internal nodes
-    uint8_t node_depth[DF_NSYM];
-    uint32_t header_bits;             // bits of block header + tables
-    uint32_t total_bits;              // bits of the whole dynamic block incl. EOB
-    uint32_t out_bytes;               // final size of the chunk piece
-    uint32_t adler_a, adler_b;        // sum b_i mod 65521, sum (clen - i) * b_i mod 65521
-    uint32_t n_match;
-    int stored;
+    uint32_t header[DF_HDR_WORDS];    // BFINAL=0/BTYPE=10 + code description, LSB first
+    uint32_t header_bits;
+    uint32_t pad[3];
 };
 
+// chunk staging: word k of thread t at [k*256 + (t ^ ((k>>2)<<3))] (transposed + swizzled: conflict-free both
+// for the coalesced 128-bit fill and for the per-thread word reads)
 DF_HD int df_in_index(int t, int k) { return k * DF_THREADS + (t ^ ((k >> 2) << 3)); }
+
+DF_HD void df_store_word(uint32_t *in32, int byte_off, uint32_t w)
+{
+    const int t = byte_off / DF_SEG, k = (byte_off % DF_SEG) >> 2;
+    in32[df_in_index(t, k)] = w;
+}
 
 // length -> (symbol, extra bits count, extra bits value); L in [3, 258]
 DF_HD void df_len_code(int L, int &sym, int &ebits, int &eval)
@@ -71,16 +73,20 @@ DF_HD void df_len_code(int L, int &sym, int &ebits, int &eval)
     const int x = L - 3;
     int e = 0;
     if (x >= 8) {
+#ifdef __CUDA_ARCH__
+        e = 29 - __clz(x);                          // floor(log2 x) - 2
+#else
         int hb = 0;
-        for (int y = x; y > 1; y >>= 1) hb++;        // floor(log2 x); x < 256 -> at most 7 steps
+        for (int y = x; y > 1; y >>= 1) hb++;
         e = hb - 2;
+#endif
     }
     sym = 257 + 4 * e + (x >> e);
     ebits = e;
     eval = x & ((1 << e) - 1);
 }
 
-// ---- sequential bit writer (single thread; header and trailer) ----------------------------------
+// ---- sequential bit writer (single thread) ----------------------------------------------------------
 struct DfBitWriter {
     uint32_t *buf;
     uint32_t pos;
@@ -96,80 +102,117 @@ struct DfBitWriter {
 
 DF_HD uint32_t df_bitrev(uint32_t c, int n)
 {
+#ifdef __CUDA_ARCH__
+    return n ? (__brev(c) >> (32 - n)) : 0;
+#else
     uint32_t r = 0;
     for (int i = 0; i < n; i++) { r = (r << 1) | (c & 1); c >>= 1; }
     return r;
+#endif
 }
 
-// ---- tokenizer --------------------------------------------------------------------------------
+// ---- tokenizer ----------------------------------------------------------------------------------------
 // Walks the nbytes of thread t's segment; E.lit(c) / E.match(L) are called in stream order.
-// prev = 0x100 means "no previous byte" (chunk start).
+// A run never crosses a segment, and the first byte of a chunk is always a literal (chunk independence).
+//
+// Two steps so that the 32 lanes of a warp stay converged: (1) a branch-free pass over the 16 words builds a
+// 64-bit mask of "break" positions (bytes that differ from their predecessor) with SIMD-in-register byte
+// compares; (2) a loop over the set bits only -- one iteration per run boundary instead of one per byte.  On
+// binary maps (85-99 % zero bytes) that is ~8x fewer divergent iterations than a per-byte state machine.
+DF_HD uint32_t df_byte_at(const uint32_t *in32, int t, int pos)
+{
+    return (in32[df_in_index(t, pos >> 2)] >> (8 * (pos & 3))) & 0xffu;
+}
+
+// bit i (i < 4) set when byte i of x differs from byte i of y
+DF_HD uint32_t df_ne_nibble(uint32_t x, uint32_t y)
+{
+    const uint32_t e = x ^ y;
+    uint32_t z = (e & 0x7f7f7f7fu) + 0x7f7f7f7fu;      // bit 7 of each byte: low 7 bits non-zero
+    z = (z | e) & 0x80808080u;                         // bit 7 set <=> byte of e non-zero
+    return ((z >> 7) * 0x00204081u >> 21) & 0xfu;     // gather bits 0, 8, 16, 24 -> bits 0..3
+}
+
 template <typename E>
-DF_HD void df_tokenize(const DeflateShared &S, int t, int nbytes, E &em)
+DF_HD void df_tokenize(const uint32_t *in32, int t, int nbytes, E &em)
 {
     if (nbytes <= 0) return;
-    uint32_t prev = 0x100;
-    if (t > 0) prev = S.in32[df_in_index(t - 1, DF_SEG_WORDS - 1)] >> 24;
-    int run = 0;
-    const int nw = (nbytes + 3) >> 2;
-    for (int k = 0; k < nw; k++) {
-        const uint32_t x = S.in32[df_in_index(t, k)];
+    uint32_t prev = 0x100;                           // "no previous byte"
+    if (t > 0) prev = in32[df_in_index(t - 1, DF_SEG_WORDS - 1)] >> 24;
+    // step 1: break mask
+    uint64_t brk = 0;
+    uint32_t carry = prev & 0xffu;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-        for (int bi = 0; bi < 4; bi++) {
-            if (k * 4 + bi < nbytes) {
-                const uint32_t c = (x >> (8 * bi)) & 0xffu;
-                if (c == prev) {
-                    run++;
-                } else {
-                    if (run >= 3) em.match(run);
-                    else for (int i = 0; i < run; i++) em.lit(prev);
-                    em.lit(c);
-                    prev = c;
-                    run = 0;
-                }
-            }
-        }
+    for (int k = 0; k < DF_SEG_WORDS; k++) {
+        const uint32_t x = in32[df_in_index(t, k)];
+        const uint32_t sh = (x << 8) | carry;         // each byte's predecessor
+        brk |= (uint64_t)df_ne_nibble(x, sh) << (4 * k);
+        carry = x >> 24;
     }
+    if (prev == 0x100) brk |= 1;                     // chunk start: byte 0 is always a literal
+    if (nbytes < DF_SEG) brk &= (1ull << nbytes) - 1;
+    // step 2: one iteration per run boundary
+    int last = -1;                                   // position of the previous break
+    uint32_t v = prev;                               // value of the run in progress
+    while (brk) {
+#ifdef __CUDA_ARCH__
+        const int pos = __ffsll((long long)brk) - 1;
+#else
+        const int pos = __builtin_ctzll(brk);
+#endif
+        brk &= brk - 1;
+        const int run = pos - last - 1;              // bytes equal to v since the previous break
+        if (run >= 3) em.match(run);
+        else for (int i = 0; i < run; i++) em.lit(v);
+        v = df_byte_at(in32, t, pos);
+        em.lit(v);
+        last = pos;
+    }
+    const int run = nbytes - last - 1;
     if (run >= 3) em.match(run);
-    else for (int i = 0; i < run; i++) em.lit(prev);
+    else for (int i = 0; i < run; i++) em.lit(v);
 }
 
-// ---- phase 0: load (device version lives in deflate.cu; this is the scalar form) -----------------
-DF_HD void df_store_word(DeflateShared &S, int byte_off, uint32_t w)
+DF_HD int df_seg_bytes(int t, int clen)
 {
-    const int t = byte_off / DF_SEG, k = (byte_off % DF_SEG) >> 2;
-    S.in32[df_in_index(t, k)] = w;
+    int nbytes = clen - t * DF_SEG;
+    return nbytes > DF_SEG ? DF_SEG : nbytes;
 }
 
-// ---- phase 1: histogram + adler partial sums -----------------------------------------------------
+// ---- histogram + Adler-32 partials (k_deflate_hist) -----------------------------------------------------
 struct DfHistEmit {
     uint32_t *hist;
-    uint32_t nmatch;
-    DF_HD void lit(uint32_t c) { DF_ATOMIC_ADD(&hist[c], 1u); }
+    uint32_t n0;                      // literal 0x00 is a third of all tokens on binary maps: count it privately
+    DF_HD void lit(uint32_t c)
+    {
+        if (c == 0) n0++;
+        else DF_ATOMIC_ADD(&hist[c], 1u);
+    }
     DF_HD void match(int L)
     {
         int sym, eb, ev;
         df_len_code(L, sym, eb, ev);
         DF_ATOMIC_ADD(&hist[sym], 1u);
-        nmatch++;
     }
 };
 
-DF_HD void df_phase_hist(DeflateShared &S, int t, int clen)
+// hist: DF_NSYM counters (shared);  adler: {sum b_i, sum (clen - i) * b_i} mod 65521 (shared)
+DF_HD void df_phase_hist(const uint32_t *in32, uint32_t *hist, uint32_t *adler, int t, int clen, bool tokens)
 {
-    int nbytes = clen - t * DF_SEG;
-    if (nbytes > DF_SEG) nbytes = DF_SEG;
+    const int nbytes = df_seg_bytes(t, clen);
     if (nbytes <= 0) return;
-    DfHistEmit em{S.hist, 0};
-    df_tokenize(S, t, nbytes, em);
-    if (em.nmatch) DF_ATOMIC_ADD(&S.n_match, em.nmatch);
-    // adler partials: A = sum b, B = sum (clen - i) * b_i  (i = absolute index in chunk)
+    if (tokens) {
+        DfHistEmit em{hist, 0};
+        df_tokenize(in32, t, nbytes, em);
+        if (em.n0) DF_ATOMIC_ADD(&hist[0], em.n0);
+    }
     uint32_t a = 0, b = 0;
     const int nw = (nbytes + 3) >> 2;
     for (int k = 0; k < nw; k++) {
-        const uint32_t x = S.in32[df_in_index(t, k)];
+        const uint32_t x = in32[df_in_index(t, k)];
+        if (x == 0) continue;
         for (int bi = 0; bi < 4; bi++) {
             const int i = k * 4 + bi;
             if (i < nbytes) {
@@ -179,16 +222,24 @@ DF_HD void df_phase_hist(DeflateShared &S, int t, int clen)
             }
         }
     }
-    DF_ATOMIC_ADD(&S.adler_a, a % 65521u);
-    DF_ATOMIC_ADD(&S.adler_b, b % 65521u);
+    if (a) {
+        DF_ATOMIC_ADD(&adler[0], a % 65521u);
+        DF_ATOMIC_ADD(&adler[1], b % 65521u);
+    }
 }
 
-// ---- phase 2: Huffman construction (one thread) --------------------------------------------------
-// keys[0..n_used) = (count << 9 | symbol) sorted ascending.  Produces S.len / S.code for the literal/length
-// alphabet, writes the dynamic block header into S.out and sets S.header_bits.
-//
-// generic builder: sorted (weight, symbol) pairs -> code lengths limited to maxbits (zlib's gen_bitlen
-// overflow repair, trees.c), using caller scratch.
+// ---- code construction (k_deflate_tables) ------------------------------------------------------------------
+struct DfBuildShared {
+    uint32_t keys[512];               // (count << 9 | symbol), sorted ascending; 0xffffffff = unused
+    uint32_t node_w[DF_NSYM];         // Huffman internal node weights
+    uint16_t node_parent[2 * DF_NSYM];  // [0,288) leaves (sorted order), [288, 576) internal nodes
+    uint8_t node_depth[DF_NSYM];
+    uint8_t seq[DF_NSYM + 2];         // code lengths to transmit
+    uint8_t rl_sym[DF_NSYM + 2], rl_ext[DF_NSYM + 2];
+    DeflateTable tab;
+};
+
+// sorted (weight, symbol) pairs -> code lengths limited to maxbits (zlib's gen_bitlen overflow repair, trees.c)
 DF_HD void df_build_lengths(const uint32_t *keys, int n_used, int maxbits, uint8_t *len_out, int nsym,
                             uint32_t *node_w, uint16_t *node_parent, uint8_t *node_depth)
 {
@@ -261,22 +312,23 @@ DF_HD void df_assign_codes(const uint8_t *len, int nsym, uint16_t *code)
     }
 }
 
-DF_HD void df_phase_build(DeflateShared &S, int n_used)
+// B.keys[0..n_used) sorted.  Fills B.tab (codes, lengths, header).  Single thread.
+DF_HD void df_phase_build(DfBuildShared &B, int n_used)
 {
-    df_build_lengths(S.keys, n_used, 15, S.len, DF_NSYM, S.node_w, S.node_parent, S.node_depth);
-    df_assign_codes(S.len, DF_NSYM, S.code);
+    DeflateTable &T = B.tab;
+    df_build_lengths(B.keys, n_used, 15, T.len, DF_NSYM, B.node_w, B.node_parent, B.node_depth);
+    df_assign_codes(T.len, DF_NSYM, T.code);
 
-    // ---- header ----
     int nlit = 286;
-    while (nlit > 257 && S.len[nlit - 1] == 0) nlit--;
+    while (nlit > 257 && T.len[nlit - 1] == 0) nlit--;
     const int ndist = 2;                       // like zlib: always two distance codes of one bit each
-    uint8_t seq[286 + 2];
-    for (int i = 0; i < nlit; i++) seq[i] = S.len[i];
+    uint8_t *seq = B.seq;
+    for (int i = 0; i < nlit; i++) seq[i] = T.len[i];
     seq[nlit] = 1; seq[nlit + 1] = 1;
     const int nseq = nlit + ndist;
 
-    // run-length encode with symbols 16 / 17 / 18 (RFC 1951 3.2.7); rl_sym/rl_ext hold the result
-    uint8_t rl_sym[286 + 2], rl_ext[286 + 2];
+    // run-length encode with symbols 16 / 17 / 18 (RFC 1951 3.2.7)
+    uint8_t *rl_sym = B.rl_sym, *rl_ext = B.rl_ext;
     int nrl = 0;
     uint32_t cl_freq[19];
     for (int i = 0; i < 19; i++) cl_freq[i] = 0;
@@ -310,14 +362,15 @@ DF_HD void df_phase_build(DeflateShared &S, int n_used)
     }
     uint8_t cl_len[19];
     uint16_t cl_code[19];
-    df_build_lengths(ckeys, cused, 7, cl_len, 19, S.node_w, S.node_parent, S.node_depth);
+    df_build_lengths(ckeys, cused, 7, cl_len, 19, B.node_w, B.node_parent, B.node_depth);
     df_assign_codes(cl_len, 19, cl_code);
 
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     int ncl = 19;
     while (ncl > 4 && cl_len[order[ncl - 1]] == 0) ncl--;
 
-    DfBitWriter bw{S.out, 0};
+    for (int i = 0; i < DF_HDR_WORDS; i++) T.header[i] = 0;
+    DfBitWriter bw{T.header, 0};
     bw.put(0, 1);                 // BFINAL = 0 (the stream is closed by the assembler)
     bw.put(2, 2);                 // BTYPE = 10 dynamic
     bw.put((uint32_t)(nlit - 257), 5);
@@ -331,36 +384,51 @@ DF_HD void df_phase_build(DeflateShared &S, int n_used)
         else if (s == 17) bw.put(rl_ext[i], 3);
         else if (s == 18) bw.put(rl_ext[i], 7);
     }
-    S.header_bits = bw.pos;
+    T.header_bits = bw.pos;
 }
 
-// ---- phase 3: per-thread bit counts ---------------------------------------------------------------
-struct DfSizeEmit {
-    const uint8_t *len;
-    uint32_t bits;
-    DF_HD void lit(uint32_t c) { bits += len[c]; }
-    DF_HD void match(int L)
-    {
-        int sym, eb, ev;
-        df_len_code(L, sym, eb, ev);
-        bits += len[sym] + eb + 1;        // + one-bit distance code (distance 1 = symbol 0, no extra bits)
-    }
+// ---- per-chunk emission (k_deflate_chunks) --------------------------------------------------------------------
+struct DfEmitShared {
+    uint32_t in32[DF_CHUNK / 4];
+    uint32_t out[DF_OUT_WORDS];       // bit stream, zero initialised
+    uint32_t cl[DF_NSYM];             // (length << 16) | bit-reversed code, literals and end-of-block
+    uint32_t mt[DF_SEG + 1];          // per match length 3..64: (total bits << 24) | length code + extra + distance bit
+    uint32_t tbits[DF_THREADS];       // per-thread bit counts -> exclusive bit offsets
+    uint32_t header_bits;
+    uint32_t out_bytes;
 };
 
-DF_HD void df_phase_size(DeflateShared &S, int t, int clen)
+// fills S.cl / S.mt from the stream's table; thread i handles entries i, i + nthreads, ...
+DF_HD void df_load_table(DfEmitShared &S, const DeflateTable &T, int i, int nthreads)
 {
-    int nbytes = clen - t * DF_SEG;
-    if (nbytes > DF_SEG) nbytes = DF_SEG;
-    DfSizeEmit em{S.len, 0};
-    if (nbytes > 0) df_tokenize(S, t, nbytes, em);
+    for (int s = i; s < DF_NSYM; s += nthreads) S.cl[s] = ((uint32_t)T.len[s] << 16) | T.code[s];
+    for (int L = 3 + i; L <= DF_SEG; L += nthreads) {
+        int sym, eb, ev;
+        df_len_code(L, sym, eb, ev);
+        const uint32_t l = T.len[sym];
+        // length code, extra bits, then distance symbol 0 = code '0' (1 bit, distance 1 has no extra bits)
+        S.mt[L] = ((l + eb + 1) << 24) | (uint32_t)T.code[sym] | ((uint32_t)ev << l);
+    }
+}
+
+struct DfSizeEmit {
+    const uint32_t *cl, *mt;
+    uint32_t bits;
+    DF_HD void lit(uint32_t c) { bits += cl[c] >> 16; }
+    DF_HD void match(int L) { bits += mt[L] >> 24; }
+};
+
+DF_HD void df_phase_size(DfEmitShared &S, int t, int clen)
+{
+    const int nbytes = df_seg_bytes(t, clen);
+    DfSizeEmit em{S.cl, S.mt, 0};
+    if (nbytes > 0) df_tokenize(S.in32, t, nbytes, em);
     S.tbits[t] = em.bits;
 }
 
-// ---- phase 4: emit ---------------------------------------------------------------------------------
 struct DfBitEmit {
     uint32_t *out;
-    const uint16_t *code;
-    const uint8_t *len;
+    const uint32_t *cl, *mt;
     uint64_t acc;
     uint32_t nb, wpos;
     DF_HD void add(uint32_t bits, int n)
@@ -374,35 +442,27 @@ struct DfBitEmit {
             wpos++;
         }
     }
-    DF_HD void lit(uint32_t c) { add(code[c], len[c]); }
-    DF_HD void match(int L)
-    {
-        int sym, eb, ev;
-        df_len_code(L, sym, eb, ev);
-        // length code, extra bits, then distance symbol 0 = code '0' (1 bit)
-        add((uint32_t)code[sym] | ((uint32_t)ev << len[sym]), len[sym] + eb + 1);
-    }
+    DF_HD void lit(uint32_t c) { const uint32_t e = cl[c]; add(e & 0xffffu, e >> 16); }
+    DF_HD void match(int L) { const uint32_t e = mt[L]; add(e & 0xffffffu, e >> 24); }
     DF_HD void flush() { if (nb) DF_ATOMIC_OR(&out[wpos], (uint32_t)acc); }
 };
 
-// S.tbits[t] must hold the exclusive prefix (bit offset relative to header end)
-DF_HD void df_phase_emit(DeflateShared &S, int t, int clen)
+// S.tbits[t] must hold the exclusive prefix (bit offset relative to the header end)
+DF_HD void df_phase_emit(DfEmitShared &S, int t, int clen)
 {
-    int nbytes = clen - t * DF_SEG;
-    if (nbytes > DF_SEG) nbytes = DF_SEG;
+    const int nbytes = df_seg_bytes(t, clen);
     if (nbytes <= 0) return;
     const uint32_t o = S.header_bits + S.tbits[t];
-    DfBitEmit em{S.out, S.code, S.len, 0, o & 31, o >> 5};
-    df_tokenize(S, t, nbytes, em);
+    DfBitEmit em{S.out, S.cl, S.mt, 0, o & 31, o >> 5};
+    df_tokenize(S.in32, t, nbytes, em);
     em.flush();
 }
 
-// ---- phase 5: trailer (one thread) -------------------------------------------------------------------
-// body_bits = header + all tokens.  Appends EOB and the sync-flush marker; sets out_bytes.
-DF_HD void df_phase_finish(DeflateShared &S, uint32_t body_bits)
+// body_bits = header + all tokens.  Appends EOB and the sync-flush marker; sets out_bytes.  Single thread.
+DF_HD void df_phase_finish(DfEmitShared &S, uint32_t body_bits)
 {
     DfBitWriter bw{S.out, body_bits};
-    bw.put(S.code[256], S.len[256]);      // end of block
+    bw.put(S.cl[256] & 0xffffu, S.cl[256] >> 16);      // end of block
     bw.put(0, 3);                         // BFINAL=0, BTYPE=00: empty stored block
     bw.pos = (bw.pos + 7) & ~7u;          // pad to a byte boundary (zero bits)
     bw.put(0x0000, 16);                   // LEN = 0
@@ -411,7 +471,7 @@ DF_HD void df_phase_finish(DeflateShared &S, uint32_t body_bits)
 }
 
 // size in bytes of the dynamic form given the body bits (header + tokens)
-DF_HD uint32_t df_dynamic_bytes(const DeflateShared &S, uint32_t body_bits)
+DF_HD uint32_t df_dynamic_bytes(uint32_t body_bits, int eob_len)
 {
-    return ((body_bits + S.len[256] + 3 + 7) >> 3) + 4;
+    return ((body_bits + eob_len + 3 + 7) >> 3) + 4;
 }

@@ -4,9 +4,9 @@
 
 // reduce.cu
 int launch_reduce_tiles(rc_ctx *ctx, const Geom &g, int itemsize, int valmode, int ccl, const void *frames,
-                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *segpre, void *vals,
+                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre, void *vals,
                         uint32_t *parent, uint32_t *acc, cudaStream_t st);
-int launch_map_counts(rc_ctx *ctx, const Geom &g, const uint32_t *maps, int F, uint32_t *tilecnt, uint16_t *segpre,
+int launch_map_counts(rc_ctx *ctx, const Geom &g, const uint32_t *maps, int F, uint32_t *tilecnt, uint16_t *wordpre,
                       cudaStream_t st);
 int launch_scan_tiles(rc_ctx *ctx, const Geom &g, const uint32_t *tilecnt, int F, uint32_t *tilepre,
                       uint32_t *counts, uint32_t *packed_bytes, int b, cudaStream_t st);
@@ -19,18 +19,18 @@ int launch_make_threshold(rc_ctx *ctx, int itemsize, const void *dark, uint64_t 
 
 // ccl.cu
 int launch_ccl_init(rc_ctx *ctx, const Geom &g, const uint32_t *tilecnt, uint32_t *parent, int F, cudaStream_t st);
-int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *segpre, uint32_t *parent,
+int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre, uint32_t *parent,
                      int F, cudaStream_t st);
-int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *segpre,
+int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
                        uint32_t *parent, uint32_t *acc, uint32_t *bbox, int F, cudaStream_t st);
 int launch_ccl_roots(rc_ctx *ctx, const Geom &g, int payload, const uint32_t *tilecnt, const uint32_t *parent,
                      const uint32_t *acc, const uint64_t *cent, uint32_t *rootcnt, uint32_t *ord, uint16_t *out16,
                      uint64_t *out64, int F, cudaStream_t st);
-int launch_ccl_label_image(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *segpre,
+int launch_ccl_label_image(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre,
                            const uint32_t *parent, const uint32_t *ord, const uint32_t *rootpre, int32_t *labels,
                            int F, cudaStream_t st);
 int launch_l4_centroids(rc_ctx *ctx, const Geom &g, int itemsize, int mode, const uint32_t *maps,
-                        const uint16_t *segpre, const uint32_t *parent, const uint32_t *bbox, const void *vals,
+                        const uint16_t *wordpre, const uint32_t *parent, const uint32_t *bbox, const void *vals,
                         uint32_t *map2, uint64_t *cent, int F, cudaStream_t st);
 int launch_gather_centroids(rc_ctx *ctx, const Geom &g, const uint64_t *cent_tiles, const uint32_t *rootpre, int F,
                             float *out, size_t capacity, cudaStream_t st);
@@ -45,6 +45,8 @@ struct DeflateWs {
     uint32_t *stream_bytes;   // [S]
     uint32_t *stream_adler;   // [S]
     uint64_t *stream_dst;     // [S]
+    uint32_t *ghist;          // [S][288] token histogram per stream
+    void *tables;             // [S] DeflateTable
     uint8_t *scratch;         // [max_chunks * slot]
     size_t max_chunks;
 };
@@ -68,8 +70,8 @@ int launch_inflate(rc_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const
 
 // unpack.cu
 int launch_unpack_sparse(rc_ctx *ctx, const Geom &g, int level, int b, const uint32_t *maps, const uint8_t *packed,
-                         size_t packed_stride, const uint16_t *segpre, const uint32_t *tilepre, int F,
+                         size_t packed_stride, const uint16_t *wordpre, const uint32_t *tilepre, int F,
                          uint64_t *triples, size_t capacity, cudaStream_t st);
 int launch_unpack_dense(rc_ctx *ctx, const Geom &g, int itemsize, int level, int b, const uint32_t *maps,
-                        const uint8_t *packed, size_t packed_stride, const uint16_t *segpre, const uint32_t *tilepre,
+                        const uint8_t *packed, size_t packed_stride, const uint16_t *wordpre, const uint32_t *tilepre,
                         int F, void *dense, uint32_t *sum, cudaStream_t st);

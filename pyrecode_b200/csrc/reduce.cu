@@ -87,11 +87,11 @@ template <> struct Px<uint8_t> {
 
 // ---- K1 ------------------------------------------------------------------------------------
 // VALMODE: 0 = no value stream (L3), 1 = frame - thr (L1), 2 = raw frame value (L2 / L4)
-// CCL:     0 = none, 1 = parent[slot] = slot and acc[slot] = value (L2), 2 = parent only (L4)
+// CCL:     0 = vals only, 1 = parent[slot] = slot and acc[slot] = value, no vals (L2), 2 = vals + parent (L4)
 template <typename T, int VALMODE, int CCL>
 __global__ void __launch_bounds__(256)
 k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P, int NT, size_t MS,
-               uint32_t *__restrict__ maps, uint32_t *__restrict__ tilecnt, uint16_t *__restrict__ segpre,
+               uint32_t *__restrict__ maps, uint32_t *__restrict__ tilecnt, uint16_t *__restrict__ wordpre,
                T *__restrict__ vals, uint32_t *__restrict__ parent, uint32_t *__restrict__ acc, int vec_ok)
 {
     constexpr int W = Px<T>::W;
@@ -146,7 +146,7 @@ k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P
     uint32_t total;
     const uint32_t excl = block_excl_scan<8>(pc, s_warp, &total);
     s_wpre[t] = (uint16_t)excl;
-    if ((t & 7) == 0) segpre[((size_t)f * NT + tile) * SEGS_PER_TILE + (t >> 3)] = (uint16_t)excl;
+    wordpre[(size_t)f * MS + (size_t)tile * TILE_WORDS + t] = (uint16_t)excl;
     if (t == 0) tilecnt[(size_t)f * NT + tile] = total;
 
     if (VALMODE) {
@@ -171,7 +171,7 @@ k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P
         const size_t sbase = (size_t)f * ((size_t)NT * TILE_PX) + base;
         for (uint32_t i = t; i < total; i += 256) {
             const T v = s_vals[i];
-            vals[sbase + i] = v;
+            if (CCL != 1) vals[sbase + i] = v;
             if (CCL) parent[sbase + i] = (uint32_t)(base + i);
             if (CCL == 1) acc[sbase + i] = (uint32_t)v;
         }
@@ -180,14 +180,14 @@ k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P
 
 template <typename T>
 static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, int ccl, const void *frames,
-                                 const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *segpre,
+                                 const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre,
                                  void *vals, uint32_t *parent, uint32_t *acc, cudaStream_t st)
 {
     const int vec_ok = ((g.P * sizeof(T)) % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)thr % 16 == 0);
     dim3 grid(F, g.NT), block(256);
 #define RC_K1(VM, C)                                                                                          \
     k_reduce_tiles<T, VM, C><<<grid, block, 0, st>>>((const T *)frames, (const T *)thr, g.P, g.NT, g.MS, maps, \
-                                                     tilecnt, segpre, (T *)vals, parent, acc, vec_ok)
+                                                     tilecnt, wordpre, (T *)vals, parent, acc, vec_ok)
     if (valmode == 0) RC_K1(0, 0);
     else if (valmode == 1) RC_K1(1, 0);
     else if (ccl == 1) RC_K1(2, 1);
@@ -199,22 +199,22 @@ static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, int cc
 }
 
 int launch_reduce_tiles(rc_ctx *ctx, const Geom &g, int itemsize, int valmode, int ccl, const void *frames,
-                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *segpre, void *vals,
+                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre, void *vals,
                         uint32_t *parent, uint32_t *acc, cudaStream_t st)
 {
     if (F <= 0) return 0;
     if (itemsize == 2)
-        return launch_reduce_tiles_t<uint16_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, segpre, vals,
+        return launch_reduce_tiles_t<uint16_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, wordpre, vals,
                                                parent, acc, st);
-    return launch_reduce_tiles_t<uint8_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, segpre, vals, parent,
+    return launch_reduce_tiles_t<uint8_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, wordpre, vals, parent,
                                           acc, st);
 }
 
 // ---- map-only tile counts (read side: a map came out of inflate) ------------------------------
-// Computes tilecnt / segpre from existing maps so the unpack kernels can rank pixels.
+// Computes tilecnt / wordpre from existing maps so the unpack kernels can rank pixels.
 __global__ void __launch_bounds__(256)
 k_map_counts(const uint32_t *__restrict__ maps, size_t MS, int NT, uint32_t *__restrict__ tilecnt,
-             uint16_t *__restrict__ segpre)
+             uint16_t *__restrict__ wordpre)
 {
     __shared__ uint32_t s_warp[9];
     const int t = threadIdx.x, f = blockIdx.x, tile = blockIdx.y;
@@ -222,15 +222,15 @@ k_map_counts(const uint32_t *__restrict__ maps, size_t MS, int NT, uint32_t *__r
     const uint32_t pc = __popc(word);
     uint32_t total;
     const uint32_t excl = block_excl_scan<8>(pc, s_warp, &total);
-    if ((t & 7) == 0) segpre[((size_t)f * NT + tile) * SEGS_PER_TILE + (t >> 3)] = (uint16_t)excl;
+    wordpre[(size_t)f * MS + (size_t)tile * TILE_WORDS + t] = (uint16_t)excl;
     if (t == 0) tilecnt[(size_t)f * NT + tile] = total;
 }
 
-int launch_map_counts(rc_ctx *ctx, const Geom &g, const uint32_t *maps, int F, uint32_t *tilecnt, uint16_t *segpre,
+int launch_map_counts(rc_ctx *ctx, const Geom &g, const uint32_t *maps, int F, uint32_t *tilecnt, uint16_t *wordpre,
                       cudaStream_t st)
 {
     if (F <= 0) return 0;
-    k_map_counts<<<dim3(F, g.NT), 256, 0, st>>>(maps, g.MS, g.NT, tilecnt, segpre);
+    k_map_counts<<<dim3(F, g.NT), 256, 0, st>>>(maps, g.MS, g.NT, tilecnt, wordpre);
     RC_LAUNCH_CHECK(ctx, "k_map_counts");
     return 0;
 }

@@ -22,7 +22,7 @@ __device__ __forceinline__ uint32_t fetch_bits(const uint32_t *__restrict__ pack
 
 __global__ void __launch_bounds__(256)
 k_unpack_sparse(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__restrict__ packed, size_t packed_stride,
-                const uint16_t *__restrict__ segpre_all, const uint32_t *__restrict__ tilepre_all, int NT, int nx,
+                const uint16_t *__restrict__ wordpre_all, const uint32_t *__restrict__ tilepre_all, int NT, int nx,
                 uint32_t MW, int level, int b, uint64_t *__restrict__ triples, size_t capacity)
 {
     const int f = blockIdx.y;
@@ -31,13 +31,10 @@ k_unpack_sparse(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__r
     const uint32_t *map = maps + (size_t)f * MS;
     uint32_t bits = map[w];
     if (!bits) return;
-    const uint16_t *segpre = segpre_all + (size_t)f * NT * SEGS_PER_TILE;
     const uint32_t *tilepre = tilepre_all + (size_t)f * (NT + 1);
     const uint32_t *pk = reinterpret_cast<const uint32_t *>(packed + (size_t)f * packed_stride);
     // global rank of the first set bit of this word
-    const uint32_t seg = w >> 3;
-    uint64_t rank = (uint64_t)tilepre[w >> 8] + segpre[seg];
-    for (uint32_t i = seg << 3; i < w; i++) rank += __popc(map[i]);
+    uint64_t rank = (uint64_t)tilepre[w >> 8] + wordpre_all[(size_t)f * MS + w];
     uint64_t *out = triples + (size_t)f * capacity * 3;
     const uint32_t p0 = w << 5;
     while (bits) {
@@ -58,7 +55,7 @@ k_unpack_sparse(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__r
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_unpack_dense(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__restrict__ packed, size_t packed_stride,
-               const uint16_t *__restrict__ segpre_all, const uint32_t *__restrict__ tilepre_all, int NT, size_t P,
+               const uint16_t *__restrict__ wordpre_all, const uint32_t *__restrict__ tilepre_all, int NT, size_t P,
                int level, int b, T *__restrict__ dense, uint32_t *__restrict__ sum, int vec_ok)
 {
     const int f = blockIdx.y;
@@ -73,7 +70,7 @@ k_unpack_dense(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__re
     const uint32_t pc = __popc(m);
     const uint32_t incl = warp_incl_scan(pc);
     uint64_t rank = (uint64_t)tilepre_all[(size_t)f * (NT + 1) + (seg >> 5)] +
-                    segpre_all[(size_t)f * nseg + seg] + (incl - pc);
+                    wordpre_all[(size_t)f * MS + (size_t)seg * SEG_WORDS] + (incl - pc);
     const uint32_t *pk = reinterpret_cast<const uint32_t *>(packed + (size_t)f * packed_stride);
     uint32_t v[8];
 #pragma unroll
@@ -106,19 +103,19 @@ k_unpack_dense(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__re
 }
 
 int launch_unpack_sparse(rc_ctx *ctx, const Geom &g, int level, int b, const uint32_t *maps, const uint8_t *packed,
-                         size_t packed_stride, const uint16_t *segpre, const uint32_t *tilepre, int F,
+                         size_t packed_stride, const uint16_t *wordpre, const uint32_t *tilepre, int F,
                          uint64_t *triples, size_t capacity, cudaStream_t st)
 {
     if (F <= 0) return 0;
     dim3 grid((unsigned)((g.MW + 255) / 256), F);
-    k_unpack_sparse<<<grid, 256, 0, st>>>(maps, g.MS, packed, packed_stride, segpre, tilepre, g.NT, g.nx,
+    k_unpack_sparse<<<grid, 256, 0, st>>>(maps, g.MS, packed, packed_stride, wordpre, tilepre, g.NT, g.nx,
                                           (uint32_t)g.MW, level, b, triples, capacity);
     RC_LAUNCH_CHECK(ctx, "k_unpack_sparse");
     return 0;
 }
 
 int launch_unpack_dense(rc_ctx *ctx, const Geom &g, int itemsize, int level, int b, const uint32_t *maps,
-                        const uint8_t *packed, size_t packed_stride, const uint16_t *segpre, const uint32_t *tilepre,
+                        const uint8_t *packed, size_t packed_stride, const uint16_t *wordpre, const uint32_t *tilepre,
                         int F, void *dense, uint32_t *sum, cudaStream_t st)
 {
     if (F <= 0) return 0;
@@ -126,10 +123,10 @@ int launch_unpack_dense(rc_ctx *ctx, const Geom &g, int itemsize, int level, int
     dim3 grid((nseg + 7) / 8, F);
     const int vec_ok = dense && ((g.P * itemsize) % 16 == 0) && ((uintptr_t)dense % 16 == 0);
     if (itemsize == 2)
-        k_unpack_dense<uint16_t><<<grid, 256, 0, st>>>(maps, g.MS, packed, packed_stride, segpre, tilepre, g.NT, g.P,
+        k_unpack_dense<uint16_t><<<grid, 256, 0, st>>>(maps, g.MS, packed, packed_stride, wordpre, tilepre, g.NT, g.P,
                                                        level, b, (uint16_t *)dense, sum, vec_ok);
     else
-        k_unpack_dense<uint8_t><<<grid, 256, 0, st>>>(maps, g.MS, packed, packed_stride, segpre, tilepre, g.NT, g.P,
+        k_unpack_dense<uint8_t><<<grid, 256, 0, st>>>(maps, g.MS, packed, packed_stride, wordpre, tilepre, g.NT, g.P,
                                                       level, b, (uint8_t *)dense, sum, vec_ok);
     RC_LAUNCH_CHECK(ctx, "k_unpack_dense");
     return 0;

@@ -319,6 +319,21 @@ class ReadEngine:
                 out.append(t)
             return out
 
+    def summary_stats(self, out_bytes):
+        """L2: unpack the per-puddle statistics of the loaded frames -> list of arrays of the target dtype
+        (intent of recode_reader.py:473-481, count = bytes * 8 // bit_depth)."""
+        F, n = self.max_frames, self.n
+        _, packed = self._views()
+        res = []
+        with torch.cuda.device(self.dev):
+            for f in range(n):
+                k = int(out_bytes[F + f]) * 8 // self.bit_depth
+                out = self.ctx.zeros(max(k, 1), torch.int64)
+                if k:
+                    self.ctx.bit_unpack(self.bit_depth, packed[f * self.stride:], k, out)
+                res.append(out[:k].cpu().numpy().astype(self.np_dtype))
+        return res
+
     def _maps_contig(self):
         F, n = self.max_frames, self.n
         maps, _ = self._views()

@@ -8,72 +8,79 @@
 #include "../../pyrecode_b200/csrc/deflate_chunk.cuh"
 #include "../../pyrecode_b200/csrc/inflate_core.cuh"
 
-static uint32_t encode_chunk(DeflateShared &S, const uint8_t *src, int clen, int level, uint8_t *dst,
-                             uint32_t *adler_a, uint32_t *adler_b)
-{
-    memset(&S, 0, sizeof(S));
-    for (int o = 0; o < DF_CHUNK; o += 4) {
-        uint32_t w = 0;
-        for (int b = 0; b < 4; b++) if (o + b < clen) w |= (uint32_t)src[o + b] << (8 * b);
-        df_store_word(S, o, w);
-    }
-    uint32_t body_bits = 0;
-    bool stored = level == 0;
-    if (!stored) {
-        for (int t = 0; t < DF_THREADS; t++) df_phase_hist(S, t, clen);
-        S.hist[256] = 1;
-        for (int i = 0; i < 512; i++) {
-            const uint32_t c = i < DF_NSYM ? S.hist[i] : 0;
-            S.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
-        }
-        std::sort(S.keys, S.keys + 512);
-        int n_used = 0;
-        while (n_used < 512 && S.keys[n_used] != 0xffffffffu) n_used++;
-        df_phase_build(S, n_used);
-        for (int t = 0; t < DF_THREADS; t++) df_phase_size(S, t, clen);
-        uint32_t run = 0;
-        for (int t = 0; t < DF_THREADS; t++) { const uint32_t v = S.tbits[t]; S.tbits[t] = run; run += v; }
-        body_bits = S.header_bits + run;
-        stored = df_dynamic_bytes(S, body_bits) >= (uint32_t)clen + 10u;
-    } else {
-        // adler partials only
-        uint32_t a = 0, b = 0;
-        for (int i = 0; i < clen; i++) { a = (a + src[i]) % 65521u; b = (b + (uint64_t)(clen - i) * src[i]) % 65521u; }
-        S.adler_a = a; S.adler_b = b;
-    }
-    if (!stored) {
-        for (int t = 0; t < DF_THREADS; t++) df_phase_emit(S, t, clen);
-        df_phase_finish(S, body_bits);
-    } else {
-        uint8_t *ob = reinterpret_cast<uint8_t *>(S.out);
-        ob[0] = 0; ob[1] = clen & 0xff; ob[2] = clen >> 8; ob[3] = ~clen & 0xff; ob[4] = (~clen >> 8) & 0xff;
-        memcpy(ob + 5, src, clen);
-        ob[5 + clen] = 0; ob[6 + clen] = 0; ob[7 + clen] = 0; ob[8 + clen] = 0xff; ob[9 + clen] = 0xff;
-        S.out_bytes = clen + 10;
-    }
-    memcpy(dst, S.out, S.out_bytes);
-    *adler_a = S.adler_a % 65521u;
-    *adler_b = S.adler_b % 65521u;
-    return S.out_bytes;
-}
-
+// mirrors k_deflate_hist / k_deflate_tables / k_deflate_chunks for one stream
 extern "C" long host_deflate_stream(const uint8_t *in, uint32_t n, int level, uint8_t *out, uint32_t cap)
 {
-    static DeflateShared S;
-    std::vector<uint8_t> piece(DF_SLOT_BYTES);
+    static DfBuildShared B;
+    static DfEmitShared S;
+    static uint32_t in32[DF_CHUNK / 4];
+    const uint32_t nchunks = (n + DF_CHUNK - 1) / DF_CHUNK;
+    std::vector<uint32_t> ghist(DF_NSYM, 0), ca(nchunks), cb(nchunks);
+    auto stage = [&](uint32_t *dst, uint32_t off, int clen) {
+        for (int o = 0; o < DF_CHUNK; o += 4) {
+            uint32_t w = 0;
+            for (int b = 0; b < 4; b++) if (o + b < clen) w |= (uint32_t)in[off + o + b] << (8 * b);
+            df_store_word(dst, o, w);
+        }
+    };
+    // pass 1
+    for (uint32_t c = 0; c < nchunks; c++) {
+        const int clen = (int)std::min<uint32_t>(DF_CHUNK, n - c * DF_CHUNK);
+        uint32_t hist[DF_NSYM] = {0}, adler[2] = {0, 0};
+        stage(in32, c * DF_CHUNK, clen);
+        for (int t = 0; t < DF_THREADS; t++) df_phase_hist(in32, hist, adler, t, clen, level > 0);
+        for (int i = 0; i < DF_NSYM; i++) ghist[i] += hist[i];
+        ca[c] = adler[0] % 65521u; cb[c] = adler[1] % 65521u;
+    }
+    // tables
+    if (level > 0 && nchunks) {
+        for (int i = 0; i < 512; i++) {
+            uint32_t c = i < DF_NSYM ? ghist[i] : 0;
+            if (i == 256) c = 1;
+            B.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
+        }
+        std::sort(B.keys, B.keys + 512);
+        int n_used = 0;
+        while (n_used < 512 && B.keys[n_used] != 0xffffffffu) n_used++;
+        df_phase_build(B, n_used);
+    }
+    // pass 2
     uint32_t pos = 0;
     if (cap < 8) return -1;
     out[pos++] = 0x78; out[pos++] = 0x01;
     uint32_t s1 = 1, s2 = 0;
-    for (uint32_t off = 0; off < n; off += DF_CHUNK) {
-        const int clen = (int)std::min<uint32_t>(DF_CHUNK, n - off);
-        uint32_t a, b;
-        const uint32_t nb = encode_chunk(S, in + off, clen, level, piece.data(), &a, &b);
-        if (pos + nb + 6 > cap) return -1;
-        memcpy(out + pos, piece.data(), nb);
-        pos += nb;
-        s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)clen * s1 + b) % 65521u);
-        s1 = (s1 + a) % 65521u;
+    for (uint32_t c = 0; c < nchunks; c++) {
+        const int clen = (int)std::min<uint32_t>(DF_CHUNK, n - c * DF_CHUNK);
+        stage(S.in32, c * DF_CHUNK, clen);
+        uint32_t body_bits = 0;
+        bool stored = level == 0;
+        if (!stored) {
+            const DeflateTable &T = B.tab;
+            const int hw = (int)((T.header_bits + 31) >> 5);
+            for (int i = 0; i < DF_OUT_WORDS; i++) S.out[i] = i < hw ? T.header[i] : 0;
+            for (int i = 0; i < DF_THREADS; i++) df_load_table(S, T, i, DF_THREADS);
+            S.header_bits = T.header_bits;
+            for (int t = 0; t < DF_THREADS; t++) df_phase_size(S, t, clen);
+            uint32_t run = 0;
+            for (int t = 0; t < DF_THREADS; t++) { const uint32_t v = S.tbits[t]; S.tbits[t] = run; run += v; }
+            body_bits = S.header_bits + run;
+            stored = df_dynamic_bytes(body_bits, (int)(S.cl[256] >> 16)) >= (uint32_t)clen + 10u;
+        }
+        if (!stored) {
+            for (int t = 0; t < DF_THREADS; t++) df_phase_emit(S, t, clen);
+            df_phase_finish(S, body_bits);
+        } else {
+            uint8_t *ob = reinterpret_cast<uint8_t *>(S.out);
+            ob[0] = 0; ob[1] = clen & 0xff; ob[2] = clen >> 8; ob[3] = ~clen & 0xff; ob[4] = (~clen >> 8) & 0xff;
+            memcpy(ob + 5, in + c * DF_CHUNK, clen);
+            ob[5 + clen] = 0; ob[6 + clen] = 0; ob[7 + clen] = 0; ob[8 + clen] = 0xff; ob[9 + clen] = 0xff;
+            S.out_bytes = clen + 10;
+        }
+        if (pos + S.out_bytes + 6 > cap) return -1;
+        memcpy(out + pos, S.out, S.out_bytes);
+        pos += S.out_bytes;
+        s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)clen * s1 + cb[c]) % 65521u);
+        s1 = (s1 + ca[c]) % 65521u;
     }
     out[pos++] = 0x03; out[pos++] = 0x00;
     const uint32_t ad = (s2 << 16) | s1;

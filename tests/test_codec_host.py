@@ -1,0 +1,115 @@
+"""CPU: the __host__ __device__ phases of the GPU deflate encoder / inflate decoder, simulated thread by thread
+(tests/csrc/codec_host_test.cpp), against stock zlib."""
+import ctypes
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope='module')
+def codec():
+    src = os.path.join(HERE, 'csrc', 'codec_host_test.cpp')
+    so = os.path.join(HERE, 'csrc', 'libcodec_host_test.so')
+    deps = [src] + [os.path.join(HERE, '..', 'pyrecode_b200', 'csrc', f) for f in ('deflate_chunk.cuh', 'inflate_core.cuh')]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-w', '-o', so, src], check=True)
+    L = ctypes.CDLL(so)
+    L.host_deflate_stream.restype = ctypes.c_long
+    L.host_inflate_stream.restype = ctypes.c_long
+    L.host_huffman_check.restype = ctypes.c_int
+    return L
+
+
+def deflate(L, data, level=1):
+    cap = len(data) + 10 * (len(data) // 16384 + 1) + 64
+    out = (ctypes.c_uint8 * cap)()
+    n = L.host_deflate_stream(data, ctypes.c_uint32(len(data)), level, out, ctypes.c_uint32(cap))
+    assert n > 0
+    return bytes(out[:n])
+
+
+def inflate(L, comp, cap, serial):
+    out = (ctypes.c_uint8 * max(cap, 1))()
+    n = L.host_inflate_stream(comp, ctypes.c_uint32(len(comp)), out, ctypes.c_uint32(cap), serial)
+    return n, bytes(out[:max(n, 0)])
+
+
+def cases():
+    rng = np.random.default_rng(1)
+    c = {'empty': b'', 'one': b'\x07', 'zeros': bytes(70000), 'ff': b'\xff' * 40000}
+    for occ in (0.0005, 0.02, 0.1, 0.5):
+        c['map%g' % occ] = np.packbits(rng.random(1 << 19) < occ, bitorder='little').tobytes()
+    for n in (16383, 16384, 16385, 50001):
+        c['rand%d' % n] = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    c['packed12'] = orc.bit_pack(rng.integers(1, 1000, 40000).astype(np.uint16), 12).tobytes()
+    c['marker'] = b'\x00\x00\xff\xff' * 3000 + rng.integers(0, 256, 20000, dtype=np.uint8).tobytes()
+    skew = np.concatenate([np.full(int(1.6 ** i) + 1, i, np.uint8) for i in range(24)])
+    rng.shuffle(skew)
+    c['skew'] = skew.tobytes()
+    return c
+
+
+def test_encoder_output_inflates_with_stock_zlib(codec):
+    for name, d in cases().items():
+        for level in (1, 0):
+            c = deflate(codec, d, level)
+            assert zlib.decompress(c) == d, (name, level)
+    m = cases()['map0.02']
+    assert len(deflate(codec, m, 1)) < len(zlib.compress(m, 1))          # beats zlib level 1 on a 2 % binary map
+
+
+def test_decoder_reads_stock_zlib_and_own_streams(codec):
+    for name, d in cases().items():
+        streams = [zlib.compress(d, lvl) for lvl in (0, 1, 6, 9)] + [deflate(codec, d, 1)]
+        co = zlib.compressobj(6, zlib.DEFLATED, 15, 9, zlib.Z_FIXED)
+        streams.append(co.compress(d) + co.flush())
+        for c in streams:
+            n, o = inflate(codec, c, len(d), 1)
+            assert n == len(d) and o == d, name
+            n, o = inflate(codec, c, len(d), 0)                         # chunk-parallel path or its fallback signal
+            assert (n == len(d) and o == d) or n == -100, name
+    # own streams without marker look-alikes take the parallel path
+    for name in ('map0.02', 'zeros', 'rand50001', 'skew'):
+        d = cases()[name]
+        n, o = inflate(codec, deflate(codec, d, 1), len(d), 0)
+        assert n == len(d) and o == d
+
+
+def test_decoder_rejects_bad_input(codec):
+    d = cases()['map0.02']
+    c = bytearray(zlib.compress(d, 1))
+    c[len(c) // 2] ^= 0x55
+    assert inflate(codec, bytes(c), len(d), 1)[0] < 0
+    assert inflate(codec, zlib.compress(d, 1), 100, 1)[0] == -2          # output capacity
+    assert inflate(codec, zlib.compress(d, 1)[:500], len(d), 1)[0] < 0   # truncated
+    assert inflate(codec, b'\x00' * 20, 100, 1)[0] < 0                   # not a zlib header
+
+
+def test_length_limited_huffman_is_complete(codec):
+    rng = np.random.default_rng(2)
+    for trial in range(600):
+        n = int(rng.integers(2, 287))
+        kind = trial % 4
+        if kind == 0:
+            f = rng.integers(0, 50, n)
+        elif kind == 1:
+            f = (1.7 ** rng.integers(0, 30, n)).astype(np.uint64)
+        elif kind == 2:
+            fib = [1, 1]
+            for i in range(2, n):
+                fib.append(min(fib[-1] + fib[-2], 8000000))
+            f = np.array(fib[:n])
+        else:
+            f = rng.integers(0, 2, n) * rng.integers(1, 16000, n)
+        f = np.ascontiguousarray(f, dtype=np.uint32)
+        for mb in (15, 7):
+            if mb == 7 and n > 19:
+                continue
+            assert codec.host_huffman_check(f.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), n, mb) == 0
