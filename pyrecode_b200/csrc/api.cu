@@ -34,6 +34,7 @@ static size_t packed_stride_of(const rc_config *c)
 struct ReduceWs {
     uint32_t *tilecnt, *tilepre, *rootcnt, *rootpre;
     uint16_t *wordpre;
+    uint8_t *tileovf;
     void *vals;
     uint32_t *parent, *acc, *bbox, *ord;
     uint16_t *stats16;
@@ -51,6 +52,7 @@ static ReduceWs carve_reduce(Carver &c, const rc_config *cfg, const Geom &g, int
     w.tilecnt = c.take<uint32_t>(F * g.NT);
     w.tilepre = c.take<uint32_t>(F * (g.NT + 1));
     w.wordpre = c.take<uint16_t>(F * g.MS);
+    w.tileovf = c.take<uint8_t>(F * g.NT);
     const bool ccl = what != 0 || level == 2 || level == 4;
     if (what == 0 && (level == 1 || level == 4)) w.vals = c.take<uint8_t>(F * g.slots * cfg->itemsize);
     if (what == 2) w.vals = c.take<uint8_t>(F * g.slots * cfg->itemsize);
@@ -85,12 +87,6 @@ struct CompressWs {
     size_t packed_stride;
     int spf;
 };
-
-static size_t max_stream_bytes(const rc_config *cfg, const Geom &g)
-{
-    const size_t ps = packed_stride_of(cfg);
-    return g.map_bytes > ps ? g.map_bytes : ps;
-}
 
 static CompressWs carve_compress(Carver &c, const rc_config *cfg, const Geom &g)
 {
@@ -252,36 +248,35 @@ static int run_reduce(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const Re
     const int level = cfg->reduction_level, b = cfg->bit_depth, isz = cfg->itemsize;
     int rc;
     if (level == 1) {
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 1, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, w.vals, nullptr,
-                                      nullptr, st))) return rc;
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 1, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, w.tileovf, w.vals,
+                                      nullptr, nullptr, 0, st))) return rc;
         rc_mark(ctx, 1, st);
         if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, packed_bytes, b, st))) return rc;
         return launch_bitpack(ctx, g, isz, w.vals, w.tilepre, F, b, packed, packed_stride, st);
     }
     if (level == 3) {
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 0, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, nullptr, nullptr,
-                                      nullptr, st))) return rc;
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 0, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, w.tileovf, nullptr,
+                                      nullptr, nullptr, 0, st))) return rc;
         rc_mark(ctx, 1, st);
         return launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, nullptr, 0, st);
     }
     if (level == 2) {
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 1, frames, thr, F, maps, w.tilecnt, w.wordpre, w.vals, w.parent,
-                                      w.acc, st))) return rc;
+        const int sum = cfg->l2_statistics == 2;
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 1, frames, thr, F, maps, w.tilecnt, w.wordpre, w.tileovf, w.vals,
+                                      w.parent, w.acc, sum, st))) return rc;
         rc_mark(ctx, 1, st);
-        if ((rc = launch_ccl_union(ctx, g, maps, w.wordpre, w.parent, F, st))) return rc;
-        if ((rc = launch_ccl_flatten(ctx, g, cfg->l2_statistics == 2 ? 2 : 1, maps, w.wordpre, w.parent, w.acc, nullptr,
-                                     F, st))) return rc;
+        if ((rc = launch_ccl_border(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tileovf, w.parent, w.acc, F, st))) return rc;
         if ((rc = launch_ccl_roots(ctx, g, 1, w.tilecnt, w.parent, w.acc, nullptr, w.rootcnt, nullptr, w.stats16,
                                    nullptr, F, st))) return rc;
         if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, packed_bytes, b, st))) return rc;
         return launch_bitpack(ctx, g, 2, w.stats16, w.rootpre, F, b, packed, packed_stride, st);
     }
     // level 4: threshold map -> map1, centroid map -> maps
-    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, frames, thr, F, w.map1, w.tilecnt, w.wordpre, w.vals, w.parent,
-                                  nullptr, st))) return rc;
+    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, frames, thr, F, w.map1, w.tilecnt, w.wordpre, w.tileovf, w.vals,
+                                  w.parent, nullptr, 0, st))) return rc;
     rc_mark(ctx, 1, st);
-    if ((rc = launch_ccl_union(ctx, g, w.map1, w.wordpre, w.parent, F, st))) return rc;
-    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, nullptr, w.bbox, F, st))) return rc;
+    if ((rc = launch_ccl_border(ctx, g, 0, w.map1, w.wordpre, w.tileovf, w.parent, nullptr, F, st))) return rc;
+    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, w.bbox, F, st))) return rc;
     RC_CUDA(ctx, cudaMemsetAsync(maps, 0, (size_t)F * g.MS * sizeof(uint32_t), st));
     if ((rc = launch_l4_centroids(ctx, g, isz, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox, w.vals, maps,
                                   nullptr, F, st))) return rc;
@@ -359,10 +354,11 @@ extern "C" int rc_ccl_label(rc_ctx *ctx, const rc_config *cfg, const uint32_t *d
     const ReduceWs w = carve_reduce(c, cfg, g, 1);
     const int F = n_frames;
     int rc;
+    if ((uintptr_t)d_maps % 16) RC_FAIL(ctx, -1, "d_maps must be 16-byte aligned");
     if ((rc = launch_map_counts(ctx, g, d_maps, F, w.tilecnt, w.wordpre, st))) return rc;
     if ((rc = launch_ccl_init(ctx, g, w.tilecnt, w.parent, F, st))) return rc;
     if ((rc = launch_ccl_union(ctx, g, d_maps, w.wordpre, w.parent, F, st))) return rc;
-    if ((rc = launch_ccl_flatten(ctx, g, 0, d_maps, w.wordpre, w.parent, nullptr, nullptr, F, st))) return rc;
+    if ((rc = launch_ccl_flatten(ctx, g, 0, d_maps, w.wordpre, w.parent, nullptr, F, st))) return rc;
     if ((rc = launch_ccl_roots(ctx, g, 0, w.tilecnt, w.parent, nullptr, nullptr, w.rootcnt, w.ord, nullptr, nullptr, F, st))) return rc;
     if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, d_counts, nullptr, 0, st))) return rc;
     return launch_ccl_label_image(ctx, g, d_maps, w.wordpre, w.parent, w.ord, w.rootpre, d_labels, F, st);
@@ -382,10 +378,10 @@ extern "C" int rc_l4_centroids(rc_ctx *ctx, const rc_config *cfg, const void *d_
     const ReduceWs w = carve_reduce(c, cfg, g, 2);
     const int F = n_frames, isz = cfg->itemsize;
     int rc;
-    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, d_frames, d_thr, F, w.map1, w.tilecnt, w.wordpre, w.vals, w.parent,
-                                  nullptr, st))) return rc;
-    if ((rc = launch_ccl_union(ctx, g, w.map1, w.wordpre, w.parent, F, st))) return rc;
-    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, nullptr, w.bbox, F, st))) return rc;
+    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, d_frames, d_thr, F, w.map1, w.tilecnt, w.wordpre, w.tileovf, w.vals,
+                                  w.parent, nullptr, 0, st))) return rc;
+    if ((rc = launch_ccl_border(ctx, g, 0, w.map1, w.wordpre, w.tileovf, w.parent, nullptr, F, st))) return rc;
+    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, w.bbox, F, st))) return rc;
     if ((rc = launch_l4_centroids(ctx, g, isz, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox, w.vals, nullptr,
                                   w.cent, F, st))) return rc;
     if ((rc = launch_ccl_roots(ctx, g, 2, w.tilecnt, w.parent, nullptr, w.cent, w.rootcnt, nullptr, nullptr, w.cent_tiles,
@@ -457,6 +453,7 @@ extern "C" int rc_unpack_sparse(rc_ctx *ctx, const rc_config *cfg, const uint32_
     if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames exceeds max_frames");
     if (workspace_bytes < rc_read_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
     if (packed_stride % 4) RC_FAIL(ctx, -1, "packed_stride must be a multiple of 4");
+    if ((uintptr_t)d_maps % 16) RC_FAIL(ctx, -1, "d_maps must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const Geom g = make_geom(cfg->ny, cfg->nx);
     Carver c(d_workspace);
@@ -477,6 +474,7 @@ extern "C" int rc_unpack_dense(rc_ctx *ctx, const rc_config *cfg, const uint32_t
     if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames exceeds max_frames");
     if (workspace_bytes < rc_read_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
     if (packed_stride % 4) RC_FAIL(ctx, -1, "packed_stride must be a multiple of 4");
+    if ((uintptr_t)d_maps % 16) RC_FAIL(ctx, -1, "d_maps must be 16-byte aligned");
     if (!d_dense && !d_sum) RC_FAIL(ctx, -1, "need d_dense and/or d_sum");
     cudaStream_t st = (cudaStream_t)stream;
     const Geom g = make_geom(cfg->ny, cfg->nx);

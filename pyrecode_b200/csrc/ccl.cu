@@ -13,9 +13,11 @@
 // whose pixels have no neighbour at all (the common case in electron-counting frames) costs a handful of
 // coalesced loads and logic ops and exits; other geometries take a per-pixel path with the same results.
 //
-//   k_ccl_union     links each foreground pixel to its W / NW / N / NE neighbours with atomicMin unions.
-//   k_ccl_flatten   parent[slot] = root; L2: folds each member's value into acc[root] (max or sum);
-//                   L4: grows the root's bounding box (row extent, left / right column extents).
+//   (k_reduce_tiles labels every 32768-pixel tile in shared memory and folds the L2 statistic there.)
+//   k_ccl_border    PASS 0 links pixels across tile boundaries with atomicMin unions; PASS 1 folds the L2
+//                   statistic of every tile-local root that was merged into an earlier tile's puddle.
+//   k_ccl_union     full-frame linking for maps that did not come from k_reduce_tiles (rc_ccl_label).
+//   k_ccl_flatten   parent[slot] = root; L4: grows the root's bounding box (row extent, left / right columns).
 //   k_ccl_roots     one warp per tile: compacts per-root payloads (L2 statistics, centroids, ordinals) in
 //                   slot order == label order.
 //   k_l4_centroids  one thread per root: replays the puddle's pixels in raster order inside its bounding
@@ -23,73 +25,9 @@
 //                   even and sets the centroid bit.  Single-pixel puddles are their own centroid.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "ccl_core.cuh"
 
-__device__ __forceinline__ uint32_t uf_find_ro(const uint32_t *parent, uint32_t x)
-{
-    // volatile: other threads lower parents concurrently; any value read is a valid ancestor
-    uint32_t p = ((const volatile uint32_t *)parent)[x];
-    while (p != x) {
-        x = p;
-        p = ((const volatile uint32_t *)parent)[x];
-    }
-    return x;
-}
-
-__device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b)
-{
-    while (true) {
-        a = uf_find_ro(parent, a);
-        b = uf_find_ro(parent, b);
-        if (a == b) return;
-        if (a > b) { uint32_t t = a; a = b; b = t; }
-        const uint32_t old = atomicMin(&parent[b], a);   // link the larger root under the smaller
-        if (old == b) return;
-        b = old;                                         // b was linked elsewhere meanwhile: merge with that
-    }
-}
-
-__device__ __forceinline__ uint32_t get_bit(const uint32_t *__restrict__ map, uint32_t q)
-{
-    return (map[q >> 5] >> (q & 31)) & 1u;
-}
-
-// Neighbour masks of the 32 pixels of word w for nx % 32 == 0.  Bit k of `west` is set when pixel k's west
-// neighbour is foreground, etc.  Rows above / below the frame and columns outside it contribute zeros.
-struct Nbr {
-    uint32_t west, east, n, nw, ne, s, sw, se;
-};
-
-template <bool WITH_SOUTH>
-__device__ __forceinline__ Nbr neighbour_masks(const uint32_t *__restrict__ map, uint32_t w, uint32_t bits,
-                                               uint32_t wpr, uint32_t ny)
-{
-    Nbr m;
-    const uint32_t row = w / wpr, wc = w - row * wpr;
-    const bool has_l = wc > 0, has_r = wc + 1 < wpr;
-    const uint32_t cl = has_l ? map[w - 1] : 0, cr = has_r ? map[w + 1] : 0;
-    m.west = (bits << 1) | (cl >> 31);
-    m.east = (bits >> 1) | (cr << 31);
-    if (row > 0) {
-        const uint32_t u = map[w - wpr];
-        const uint32_t ul = has_l ? map[w - wpr - 1] : 0, ur = has_r ? map[w - wpr + 1] : 0;
-        m.n = u;
-        m.nw = (u << 1) | (ul >> 31);
-        m.ne = (u >> 1) | (ur << 31);
-    } else {
-        m.n = m.nw = m.ne = 0;
-    }
-    if (WITH_SOUTH && row + 1 < ny) {
-        const uint32_t d = map[w + wpr];
-        const uint32_t dl = has_l ? map[w + wpr - 1] : 0, dr = has_r ? map[w + wpr + 1] : 0;
-        m.s = d;
-        m.sw = (d << 1) | (dl >> 31);
-        m.se = (d >> 1) | (dr << 31);
-    } else {
-        m.s = m.sw = m.se = 0;
-    }
-    return m;
-}
-
+// full-frame union (maps that did not come from k_reduce_tiles: rc_ccl_label)
 __global__ void __launch_bounds__(256)
 k_ccl_union(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
             uint32_t *__restrict__ parent_all, int ny, int nx, uint32_t MW)
@@ -100,63 +38,66 @@ k_ccl_union(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     const uint32_t *map = maps + (size_t)f * MS;
     const uint32_t bits = map[w];
     if (!bits) return;
-    const uint16_t *wordpre = wordpre_all + (size_t)f * MS;
-    uint32_t *parent = parent_all + (size_t)f * ((size_t)NT * TILE_PX);
-    const uint32_t p0 = w << 5;
-    if ((nx & 31) == 0) {
-        const uint32_t wpr = (uint32_t)nx >> 5;
-        const Nbr m = neighbour_masks<false>(map, w, bits, wpr, (uint32_t)ny);
-        uint32_t need = bits & (m.west | m.n | m.nw | m.ne);
-        if (!need) return;
-        const uint32_t sb = word_slot_base(wordpre, w);
-        while (need) {
-            const uint32_t k = __ffs(need) - 1;
-            need &= need - 1;
-            const uint32_t bk = 1u << k;
-            const uint32_t s = sb + __popc(bits & (bk - 1u));
-            const uint32_t p = p0 + k;
-            if (m.west & bk) uf_union(parent, s, k ? s - 1 : slot_of(map, wordpre, p - 1));
-            if (m.n & bk) {
-                // N is set: NW and NE are horizontally adjacent to N, their own W-links connect them
-                uf_union(parent, s, slot_of(map, wordpre, p - nx));
-            } else {
-                if (m.nw & bk) uf_union(parent, s, slot_of(map, wordpre, p - nx - 1));
-                if (m.ne & bk) uf_union(parent, s, slot_of(map, wordpre, p - nx + 1));
-            }
-        }
-        return;
+    GlobalSpace sp{map, wordpre_all + (size_t)f * MS, parent_all + (size_t)f * ((size_t)NT * TILE_PX)};
+    link_word(sp, UnionAct{sp.parent}, w, bits, ny, nx, 0xffffffffu);
+}
+
+// L2 fold of a tile-local root that lost its root status in k_ccl_border<0>: exactly once (claimed by setting
+// UF_FLAG on its parent entry), its accumulated statistic goes to the final root of its puddle.
+struct FoldAct {
+    uint32_t *parent, *acc;
+    int sum;
+    __device__ __forceinline__ void one(uint32_t x) const
+    {
+        const uint32_t px = parent[x];
+        const uint32_t r = (px & UF_FLAG) ? (px & ~UF_FLAG) : x;     // tile-local root of x
+        const uint32_t pr = parent[r];
+        if (pr == r || (pr & UF_FLAG)) return;                       // still a root, or already folded
+        if (atomicOr(&parent[r], UF_FLAG) & UF_FLAG) return;
+        const uint32_t g = uf_find_ro(parent, r);
+        if (sum) atomicAdd(&acc[g], acc[r]);
+        else atomicMax(&acc[g], acc[r]);
     }
-    // generic geometry: per-pixel neighbour tests
-    uint32_t s = word_slot_base(wordpre, w);
-    uint32_t r = p0 / (uint32_t)nx, c = p0 - r * (uint32_t)nx;   // of bit 0; advanced incrementally
-    uint32_t prev_k = 0, rest = bits;
-    while (rest) {
-        const uint32_t k = __ffs(rest) - 1;
-        rest &= rest - 1;
-        c += k - prev_k;
-        prev_k = k;
-        while (c >= (uint32_t)nx) { c -= nx; r++; }
-        const uint32_t p = p0 + k;
-        if (c > 0 && get_bit(map, p - 1)) uf_union(parent, s, slot_of(map, wordpre, p - 1));
-        if (r > 0) {
-            const uint32_t up = p - nx;
-            if (get_bit(map, up)) {
-                uf_union(parent, s, slot_of(map, wordpre, up));
-            } else {
-                if (c > 0 && get_bit(map, up - 1)) uf_union(parent, s, slot_of(map, wordpre, up - 1));
-                if (c + 1 < (uint32_t)nx && get_bit(map, up + 1)) uf_union(parent, s, slot_of(map, wordpre, up + 1));
-            }
-        }
-        s++;
+    __device__ __forceinline__ void operator()(uint32_t a, uint32_t b) const { one(a); one(b); }
+};
+
+// Links across tile boundaries.  k_reduce_tiles labelled every tile on its own; what is left are the links
+// from the first nx + 1 pixels of a tile to pixels of earlier tiles (q < tile base).  A tile that overflowed
+// the shared-memory labelling (tileovf) has all of its links made here instead.
+// PASS 0: union.  PASS 1: L2 fold of the re-parented tile-local roots (separate launch: needs final roots).
+template <int PASS>
+__global__ void __launch_bounds__(128)
+k_ccl_border(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
+             const uint8_t *__restrict__ tileovf, uint32_t *__restrict__ parent_all, uint32_t *__restrict__ acc_all,
+             int ny, int nx, uint32_t MW, int sum)
+{
+    const int tile = blockIdx.x, f = blockIdx.y;
+    const bool ovf = tileovf[(size_t)f * NT + tile] != 0;
+    if (tile == 0 && !ovf) return;
+    const uint32_t w0 = (uint32_t)tile * TILE_WORDS;
+    uint32_t w1 = w0 + TILE_WORDS;                                   // exclusive
+    if (!ovf) {
+        const uint32_t wl = (((uint32_t)tile << TILE_LOG2) + (uint32_t)nx) >> 5;   // word of pixel base + nx
+        if (wl + 1 < w1) w1 = wl + 1;
+    }
+    if (w1 > MW) w1 = MW;
+    const uint32_t q_hi = ovf ? 0xffffffffu : ((uint32_t)tile << TILE_LOG2);
+    const size_t slots = (size_t)NT * TILE_PX;
+    const uint32_t *map = maps + (size_t)f * MS;
+    GlobalSpace sp{map, wordpre_all + (size_t)f * MS, parent_all + (size_t)f * slots};
+    for (uint32_t w = w0 + threadIdx.x; w < w1; w += 128) {
+        const uint32_t bits = map[w];
+        if (!bits) continue;
+        if (PASS == 0) link_word(sp, UnionAct{sp.parent}, w, bits, ny, nx, q_hi);
+        else link_word(sp, FoldAct{sp.parent, acc_all + (size_t)f * slots, sum}, w, bits, ny, nx, q_hi);
     }
 }
 
-// MODE 0: labels only.  MODE 1: L2 max.  MODE 2: L2 sum.  MODE 3: L4 bounding boxes.
+// MODE 0: labels only.  MODE 3: L4 bounding boxes.  Afterwards every parent entry is the plain root slot.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_ccl_flatten(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
-              uint32_t *__restrict__ parent_all, uint32_t *__restrict__ acc_all, uint32_t *__restrict__ bbox_all,
-              int ny, int nx, uint32_t MW)
+              uint32_t *__restrict__ parent_all, uint32_t *__restrict__ bbox_all, int ny, int nx, uint32_t MW)
 {
     const int f = blockIdx.y;
     const uint32_t w = blockIdx.x * 256 + threadIdx.x;
@@ -164,15 +105,16 @@ k_ccl_flatten(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__re
     const uint32_t *map = maps + (size_t)f * MS;
     const uint32_t bits = map[w];
     if (!bits) return;
+    const size_t slots = (size_t)NT * TILE_PX;
+    uint32_t *parent = parent_all + (size_t)f * slots;
     uint32_t todo = bits;
     if ((nx & 31) == 0) {
-        // a pixel without any of its 8 neighbours set is a single-pixel puddle: already its own root
-        const Nbr m = neighbour_masks<true>(map, w, bits, (uint32_t)nx >> 5, (uint32_t)ny);
+        // a pixel without any of its 8 neighbours set is a single-pixel puddle: already its own (plain) root
+        GlobalSpace sp{map, wordpre_all + (size_t)f * MS, parent};
+        const Nbr m = neighbour_masks<true>(sp, w, bits, (uint32_t)nx >> 5, (uint32_t)ny);
         todo = bits & (m.west | m.east | m.n | m.nw | m.ne | m.s | m.sw | m.se);
         if (!todo) return;
     }
-    const size_t slots = (size_t)NT * TILE_PX;
-    uint32_t *parent = parent_all + (size_t)f * slots;
     const uint32_t sb = word_slot_base(wordpre_all + (size_t)f * MS, w);
     const uint32_t p0 = w << 5;
     while (todo) {
@@ -182,8 +124,6 @@ k_ccl_flatten(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__re
         const uint32_t root = uf_find_ro(parent, s);
         if (root != s) {
             parent[s] = root;
-            if (MODE == 1) atomicMax(&acc_all[(size_t)f * slots + root], acc_all[(size_t)f * slots + s]);
-            if (MODE == 2) atomicAdd(&acc_all[(size_t)f * slots + root], acc_all[(size_t)f * slots + s]);
             if (MODE == 3) {
                 // the root's pixel index was stored in bbox[3] by k_l4_init_bbox
                 const uint32_t p = p0 + k;
@@ -289,7 +229,7 @@ k_ccl_label_image(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *
         int32_t L = 0;
         if (bits & (1u << k)) {
             const uint32_t root = parent[s];
-            L = (int32_t)(rootpre[root >> 13] + ord[root]) + 1;
+            L = (int32_t)(rootpre[root >> TILE_LOG2] + ord[root]) + 1;
             s++;
         }
         out[p0 + k] = L;
@@ -431,8 +371,24 @@ int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uin
     return 0;
 }
 
+// fold: 0 = links only (L4), 1 = + L2 max fold, 2 = + L2 sum fold
+int launch_ccl_border(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps, const uint16_t *wordpre,
+                      const uint8_t *tileovf, uint32_t *parent, uint32_t *acc, int F, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    dim3 grid((unsigned)g.NT, F);
+    k_ccl_border<0><<<grid, 128, 0, st>>>(maps, g.MS, wordpre, g.NT, tileovf, parent, acc, g.ny, g.nx, (uint32_t)g.MW, 0);
+    RC_LAUNCH_CHECK(ctx, "k_ccl_border<0>");
+    if (fold) {
+        k_ccl_border<1><<<grid, 128, 0, st>>>(maps, g.MS, wordpre, g.NT, tileovf, parent, acc, g.ny, g.nx,
+                                              (uint32_t)g.MW, fold == 2);
+        RC_LAUNCH_CHECK(ctx, "k_ccl_border<1>");
+    }
+    return 0;
+}
+
 int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
-                       uint32_t *parent, uint32_t *acc, uint32_t *bbox, int F, cudaStream_t st)
+                       uint32_t *parent, uint32_t *bbox, int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
     dim3 grid((unsigned)((g.MW + 255) / 256), F);
@@ -440,12 +396,9 @@ int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *map
     if (mode == 3) {
         k_l4_init_bbox<<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, bbox, MW);
         RC_LAUNCH_CHECK(ctx, "k_l4_init_bbox");
-    }
-    switch (mode) {
-    case 0: k_ccl_flatten<0><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, acc, bbox, g.ny, g.nx, MW); break;
-    case 1: k_ccl_flatten<1><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, acc, bbox, g.ny, g.nx, MW); break;
-    case 2: k_ccl_flatten<2><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, acc, bbox, g.ny, g.nx, MW); break;
-    default: k_ccl_flatten<3><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, acc, bbox, g.ny, g.nx, MW); break;
+        k_ccl_flatten<3><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, bbox, g.ny, g.nx, MW);
+    } else {
+        k_ccl_flatten<0><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, bbox, g.ny, g.nx, MW);
     }
     RC_LAUNCH_CHECK(ctx, "k_ccl_flatten");
     return 0;

@@ -3,15 +3,18 @@
 // Device data layout (all per batch of F frames; P = ny*nx pixels per frame):
 //   map      uint32 [F][MS]        binary map words, pixel i -> word i>>5, bit i&31 (== byte i>>3, bit i&7
 //                                  on a little-endian host: recode_writer.py:622-634).  MS = MW rounded up to 8.
-//   tile     8192 consecutive pixels (256 map words) in linear (raster) order; NT tiles per frame.
-//   segment  256 consecutive pixels (8 map words = one 32-byte sector); 32 segments per tile.
-//   slot     index of a foreground pixel in the "tile-compacted" space: tile*8192 + rank of the pixel
+//   tile     32768 consecutive pixels (1024 map words) in linear (raster) order; NT tiles per frame.  For
+//            nx = 4096 a tile is a strip of 8 whole rows: most puddles are labelled entirely inside one tile.
+//   segment  256 consecutive pixels (8 map words = one 32-byte sector); 128 segments per tile.
+//   slot     index of a foreground pixel in the "tile-compacted" space: tile*32768 + rank of the pixel
 //            among the foreground pixels of its tile.  Monotone in raster order.  All per-foreground
 //            arrays (vals, parent, acc ...) are indexed by slot, so a tile never needs another tile's
 //            prefix to place its data, and only tilecnt[tile] entries per tile are ever touched.
 //   tilecnt  uint32 [F][NT]        foreground pixels per tile
 //   tilepre  uint32 [F][NT+1]      exclusive scan of tilecnt (tilepre[NT] = n foreground pixels of the frame)
 //   wordpre  uint16 [F][MS]        foreground pixels of the tile before each map word (exclusive, per tile)
+//   tileovf  uint8  [F][NT]        1 when a tile had more foreground pixels than the shared-memory labelling
+//                                  handles (CCL_CAP): its pixels are then linked by the global kernels instead
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,11 +24,18 @@
 
 #define RC_VERSION 100
 
-constexpr int TILE_PX = 8192;
-constexpr int TILE_WORDS = TILE_PX / 32;     // 256
+constexpr int TILE_LOG2 = 15;
+constexpr int TILE_PX = 1 << TILE_LOG2;      // 32768
+constexpr int TILE_WORDS = TILE_PX / 32;     // 1024
+constexpr int TILE_WORDS_LOG2 = TILE_LOG2 - 5;
 constexpr int SEG_PX = 256;
 constexpr int SEG_WORDS = SEG_PX / 32;       // 8
-constexpr int SEGS_PER_TILE = TILE_PX / SEG_PX;  // 32
+constexpr int SEGS_PER_TILE = TILE_PX / SEG_PX;  // 128
+constexpr int SEGS_PER_TILE_LOG2 = TILE_LOG2 - 8;
+
+// union-find parent encoding: bit 31 set = "not a tile-local root; low bits = slot of my tile-local root"
+// (written by k_reduce_tiles after the tile-local labelling).  Roots and re-parented tile-local roots are plain.
+constexpr uint32_t UF_FLAG = 0x80000000u;
 
 constexpr int RC_MAX_MARKS = 8;
 
@@ -176,5 +186,5 @@ __device__ __forceinline__ uint32_t slot_of(const uint32_t *__restrict__ map, co
 // slot of the first pixel of word w (whether or not it is set)
 __device__ __forceinline__ uint32_t word_slot_base(const uint16_t *__restrict__ wordpre, uint32_t w)
 {
-    return ((w >> 8) << 13) + wordpre[w];
+    return ((w >> TILE_WORDS_LOG2) << TILE_LOG2) + wordpre[w];
 }

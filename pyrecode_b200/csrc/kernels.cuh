@@ -4,8 +4,8 @@
 
 // reduce.cu
 int launch_reduce_tiles(rc_ctx *ctx, const Geom &g, int itemsize, int valmode, int ccl, const void *frames,
-                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre, void *vals,
-                        uint32_t *parent, uint32_t *acc, cudaStream_t st);
+                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre,
+                        uint8_t *tileovf, void *vals, uint32_t *parent, uint32_t *acc, int stat_sum, cudaStream_t st);
 int launch_map_counts(rc_ctx *ctx, const Geom &g, const uint32_t *maps, int F, uint32_t *tilecnt, uint16_t *wordpre,
                       cudaStream_t st);
 int launch_scan_tiles(rc_ctx *ctx, const Geom &g, const uint32_t *tilecnt, int F, uint32_t *tilepre,
@@ -21,8 +21,10 @@ int launch_make_threshold(rc_ctx *ctx, int itemsize, const void *dark, uint64_t 
 int launch_ccl_init(rc_ctx *ctx, const Geom &g, const uint32_t *tilecnt, uint32_t *parent, int F, cudaStream_t st);
 int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre, uint32_t *parent,
                      int F, cudaStream_t st);
+int launch_ccl_border(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps, const uint16_t *wordpre,
+                      const uint8_t *tileovf, uint32_t *parent, uint32_t *acc, int F, cudaStream_t st);
 int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
-                       uint32_t *parent, uint32_t *acc, uint32_t *bbox, int F, cudaStream_t st);
+                       uint32_t *parent, uint32_t *bbox, int F, cudaStream_t st);
 int launch_ccl_roots(rc_ctx *ctx, const Geom &g, int payload, const uint32_t *tilecnt, const uint32_t *parent,
                      const uint32_t *acc, const uint64_t *cent, uint32_t *rootcnt, uint32_t *ord, uint16_t *out16,
                      uint64_t *out64, int F, cudaStream_t st);

@@ -12,8 +12,12 @@
 //                    per 32-bit output word, no atomics.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "ccl_core.cuh"
 
 // ---- pixel-type helpers --------------------------------------------------------------------
+// 8 pixels = W 32-bit words.  fg_words: d = max(f, t) - t per lane (= f - t where f > t, else 0; no borrow
+// crosses a lane because max >= t), so the L1 value and the foreground test come out of the same two
+// instructions; the mask bit of a lane is min(d, 1).
 template <typename T> struct Px;
 
 template <> struct Px<uint16_t> {
@@ -28,27 +32,25 @@ template <> struct Px<uint16_t> {
         uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     }
-    static __device__ __forceinline__ uint32_t get(const uint32_t (&w)[4], int k)
-    {
-        return (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-    }
     static __device__ __forceinline__ void set(uint32_t (&w)[4], int k, uint32_t v)
     {
         w[k >> 1] |= v << ((k & 1) * 16);
     }
-    // bit k = frame pixel k > threshold pixel k.  VIMNMX.U16x2 gives both halfword predicates of
-    // (t >= f) in one instruction; foreground is its complement.
-    static __device__ __forceinline__ uint32_t gt_mask(const uint32_t (&f)[4], const uint32_t (&t)[4])
+    // d = frame - threshold where frame > threshold else 0; returns the 8-bit foreground mask
+    static __device__ __forceinline__ uint32_t fg_words(const uint32_t (&f)[4], const uint32_t (&t)[4], uint32_t (&d)[4])
     {
-        uint32_t m = 0;
+        uint32_t e[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            bool ge_hi, ge_lo;
-            (void)__vibmax_u16x2(t[i], f[i], &ge_hi, &ge_lo);
-            m |= (ge_lo ? 0u : 1u) << (2 * i);
-            m |= (ge_hi ? 0u : 2u) << (2 * i);
+            d[i] = __vmaxu2(f[i], t[i]) - t[i];
+            e[i] = __vminu2(d[i], 0x00010001u);          // bit 0 / bit 16 = lane is foreground
         }
-        return m;
+        const uint32_t c = e[0] | (e[1] << 2) | (e[2] << 4) | (e[3] << 6);   // even pixels at bits 0..6, odd at 16..22
+        return (c | (c >> 15)) & 0xffu;
+    }
+    static __device__ __forceinline__ void store_raw(uint16_t *dst, const uint32_t (&w)[4])
+    {
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 };
 
@@ -64,38 +66,60 @@ template <> struct Px<uint8_t> {
         uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
         w[0] = v.x; w[1] = v.y;
     }
-    static __device__ __forceinline__ uint32_t get(const uint32_t (&w)[2], int k)
-    {
-        return (w[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-    }
     static __device__ __forceinline__ void set(uint32_t (&w)[2], int k, uint32_t v)
     {
         w[k >> 2] |= v << ((k & 3) * 8);
     }
-    static __device__ __forceinline__ uint32_t gt_mask(const uint32_t (&f)[2], const uint32_t (&t)[2])
+    static __device__ __forceinline__ uint32_t fg_words(const uint32_t (&f)[2], const uint32_t (&t)[2], uint32_t (&d)[2])
     {
         uint32_t m = 0;
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-            uint32_t r = __vcmpgtu4(f[i], t[i]) & 0x01010101u;    // bit 0 of each byte
+            d[i] = __vmaxu4(f[i], t[i]) - t[i];
+            uint32_t r = __vminu4(d[i], 0x01010101u);    // bit 0 of each byte
             r = (r | (r >> 7) | (r >> 14) | (r >> 21)) & 0xfu;
             m |= r << (4 * i);
         }
         return m;
     }
+    static __device__ __forceinline__ void store_raw(uint8_t *dst, const uint32_t (&w)[2])
+    {
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+    }
 };
 
 // ---- K1 ------------------------------------------------------------------------------------
+// One CTA (256 threads = 8 warps) per (frame, tile of 32768 pixels), processed as 4 sub-tiles of 8192
+// pixels.  Within a sub-tile warp w owns the 1024 consecutive pixels [1024 w, 1024 w + 1024): four
+// 128-bit loads per lane (512 contiguous bytes per warp-level load), and lane l then owns map word l of
+// those 32 words.  Mask bytes and raw values are staged in warp-private shared memory, so the only
+// block-level barrier per sub-tile is the one for the cross-warp prefix of the foreground counts.
+//
 // VALMODE: 0 = no value stream (L3), 1 = frame - thr (L1), 2 = raw frame value (L2 / L4)
-// CCL:     0 = vals only, 1 = parent[slot] = slot and acc[slot] = value, no vals (L2), 2 = vals + parent (L4)
+// CCL:     0 = vals only
+//          1 = L2: 8-connected labelling of the tile in shared memory + per-puddle max / sum folded into
+//              acc[tile-local root]; parent[slot] = root slot (| UF_FLAG for non-roots); no vals
+//          2 = L4: vals + the same parent array
+// A tile with more than CCL_CAP foreground pixels (> 6 % occupancy) is not labelled here: it gets
+// parent[slot] = slot, acc[slot] = value, tileovf = 1 and the global kernels of ccl.cu link all its pixels.
+constexpr int SUB_PX = 8192;
+constexpr int SUB_WORDS = SUB_PX / 32;            // 256 = threads per CTA
+constexpr int NSUB = TILE_PX / SUB_PX;            // 4
+constexpr int CCL_CAP = 2048;
+
+// position (in 8-pixel granules) of granule g inside the sub-tile's raw staging: the XOR spreads the word
+// owners' 16-bit reads (stride 64 bytes) over the banks; 128-bit writes stay conflict-free
+__device__ __forceinline__ uint32_t raw_pos(uint32_t g) { return g ^ ((g >> 3) & 7u); }
+
 template <typename T, int VALMODE, int CCL>
 __global__ void __launch_bounds__(256)
-k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P, int NT, size_t MS,
+k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P, int NT, size_t MS, int ny, int nx,
                uint32_t *__restrict__ maps, uint32_t *__restrict__ tilecnt, uint16_t *__restrict__ wordpre,
-               T *__restrict__ vals, uint32_t *__restrict__ parent, uint32_t *__restrict__ acc, int vec_ok)
+               uint8_t *__restrict__ tileovf, T *__restrict__ vals, uint32_t *__restrict__ parent,
+               uint32_t *__restrict__ acc, int stat_sum, int vec_ok)
 {
     constexpr int W = Px<T>::W;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int f = blockIdx.x;                 // frame fastest: CTAs running together share the threshold tile
     const int tile = blockIdx.y;
     const size_t base = (size_t)tile * TILE_PX;
@@ -103,91 +127,193 @@ k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P
     const int npx = left < (size_t)TILE_PX ? (int)left : TILE_PX;
     const T *fr = frames + (size_t)f * P + base;
     const T *th = thr + base;
+    const size_t sbase = (size_t)f * ((size_t)NT * TILE_PX) + base;      // first slot of this tile
 
-    __shared__ uint32_t s_mask[TILE_WORDS];
-    __shared__ uint16_t s_wpre[TILE_WORDS];
-    __shared__ uint32_t s_warp[9];
-    __shared__ T s_vals[VALMODE ? TILE_PX : 1];
+    __shared__ __align__(16) uint32_t s_mask[TILE_WORDS];
+    __shared__ __align__(16) uint16_t s_wpre[TILE_WORDS];
+    __shared__ __align__(16) T s_raw[VALMODE ? SUB_PX : 8];
+    __shared__ __align__(16) uint32_t s_wsum[2][8];
+    __shared__ uint32_t s_parent[CCL ? CCL_CAP : 1];
+    __shared__ uint16_t s_pos[CCL ? CCL_CAP : 1];              // pixel (within the tile) of each foreground slot
+    __shared__ uint32_t s_acc[CCL == 1 ? CCL_CAP : 1];
 
-    uint32_t fw[4][W], tw[4][W];
-    uint32_t m = 0;
-    const bool fast = vec_ok && npx == TILE_PX;
-    if (fast) {
+    uint32_t run = 0;                         // foreground pixels of the tile before the current sub-tile
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; sub++) {
+        const int sub_px0 = sub * SUB_PX;
+        const int wpx0 = sub_px0 + warp * 1024;                 // first pixel of this warp's region
+        uint32_t fw[4][W], tw[4][W];
+        const bool fast = vec_ok && sub_px0 + SUB_PX <= npx;
+        if (fast) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) Px<T>::load_stream(fr + j * 2048 + t * 8, fw[j]);
+            for (int j = 0; j < 4; j++) Px<T>::load_stream(fr + wpx0 + j * 256 + lane * 8, fw[j]);
 #pragma unroll
-        for (int j = 0; j < 4; j++) Px<T>::load_cached(th + j * 2048 + t * 8, tw[j]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-#pragma unroll
-            for (int i = 0; i < W; i++) { fw[j][i] = 0; tw[j][i] = 0; }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int q = j * 2048 + t * 8 + k;
-                if (q < npx) {
-                    Px<T>::set(fw[j], k, fr[q]);
-                    Px<T>::set(tw[j], k, th[q]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t mj = Px<T>::gt_mask(fw[j], tw[j]);
-        m |= mj << (8 * j);
-        reinterpret_cast<uint8_t *>(s_mask)[j * 256 + t] = (uint8_t)mj;
-    }
-    __syncthreads();
-
-    const uint32_t word = s_mask[t];          // pixels [32t, 32t+32) of the tile
-    maps[(size_t)f * MS + (size_t)tile * TILE_WORDS + t] = word;
-    const uint32_t pc = __popc(word);
-    uint32_t total;
-    const uint32_t excl = block_excl_scan<8>(pc, s_warp, &total);
-    s_wpre[t] = (uint16_t)excl;
-    wordpre[(size_t)f * MS + (size_t)tile * TILE_WORDS + t] = (uint16_t)excl;
-    if (t == 0) tilecnt[(size_t)f * NT + tile] = total;
-
-    if (VALMODE) {
-        __syncthreads();
-        if (m) {
+            for (int j = 0; j < 4; j++) Px<T>::load_cached(th + wpx0 + j * 256 + lane * 8, tw[j]);
+        } else {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t wq = j * 64 + (t >> 2);
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    if (m & (1u << (8 * j + k))) {
-                        const uint32_t bp = ((t & 3) << 3) + k;
-                        const uint32_t rank = s_wpre[wq] + __popc(s_mask[wq] & ((1u << bp) - 1u));
-                        uint32_t v = Px<T>::get(fw[j], k);
-                        if (VALMODE == 1) v -= Px<T>::get(tw[j], k);
-                        s_vals[rank] = (T)v;
+                for (int i = 0; i < W; i++) { fw[j][i] = 0; tw[j][i] = 0; }
+                const int q0 = wpx0 + j * 256 + lane * 8;
+                if (q0 < npx) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (q0 + k < npx) {
+                            Px<T>::set(fw[j], k, fr[q0 + k]);
+                            Px<T>::set(tw[j], k, th[q0 + k]);
+                        }
                     }
                 }
             }
         }
-        __syncthreads();
-        const size_t sbase = (size_t)f * ((size_t)NT * TILE_PX) + base;
-        for (uint32_t i = t; i < total; i += 256) {
-            const T v = s_vals[i];
-            if (CCL != 1) vals[sbase + i] = v;
-            if (CCL) parent[sbase + i] = (uint32_t)(base + i);
-            if (CCL == 1) acc[sbase + i] = (uint32_t)v;
+        uint8_t *mb = reinterpret_cast<uint8_t *>(s_mask + sub * SUB_WORDS + warp * 32);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t d[W];
+            const uint32_t mj = Px<T>::fg_words(fw[j], tw[j], d);
+            mb[j * 32 + lane] = (uint8_t)mj;
+            if (VALMODE) {
+                const uint32_t g = (uint32_t)(warp * 128 + j * 32 + lane);
+                Px<T>::store_raw(s_raw + raw_pos(g) * 8, VALMODE == 1 ? d : fw[j]);
+            }
         }
+        __syncwarp();
+        const uint32_t word = s_mask[sub * SUB_WORDS + t];      // pixels [32 t, 32 t + 32) of the sub-tile
+        const uint32_t pc = __popc(word);
+        const uint32_t incl = warp_incl_scan(pc);
+        if (lane == 31) s_wsum[sub & 1][warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        {
+            const uint4 a = *reinterpret_cast<const uint4 *>(&s_wsum[sub & 1][0]);
+            const uint4 b = *reinterpret_cast<const uint4 *>(&s_wsum[sub & 1][4]);
+            const uint32_t ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (i < warp) before += ws[i];
+                total += ws[i];
+            }
+        }
+        uint32_t rank = run + before + incl - pc;               // tile-local slot of this word's first pixel
+        s_wpre[sub * SUB_WORDS + t] = (uint16_t)rank;
+        if (VALMODE) {
+            uint32_t bits = word;
+            while (bits) {
+                const uint32_t k = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint32_t q = (uint32_t)(t * 32) + k;       // pixel within the sub-tile
+                const T v = s_raw[raw_pos(q >> 3) * 8 + (q & 7)];
+                if (CCL != 1) vals[sbase + rank] = v;
+                if (CCL && rank < (uint32_t)CCL_CAP) {
+                    s_pos[rank] = (uint16_t)(sub * SUB_PX + q);
+                    if (CCL == 1) s_acc[rank] = (uint32_t)v;
+                }
+                rank++;
+            }
+            __syncwarp();                                       // s_raw of this warp is rewritten next sub-tile
+        }
+        run += total;
+    }
+    __syncthreads();
+
+    // whole-tile outputs: map words, per-word prefixes, tile count
+    {
+        const uint4 mw = *reinterpret_cast<const uint4 *>(&s_mask[t * 4]);
+        *reinterpret_cast<uint4 *>(&maps[(size_t)f * MS + (size_t)tile * TILE_WORDS + t * 4]) = mw;
+        const uint2 wp = *reinterpret_cast<const uint2 *>(&s_wpre[t * 4]);
+        *reinterpret_cast<uint2 *>(&wordpre[(size_t)f * MS + (size_t)tile * TILE_WORDS + t * 4]) = wp;
+        if (t == 0) tilecnt[(size_t)f * NT + tile] = run;
+    }
+    if (!CCL) return;
+
+    const uint32_t total = run;
+    const bool overflow = total > (uint32_t)CCL_CAP;
+    if (t == 0) tileovf[(size_t)f * NT + tile] = overflow ? 1 : 0;
+    if (overflow) {
+        // rare: every pixel starts as its own root; the global kernels link the whole tile
+        for (int wi = t; wi < TILE_WORDS; wi += 256) {
+            uint32_t bits = s_mask[wi];
+            uint32_t s = s_wpre[wi];
+            while (bits) {
+                const uint32_t k = __ffs(bits) - 1;
+                bits &= bits - 1;
+                parent[sbase + s] = (uint32_t)base + s;
+                if (CCL == 1) acc[sbase + s] = (uint32_t)fr[wi * 32 + k];
+                s++;
+            }
+        }
+        return;
+    }
+    // tile-local 8-connected labelling, one foreground pixel at a time (a tile holds a few hundred of them).
+    // Backward neighbours W, NW, N, NE inside the tile are tested on the shared-memory map; the W neighbour's
+    // slot is simply i - 1, the others come from the per-word prefixes.  Links that leave the tile are made
+    // later by k_ccl_border.
+    for (uint32_t i = t; i < total; i += 256) s_parent[i] = i;
+    __syncthreads();
+    {
+        const uint32_t unx = (uint32_t)nx;
+        const bool pow2 = (unx & (unx - 1u)) == 0;
+        for (uint32_t i = t; i < total; i += 256) {
+            const uint32_t p = s_pos[i];                              // pixel within the tile
+            const uint32_t gp = (uint32_t)base + p;
+            const uint32_t col = pow2 ? (gp & (unx - 1u)) : (gp % unx);
+            if (col > 0 && p >= 1 && ((s_mask[(p - 1) >> 5] >> ((p - 1) & 31)) & 1u)) uf_union(s_parent, i, i - 1);
+            if (p + 1 < unx) continue;                                // the whole row above is outside the tile
+            // bits q-1, q, q+1 of the row above (q = p - nx); q - 1 may be -1 and q + 1 may leave the row
+            const int q = (int)p - (int)unx;
+            uint32_t nb = 0;                                          // bit 0 = NW, 1 = N, 2 = NE
+            if (q >= 1 && col > 0) nb |= (s_mask[(q - 1) >> 5] >> ((q - 1) & 31)) & 1u;
+            if (q >= 0) nb |= ((s_mask[q >> 5] >> (q & 31)) & 1u) << 1;
+            if (col + 1 < unx) nb |= ((s_mask[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u) << 2;
+            if (!nb) continue;
+            if (nb & 2u) {
+                // N is set: NW and NE are horizontally adjacent to N, their own W-links connect them
+                const uint32_t w = (uint32_t)q >> 5;
+                uf_union(s_parent, i, s_wpre[w] + __popc(s_mask[w] & ((1u << (q & 31)) - 1u)));
+            } else {
+                if (nb & 1u) {
+                    const uint32_t w = (uint32_t)(q - 1) >> 5;
+                    uf_union(s_parent, i, s_wpre[w] + __popc(s_mask[w] & ((1u << ((q - 1) & 31)) - 1u)));
+                }
+                if (nb & 4u) {
+                    const uint32_t w = (uint32_t)(q + 1) >> 5;
+                    uf_union(s_parent, i, s_wpre[w] + __popc(s_mask[w] & ((1u << ((q + 1) & 31)) - 1u)));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // flatten; L2 folds every member's value into its root (values of non-roots are never written again)
+    for (uint32_t i = t; i < total; i += 256) {
+        const uint32_t r = uf_find_ro(s_parent, i);
+        if (r != i) {
+            s_parent[i] = r;
+            if (CCL == 1) {
+                if (stat_sum) atomicAdd(&s_acc[r], s_acc[i]);
+                else atomicMax(&s_acc[r], s_acc[i]);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = t; i < total; i += 256) {
+        const uint32_t r = s_parent[i];
+        parent[sbase + i] = r == i ? (uint32_t)base + i : (((uint32_t)base + r) | UF_FLAG);
+        if (CCL == 1) acc[sbase + i] = s_acc[i];
     }
 }
 
 template <typename T>
 static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, int ccl, const void *frames,
                                  const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre,
-                                 void *vals, uint32_t *parent, uint32_t *acc, cudaStream_t st)
+                                 uint8_t *tileovf, void *vals, uint32_t *parent, uint32_t *acc, int stat_sum,
+                                 cudaStream_t st)
 {
     const int vec_ok = ((g.P * sizeof(T)) % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)thr % 16 == 0);
     dim3 grid(F, g.NT), block(256);
 #define RC_K1(VM, C)                                                                                          \
-    k_reduce_tiles<T, VM, C><<<grid, block, 0, st>>>((const T *)frames, (const T *)thr, g.P, g.NT, g.MS, maps, \
-                                                     tilecnt, wordpre, (T *)vals, parent, acc, vec_ok)
+    k_reduce_tiles<T, VM, C><<<grid, block, 0, st>>>((const T *)frames, (const T *)thr, g.P, g.NT, g.MS, g.ny, \
+                                                     g.nx, maps, tilecnt, wordpre, tileovf, (T *)vals, parent, \
+                                                     acc, stat_sum, vec_ok)
     if (valmode == 0) RC_K1(0, 0);
     else if (valmode == 1) RC_K1(1, 0);
     else if (ccl == 1) RC_K1(2, 1);
@@ -199,15 +325,15 @@ static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, int cc
 }
 
 int launch_reduce_tiles(rc_ctx *ctx, const Geom &g, int itemsize, int valmode, int ccl, const void *frames,
-                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre, void *vals,
-                        uint32_t *parent, uint32_t *acc, cudaStream_t st)
+                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre,
+                        uint8_t *tileovf, void *vals, uint32_t *parent, uint32_t *acc, int stat_sum, cudaStream_t st)
 {
     if (F <= 0) return 0;
     if (itemsize == 2)
-        return launch_reduce_tiles_t<uint16_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, wordpre, vals,
-                                               parent, acc, st);
-    return launch_reduce_tiles_t<uint8_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, wordpre, vals, parent,
-                                          acc, st);
+        return launch_reduce_tiles_t<uint16_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, wordpre, tileovf,
+                                               vals, parent, acc, stat_sum, st);
+    return launch_reduce_tiles_t<uint8_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, wordpre, tileovf, vals,
+                                          parent, acc, stat_sum, st);
 }
 
 // ---- map-only tile counts (read side: a map came out of inflate) ------------------------------
@@ -218,11 +344,14 @@ k_map_counts(const uint32_t *__restrict__ maps, size_t MS, int NT, uint32_t *__r
 {
     __shared__ uint32_t s_warp[9];
     const int t = threadIdx.x, f = blockIdx.x, tile = blockIdx.y;
-    const uint32_t word = maps[(size_t)f * MS + (size_t)tile * TILE_WORDS + t];
-    const uint32_t pc = __popc(word);
+    const size_t o = (size_t)f * MS + (size_t)tile * TILE_WORDS + t * 4;      // thread t: words 4t .. 4t+3
+    const uint4 w = *reinterpret_cast<const uint4 *>(maps + o);
+    const uint32_t p0 = __popc(w.x), p1 = __popc(w.y), p2 = __popc(w.z), p3 = __popc(w.w);
     uint32_t total;
-    const uint32_t excl = block_excl_scan<8>(pc, s_warp, &total);
-    wordpre[(size_t)f * MS + (size_t)tile * TILE_WORDS + t] = (uint16_t)excl;
+    const uint32_t e = block_excl_scan<8>(p0 + p1 + p2 + p3, s_warp, &total);
+    ushort4 o4;
+    o4.x = (uint16_t)e; o4.y = (uint16_t)(e + p0); o4.z = (uint16_t)(e + p0 + p1); o4.w = (uint16_t)(e + p0 + p1 + p2);
+    *reinterpret_cast<ushort4 *>(wordpre + o) = o4;
     if (t == 0) tilecnt[(size_t)f * NT + tile] = total;
 }
 

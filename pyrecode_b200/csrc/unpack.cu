@@ -34,7 +34,7 @@ k_unpack_sparse(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__r
     const uint32_t *tilepre = tilepre_all + (size_t)f * (NT + 1);
     const uint32_t *pk = reinterpret_cast<const uint32_t *>(packed + (size_t)f * packed_stride);
     // global rank of the first set bit of this word
-    uint64_t rank = (uint64_t)tilepre[w >> 8] + wordpre_all[(size_t)f * MS + w];
+    uint64_t rank = (uint64_t)tilepre[w >> TILE_WORDS_LOG2] + wordpre_all[(size_t)f * MS + w];
     uint64_t *out = triples + (size_t)f * capacity * 3;
     const uint32_t p0 = w << 5;
     while (bits) {
@@ -69,7 +69,7 @@ k_unpack_dense(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__re
     const uint32_t m = mapb[(size_t)seg * 32 + lane];
     const uint32_t pc = __popc(m);
     const uint32_t incl = warp_incl_scan(pc);
-    uint64_t rank = (uint64_t)tilepre_all[(size_t)f * (NT + 1) + (seg >> 5)] +
+    uint64_t rank = (uint64_t)tilepre_all[(size_t)f * (NT + 1) + (seg >> SEGS_PER_TILE_LOG2)] +
                     wordpre_all[(size_t)f * MS + (size_t)seg * SEG_WORDS] + (incl - pc);
     const uint32_t *pk = reinterpret_cast<const uint32_t *>(packed + (size_t)f * packed_stride);
     uint32_t v[8];

@@ -174,6 +174,72 @@ def test_l2_reduce(ny, nx, b, occ, stat):
         assert packed[f] == v, first_diff(packed[f], v)
 
 
+def _cross_tile_frames(ny, nx, rng, vmax):
+    """Frames whose puddles cross the 32768-pixel tile boundaries of the labelling kernel in every way:
+    full-height vertical lines, diagonals, U shapes closed only in a later tile, combs, one tile dense enough
+    to overflow the shared-memory labelling next to sparse tiles."""
+    f = np.zeros((4, ny, nx), np.uint16)
+    val = lambda shape: rng.integers(1, vmax + 1, size=shape).astype(np.uint16)
+    # 0: vertical lines + both diagonals over the whole frame
+    for c in range(3, nx, 37):
+        f[0, :, c] = val(ny)
+    d = np.arange(min(ny, nx))
+    f[0, d, d] = val(d.size)
+    f[0, d, nx - 1 - d] = val(d.size)
+    # 1: U shapes: two separate columns joined only at the bottom row, and an inverted comb from the top row
+    for c in range(2, nx - 8, 40):
+        f[1, : ny - 1, c] = val(ny - 1)
+        f[1, : ny - 1, c + 4] = val(ny - 1)
+        f[1, ny - 1, c:c + 5] = val(5)
+    f[1, 0, :] = 0
+    # 2: sparse random everywhere, but a dense band (overflow tile) in the middle rows touching its neighbours
+    m = rng.random((ny, nx)) < 0.02
+    f[2][m] = val(int(m.sum()))
+    r0 = ny // 2
+    band = rng.random((min(40, ny - r0), nx)) < 0.55
+    f[2, r0:r0 + band.shape[0]][band] = val(int(band.sum()))
+    # 3: horizontal serpentine: rows fully set every 3rd row, joined alternately at the left / right end
+    for i, r in enumerate(range(0, ny - 3, 3)):
+        f[3, r, :] = val(nx)
+        f[3, r + 1: r + 3, 0 if i % 2 else nx - 1] = val(2)
+    return f
+
+
+@pytest.mark.parametrize('stat', [0, 2])
+@pytest.mark.parametrize('ny,nx', [(512, 512), (300, 1000), (257, 4096), (1030, 96), (200, 333)])
+def test_l2_cross_tile_puddles(ny, nx, stat):
+    rng = np.random.default_rng(ny * 7 + nx + stat)
+    frames = _cross_tile_frames(ny, nx, rng, 4095)
+    dark = np.zeros((ny, nx), np.uint16)
+    eng = engine(ny, nx, 2, 12, 2, l2=stat, F=4)
+    eng.set_threshold(dark, 0)
+    maps, packed, counts = eng.reduce(frames)
+    for f in range(4):
+        m, v, n = orc.reduce_frame(frames[f], dark, 2, 12, l2_statistics=stat)
+        assert counts[f] == n, 'frame %d: %d puddles, expected %d' % (f, counts[f], n)
+        assert maps[f] == m
+        assert packed[f] == v, 'frame %d: %s' % (f, first_diff(packed[f], v))
+
+
+@pytest.mark.parametrize('ny,nx', [(512, 512), (300, 1000), (1030, 96)])
+def test_l4_cross_tile_puddles(ny, nx):
+    rng = np.random.default_rng(ny * 11 + nx)
+    frames = _cross_tile_frames(ny, nx, rng, 4095)
+    dark = np.zeros((ny, nx), np.uint16)
+    eng = engine(ny, nx, 2, 12, 4, F=4)
+    eng.set_threshold(dark, 0)
+    cents = eng.centroids(frames)
+    maps, packed, counts = eng.reduce(frames)
+    for f in range(4):
+        lab, k = orc.label8(frames[f] > 0)
+        oc = orc.l4_centroids(lab, frames[f], k, 0)
+        assert cents[f].shape == oc.shape
+        assert np.array_equal(cents[f].view(np.uint32), oc.view(np.uint32)), first_diff(cents[f].view(np.uint32), oc.view(np.uint32))
+        m, v, n = orc.reduce_frame(frames[f], dark, 4, 12)
+        assert counts[f] == n == k
+        assert maps[f] == m, first_diff(maps[f], m)
+
+
 def test_l2_synthetic_4096():
     dark = orc.synth_dark(4096, 4096)
     frames = orc.synth_frames('l2', 1, 4096, 4096, dark, seed=1234)
