@@ -35,6 +35,8 @@ struct ReduceWs {
     uint32_t *tilecnt, *tilepre, *rootcnt, *rootpre;
     uint16_t *wordpre;
     uint8_t *tileovf;
+    uint32_t *xcount;
+    void *xlinks;
     void *vals;
     uint32_t *parent, *acc, *bbox, *ord;
     uint16_t *stats16;
@@ -54,9 +56,12 @@ static ReduceWs carve_reduce(Carver &c, const rc_config *cfg, const Geom &g, int
     w.wordpre = c.take<uint16_t>(F * g.MS);
     w.tileovf = c.take<uint8_t>(F * g.NT);
     const bool ccl = what != 0 || level == 2 || level == 4;
-    if (what == 0 && (level == 1 || level == 4)) w.vals = c.take<uint8_t>(F * g.slots * cfg->itemsize);
-    if (what == 2) w.vals = c.take<uint8_t>(F * g.slots * cfg->itemsize);
+    // L1: foreground values in the source dtype.  L2 / L4: (value << 16) | position words
+    if (what == 0 && level == 1) w.vals = c.take<uint8_t>(F * g.slots * cfg->itemsize);
+    if ((what == 0 && (level == 2 || level == 4)) || what == 2) w.vals = c.take<uint32_t>(F * g.slots);
     if (ccl) {
+        w.xcount = c.take<uint32_t>(F * g.NT);
+        w.xlinks = c.take<uint8_t>(ccl_xlinks_bytes(g, F));
         w.parent = c.take<uint32_t>(F * g.slots);
         w.rootcnt = c.take<uint32_t>(F * g.NT);
         w.rootpre = c.take<uint32_t>(F * (g.NT + 1));
@@ -248,37 +253,39 @@ static int run_reduce(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const Re
     const int level = cfg->reduction_level, b = cfg->bit_depth, isz = cfg->itemsize;
     int rc;
     if (level == 1) {
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 1, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, w.tileovf, w.vals,
-                                      nullptr, nullptr, 0, st))) return rc;
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 1, frames, thr, F, maps, w.tilecnt, w.wordpre, w.vals, st))) return rc;
         rc_mark(ctx, 1, st);
         if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, packed_bytes, b, st))) return rc;
         return launch_bitpack(ctx, g, isz, w.vals, w.tilepre, F, b, packed, packed_stride, st);
     }
     if (level == 3) {
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 0, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, w.tileovf, nullptr,
-                                      nullptr, nullptr, 0, st))) return rc;
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, nullptr, st))) return rc;
         rc_mark(ctx, 1, st);
         return launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, nullptr, 0, st);
     }
     if (level == 2) {
         const int sum = cfg->l2_statistics == 2;
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 1, frames, thr, F, maps, w.tilecnt, w.wordpre, w.tileovf, w.vals,
-                                      w.parent, w.acc, sum, st))) return rc;
+        if ((rc = launch_reduce_tiles(ctx, g, isz, 2, frames, thr, F, maps, w.tilecnt, w.wordpre, w.vals, st))) return rc;
         rc_mark(ctx, 1, st);
-        if ((rc = launch_ccl_border(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tileovf, w.parent, w.acc, F, st))) return rc;
+        if ((rc = launch_ccl_tiles(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf,
+                                   w.xcount, w.xlinks, w.parent, w.acc, F, st))) return rc;
+        if ((rc = launch_ccl_border(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, w.acc,
+                                    F, st))) return rc;
         if ((rc = launch_ccl_roots(ctx, g, 1, w.tilecnt, w.parent, w.acc, nullptr, w.rootcnt, nullptr, w.stats16,
                                    nullptr, F, st))) return rc;
         if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, packed_bytes, b, st))) return rc;
         return launch_bitpack(ctx, g, 2, w.stats16, w.rootpre, F, b, packed, packed_stride, st);
     }
     // level 4: threshold map -> map1, centroid map -> maps
-    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, frames, thr, F, w.map1, w.tilecnt, w.wordpre, w.tileovf, w.vals,
-                                  w.parent, nullptr, 0, st))) return rc;
+    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, frames, thr, F, w.map1, w.tilecnt, w.wordpre, w.vals, st))) return rc;
     rc_mark(ctx, 1, st);
-    if ((rc = launch_ccl_border(ctx, g, 0, w.map1, w.wordpre, w.tileovf, w.parent, nullptr, F, st))) return rc;
+    if ((rc = launch_ccl_tiles(ctx, g, 0, w.map1, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf, w.xcount,
+                               w.xlinks, w.parent, nullptr, F, st))) return rc;
+    if ((rc = launch_ccl_border(ctx, g, 0, w.map1, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, nullptr, F,
+                                st))) return rc;
     if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, w.bbox, F, st))) return rc;
     RC_CUDA(ctx, cudaMemsetAsync(maps, 0, (size_t)F * g.MS * sizeof(uint32_t), st));
-    if ((rc = launch_l4_centroids(ctx, g, isz, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox, w.vals, maps,
+    if ((rc = launch_l4_centroids(ctx, g, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox, (const uint32_t *)w.vals, maps,
                                   nullptr, F, st))) return rc;
     // puddle count = number of roots
     if ((rc = launch_ccl_roots(ctx, g, 3, w.tilecnt, w.parent, nullptr, nullptr, w.rootcnt, nullptr, nullptr, nullptr,
@@ -378,11 +385,13 @@ extern "C" int rc_l4_centroids(rc_ctx *ctx, const rc_config *cfg, const void *d_
     const ReduceWs w = carve_reduce(c, cfg, g, 2);
     const int F = n_frames, isz = cfg->itemsize;
     int rc;
-    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, 2, d_frames, d_thr, F, w.map1, w.tilecnt, w.wordpre, w.tileovf, w.vals,
-                                  w.parent, nullptr, 0, st))) return rc;
-    if ((rc = launch_ccl_border(ctx, g, 0, w.map1, w.wordpre, w.tileovf, w.parent, nullptr, F, st))) return rc;
+    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, d_frames, d_thr, F, w.map1, w.tilecnt, w.wordpre, w.vals, st))) return rc;
+    if ((rc = launch_ccl_tiles(ctx, g, 0, w.map1, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf, w.xcount,
+                               w.xlinks, w.parent, nullptr, F, st))) return rc;
+    if ((rc = launch_ccl_border(ctx, g, 0, w.map1, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, nullptr, F,
+                                st))) return rc;
     if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, w.bbox, F, st))) return rc;
-    if ((rc = launch_l4_centroids(ctx, g, isz, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox, w.vals, nullptr,
+    if ((rc = launch_l4_centroids(ctx, g, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox, (const uint32_t *)w.vals, nullptr,
                                   w.cent, F, st))) return rc;
     if ((rc = launch_ccl_roots(ctx, g, 2, w.tilecnt, w.parent, nullptr, w.cent, w.rootcnt, nullptr, nullptr, w.cent_tiles,
                                F, st))) return rc;

@@ -27,6 +27,185 @@
 #include "kernels.cuh"
 #include "ccl_core.cuh"
 
+// ---- tile-local labelling ----------------------------------------------------------------------
+// One CTA per (tile, frame).  A tile of an electron-counting frame holds a few hundred foreground pixels in
+// puddles of a few pixels, so the work is organised per foreground pixel, not per map word:
+//   phase 1  every foreground pixel (position from k_reduce_tiles) tests its W / NW / N / NE neighbours on
+//            the shared-memory copy of the tile's map and appends the links it finds to a dense list
+//            (warp-aggregated).  Links to pixels of earlier tiles go to the tile's global cross-link list.
+//   phase 2  the dense list is processed with atomicMin unions in shared memory (all lanes busy).
+//   phase 3  flatten; L2 folds each member's value into its root (max or sum).
+//   phase 4  parent[slot] = slot of the tile-local root (| UF_FLAG for non-roots), acc[slot].
+// A tile with more than CCL_CAP foreground pixels (> 6 % occupancy), or whose link lists overflow, is not
+// labelled here: it gets parent[slot] = slot, acc[slot] = value, tileovf = 1 and k_ccl_border links all of
+// its pixels with the global word-parallel path.
+constexpr int CCL_CAP = 2048;          // foreground pixels per tile handled in shared memory
+constexpr int CCL_LINKS = 3072;        // tile-local links
+constexpr int CCL_XCAP = 256;          // cross-tile links per tile (global list)
+constexpr int CCL_THREADS = 256;
+
+// FOLD: 0 = labels only (L4), 1 = L2 max, 2 = L2 sum
+template <int FOLD>
+__global__ void __launch_bounds__(CCL_THREADS)
+k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
+            const uint32_t *__restrict__ tilecnt, const uint32_t *__restrict__ vp_all, uint8_t *__restrict__ tileovf,
+            uint32_t *__restrict__ xcount, uint2 *__restrict__ xlinks, uint32_t *__restrict__ parent_all,
+            uint32_t *__restrict__ acc_all, int ny, int nx)
+{
+    __shared__ __align__(16) uint32_t s_mask[TILE_WORDS];
+    __shared__ __align__(16) uint16_t s_wpre[TILE_WORDS];
+    __shared__ uint32_t s_parent[CCL_CAP];
+    __shared__ uint32_t s_acc[FOLD ? CCL_CAP : 1];
+    __shared__ uint16_t s_pos[CCL_CAP];
+    __shared__ uint32_t s_links[CCL_LINKS];            // (a << 16) | b, tile-local slots
+    __shared__ uint32_t s_nlinks, s_nx, s_bad;
+    const int tile = blockIdx.x, f = blockIdx.y, t = threadIdx.x, lane = t & 31;
+    const size_t ti = (size_t)f * NT + tile;
+    const uint32_t total = tilecnt[ti];
+    const uint32_t base = (uint32_t)tile << TILE_LOG2;
+    const size_t sbase = (size_t)f * ((size_t)NT * TILE_PX) + base;
+    uint32_t *parent = parent_all + sbase;
+    const uint32_t *vp = vp_all + sbase;
+    if (total == 0) {
+        if (t == 0) { tileovf[ti] = 0; xcount[ti] = 0; }
+        return;
+    }
+    bool overflow = total > (uint32_t)CCL_CAP;
+    if (!overflow) {
+        const size_t wo = (size_t)f * MS + (size_t)tile * TILE_WORDS;
+        reinterpret_cast<uint4 *>(s_mask)[t] = reinterpret_cast<const uint4 *>(maps + wo)[t];
+        if (t < TILE_WORDS / 8) reinterpret_cast<uint4 *>(s_wpre)[t] = reinterpret_cast<const uint4 *>(wordpre_all + wo)[t];
+        for (uint32_t i = t; i < total; i += CCL_THREADS) {
+            const uint32_t v = vp[i];
+            s_pos[i] = (uint16_t)v;
+            if (FOLD) s_acc[i] = v >> 16;
+            s_parent[i] = i;
+        }
+        if (t == 0) { s_nlinks = 0; s_nx = 0; s_bad = 0; }
+        __syncthreads();
+
+        // ---- phase 1: link detection
+        const uint32_t unx = (uint32_t)nx;
+        const bool pow2 = (unx & (unx - 1u)) == 0;
+        const uint32_t *gmap = maps + (size_t)f * MS;
+        const uint16_t *gwpre = wordpre_all + (size_t)f * MS;
+        uint2 *xl = xlinks + ti * CCL_XCAP;
+        for (uint32_t i0 = 0; i0 < total; i0 += CCL_THREADS) {
+            const uint32_t i = i0 + t;
+            uint32_t l0 = 0, l1 = 0, l2 = 0;           // local links found by this pixel: (i << 16) | other
+            uint32_t n = 0;
+            if (i < total) {
+                const uint32_t p = s_pos[i];
+                const uint32_t gp = base + p;
+                const uint32_t col = pow2 ? (gp & (unx - 1u)) : (gp % unx);
+                if (p > unx) {
+                    // common case: all four backward neighbours are inside the tile
+                    const uint32_t q = p - unx;
+                    const uint32_t bw = (s_mask[(p - 1) >> 5] >> ((p - 1) & 31)) & 1u;
+                    const uint32_t bnw = (s_mask[(q - 1) >> 5] >> ((q - 1) & 31)) & 1u;
+                    const uint32_t bn = (s_mask[q >> 5] >> (q & 31)) & 1u;
+                    const uint32_t bne = (s_mask[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u;
+                    const bool hl = col > 0, hr = col + 1 < unx;
+                    if (bw && hl) { l0 = (i << 16) | (i - 1); n = 1; }
+                    uint32_t qa = 0xffffffffu, qb = 0xffffffffu;
+                    if (bn) qa = q;
+                    else {
+                        if (bnw && hl) qa = q - 1;
+                        if (bne && hr) qb = q + 1;
+                    }
+                    if (qa != 0xffffffffu) {
+                        const uint32_t w = qa >> 5;
+                        const uint32_t s = s_wpre[w] + __popc(s_mask[w] & ((1u << (qa & 31)) - 1u));
+                        if (n) l1 = (i << 16) | s; else l0 = (i << 16) | s;
+                        n++;
+                    }
+                    if (qb != 0xffffffffu) {
+                        const uint32_t w = qb >> 5;
+                        const uint32_t s = s_wpre[w] + __popc(s_mask[w] & ((1u << (qb & 31)) - 1u));
+                        if (n == 0) l0 = (i << 16) | s; else if (n == 1) l1 = (i << 16) | s; else l2 = (i << 16) | s;
+                        n++;
+                    }
+                } else {
+                    // first rows of the tile: a neighbour may belong to an earlier tile (global lookup)
+                    const bool hl = col > 0, hr = col + 1 < unx, up = gp >= unx;
+                    uint32_t cand[3];
+                    int nc = 0;
+                    if (hl && ((gmap[(gp - 1) >> 5] >> ((gp - 1) & 31)) & 1u)) cand[nc++] = gp - 1;
+                    if (up) {
+                        const uint32_t gq = gp - unx;
+                        if ((gmap[gq >> 5] >> (gq & 31)) & 1u) cand[nc++] = gq;
+                        else {
+                            if (hl && ((gmap[(gq - 1) >> 5] >> ((gq - 1) & 31)) & 1u)) cand[nc++] = gq - 1;
+                            if (hr && ((gmap[(gq + 1) >> 5] >> ((gq + 1) & 31)) & 1u)) cand[nc++] = gq + 1;
+                        }
+                    }
+                    for (int c = 0; c < nc; c++) {
+                        const uint32_t gq = cand[c];
+                        if (gq >= base) {
+                            const uint32_t ql = gq - base, w = ql >> 5;
+                            const uint32_t s = s_wpre[w] + __popc(s_mask[w] & ((1u << (ql & 31)) - 1u));
+                            const uint32_t e = (i << 16) | s;
+                            if (n == 0) l0 = e; else if (n == 1) l1 = e; else l2 = e;
+                            n++;
+                        } else {
+                            const uint32_t k = atomicAdd(&s_nx, 1u);
+                            if (k < (uint32_t)CCL_XCAP) xl[k] = make_uint2(base + i, slot_of(gmap, gwpre, gq));
+                            else s_bad = 1;
+                        }
+                    }
+                }
+            }
+            // warp-aggregated append of n in {0..3} entries per lane
+            const uint32_t b0 = __ballot_sync(0xffffffffu, n & 1u), b1 = __ballot_sync(0xffffffffu, n & 2u);
+            const uint32_t lt = (1u << lane) - 1u;
+            const uint32_t pre = __popc(b0 & lt) + 2u * __popc(b1 & lt);
+            const uint32_t tot = __popc(b0) + 2u * __popc(b1);
+            uint32_t wbase = 0;
+            if (lane == 0 && tot) wbase = atomicAdd(&s_nlinks, tot);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            const uint32_t o = wbase + pre;
+            if (n > 0 && o < (uint32_t)CCL_LINKS) s_links[o] = l0;
+            if (n > 1 && o + 1 < (uint32_t)CCL_LINKS) s_links[o + 1] = l1;
+            if (n > 2 && o + 2 < (uint32_t)CCL_LINKS) s_links[o + 2] = l2;
+        }
+        __syncthreads();
+        overflow = s_bad || s_nlinks > (uint32_t)CCL_LINKS;
+    }
+    if (overflow) {
+        for (uint32_t i = t; i < total; i += CCL_THREADS) {
+            parent[i] = base + i;
+            if (FOLD) acc_all[sbase + i] = vp[i] >> 16;
+        }
+        if (t == 0) { tileovf[ti] = 1; xcount[ti] = 0; }
+        return;
+    }
+    if (t == 0) { tileovf[ti] = 0; xcount[ti] = s_nx; }
+
+    // ---- phase 2: unions
+    const uint32_t nl = s_nlinks;
+    for (uint32_t j = t; j < nl; j += CCL_THREADS) {
+        const uint32_t e = s_links[j];
+        uf_union(s_parent, e >> 16, e & 0xffffu);
+    }
+    __syncthreads();
+    // ---- phase 3: flatten; L2 folds every member's value into its root (non-roots are never written again)
+    for (uint32_t i = t; i < total; i += CCL_THREADS) {
+        const uint32_t r = uf_find_ro(s_parent, i);
+        if (r != i) {
+            s_parent[i] = r;
+            if (FOLD == 1) atomicMax(&s_acc[r], s_acc[i]);
+            if (FOLD == 2) atomicAdd(&s_acc[r], s_acc[i]);
+        }
+    }
+    __syncthreads();
+    // ---- phase 4
+    for (uint32_t i = t; i < total; i += CCL_THREADS) {
+        const uint32_t r = s_parent[i];
+        parent[i] = r == i ? base + i : ((base + r) | UF_FLAG);
+        if (FOLD) acc_all[sbase + i] = s_acc[i];
+    }
+}
+
 // full-frame union (maps that did not come from k_reduce_tiles: rc_ccl_label)
 __global__ void __launch_bounds__(256)
 k_ccl_union(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
@@ -61,35 +240,44 @@ struct FoldAct {
     __device__ __forceinline__ void operator()(uint32_t a, uint32_t b) const { one(a); one(b); }
 };
 
-// Links across tile boundaries.  k_reduce_tiles labelled every tile on its own; what is left are the links
-// from the first nx + 1 pixels of a tile to pixels of earlier tiles (q < tile base).  A tile that overflowed
-// the shared-memory labelling (tileovf) has all of its links made here instead.
+// Links across tile boundaries.  k_ccl_tiles labelled every tile on its own and listed the links from its
+// first rows to pixels of earlier tiles; a tile that overflowed the shared-memory labelling (tileovf) has all
+// of its links made here instead, with the word-parallel global path.
 // PASS 0: union.  PASS 1: L2 fold of the re-parented tile-local roots (separate launch: needs final roots).
+// One warp per tile.
 template <int PASS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_ccl_border(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
-             const uint8_t *__restrict__ tileovf, uint32_t *__restrict__ parent_all, uint32_t *__restrict__ acc_all,
+             const uint8_t *__restrict__ tileovf, const uint32_t *__restrict__ xcount,
+             const uint2 *__restrict__ xlinks, uint32_t *__restrict__ parent_all, uint32_t *__restrict__ acc_all,
              int ny, int nx, uint32_t MW, int sum)
 {
-    const int tile = blockIdx.x, f = blockIdx.y;
-    const bool ovf = tileovf[(size_t)f * NT + tile] != 0;
-    if (tile == 0 && !ovf) return;
-    const uint32_t w0 = (uint32_t)tile * TILE_WORDS;
-    uint32_t w1 = w0 + TILE_WORDS;                                   // exclusive
-    if (!ovf) {
-        const uint32_t wl = (((uint32_t)tile << TILE_LOG2) + (uint32_t)nx) >> 5;   // word of pixel base + nx
-        if (wl + 1 < w1) w1 = wl + 1;
-    }
-    if (w1 > MW) w1 = MW;
-    const uint32_t q_hi = ovf ? 0xffffffffu : ((uint32_t)tile << TILE_LOG2);
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5), f = blockIdx.y, lane = threadIdx.x & 31;
+    if (tile >= NT) return;
+    const size_t ti = (size_t)f * NT + tile;
     const size_t slots = (size_t)NT * TILE_PX;
+    uint32_t *parent = parent_all + (size_t)f * slots;
+    uint32_t *acc = acc_all + (size_t)f * slots;
+    if (!tileovf[ti]) {
+        const uint32_t n = xcount[ti];
+        const uint2 *xl = xlinks + ti * CCL_XCAP;
+        for (uint32_t j = lane; j < n; j += 32) {
+            const uint2 e = xl[j];
+            if (PASS == 0) uf_union(parent, e.x, e.y);
+            else FoldAct{parent, acc, sum}(e.x, e.y);
+        }
+        return;
+    }
+    const uint32_t w0 = (uint32_t)tile * TILE_WORDS;
+    uint32_t w1 = w0 + TILE_WORDS;
+    if (w1 > MW) w1 = MW;
     const uint32_t *map = maps + (size_t)f * MS;
-    GlobalSpace sp{map, wordpre_all + (size_t)f * MS, parent_all + (size_t)f * slots};
-    for (uint32_t w = w0 + threadIdx.x; w < w1; w += 128) {
+    GlobalSpace sp{map, wordpre_all + (size_t)f * MS, parent};
+    for (uint32_t w = w0 + lane; w < w1; w += 32) {
         const uint32_t bits = map[w];
         if (!bits) continue;
-        if (PASS == 0) link_word(sp, UnionAct{sp.parent}, w, bits, ny, nx, q_hi);
-        else link_word(sp, FoldAct{sp.parent, acc_all + (size_t)f * slots, sum}, w, bits, ny, nx, q_hi);
+        if (PASS == 0) link_word(sp, UnionAct{parent}, w, bits, ny, nx, 0xffffffffu);
+        else link_word(sp, FoldAct{parent, acc, sum}, w, bits, ny, nx, 0xffffffffu);
     }
 }
 
@@ -257,11 +445,10 @@ k_gather_centroids(const uint64_t *__restrict__ cent_tiles, const uint32_t *__re
 // ---- L4 centroids ------------------------------------------------------------------------------
 // One thread per root.  mode: 0/1 weighted (converters.py:167-197), 2 max pixel (:229-259), 3 unweighted (:200-226).
 // Each += of the reference is float64 arithmetic rounded to float32 (numba: float32 element += float64 value).
-template <typename T>
 __global__ void __launch_bounds__(128)
 k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
                const uint32_t *__restrict__ parent_all, const uint32_t *__restrict__ bbox_all,
-               const T *__restrict__ vals_all, int ny, int nx, uint32_t MW, int mode,
+               const uint32_t *__restrict__ vp_all, int ny, int nx, uint32_t MW, int mode,
                uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all)
 {
     const int f = blockIdx.y;
@@ -273,7 +460,7 @@ k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__r
     const size_t slots = (size_t)NT * TILE_PX;
     const uint16_t *wordpre = wordpre_all + (size_t)f * MS;
     const uint32_t *parent = parent_all + (size_t)f * slots;
-    const T *vals = vals_all + (size_t)f * slots;
+    const uint32_t *vp = vp_all + (size_t)f * slots;            // (value << 16) | position, from k_reduce_tiles
     uint32_t *map2 = map2_all + (size_t)f * MS;
     uint32_t s = word_slot_base(wordpre, w);
     const uint32_t p0 = w << 5;
@@ -287,7 +474,7 @@ k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__r
         float fr, fc;
         if ((bb.x | bb.y | bb.z) == 0) {
             // single-pixel puddle: the reference computes RN32(v*r) / RN32(v)
-            const float v = (float)vals[s];
+            const float v = (float)(vp[s] >> 16);
             if (mode == 2 || mode == 3) { fr = (float)r0; fc = (float)c0; }
             else {
                 fr = __fdiv_rn((float)((double)v * (double)r0), v);
@@ -309,7 +496,7 @@ k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__r
                         const uint32_t q = (ww << 5) + kk;
                         const uint32_t sq = slot_of(map, wordpre, q);
                         if (parent[sq] != s) continue;
-                        const double v = (double)vals[sq];
+                        const double v = (double)(vp[sq] >> 16);
                         const uint32_t c = q - r * (uint32_t)nx;
                         if (mode == 2) {
                             if (first || v > (double)a2) { a0 = (float)r; a1 = (float)c; a2 = (float)v; }
@@ -361,6 +548,26 @@ int launch_gather_centroids(rc_ctx *ctx, const Geom &g, const uint64_t *cent_til
     return 0;
 }
 
+// fold: 0 = labels only (L4), 1 = L2 max, 2 = L2 sum
+int launch_ccl_tiles(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps, const uint16_t *wordpre,
+                     const uint32_t *tilecnt, const uint32_t *vp, uint8_t *tileovf, uint32_t *xcount, void *xlinks,
+                     uint32_t *parent, uint32_t *acc, int F, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    dim3 grid((unsigned)g.NT, F);
+#define RC_CT(FO)                                                                                              \
+    k_ccl_tiles<FO><<<grid, CCL_THREADS, 0, st>>>(maps, g.MS, wordpre, g.NT, tilecnt, vp, tileovf, xcount,       \
+                                                  (uint2 *)xlinks, parent, acc, g.ny, g.nx)
+    if (fold == 0) RC_CT(0);
+    else if (fold == 1) RC_CT(1);
+    else RC_CT(2);
+#undef RC_CT
+    RC_LAUNCH_CHECK(ctx, "k_ccl_tiles");
+    return 0;
+}
+
+size_t ccl_xlinks_bytes(const Geom &g, size_t F) { return F * (size_t)g.NT * CCL_XCAP * sizeof(uint2); }
+
 int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre, uint32_t *parent,
                      int F, cudaStream_t st)
 {
@@ -373,15 +580,17 @@ int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uin
 
 // fold: 0 = links only (L4), 1 = + L2 max fold, 2 = + L2 sum fold
 int launch_ccl_border(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps, const uint16_t *wordpre,
-                      const uint8_t *tileovf, uint32_t *parent, uint32_t *acc, int F, cudaStream_t st)
+                      const uint8_t *tileovf, const uint32_t *xcount, const void *xlinks, uint32_t *parent,
+                      uint32_t *acc, int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
-    dim3 grid((unsigned)g.NT, F);
-    k_ccl_border<0><<<grid, 128, 0, st>>>(maps, g.MS, wordpre, g.NT, tileovf, parent, acc, g.ny, g.nx, (uint32_t)g.MW, 0);
+    dim3 grid((unsigned)((g.NT + 7) / 8), F);
+    k_ccl_border<0><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, tileovf, xcount, (const uint2 *)xlinks, parent, acc,
+                                          g.ny, g.nx, (uint32_t)g.MW, 0);
     RC_LAUNCH_CHECK(ctx, "k_ccl_border<0>");
     if (fold) {
-        k_ccl_border<1><<<grid, 128, 0, st>>>(maps, g.MS, wordpre, g.NT, tileovf, parent, acc, g.ny, g.nx,
-                                              (uint32_t)g.MW, fold == 2);
+        k_ccl_border<1><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, tileovf, xcount, (const uint2 *)xlinks, parent,
+                                              acc, g.ny, g.nx, (uint32_t)g.MW, fold == 2);
         RC_LAUNCH_CHECK(ctx, "k_ccl_border<1>");
     }
     return 0;
@@ -435,18 +644,14 @@ int launch_ccl_label_image(rc_ctx *ctx, const Geom &g, const uint32_t *maps, con
     return 0;
 }
 
-int launch_l4_centroids(rc_ctx *ctx, const Geom &g, int itemsize, int mode, const uint32_t *maps,
-                        const uint16_t *wordpre, const uint32_t *parent, const uint32_t *bbox, const void *vals,
-                        uint32_t *map2, uint64_t *cent, int F, cudaStream_t st)
+int launch_l4_centroids(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
+                        const uint32_t *parent, const uint32_t *bbox, const uint32_t *vp, uint32_t *map2,
+                        uint64_t *cent, int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
     dim3 grid((unsigned)((g.MW + 127) / 128), F);
-    if (itemsize == 2)
-        k_l4_centroids<uint16_t><<<grid, 128, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, bbox, (const uint16_t *)vals,
-                                                       g.ny, g.nx, (uint32_t)g.MW, mode, map2, cent);
-    else
-        k_l4_centroids<uint8_t><<<grid, 128, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, bbox, (const uint8_t *)vals,
-                                                      g.ny, g.nx, (uint32_t)g.MW, mode, map2, cent);
+    k_l4_centroids<<<grid, 128, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, bbox, vp, g.ny, g.nx, (uint32_t)g.MW, mode,
+                                         map2, cent);
     RC_LAUNCH_CHECK(ctx, "k_l4_centroids");
     return 0;
 }

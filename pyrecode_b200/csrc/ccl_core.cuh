@@ -45,7 +45,7 @@ template <bool WITH_SOUTH, class S>
 __device__ __forceinline__ Nbr neighbour_masks(const S &sp, uint32_t w, uint32_t bits, uint32_t wpr, uint32_t ny)
 {
     Nbr m;
-    const uint32_t row = w / wpr, wc = w - row * wpr;
+    const uint32_t row = (wpr & (wpr - 1u)) == 0 ? w >> (31 - __clz(wpr)) : w / wpr, wc = w - row * wpr;
     const bool has_l = wc > 0, has_r = wc + 1 < wpr;
     const uint32_t cl = has_l ? sp.word(w - 1) : 0, cr = has_r ? sp.word(w + 1) : 0;
     m.west = (bits << 1) | (cl >> 31);
@@ -148,7 +148,7 @@ struct GlobalSpace {
 struct TileSpace {
     const uint32_t *mask;      // [TILE_WORDS]
     const uint16_t *wpre;      // [TILE_WORDS]
-    uint32_t *parent;          // [CCL_CAP]
+    uint32_t *parent;          // [tile capacity]
     uint32_t w0;               // first word of the tile within the frame
     __device__ __forceinline__ uint32_t word(uint32_t w) const
     {

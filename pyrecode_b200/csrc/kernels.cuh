@@ -3,9 +3,8 @@
 #include "common.cuh"
 
 // reduce.cu
-int launch_reduce_tiles(rc_ctx *ctx, const Geom &g, int itemsize, int valmode, int ccl, const void *frames,
-                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre,
-                        uint8_t *tileovf, void *vals, uint32_t *parent, uint32_t *acc, int stat_sum, cudaStream_t st);
+int launch_reduce_tiles(rc_ctx *ctx, const Geom &g, int itemsize, int valmode, const void *frames, const void *thr,
+                        int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre, void *vals, cudaStream_t st);
 int launch_map_counts(rc_ctx *ctx, const Geom &g, const uint32_t *maps, int F, uint32_t *tilecnt, uint16_t *wordpre,
                       cudaStream_t st);
 int launch_scan_tiles(rc_ctx *ctx, const Geom &g, const uint32_t *tilecnt, int F, uint32_t *tilepre,
@@ -21,8 +20,13 @@ int launch_make_threshold(rc_ctx *ctx, int itemsize, const void *dark, uint64_t 
 int launch_ccl_init(rc_ctx *ctx, const Geom &g, const uint32_t *tilecnt, uint32_t *parent, int F, cudaStream_t st);
 int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre, uint32_t *parent,
                      int F, cudaStream_t st);
+int launch_ccl_tiles(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps, const uint16_t *wordpre,
+                     const uint32_t *tilecnt, const uint32_t *vp, uint8_t *tileovf, uint32_t *xcount, void *xlinks,
+                     uint32_t *parent, uint32_t *acc, int F, cudaStream_t st);
+size_t ccl_xlinks_bytes(const Geom &g, size_t F);
 int launch_ccl_border(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps, const uint16_t *wordpre,
-                      const uint8_t *tileovf, uint32_t *parent, uint32_t *acc, int F, cudaStream_t st);
+                      const uint8_t *tileovf, const uint32_t *xcount, const void *xlinks, uint32_t *parent,
+                      uint32_t *acc, int F, cudaStream_t st);
 int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
                        uint32_t *parent, uint32_t *bbox, int F, cudaStream_t st);
 int launch_ccl_roots(rc_ctx *ctx, const Geom &g, int payload, const uint32_t *tilecnt, const uint32_t *parent,
@@ -31,9 +35,9 @@ int launch_ccl_roots(rc_ctx *ctx, const Geom &g, int payload, const uint32_t *ti
 int launch_ccl_label_image(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre,
                            const uint32_t *parent, const uint32_t *ord, const uint32_t *rootpre, int32_t *labels,
                            int F, cudaStream_t st);
-int launch_l4_centroids(rc_ctx *ctx, const Geom &g, int itemsize, int mode, const uint32_t *maps,
-                        const uint16_t *wordpre, const uint32_t *parent, const uint32_t *bbox, const void *vals,
-                        uint32_t *map2, uint64_t *cent, int F, cudaStream_t st);
+int launch_l4_centroids(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
+                        const uint32_t *parent, const uint32_t *bbox, const uint32_t *vp, uint32_t *map2,
+                        uint64_t *cent, int F, cudaStream_t st);
 int launch_gather_centroids(rc_ctx *ctx, const Geom &g, const uint64_t *cent_tiles, const uint32_t *rootpre, int F,
                             float *out, size_t capacity, cudaStream_t st);
 

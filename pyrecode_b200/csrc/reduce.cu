@@ -12,7 +12,6 @@
 //                    per 32-bit output word, no atomics.
 #include "common.cuh"
 #include "kernels.cuh"
-#include "ccl_core.cuh"
 
 // ---- pixel-type helpers --------------------------------------------------------------------
 // 8 pixels = W 32-bit words.  fg_words: d = max(f, t) - t per lane (= f - t where f > t, else 0; no borrow
@@ -95,28 +94,23 @@ template <> struct Px<uint8_t> {
 // those 32 words.  Mask bytes and raw values are staged in warp-private shared memory, so the only
 // block-level barrier per sub-tile is the one for the cross-warp prefix of the foreground counts.
 //
-// VALMODE: 0 = no value stream (L3), 1 = frame - thr (L1), 2 = raw frame value (L2 / L4)
-// CCL:     0 = vals only
-//          1 = L2: 8-connected labelling of the tile in shared memory + per-puddle max / sum folded into
-//              acc[tile-local root]; parent[slot] = root slot (| UF_FLAG for non-roots); no vals
-//          2 = L4: vals + the same parent array
-// A tile with more than CCL_CAP foreground pixels (> 6 % occupancy) is not labelled here: it gets
-// parent[slot] = slot, acc[slot] = value, tileovf = 1 and the global kernels of ccl.cu link all its pixels.
+// VALMODE: 0 = no value stream (L3), 1 = frame - thr as T (L1), 2 = (raw frame value << 16) | pixel index
+//          within the tile, as uint32 (L2 / L4)
+// This kernel only streams: the latency-bound puddle labelling of L2 / L4 runs afterwards on the compact
+// per-tile data (k_ccl_tiles, ccl.cu).
 constexpr int SUB_PX = 8192;
 constexpr int SUB_WORDS = SUB_PX / 32;            // 256 = threads per CTA
 constexpr int NSUB = TILE_PX / SUB_PX;            // 4
-constexpr int CCL_CAP = 2048;
 
 // position (in 8-pixel granules) of granule g inside the sub-tile's raw staging: the XOR spreads the word
 // owners' 16-bit reads (stride 64 bytes) over the banks; 128-bit writes stay conflict-free
 __device__ __forceinline__ uint32_t raw_pos(uint32_t g) { return g ^ ((g >> 3) & 7u); }
 
-template <typename T, int VALMODE, int CCL>
-__global__ void __launch_bounds__(256)
-k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P, int NT, size_t MS, int ny, int nx,
+template <typename T, int VALMODE>
+__global__ void __launch_bounds__(256, 5)
+k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P, int NT, size_t MS,
                uint32_t *__restrict__ maps, uint32_t *__restrict__ tilecnt, uint16_t *__restrict__ wordpre,
-               uint8_t *__restrict__ tileovf, T *__restrict__ vals, uint32_t *__restrict__ parent,
-               uint32_t *__restrict__ acc, int stat_sum, int vec_ok)
+               void *__restrict__ vals_out, int vec_ok)
 {
     constexpr int W = Px<T>::W;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -133,9 +127,6 @@ k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P
     __shared__ __align__(16) uint16_t s_wpre[TILE_WORDS];
     __shared__ __align__(16) T s_raw[VALMODE ? SUB_PX : 8];
     __shared__ __align__(16) uint32_t s_wsum[2][8];
-    __shared__ uint32_t s_parent[CCL ? CCL_CAP : 1];
-    __shared__ uint16_t s_pos[CCL ? CCL_CAP : 1];              // pixel (within the tile) of each foreground slot
-    __shared__ uint32_t s_acc[CCL == 1 ? CCL_CAP : 1];
 
     uint32_t run = 0;                         // foreground pixels of the tile before the current sub-tile
 #pragma unroll 1
@@ -203,11 +194,10 @@ k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P
                 bits &= bits - 1;
                 const uint32_t q = (uint32_t)(t * 32) + k;       // pixel within the sub-tile
                 const T v = s_raw[raw_pos(q >> 3) * 8 + (q & 7)];
-                if (CCL != 1) vals[sbase + rank] = v;
-                if (CCL && rank < (uint32_t)CCL_CAP) {
-                    s_pos[rank] = (uint16_t)(sub * SUB_PX + q);
-                    if (CCL == 1) s_acc[rank] = (uint32_t)v;
-                }
+                // L1: the value stream itself.  L2 / L4: value and tile-local pixel position in one word, the
+                // input of the per-tile labelling (k_ccl_tiles)
+                if (VALMODE == 1) reinterpret_cast<T *>(vals_out)[sbase + rank] = v;
+                else reinterpret_cast<uint32_t *>(vals_out)[sbase + rank] = ((uint32_t)v << 16) | (uint32_t)(sub * SUB_PX) | q;
                 rank++;
             }
             __syncwarp();                                       // s_raw of this warp is rewritten next sub-tile
@@ -224,116 +214,32 @@ k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P
         *reinterpret_cast<uint2 *>(&wordpre[(size_t)f * MS + (size_t)tile * TILE_WORDS + t * 4]) = wp;
         if (t == 0) tilecnt[(size_t)f * NT + tile] = run;
     }
-    if (!CCL) return;
-
-    const uint32_t total = run;
-    const bool overflow = total > (uint32_t)CCL_CAP;
-    if (t == 0) tileovf[(size_t)f * NT + tile] = overflow ? 1 : 0;
-    if (overflow) {
-        // rare: every pixel starts as its own root; the global kernels link the whole tile
-        for (int wi = t; wi < TILE_WORDS; wi += 256) {
-            uint32_t bits = s_mask[wi];
-            uint32_t s = s_wpre[wi];
-            while (bits) {
-                const uint32_t k = __ffs(bits) - 1;
-                bits &= bits - 1;
-                parent[sbase + s] = (uint32_t)base + s;
-                if (CCL == 1) acc[sbase + s] = (uint32_t)fr[wi * 32 + k];
-                s++;
-            }
-        }
-        return;
-    }
-    // tile-local 8-connected labelling, one foreground pixel at a time (a tile holds a few hundred of them).
-    // Backward neighbours W, NW, N, NE inside the tile are tested on the shared-memory map; the W neighbour's
-    // slot is simply i - 1, the others come from the per-word prefixes.  Links that leave the tile are made
-    // later by k_ccl_border.
-    for (uint32_t i = t; i < total; i += 256) s_parent[i] = i;
-    __syncthreads();
-    {
-        const uint32_t unx = (uint32_t)nx;
-        const bool pow2 = (unx & (unx - 1u)) == 0;
-        for (uint32_t i = t; i < total; i += 256) {
-            const uint32_t p = s_pos[i];                              // pixel within the tile
-            const uint32_t gp = (uint32_t)base + p;
-            const uint32_t col = pow2 ? (gp & (unx - 1u)) : (gp % unx);
-            if (col > 0 && p >= 1 && ((s_mask[(p - 1) >> 5] >> ((p - 1) & 31)) & 1u)) uf_union(s_parent, i, i - 1);
-            if (p + 1 < unx) continue;                                // the whole row above is outside the tile
-            // bits q-1, q, q+1 of the row above (q = p - nx); q - 1 may be -1 and q + 1 may leave the row
-            const int q = (int)p - (int)unx;
-            uint32_t nb = 0;                                          // bit 0 = NW, 1 = N, 2 = NE
-            if (q >= 1 && col > 0) nb |= (s_mask[(q - 1) >> 5] >> ((q - 1) & 31)) & 1u;
-            if (q >= 0) nb |= ((s_mask[q >> 5] >> (q & 31)) & 1u) << 1;
-            if (col + 1 < unx) nb |= ((s_mask[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u) << 2;
-            if (!nb) continue;
-            if (nb & 2u) {
-                // N is set: NW and NE are horizontally adjacent to N, their own W-links connect them
-                const uint32_t w = (uint32_t)q >> 5;
-                uf_union(s_parent, i, s_wpre[w] + __popc(s_mask[w] & ((1u << (q & 31)) - 1u)));
-            } else {
-                if (nb & 1u) {
-                    const uint32_t w = (uint32_t)(q - 1) >> 5;
-                    uf_union(s_parent, i, s_wpre[w] + __popc(s_mask[w] & ((1u << ((q - 1) & 31)) - 1u)));
-                }
-                if (nb & 4u) {
-                    const uint32_t w = (uint32_t)(q + 1) >> 5;
-                    uf_union(s_parent, i, s_wpre[w] + __popc(s_mask[w] & ((1u << ((q + 1) & 31)) - 1u)));
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // flatten; L2 folds every member's value into its root (values of non-roots are never written again)
-    for (uint32_t i = t; i < total; i += 256) {
-        const uint32_t r = uf_find_ro(s_parent, i);
-        if (r != i) {
-            s_parent[i] = r;
-            if (CCL == 1) {
-                if (stat_sum) atomicAdd(&s_acc[r], s_acc[i]);
-                else atomicMax(&s_acc[r], s_acc[i]);
-            }
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = t; i < total; i += 256) {
-        const uint32_t r = s_parent[i];
-        parent[sbase + i] = r == i ? (uint32_t)base + i : (((uint32_t)base + r) | UF_FLAG);
-        if (CCL == 1) acc[sbase + i] = s_acc[i];
-    }
 }
 
 template <typename T>
-static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, int ccl, const void *frames,
-                                 const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre,
-                                 uint8_t *tileovf, void *vals, uint32_t *parent, uint32_t *acc, int stat_sum,
-                                 cudaStream_t st)
+static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, const void *frames, const void *thr, int F,
+                                 uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre, void *vals, cudaStream_t st)
 {
     const int vec_ok = ((g.P * sizeof(T)) % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)thr % 16 == 0);
     dim3 grid(F, g.NT), block(256);
-#define RC_K1(VM, C)                                                                                          \
-    k_reduce_tiles<T, VM, C><<<grid, block, 0, st>>>((const T *)frames, (const T *)thr, g.P, g.NT, g.MS, g.ny, \
-                                                     g.nx, maps, tilecnt, wordpre, tileovf, (T *)vals, parent, \
-                                                     acc, stat_sum, vec_ok)
-    if (valmode == 0) RC_K1(0, 0);
-    else if (valmode == 1) RC_K1(1, 0);
-    else if (ccl == 1) RC_K1(2, 1);
-    else if (ccl == 2) RC_K1(2, 2);
-    else RC_K1(2, 0);
+#define RC_K1(VM)                                                                                          \
+    k_reduce_tiles<T, VM><<<grid, block, 0, st>>>((const T *)frames, (const T *)thr, g.P, g.NT, g.MS, maps, \
+                                                  tilecnt, wordpre, vals, vec_ok)
+    if (valmode == 0) RC_K1(0);
+    else if (valmode == 1) RC_K1(1);
+    else RC_K1(2);
 #undef RC_K1
     RC_LAUNCH_CHECK(ctx, "k_reduce_tiles");
     return 0;
 }
 
-int launch_reduce_tiles(rc_ctx *ctx, const Geom &g, int itemsize, int valmode, int ccl, const void *frames,
-                        const void *thr, int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre,
-                        uint8_t *tileovf, void *vals, uint32_t *parent, uint32_t *acc, int stat_sum, cudaStream_t st)
+int launch_reduce_tiles(rc_ctx *ctx, const Geom &g, int itemsize, int valmode, const void *frames, const void *thr,
+                        int F, uint32_t *maps, uint32_t *tilecnt, uint16_t *wordpre, void *vals, cudaStream_t st)
 {
     if (F <= 0) return 0;
     if (itemsize == 2)
-        return launch_reduce_tiles_t<uint16_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, wordpre, tileovf,
-                                               vals, parent, acc, stat_sum, st);
-    return launch_reduce_tiles_t<uint8_t>(ctx, g, valmode, ccl, frames, thr, F, maps, tilecnt, wordpre, tileovf, vals,
-                                          parent, acc, stat_sum, st);
+        return launch_reduce_tiles_t<uint16_t>(ctx, g, valmode, frames, thr, F, maps, tilecnt, wordpre, vals, st);
+    return launch_reduce_tiles_t<uint8_t>(ctx, g, valmode, frames, thr, F, maps, tilecnt, wordpre, vals, st);
 }
 
 // ---- map-only tile counts (read side: a map came out of inflate) ------------------------------
