@@ -40,8 +40,9 @@
 // labelled here: it gets parent[slot] = slot, acc[slot] = value, tileovf = 1 and k_ccl_border links all of
 // its pixels with the global word-parallel path.
 constexpr int CCL_CAP = 2048;          // foreground pixels per tile handled in shared memory
-constexpr int CCL_LINKS = 3072;        // tile-local links
+constexpr int CCL_LINKS = 2560;        // tile-local links
 constexpr int CCL_XCAP = 256;          // cross-tile links per tile (global list)
+constexpr int CCL_HALO = 264;          // map words kept in front of the tile (multiple of 4): nx <= 8447
 constexpr int CCL_THREADS = 256;
 
 // FOLD: 0 = labels only (L4), 1 = L2 max, 2 = L2 sum
@@ -52,7 +53,9 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
             uint32_t *__restrict__ xcount, uint2 *__restrict__ xlinks, uint32_t *__restrict__ parent_all,
             uint32_t *__restrict__ acc_all, int ny, int nx)
 {
-    __shared__ __align__(16) uint32_t s_mask[TILE_WORDS];
+    // map words of the tile preceded by a halo: the CCL_HALO words before the tile (zeros before the frame),
+    // so that the W / NW / N / NE probes of every pixel are plain shared-memory reads
+    __shared__ __align__(16) uint32_t s_maskx[CCL_HALO + TILE_WORDS];
     __shared__ __align__(16) uint16_t s_wpre[TILE_WORDS];
     __shared__ uint32_t s_parent[CCL_CAP];
     __shared__ uint32_t s_acc[FOLD ? CCL_CAP : 1];
@@ -61,20 +64,29 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     __shared__ uint32_t s_nlinks, s_nx, s_bad;
     const int tile = blockIdx.x, f = blockIdx.y, t = threadIdx.x, lane = t & 31;
     const size_t ti = (size_t)f * NT + tile;
-    const uint32_t total = tilecnt[ti];
     const uint32_t base = (uint32_t)tile << TILE_LOG2;
     const size_t sbase = (size_t)f * ((size_t)NT * TILE_PX) + base;
+    const size_t wo = (size_t)f * MS + (size_t)tile * TILE_WORDS;
     uint32_t *parent = parent_all + sbase;
     const uint32_t *vp = vp_all + sbase;
+    const uint32_t *s_mask = s_maskx + CCL_HALO;
+    // issue the tile's loads before the (dependent) per-pixel ones
+    const uint4 r_map = reinterpret_cast<const uint4 *>(maps + wo)[t];
+    uint4 r_wpre = make_uint4(0, 0, 0, 0), r_halo = make_uint4(0, 0, 0, 0);
+    if (t < TILE_WORDS / 8) r_wpre = reinterpret_cast<const uint4 *>(wordpre_all + wo)[t];
+    if (t < CCL_HALO / 4 && tile > 0) r_halo = reinterpret_cast<const uint4 *>(maps + wo - CCL_HALO)[t];
+    const uint32_t total = tilecnt[ti];
     if (total == 0) {
         if (t == 0) { tileovf[ti] = 0; xcount[ti] = 0; }
         return;
     }
-    bool overflow = total > (uint32_t)CCL_CAP;
+    const uint32_t unx = (uint32_t)nx;
+    // the probes reach nx + 1 pixels back; wider frames than the halo covers take the global path
+    bool overflow = total > (uint32_t)CCL_CAP || unx + 1 > (uint32_t)CCL_HALO * 32;
     if (!overflow) {
-        const size_t wo = (size_t)f * MS + (size_t)tile * TILE_WORDS;
-        reinterpret_cast<uint4 *>(s_mask)[t] = reinterpret_cast<const uint4 *>(maps + wo)[t];
-        if (t < TILE_WORDS / 8) reinterpret_cast<uint4 *>(s_wpre)[t] = reinterpret_cast<const uint4 *>(wordpre_all + wo)[t];
+        reinterpret_cast<uint4 *>(s_maskx + CCL_HALO)[t] = r_map;
+        if (t < TILE_WORDS / 8) reinterpret_cast<uint4 *>(s_wpre)[t] = r_wpre;
+        if (t < CCL_HALO / 4) reinterpret_cast<uint4 *>(s_maskx)[t] = r_halo;
         for (uint32_t i = t; i < total; i += CCL_THREADS) {
             const uint32_t v = vp[i];
             s_pos[i] = (uint16_t)v;
@@ -85,11 +97,9 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
         __syncthreads();
 
         // ---- phase 1: link detection
-        const uint32_t unx = (uint32_t)nx;
         const bool pow2 = (unx & (unx - 1u)) == 0;
-        const uint32_t *gmap = maps + (size_t)f * MS;
-        const uint16_t *gwpre = wordpre_all + (size_t)f * MS;
         uint2 *xl = xlinks + ti * CCL_XCAP;
+        constexpr uint32_t HP = CCL_HALO * 32;         // halo pixels
         for (uint32_t i0 = 0; i0 < total; i0 += CCL_THREADS) {
             const uint32_t i = i0 + t;
             uint32_t l0 = 0, l1 = 0, l2 = 0;           // local links found by this pixel: (i << 16) | other
@@ -98,60 +108,38 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
                 const uint32_t p = s_pos[i];
                 const uint32_t gp = base + p;
                 const uint32_t col = pow2 ? (gp & (unx - 1u)) : (gp % unx);
-                if (p > unx) {
-                    // common case: all four backward neighbours are inside the tile
-                    const uint32_t q = p - unx;
-                    const uint32_t bw = (s_mask[(p - 1) >> 5] >> ((p - 1) & 31)) & 1u;
-                    const uint32_t bnw = (s_mask[(q - 1) >> 5] >> ((q - 1) & 31)) & 1u;
-                    const uint32_t bn = (s_mask[q >> 5] >> (q & 31)) & 1u;
-                    const uint32_t bne = (s_mask[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u;
-                    const bool hl = col > 0, hr = col + 1 < unx;
-                    if (bw && hl) { l0 = (i << 16) | (i - 1); n = 1; }
-                    uint32_t qa = 0xffffffffu, qb = 0xffffffffu;
-                    if (bn) qa = q;
+                const bool hl = col > 0, hr = col + 1 < unx, up = gp >= unx;
+                const uint32_t e = p + HP;             // pixel index in the halo-extended map
+                const uint32_t q = e - unx;            // >= 0: the halo covers nx + 1 pixels
+                const uint32_t bw = (s_maskx[(e - 1) >> 5] >> ((e - 1) & 31)) & 1u;
+                const uint32_t bnw = (s_maskx[(q - 1) >> 5] >> ((q - 1) & 31)) & 1u;
+                const uint32_t bn = (s_maskx[q >> 5] >> (q & 31)) & 1u;
+                const uint32_t bne = (s_maskx[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u;
+                // up to three links: W, and N or (NW, NE) -- NW / NE are implied when N is set
+                uint32_t c0 = 0xffffffffu, c1 = 0xffffffffu, c2 = 0xffffffffu;
+                if (bw && hl) c0 = e - 1;
+                if (up) {
+                    if (bn) c1 = q;
                     else {
-                        if (bnw && hl) qa = q - 1;
-                        if (bne && hr) qb = q + 1;
+                        if (bnw && hl) c1 = q - 1;
+                        if (bne && hr) c2 = q + 1;
                     }
-                    if (qa != 0xffffffffu) {
-                        const uint32_t w = qa >> 5;
-                        const uint32_t s = s_wpre[w] + __popc(s_mask[w] & ((1u << (qa & 31)) - 1u));
-                        if (n) l1 = (i << 16) | s; else l0 = (i << 16) | s;
+                }
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const uint32_t ce = c == 0 ? c0 : (c == 1 ? c1 : c2);
+                    if (ce == 0xffffffffu) continue;
+                    if (ce >= HP) {
+                        const uint32_t ql = ce - HP, w = ql >> 5;
+                        const uint32_t s = c == 0 ? i - 1 : s_wpre[w] + __popc(s_mask[w] & ((1u << (ql & 31)) - 1u));
+                        const uint32_t en = (i << 16) | s;
+                        if (n == 0) l0 = en; else if (n == 1) l1 = en; else l2 = en;
                         n++;
-                    }
-                    if (qb != 0xffffffffu) {
-                        const uint32_t w = qb >> 5;
-                        const uint32_t s = s_wpre[w] + __popc(s_mask[w] & ((1u << (qb & 31)) - 1u));
-                        if (n == 0) l0 = (i << 16) | s; else if (n == 1) l1 = (i << 16) | s; else l2 = (i << 16) | s;
-                        n++;
-                    }
-                } else {
-                    // first rows of the tile: a neighbour may belong to an earlier tile (global lookup)
-                    const bool hl = col > 0, hr = col + 1 < unx, up = gp >= unx;
-                    uint32_t cand[3];
-                    int nc = 0;
-                    if (hl && ((gmap[(gp - 1) >> 5] >> ((gp - 1) & 31)) & 1u)) cand[nc++] = gp - 1;
-                    if (up) {
-                        const uint32_t gq = gp - unx;
-                        if ((gmap[gq >> 5] >> (gq & 31)) & 1u) cand[nc++] = gq;
-                        else {
-                            if (hl && ((gmap[(gq - 1) >> 5] >> ((gq - 1) & 31)) & 1u)) cand[nc++] = gq - 1;
-                            if (hr && ((gmap[(gq + 1) >> 5] >> ((gq + 1) & 31)) & 1u)) cand[nc++] = gq + 1;
-                        }
-                    }
-                    for (int c = 0; c < nc; c++) {
-                        const uint32_t gq = cand[c];
-                        if (gq >= base) {
-                            const uint32_t ql = gq - base, w = ql >> 5;
-                            const uint32_t s = s_wpre[w] + __popc(s_mask[w] & ((1u << (ql & 31)) - 1u));
-                            const uint32_t e = (i << 16) | s;
-                            if (n == 0) l0 = e; else if (n == 1) l1 = e; else l2 = e;
-                            n++;
-                        } else {
-                            const uint32_t k = atomicAdd(&s_nx, 1u);
-                            if (k < (uint32_t)CCL_XCAP) xl[k] = make_uint2(base + i, slot_of(gmap, gwpre, gq));
-                            else s_bad = 1;
-                        }
+                    } else {
+                        // neighbour in an earlier tile: (slot, neighbour PIXEL); k_ccl_border resolves its slot
+                        const uint32_t k = atomicAdd(&s_nx, 1u);
+                        if (k < (uint32_t)CCL_XCAP) xl[k] = make_uint2(base + i, base - (HP - ce));
+                        else s_bad = 1;
                     }
                 }
             }
@@ -261,10 +249,13 @@ k_ccl_border(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__res
     if (!tileovf[ti]) {
         const uint32_t n = xcount[ti];
         const uint2 *xl = xlinks + ti * CCL_XCAP;
+        const uint32_t *map = maps + (size_t)f * MS;
+        const uint16_t *wordpre = wordpre_all + (size_t)f * MS;
         for (uint32_t j = lane; j < n; j += 32) {
-            const uint2 e = xl[j];
-            if (PASS == 0) uf_union(parent, e.x, e.y);
-            else FoldAct{parent, acc, sum}(e.x, e.y);
+            const uint2 e = xl[j];                       // (slot in this tile, neighbour pixel in an earlier tile)
+            const uint32_t sq = slot_of(map, wordpre, e.y);
+            if (PASS == 0) uf_union(parent, e.x, sq);
+            else FoldAct{parent, acc, sum}(e.x, sq);
         }
         return;
     }

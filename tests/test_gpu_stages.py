@@ -206,7 +206,7 @@ def _cross_tile_frames(ny, nx, rng, vmax):
 
 
 @pytest.mark.parametrize('stat', [0, 2])
-@pytest.mark.parametrize('ny,nx', [(512, 512), (300, 1000), (257, 4096), (1030, 96), (200, 333)])
+@pytest.mark.parametrize('ny,nx', [(512, 512), (300, 1000), (257, 4096), (1030, 96), (200, 333), (9, 9000)])
 def test_l2_cross_tile_puddles(ny, nx, stat):
     rng = np.random.default_rng(ny * 7 + nx + stat)
     frames = _cross_tile_frames(ny, nx, rng, 4095)
