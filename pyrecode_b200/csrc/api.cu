@@ -86,9 +86,9 @@ struct CompressWs {
     uint32_t *maps;
     uint8_t *packed;
     uint32_t *packed_bytes;
-    uint64_t *in_off;
-    uint32_t *in_bytes;
-    DeflateWs d;
+    uint64_t *map_off, *val_off;
+    uint32_t *map_len, *val_len;
+    DeflateWs dm, dv;              // deflate groups: map streams, value streams (one stream per frame each)
     size_t packed_stride;
     int spf;
 };
@@ -102,26 +102,25 @@ static CompressWs carve_compress(Carver &c, const rc_config *cfg, const Geom &g)
     w.maps = c.take<uint32_t>(F * g.MS + 16);
     w.packed = c.take<uint8_t>(F * w.packed_stride + 16);
     w.packed_bytes = c.take<uint32_t>(F + 1);
-    w.in_off = c.take<uint64_t>(F * 2 + 1);
-    w.in_bytes = c.take<uint32_t>(F * 2 + 1);
-    const size_t chunks = F * ((g.map_bytes + DF_CHUNK - 1) / DF_CHUNK) +
-                          (w.spf == 2 ? F * ((w.packed_stride + DF_CHUNK - 1) / DF_CHUNK) : 0);
-    w.d = carve_deflate_ws(c, (int)F * w.spf, chunks, cfg->rc_operation_mode == 1);
+    w.map_off = c.take<uint64_t>(F + 1);
+    w.val_off = c.take<uint64_t>(F + 1);
+    w.map_len = c.take<uint32_t>(F + 1);
+    w.val_len = c.take<uint32_t>(F + 1);
+    const bool scratch = cfg->rc_operation_mode == 1;
+    w.dm = carve_deflate_ws(c, (int)F, F * ((g.map_bytes + DF_CHUNK - 1) / DF_CHUNK), scratch);
+    w.dv = carve_deflate_ws(c, (int)F, w.spf == 2 ? F * ((w.packed_stride + DF_CHUNK - 1) / DF_CHUNK) : 1,
+                            scratch && w.spf == 2);
     return w;
 }
 
-__global__ void k_stream_desc(const uint8_t *base, const uint32_t *maps, size_t MS, uint32_t map_bytes,
-                              const uint8_t *packed, size_t packed_stride, const uint32_t *packed_bytes, int F, int spf,
-                              uint64_t *in_off, uint32_t *in_bytes)
+// stream f of a deflate group: base + f * stride, len[f] bytes (uniform when len == nullptr)
+__global__ void k_stream_desc(const uint8_t *base, const uint8_t *first, size_t stride, const uint32_t *len,
+                              uint32_t uniform_len, int F, uint64_t *in_off, uint32_t *in_bytes)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
-    in_off[f * spf] = (uint64_t)((const uint8_t *)(maps + (size_t)f * MS) - base);
-    in_bytes[f * spf] = map_bytes;
-    if (spf == 2) {
-        in_off[f * spf + 1] = (uint64_t)(packed + (size_t)f * packed_stride - base);
-        in_bytes[f * spf + 1] = packed_bytes[f];
-    }
+    in_off[f] = (uint64_t)(first + (size_t)f * stride - base);
+    in_bytes[f] = len ? len[f] : uniform_len;
 }
 
 // ---- lifecycle ---------------------------------------------------------------------------------
@@ -147,6 +146,11 @@ extern "C" void rc_destroy(rc_ctx *ctx)
 {
     if (!ctx) return;
     if (ctx->profile) for (int i = 0; i < RC_MAX_MARKS; i++) cudaEventDestroy(ctx->marks[i]);
+    if (ctx->side_ready) {
+        cudaStreamDestroy(ctx->side);
+        cudaEventDestroy(ctx->ev_fork);
+        cudaEventDestroy(ctx->ev_join);
+    }
     free(ctx);
 }
 
@@ -245,28 +249,32 @@ extern "C" int rc_make_threshold(rc_ctx *ctx, const rc_config *cfg, const void *
     return launch_make_threshold(ctx, cfg->itemsize, d_dark, eps, d_thr, (size_t)cfg->ny * cfg->nx, (cudaStream_t)stream);
 }
 
-// shared body of rc_reduce / rc_reduce_compress
-static int run_reduce(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const ReduceWs &w, const void *frames, int F,
-                      const void *thr, uint32_t *maps, uint8_t *packed, size_t packed_stride, uint32_t *packed_bytes,
-                      uint32_t *counts, cudaStream_t st)
+// The reduction in two stages.  Stage 1 is the streaming kernel (threshold, binary map, value compaction); for
+// L1 / L2 / L3 the binary map is final after it.  Stage 2 is everything that follows on the compact data.
+static int reduce_stage1(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const ReduceWs &w, const void *frames, int F,
+                         const void *thr, uint32_t *maps, cudaStream_t st)
+{
+    const int level = cfg->reduction_level, isz = cfg->itemsize;
+    if (level == 1) return launch_reduce_tiles(ctx, g, isz, 1, frames, thr, F, maps, w.tilecnt, w.wordpre, w.vals, st);
+    if (level == 3) return launch_reduce_tiles(ctx, g, isz, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, nullptr, st);
+    if (level == 2) return launch_reduce_tiles(ctx, g, isz, 2, frames, thr, F, maps, w.tilecnt, w.wordpre, w.vals, st);
+    // level 4: the threshold map goes to map1, the centroid map (stage 2) to maps
+    return launch_reduce_tiles(ctx, g, isz, 2, frames, thr, F, w.map1, w.tilecnt, w.wordpre, w.vals, st);
+}
+
+static int reduce_stage2(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const ReduceWs &w, int F, uint32_t *maps,
+                         uint8_t *packed, size_t packed_stride, uint32_t *packed_bytes, uint32_t *counts,
+                         cudaStream_t st)
 {
     const int level = cfg->reduction_level, b = cfg->bit_depth, isz = cfg->itemsize;
     int rc;
     if (level == 1) {
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 1, frames, thr, F, maps, w.tilecnt, w.wordpre, w.vals, st))) return rc;
-        rc_mark(ctx, 1, st);
         if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, packed_bytes, b, st))) return rc;
         return launch_bitpack(ctx, g, isz, w.vals, w.tilepre, F, b, packed, packed_stride, st);
     }
-    if (level == 3) {
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 0, frames, thr, F, maps, w.tilecnt, w.wordpre, nullptr, st))) return rc;
-        rc_mark(ctx, 1, st);
-        return launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, nullptr, 0, st);
-    }
+    if (level == 3) return launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, nullptr, 0, st);
     if (level == 2) {
         const int sum = cfg->l2_statistics == 2;
-        if ((rc = launch_reduce_tiles(ctx, g, isz, 2, frames, thr, F, maps, w.tilecnt, w.wordpre, w.vals, st))) return rc;
-        rc_mark(ctx, 1, st);
         if ((rc = launch_ccl_tiles(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf,
                                    w.xcount, w.xlinks, w.parent, w.acc, F, st))) return rc;
         if ((rc = launch_ccl_border(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, w.acc,
@@ -276,21 +284,39 @@ static int run_reduce(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const Re
         if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, packed_bytes, b, st))) return rc;
         return launch_bitpack(ctx, g, 2, w.stats16, w.rootpre, F, b, packed, packed_stride, st);
     }
-    // level 4: threshold map -> map1, centroid map -> maps
-    if ((rc = launch_reduce_tiles(ctx, g, isz, 2, frames, thr, F, w.map1, w.tilecnt, w.wordpre, w.vals, st))) return rc;
-    rc_mark(ctx, 1, st);
     if ((rc = launch_ccl_tiles(ctx, g, 0, w.map1, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf, w.xcount,
                                w.xlinks, w.parent, nullptr, F, st))) return rc;
     if ((rc = launch_ccl_border(ctx, g, 0, w.map1, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, nullptr, F,
                                 st))) return rc;
     if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, w.bbox, F, st))) return rc;
     RC_CUDA(ctx, cudaMemsetAsync(maps, 0, (size_t)F * g.MS * sizeof(uint32_t), st));
-    if ((rc = launch_l4_centroids(ctx, g, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox, (const uint32_t *)w.vals, maps,
-                                  nullptr, F, st))) return rc;
+    if ((rc = launch_l4_centroids(ctx, g, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox,
+                                  (const uint32_t *)w.vals, maps, nullptr, F, st))) return rc;
     // puddle count = number of roots
     if ((rc = launch_ccl_roots(ctx, g, 3, w.tilecnt, w.parent, nullptr, nullptr, w.rootcnt, nullptr, nullptr, nullptr,
                                F, st))) return rc;
     return launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, nullptr, 0, st);
+}
+
+// one deflate group (F streams): descriptors, then encode (wrap = 1) or size (wrap = 0) its chunks
+static int deflate_group(rc_ctx *ctx, const rc_config *cfg, const uint8_t *base, const uint8_t *first, size_t stride,
+                         const uint32_t *len, uint32_t uniform_len, int F, uint64_t *in_off, uint32_t *in_bytes,
+                         const DeflateWs &d, cudaStream_t st)
+{
+    k_stream_desc<<<(F + 127) / 128, 128, 0, st>>>(base, first, stride, len, uniform_len, F, in_off, in_bytes);
+    RC_LAUNCH_CHECK(ctx, "k_stream_desc");
+    return launch_deflate_streams(ctx, cfg->compression_level, cfg->rc_operation_mode == 1, base, in_off, in_bytes, F, d,
+                                  st);
+}
+
+static int ensure_side_stream(rc_ctx *ctx)
+{
+    if (ctx->side_ready) return 0;
+    RC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    RC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    RC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    ctx->side_ready = 1;
+    return 0;
 }
 
 extern "C" int rc_reduce(rc_ctx *ctx, const rc_config *cfg, const void *d_frames, int n_frames, const void *d_thr,
@@ -304,8 +330,10 @@ extern "C" int rc_reduce(rc_ctx *ctx, const rc_config *cfg, const void *d_frames
     const Geom g = make_geom(cfg->ny, cfg->nx);
     Carver c(d_workspace);
     const ReduceWs w = carve_reduce(c, cfg, g, 0);
-    return run_reduce(ctx, cfg, g, w, d_frames, n_frames, d_thr, d_maps, d_packed, packed_stride_of(cfg), d_packed_bytes,
-                      d_counts, (cudaStream_t)stream);
+    int rc;
+    if ((rc = reduce_stage1(ctx, cfg, g, w, d_frames, n_frames, d_thr, d_maps, (cudaStream_t)stream))) return rc;
+    return reduce_stage2(ctx, cfg, g, w, n_frames, d_maps, d_packed, packed_stride_of(cfg), d_packed_bytes, d_counts,
+                         (cudaStream_t)stream);
 }
 
 extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void *d_frames, int n_frames,
@@ -329,23 +357,42 @@ extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void 
         RC_CUDA(ctx, cudaMemsetAsync(d_record_offsets, 0, sizeof(uint64_t), st));
         return 0;
     }
-    rc_mark(ctx, 0, st);
-    if ((rc = run_reduce(ctx, cfg, g, w, d_frames, F, d_thr, cw.maps, cw.packed, cw.packed_stride, cw.packed_bytes,
-                         d_counts, st))) return rc;
-    rc_mark(ctx, 2, st);
-    const int S = F * cw.spf;
     const uint8_t *base = (const uint8_t *)d_workspace;
-    k_stream_desc<<<(F + 127) / 128, 128, 0, st>>>(base, cw.maps, g.MS, (uint32_t)g.map_bytes, cw.packed, cw.packed_stride,
-                                                  cw.packed_bytes, F, cw.spf, cw.in_off, cw.in_bytes);
-    RC_LAUNCH_CHECK(ctx, "k_stream_desc");
-    const int wrap = cfg->rc_operation_mode == 1;
-    if ((rc = launch_deflate_streams(ctx, cfg->compression_level, wrap, base, cw.in_off, cw.in_bytes, S, cw.d, st))) return rc;
+    const int level = cfg->reduction_level;
+    // The map streams of L1 / L2 / L3 are final after stage 1: they are deflated on the side stream while the main
+    // stream labels puddles and packs the values.  (L4's map is the last product of stage 2.)
+    const bool fork = level != 4 && F > 0;
+    rc_mark(ctx, 0, st);
+    if ((rc = reduce_stage1(ctx, cfg, g, w, d_frames, F, d_thr, cw.maps, st))) return rc;
+    rc_mark(ctx, 1, st);
+    cudaStream_t sm = st;
+    if (fork) {
+        if ((rc = ensure_side_stream(ctx))) return rc;
+        sm = ctx->side;
+        RC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        RC_CUDA(ctx, cudaStreamWaitEvent(sm, ctx->ev_fork, 0));
+        if ((rc = deflate_group(ctx, cfg, base, (const uint8_t *)cw.maps, g.MS * 4, nullptr, (uint32_t)g.map_bytes, F,
+                                cw.map_off, cw.map_len, cw.dm, sm))) return rc;
+        RC_CUDA(ctx, cudaEventRecord(ctx->ev_join, sm));
+    }
+    if ((rc = reduce_stage2(ctx, cfg, g, w, F, cw.maps, cw.packed, cw.packed_stride, cw.packed_bytes, d_counts, st)))
+        return rc;
+    rc_mark(ctx, 2, st);
+    if (!fork && (rc = deflate_group(ctx, cfg, base, (const uint8_t *)cw.maps, g.MS * 4, nullptr, (uint32_t)g.map_bytes,
+                                     F, cw.map_off, cw.map_len, cw.dm, st))) return rc;
+    if (cw.spf == 2 && (rc = deflate_group(ctx, cfg, base, cw.packed, cw.packed_stride, cw.packed_bytes, 0, F, cw.val_off,
+                                           cw.val_len, cw.dv, st))) return rc;
+    if (fork) RC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     rc_mark(ctx, 3, st);
-    if ((rc = launch_layout_records(ctx, cw.d, cw.packed_bytes, F, cw.spf, cfg->rc_operation_mode, first_frame_id,
+    const int wrap = cfg->rc_operation_mode == 1;
+    if ((rc = launch_layout_records(ctx, cw.dm, cw.dv, cw.packed_bytes, F, cw.spf, cfg->rc_operation_mode, first_frame_id,
                                     d_records, records_capacity, d_record_offsets, d_status, st))) return rc;
-    rc = launch_copy_pieces(ctx, cw.d, wrap, base, cw.in_off, cw.in_bytes, S, d_records, records_capacity, d_status, st);
+    if ((rc = launch_copy_pieces(ctx, cw.dm, wrap, base, cw.map_off, cw.map_len, F, d_records, records_capacity, d_status,
+                                 st))) return rc;
+    if (cw.spf == 2 && (rc = launch_copy_pieces(ctx, cw.dv, wrap, base, cw.val_off, cw.val_len, F, d_records,
+                                                records_capacity, d_status, st))) return rc;
     rc_mark(ctx, 4, st);
-    return rc;
+    return 0;
 }
 
 extern "C" int rc_ccl_label(rc_ctx *ctx, const rc_config *cfg, const uint32_t *d_maps, int n_frames, void *d_workspace,

@@ -48,6 +48,10 @@ struct rc_ctx {
     int n_marks;
     cudaEvent_t marks[RC_MAX_MARKS];
     bool deflate_attr_set;
+    // side stream: the map streams are deflated while the main stream still labels puddles / packs values
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join;
+    int side_ready;
 };
 
 static inline void rc_mark(rc_ctx *ctx, int idx, cudaStream_t st)

@@ -202,6 +202,7 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
 
         stage_chunk(S.in32, in + in_off[s] + (size_t)ci * DF_CHUNK, clen, t);
         uint32_t body_bits = 0;
+        DfMasks tm{0, 0, 0};
         bool stored = level == 0;
         if (!stored) {
             const DeflateTable &T = tables[s];
@@ -216,7 +217,8 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
             df_load_table(S, T, t, DF_THREADS);
             if (t == 0) S.header_bits = hb;
             __syncthreads();
-            df_phase_size(S, t, clen);
+            tm = df_phase_masks(S, t, clen);
+            df_phase_size_m(S, t, tm);
             uint32_t tok_bits;
             const uint32_t e = block_excl_scan<8>(S.tbits[t], s_warp, &tok_bits);
             S.tbits[t] = e;
@@ -228,7 +230,7 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
         }
 
         if (!stored) {
-            df_phase_emit(S, t, clen);
+            df_phase_emit_m(S, t, tm);
             __syncthreads();
             if (t == 0) df_phase_finish(S, body_bits);
         } else {
@@ -311,12 +313,15 @@ __device__ __forceinline__ void put_u32le(uint8_t *p, uint32_t v)
     p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
 }
 
-// ReCoDe records.  streams_per_frame = 2 (L1/L2: map, vals) or 1 (L3/L4: map); stream index = f*spf + j.
+// ReCoDe records.  streams_per_frame = 2 (L1/L2: map, vals) or 1 (L3/L4: map).  The map streams and the value
+// streams are two separate deflate groups (they are encoded on different CUDA streams): stream f of each.
 // mode 1 header: [frame_id][n_comp_map]([n_comp_vals][n_packed]); mode 0 header: [frame_id]([n_packed]).
 __global__ void __launch_bounds__(256)
-k_layout_records(const uint32_t *__restrict__ stream_bytes, const uint32_t *__restrict__ packed_bytes, int n_frames,
+k_layout_records(const uint32_t *__restrict__ map_bytes, const uint32_t *__restrict__ val_bytes,
+                 const uint32_t *__restrict__ packed_bytes, int n_frames,
                  int spf, int mode, uint32_t first_frame_id, size_t capacity, uint8_t *__restrict__ records,
-                 uint64_t *__restrict__ record_off, uint64_t *__restrict__ stream_dst, uint32_t *__restrict__ status)
+                 uint64_t *__restrict__ record_off, uint64_t *__restrict__ map_dst, uint64_t *__restrict__ val_dst,
+                 uint32_t *__restrict__ status)
 {
     __shared__ uint32_t s_warp[9];
     __shared__ uint64_t s_carry;
@@ -328,8 +333,8 @@ k_layout_records(const uint32_t *__restrict__ stream_bytes, const uint32_t *__re
         const int f = f0 + t;
         uint32_t len = 0, l0 = 0, l1 = 0;
         if (f < n_frames) {
-            l0 = stream_bytes[f * spf];
-            l1 = spf == 2 ? stream_bytes[f * spf + 1] : 0;
+            l0 = map_bytes[f];
+            l1 = spf == 2 ? val_bytes[f] : 0;
             len = hdr + l0 + l1;        // < 2^32: bounded by the records capacity check below
         }
         uint32_t total;
@@ -337,8 +342,8 @@ k_layout_records(const uint32_t *__restrict__ stream_bytes, const uint32_t *__re
         const uint64_t off = s_carry + e;
         if (f < n_frames) {
             record_off[f] = off;
-            stream_dst[f * spf] = off + hdr;
-            if (spf == 2) stream_dst[f * spf + 1] = off + hdr + l0;
+            map_dst[f] = off + hdr;
+            if (spf == 2) val_dst[f] = off + hdr + l0;
             if (off + len <= capacity) {
                 uint8_t *r = records + off;
                 put_u32le(r, first_frame_id + (uint32_t)f);
@@ -508,12 +513,13 @@ int launch_layout_strided(rc_ctx *ctx, const DeflateWs &w, int n_streams, size_t
     return 0;
 }
 
-int launch_layout_records(rc_ctx *ctx, const DeflateWs &w, const uint32_t *packed_bytes, int n_frames, int spf,
-                          int mode, uint32_t first_frame_id, uint8_t *records, size_t capacity,
+int launch_layout_records(rc_ctx *ctx, const DeflateWs &wm, const DeflateWs &wv, const uint32_t *packed_bytes,
+                          int n_frames, int spf, int mode, uint32_t first_frame_id, uint8_t *records, size_t capacity,
                           uint64_t *record_off, uint32_t *status, cudaStream_t st)
 {
-    k_layout_records<<<1, 256, 0, st>>>(w.stream_bytes, packed_bytes, n_frames, spf, mode, first_frame_id, capacity,
-                                        records, record_off, w.stream_dst, status);
+    k_layout_records<<<1, 256, 0, st>>>(wm.stream_bytes, wv.stream_bytes, packed_bytes, n_frames, spf, mode,
+                                        first_frame_id, capacity, records, record_off, wm.stream_dst, wv.stream_dst,
+                                        status);
     RC_LAUNCH_CHECK(ctx, "k_layout_records");
     return 0;
 }

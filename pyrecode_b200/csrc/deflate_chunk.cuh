@@ -112,13 +112,8 @@ DF_HD uint32_t df_bitrev(uint32_t c, int n)
 }
 
 // ---- tokenizer ----------------------------------------------------------------------------------------
-// Walks the nbytes of thread t's segment; E.lit(c) / E.match(L) are called in stream order.
+// E.lit(c) / E.match(L) are called in stream order for the nbytes of thread t's segment.
 // A run never crosses a segment, and the first byte of a chunk is always a literal (chunk independence).
-//
-// Two steps so that the 32 lanes of a warp stay converged: (1) a branch-free pass over the 16 words builds a
-// 64-bit mask of "break" positions (bytes that differ from their predecessor) with SIMD-in-register byte
-// compares; (2) a loop over the set bits only -- one iteration per run boundary instead of one per byte.  On
-// binary maps (85-99 % zero bytes) that is ~8x fewer divergent iterations than a per-byte state machine.
 DF_HD uint32_t df_byte_at(const uint32_t *in32, int t, int pos)
 {
     return (in32[df_in_index(t, pos >> 2)] >> (8 * (pos & 3))) & 0xffu;
@@ -133,14 +128,30 @@ DF_HD uint32_t df_ne_nibble(uint32_t x, uint32_t y)
     return ((z >> 7) * 0x00204081u >> 21) & 0xfu;     // gather bits 0, 8, 16, 24 -> bits 0..3
 }
 
-template <typename E>
-DF_HD void df_tokenize(const uint32_t *in32, int t, int nbytes, E &em)
+// Token masks of thread t's segment (bit i = byte i of the segment):
+//   lit  bytes emitted as literals: bytes that differ from their predecessor, and members of runs shorter than 3
+//   lng  members of runs (>= 3 bytes equal to the byte before the run): covered by a distance-1 match
+//   ms   first byte of each such run = where the match token is emitted; its length is the run of lng bits
+// All of it is branch-free SIMD-in-register work on the 64-bit "same as predecessor" mask, so the 32 lanes of
+// a warp stay converged; the only data-dependent loop left is one iteration per TOKEN (df_for_tokens).
+struct DfMasks {
+    uint64_t lit, ms, lng;
+};
+
+DF_HD int df_ctz64(uint64_t x)
 {
-    if (nbytes <= 0) return;
-    uint32_t prev = 0x100;                           // "no previous byte"
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+
+DF_HD DfMasks df_token_masks(const uint32_t *in32, int t, int nbytes)
+{
+    uint32_t prev = 0x100;                           // "no previous byte": a chunk never looks behind its start
     if (t > 0) prev = in32[df_in_index(t - 1, DF_SEG_WORDS - 1)] >> 24;
-    // step 1: break mask
-    uint64_t brk = 0;
+    uint32_t blo = 0, bhi = 0;                       // break mask: byte differs from its predecessor
     uint32_t carry = prev & 0xffu;
 #ifdef __CUDA_ARCH__
 #pragma unroll
@@ -148,31 +159,45 @@ DF_HD void df_tokenize(const uint32_t *in32, int t, int nbytes, E &em)
     for (int k = 0; k < DF_SEG_WORDS; k++) {
         const uint32_t x = in32[df_in_index(t, k)];
         const uint32_t sh = (x << 8) | carry;         // each byte's predecessor
-        brk |= (uint64_t)df_ne_nibble(x, sh) << (4 * k);
+        const uint32_t nz = df_ne_nibble(x, sh);
+        if (k < 8) blo |= nz << (4 * k); else bhi |= nz << (4 * (k - 8));
         carry = x >> 24;
     }
+    uint64_t brk = ((uint64_t)bhi << 32) | blo;
     if (prev == 0x100) brk |= 1;                     // chunk start: byte 0 is always a literal
-    if (nbytes < DF_SEG) brk &= (1ull << nbytes) - 1;
-    // step 2: one iteration per run boundary
-    int last = -1;                                   // position of the previous break
-    uint32_t v = prev;                               // value of the run in progress
-    while (brk) {
-#ifdef __CUDA_ARCH__
-        const int pos = __ffsll((long long)brk) - 1;
-#else
-        const int pos = __builtin_ctzll(brk);
-#endif
-        brk &= brk - 1;
-        const int run = pos - last - 1;              // bytes equal to v since the previous break
-        if (run >= 3) em.match(run);
-        else for (int i = 0; i < run; i++) em.lit(v);
-        v = df_byte_at(in32, t, pos);
-        em.lit(v);
-        last = pos;
+    const uint64_t valid = nbytes >= DF_SEG ? ~0ull : ((1ull << nbytes) - 1);
+    const uint64_t nb = ~brk & valid;                // same as predecessor
+    const uint64_t a = nb & (nb << 1) & (nb << 2);   // third or later member of a run
+    DfMasks m;
+    m.lng = (a | (a >> 1) | (a >> 2)) & nb;          // every member of a run of >= 3
+    m.lit = valid & ~m.lng;
+    m.ms = m.lng & ~(m.lng << 1);
+    return m;
+}
+
+// E.lit(c) / E.match(L) in stream order, one loop iteration per token
+template <typename E>
+DF_HD void df_for_tokens(const uint32_t *in32, int t, const DfMasks &m, E &em)
+{
+    uint64_t tk = m.lit | m.ms;
+    while (tk) {
+        const int pos = df_ctz64(tk);
+        tk &= tk - 1;
+        if ((m.lit >> pos) & 1) {
+            em.lit(df_byte_at(in32, t, pos));
+        } else {
+            const uint64_t r = ~(m.lng >> pos);
+            em.match(r ? df_ctz64(r) : DF_SEG);
+        }
     }
-    const int run = nbytes - last - 1;
-    if (run >= 3) em.match(run);
-    else for (int i = 0; i < run; i++) em.lit(v);
+}
+
+template <typename E>
+DF_HD void df_tokenize(const uint32_t *in32, int t, int nbytes, E &em)
+{
+    if (nbytes <= 0) return;
+    const DfMasks m = df_token_masks(in32, t, nbytes);
+    df_for_tokens(in32, t, m, em);
 }
 
 DF_HD int df_seg_bytes(int t, int clen)
@@ -418,12 +443,26 @@ struct DfSizeEmit {
     DF_HD void match(int L) { bits += mt[L] >> 24; }
 };
 
-DF_HD void df_phase_size(DfEmitShared &S, int t, int clen)
+// masks computed once per thread (k_deflate_chunks keeps them in registers for the size and the emit pass)
+DF_HD DfMasks df_phase_masks(const DfEmitShared &S, int t, int clen)
 {
     const int nbytes = df_seg_bytes(t, clen);
+    DfMasks m{0, 0, 0};
+    if (nbytes > 0) m = df_token_masks(S.in32, t, nbytes);
+    return m;
+}
+
+DF_HD void df_phase_size_m(DfEmitShared &S, int t, const DfMasks &m)
+{
     DfSizeEmit em{S.cl, S.mt, 0};
-    if (nbytes > 0) df_tokenize(S.in32, t, nbytes, em);
+    df_for_tokens(S.in32, t, m, em);
     S.tbits[t] = em.bits;
+}
+
+DF_HD void df_phase_size(DfEmitShared &S, int t, int clen)
+{
+    const DfMasks m = df_phase_masks(S, t, clen);
+    df_phase_size_m(S, t, m);
 }
 
 struct DfBitEmit {
@@ -448,14 +487,19 @@ struct DfBitEmit {
 };
 
 // S.tbits[t] must hold the exclusive prefix (bit offset relative to the header end)
-DF_HD void df_phase_emit(DfEmitShared &S, int t, int clen)
+DF_HD void df_phase_emit_m(DfEmitShared &S, int t, const DfMasks &m)
 {
-    const int nbytes = df_seg_bytes(t, clen);
-    if (nbytes <= 0) return;
+    if (!(m.lit | m.ms)) return;
     const uint32_t o = S.header_bits + S.tbits[t];
     DfBitEmit em{S.out, S.cl, S.mt, 0, o & 31, o >> 5};
-    df_tokenize(S.in32, t, nbytes, em);
+    df_for_tokens(S.in32, t, m, em);
     em.flush();
+}
+
+DF_HD void df_phase_emit(DfEmitShared &S, int t, int clen)
+{
+    const DfMasks m = df_phase_masks(S, t, clen);
+    df_phase_emit_m(S, t, m);
 }
 
 // body_bits = header + all tokens.  Appends EOB and the sync-flush marker; sets out_bytes.  Single thread.

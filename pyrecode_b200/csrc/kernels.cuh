@@ -62,8 +62,8 @@ int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, const uint8_t *in, 
                            const uint32_t *in_bytes, int n_streams, const DeflateWs &w, cudaStream_t st);
 int launch_layout_strided(rc_ctx *ctx, const DeflateWs &w, int n_streams, size_t stride, uint32_t *out_bytes,
                           cudaStream_t st);
-int launch_layout_records(rc_ctx *ctx, const DeflateWs &w, const uint32_t *packed_bytes, int n_frames, int spf,
-                          int mode, uint32_t first_frame_id, uint8_t *records, size_t capacity,
+int launch_layout_records(rc_ctx *ctx, const DeflateWs &wm, const DeflateWs &wv, const uint32_t *packed_bytes,
+                          int n_frames, int spf, int mode, uint32_t first_frame_id, uint8_t *records, size_t capacity,
                           uint64_t *record_off, uint32_t *status, cudaStream_t st);
 int launch_copy_pieces(rc_ctx *ctx, const DeflateWs &w, int wrap, const uint8_t *raw_in, const uint64_t *in_off,
                        const uint32_t *in_bytes, int n_streams, uint8_t *out, size_t capacity, uint32_t *status,
