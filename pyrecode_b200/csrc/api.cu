@@ -305,8 +305,9 @@ static int deflate_group(rc_ctx *ctx, const rc_config *cfg, const uint8_t *base,
 {
     k_stream_desc<<<(F + 127) / 128, 128, 0, st>>>(base, first, stride, len, uniform_len, F, in_off, in_bytes);
     RC_LAUNCH_CHECK(ctx, "k_stream_desc");
-    return launch_deflate_streams(ctx, cfg->compression_level, cfg->rc_operation_mode == 1, base, in_off, in_bytes, F, d,
-                                  st);
+    // the frames of one batch are statistically alike: levels 1..5 share one sampled code per group
+    return launch_deflate_streams(ctx, cfg->compression_level, cfg->rc_operation_mode == 1, cfg->compression_level < 6,
+                                  base, in_off, in_bytes, F, d, st);
 }
 
 static int ensure_side_stream(rc_ctx *ctx)
@@ -461,7 +462,7 @@ extern "C" int rc_deflate_zlib(rc_ctx *ctx, int compression_level, const uint8_t
     DeflateWs w = carve_deflate_ws(c, n_streams, deflate_max_chunks(n_streams, max_in_bytes), true);
     uint32_t *status = w.counters + 4;
     int rc;
-    if ((rc = launch_deflate_streams(ctx, compression_level, 1, d_in, d_in_offsets, d_in_bytes, n_streams, w, st))) return rc;
+    if ((rc = launch_deflate_streams(ctx, compression_level, 1, 0, d_in, d_in_offsets, d_in_bytes, n_streams, w, st))) return rc;
     if ((rc = launch_layout_strided(ctx, w, n_streams, out_stride, d_out_bytes, st))) return rc;
     return launch_copy_pieces(ctx, w, 1, d_in, d_in_offsets, d_in_bytes, n_streams, d_out, (size_t)n_streams * out_stride,
                               status, st);

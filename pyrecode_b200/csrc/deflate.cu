@@ -5,6 +5,9 @@
 //
 // Pipeline over S input streams (for the writer: 2 per frame, map and packed values):
 //   k_deflate_plan      1 CTA    chunks per stream (16 KiB each), exclusive scan -> chunk_base, total
+//   k_deflate_hist      token histogram: a 1-in-8 sample of the chunks into one shared histogram (levels 1..5)
+//                       or every chunk into per-stream histograms (levels 6..9)
+//   k_deflate_tables    Huffman code + block header, once per group (or per stream)
 //   k_deflate_chunks    persistent CTAs pull chunk tickets; each chunk is an independent, byte-aligned
 //                       piece (deflate_chunk.cuh) written to its scratch slot, plus its Adler-32 partials
 //   k_stream_finalize   1 CTA per stream: prefix of piece sizes, Adler-32 combine, total stream size
@@ -39,6 +42,7 @@ k_deflate_plan(const uint32_t *__restrict__ in_bytes, int n_streams, uint32_t *_
         counters[0] = 0;      // histogram ticket
         counters[1] = 0;      // copy ticket
         counters[2] = 0;      // emit ticket
+        counters[3] = 0;      // bytes tokenized by k_deflate_hist
     }
 }
 
@@ -52,7 +56,7 @@ __device__ __forceinline__ int find_stream(const uint32_t *__restrict__ chunk_ba
     return lo;
 }
 
-// coalesced 128-bit loads of one chunk -> transposed, swizzled shared staging (zero padded past clen)
+// coalesced 128-bit loads of one chunk -> per-thread segments in shared staging (zero padded past clen)
 __device__ __forceinline__ void stage_chunk(uint32_t *in32, const uint8_t *__restrict__ src, int clen, int t)
 {
     const bool aligned = ((uintptr_t)src & 15) == 0;
@@ -71,57 +75,71 @@ __device__ __forceinline__ void stage_chunk(uint32_t *in32, const uint8_t *__res
     }
 }
 
-// pass 1 over every chunk: token histogram summed per stream + per-chunk Adler-32 partials
+// Token histogram.  shared_table = 1 (levels 1..5): every DF_SAMPLE-th chunk of the group is tokenized and all
+// streams share one histogram (ghist[0]); shared_table = 0 (levels 6..9): every chunk, one histogram per stream.
+// counters[3] accumulates the number of input bytes that were tokenized (for the entropy estimate).
+constexpr uint32_t DF_SAMPLE = 8;
+
 __global__ void __launch_bounds__(DF_THREADS)
 k_deflate_hist(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                const uint32_t *__restrict__ in_bytes, int n_streams, const uint32_t *__restrict__ chunk_base,
-               uint32_t *__restrict__ counters, int level, uint32_t *__restrict__ ghist,
-               uint2 *__restrict__ chunk_adler)
+               uint32_t *__restrict__ counters, int shared_table, uint32_t *__restrict__ ghist)
 {
-    __shared__ uint32_t s_in[DF_CHUNK / 4];
+    __shared__ uint32_t s_in[DF_STAGE_WORDS];
     __shared__ uint32_t s_hist[DF_NSYM];
-    __shared__ uint32_t s_adler[2];
     __shared__ uint32_t s_ticket;
     const int t = threadIdx.x;
     const uint32_t total_chunks = chunk_base[n_streams];
+    const uint32_t step = shared_table ? DF_SAMPLE : 1u;
+    const uint32_t n_tasks = (total_chunks + step - 1) / step;
     while (true) {
         if (t == 0) s_ticket = atomicAdd(&counters[0], 1u);
         __syncthreads();
-        const uint32_t gci = s_ticket;
-        if (gci >= total_chunks) break;
+        const uint32_t task = s_ticket;
+        if (task >= n_tasks) break;
+        const uint32_t gci = task * step;
         const int s = find_stream(chunk_base, n_streams, gci);
         const uint32_t ci = gci - chunk_base[s];
         const int clen = (int)min((uint32_t)DF_CHUNK, in_bytes[s] - ci * DF_CHUNK);
         for (int i = t; i < DF_NSYM; i += DF_THREADS) s_hist[i] = 0;
-        if (t < 2) s_adler[t] = 0;
         stage_chunk(s_in, in + in_off[s] + (size_t)ci * DF_CHUNK, clen, t);
         __syncthreads();
-        df_phase_hist(s_in, s_hist, s_adler, t, clen, level > 0);
+        df_phase_hist(s_in, s_hist, t, clen);
         __syncthreads();
-        if (level > 0)
-            for (int i = t; i < DF_NSYM; i += DF_THREADS) {
-                const uint32_t h = s_hist[i];
-                if (h) atomicAdd(&ghist[(size_t)s * DF_NSYM + i], h);
-            }
-        if (t == 0) chunk_adler[gci] = make_uint2(s_adler[0] % 65521u, s_adler[1] % 65521u);
+        uint32_t *gh = ghist + (shared_table ? 0 : (size_t)s * DF_NSYM);
+        for (int i = t; i < DF_NSYM; i += DF_THREADS) {
+            const uint32_t h = s_hist[i];
+            if (h) atomicAdd(&gh[i], h);
+        }
+        if (t == 0) atomicAdd(&counters[3], (uint32_t)clen);
         __syncthreads();
     }
 }
 
-// one CTA per stream: sort the symbols by count (bitonic, 512 keys), build the code and its header
+// one CTA per code: sort the symbols by count (bitonic, 512 keys), build the code and its header.
+// shared_table = 1: a single CTA builds tables[0] from ghist[0], with every producible symbol smoothed to a
+// non-zero count so that chunks that were not sampled can always be encoded.
 __global__ void __launch_bounds__(DF_THREADS)
 k_deflate_tables(const uint32_t *__restrict__ ghist, const uint32_t *__restrict__ chunk_base,
-                 const uint32_t *__restrict__ in_bytes, DeflateTable *__restrict__ tables)
+                 const uint32_t *__restrict__ in_bytes, const uint32_t *__restrict__ counters, int shared_table,
+                 int n_streams, DeflateTable *__restrict__ tables)
 {
     __shared__ DfBuildShared B;
     __shared__ float s_bits[DF_THREADS];
     __shared__ uint32_t s_tok[DF_THREADS];
     __shared__ int s_skip;
     const int s = blockIdx.x, t = threadIdx.x;
-    if (chunk_base[s + 1] == chunk_base[s]) return;          // empty stream: no chunk will ask for a table
-    // Entropy estimate of the token stream: a stream that would shrink by < 3 % (bit-packed intensities are
-    // close to random bytes) is emitted as stored blocks, which skips the code construction and both
-    // tokenizer passes for all of its chunks.
+    uint32_t sampled_bytes;
+    if (shared_table) {
+        if (chunk_base[n_streams] == 0) return;
+        sampled_bytes = counters[3];
+    } else {
+        if (chunk_base[s + 1] == chunk_base[s]) return;      // empty stream: no chunk will ask for a table
+        sampled_bytes = in_bytes[s];
+    }
+    // Entropy estimate of the token stream: data that would shrink by < 3 % (bit-packed intensities are
+    // close to random bytes) is emitted as stored blocks, which skips the code construction and the
+    // tokenizer for all of its chunks.
     {
         uint32_t tok = 0;
         for (int i = t; i < DF_NSYM; i += DF_THREADS) tok += ghist[(size_t)s * DF_NSYM + i];
@@ -140,17 +158,18 @@ k_deflate_tables(const uint32_t *__restrict__ ghist, const uint32_t *__restrict_
         if (t == 0) {
             float b = 0.f;
             for (int i = 0; i < DF_THREADS; i++) b += s_bits[i];
-            s_skip = b * 0.125f + 128.f >= 0.97f * (float)in_bytes[s];
+            s_skip = b * 0.125f + 128.f >= 0.97f * (float)sampled_bytes;
         }
         __syncthreads();
         if (s_skip) {
-            if (t == 0) tables[s].header_bits = 0xffffffffu;    // sentinel: store every chunk of this stream
+            if (t == 0) tables[s].header_bits = 0xffffffffu;    // sentinel: store every chunk that uses this code
             return;
         }
     }
     for (int i = t; i < 512; i += DF_THREADS) {
         uint32_t c = i < DF_NSYM ? ghist[(size_t)s * DF_NSYM + i] : 0;
-        if (i == 256) c = 1;                                  // end-of-block is used once per chunk; any count > 0 works
+        if (shared_table && i < DF_LEN_SYMS) c = c * 16u + 1u;   // smoothing (counts stay far below 2^23)
+        if (i == 256 && c == 0) c = 1;                        // end-of-block is used once per chunk; any count > 0 works
         B.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
     }
     __syncthreads();
@@ -178,83 +197,99 @@ k_deflate_tables(const uint32_t *__restrict__ ghist, const uint32_t *__restrict_
     for (int i = t; i < (int)(sizeof(DeflateTable) / 4); i += DF_THREADS) dst[i] = src[i];
 }
 
-// pass 2 over every chunk: encode with the stream's code
+// every chunk: Adler-32 partials, then encode with its code (or store)
 __global__ void __launch_bounds__(DF_THREADS)
 k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                  const uint32_t *__restrict__ in_bytes, int n_streams, const uint32_t *__restrict__ chunk_base,
-                 uint32_t *__restrict__ counters, int level, const DeflateTable *__restrict__ tables,
-                 uint8_t *__restrict__ scratch, uint32_t *__restrict__ chunk_bytes)
+                 uint32_t *__restrict__ counters, int level, int shared_table,
+                 const DeflateTable *__restrict__ tables, uint8_t *__restrict__ scratch,
+                 uint32_t *__restrict__ chunk_bytes, uint2 *__restrict__ chunk_adler)
 {
     __shared__ DfEmitShared S;
     __shared__ uint32_t s_ticket;
     __shared__ uint32_t s_warp[9];
+    __shared__ uint32_t s_adler[2];
     const int t = threadIdx.x;
     const uint32_t total_chunks = chunk_base[n_streams];
 
     while (true) {
-        if (t == 0) s_ticket = atomicAdd(&counters[2], 1u);
+        if (t == 0) { s_ticket = atomicAdd(&counters[2], 1u); s_adler[0] = 0; s_adler[1] = 0; S.overflow = 0; }
         __syncthreads();
         const uint32_t gci = s_ticket;
         if (gci >= total_chunks) break;
         const int s = find_stream(chunk_base, n_streams, gci);
         const uint32_t ci = gci - chunk_base[s];
         const int clen = (int)min((uint32_t)DF_CHUNK, in_bytes[s] - ci * DF_CHUNK);
+        const uint8_t *src = in + in_off[s] + (size_t)ci * DF_CHUNK;
 
-        stage_chunk(S.in32, in + in_off[s] + (size_t)ci * DF_CHUNK, clen, t);
-        uint32_t body_bits = 0;
-        DfMasks tm{0, 0, 0};
+        stage_chunk(S.io, src, clen, t);
         bool stored = level == 0;
+        uint32_t hb = 0;
+        const DeflateTable &T = tables[shared_table ? 0 : s];
         if (!stored) {
-            const DeflateTable &T = tables[s];
-            const uint32_t hb = T.header_bits;
+            hb = T.header_bits;
             stored = hb == 0xffffffffu;
         }
-        if (!stored) {
-            const DeflateTable &T = tables[s];
-            const uint32_t hb = T.header_bits;
-            const int hw = (int)((hb + 31) >> 5);
-            for (int i = t; i < DF_OUT_WORDS; i += DF_THREADS) S.out[i] = i < hw ? T.header[i] : 0;
-            df_load_table(S, T, t, DF_THREADS);
-            if (t == 0) S.header_bits = hb;
-            __syncthreads();
-            tm = df_phase_masks(S, t, clen);
-            df_phase_size_m(S, t, tm);
-            uint32_t tok_bits;
-            const uint32_t e = block_excl_scan<8>(S.tbits[t], s_warp, &tok_bits);
-            S.tbits[t] = e;
-            body_bits = hb + tok_bits;
-            stored = df_dynamic_bytes(body_bits, (int)(S.cl[256] >> 16)) >= (uint32_t)clen + 10u;
-            __syncthreads();
-        } else {
-            __syncthreads();
-        }
-
-        if (!stored) {
-            df_phase_emit_m(S, t, tm);
-            __syncthreads();
-            if (t == 0) df_phase_finish(S, body_bits);
-        } else {
-            // stored block: 00 | LEN | ~LEN | data | sync marker (00 0000 FFFF); every byte below is overwritten
-            uint8_t *ob = reinterpret_cast<uint8_t *>(S.out);
-            if (t == 0) {
-                ob[0] = 0;
-                ob[1] = (uint8_t)(clen & 0xff); ob[2] = (uint8_t)(clen >> 8);
-                ob[3] = (uint8_t)(~clen & 0xff); ob[4] = (uint8_t)((~clen >> 8) & 0xff);
-                ob[5 + clen] = 0; ob[6 + clen] = 0; ob[7 + clen] = 0; ob[8 + clen] = 0xff; ob[9 + clen] = 0xff;
-                S.out_bytes = (uint32_t)clen + 10u;
-            }
-            for (int i = t; i < clen; i += DF_THREADS) {
-                const int tt = i / DF_SEG, bi = i % DF_SEG;
-                ob[5 + i] = (uint8_t)(S.in32[df_in_index(tt, bi >> 2)] >> (8 * (bi & 3)));
-            }
-        }
+        if (!stored) df_load_table(S, T, t, DF_THREADS);
         __syncthreads();
 
-        const uint32_t nb = S.out_bytes;
-        uint4 *dst = reinterpret_cast<uint4 *>(scratch + (size_t)gci * DF_SLOT_BYTES);
-        const uint4 *so = reinterpret_cast<const uint4 *>(S.out);
-        for (uint32_t i = t; i < (nb + 15) / 16; i += DF_THREADS) dst[i] = so[i];
-        if (t == 0) chunk_bytes[gci] = nb;
+        // Adler-32 partials of the chunk (warp shuffle reduction, one shared atomic per warp)
+        {
+            uint32_t a, b;
+            df_adler_partial(S.io, t, clen, a, b);
+            a %= 65521u; b %= 65521u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                a += __shfl_down_sync(0xffffffffu, a, d);
+                b += __shfl_down_sync(0xffffffffu, b, d);
+            }
+            if ((t & 31) == 0 && (a | b)) { atomicAdd(&s_adler[0], a % 65521u); atomicAdd(&s_adler[1], b % 65521u); }
+        }
+
+        uint32_t body_bits = 0, my_bits = 0;
+        if (!stored) {
+            if (t == 0) S.header_bits = hb;
+            my_bits = df_encode_segment(S, t, clen);
+            uint32_t tok_bits;
+            const uint32_t e = block_excl_scan<8>(my_bits, s_warp, &tok_bits);     // two barriers: encode pass is over
+            S.tbits[t] = e;
+            body_bits = hb + tok_bits;
+            stored = S.overflow || df_dynamic_bytes(body_bits, (int)(S.tbl[256] >> 24)) >= (uint32_t)clen + 10u;
+        } else {
+            __syncthreads();
+        }
+
+        uint8_t *slot = scratch + (size_t)gci * DF_SLOT_BYTES;
+        if (!stored) {
+            // the staged input is no longer needed: its area becomes the zero-initialised output bit stream
+            const int hw = (int)((hb + 31) >> 5);
+            const int ow = (int)((df_dynamic_bytes(body_bits, (int)(S.tbl[256] >> 24)) + 3 + 4) >> 2);
+            for (int i = t; i < ow && i < DF_STAGE_WORDS; i += DF_THREADS) S.io[i] = i < hw ? T.header[i] : 0;
+            __syncthreads();
+            df_place_segment(S, t, my_bits);
+            __syncthreads();
+            if (t == 0) df_phase_finish(S, body_bits);
+            __syncthreads();
+            const uint32_t nb = S.out_bytes;
+            uint4 *dst = reinterpret_cast<uint4 *>(slot);
+            const uint4 *so = reinterpret_cast<const uint4 *>(S.io);
+            for (uint32_t i = t; i < (nb + 15) / 16; i += DF_THREADS) dst[i] = so[i];
+            if (t == 0) chunk_bytes[gci] = nb;
+        } else {
+            // stored block: 00 | LEN | ~LEN | data | sync marker (00 0000 FFFF), straight from the staged input
+            if (t == 0) {
+                slot[0] = 0;
+                slot[1] = (uint8_t)(clen & 0xff); slot[2] = (uint8_t)(clen >> 8);
+                slot[3] = (uint8_t)(~clen & 0xff); slot[4] = (uint8_t)((~clen >> 8) & 0xff);
+                slot[5 + clen] = 0; slot[6 + clen] = 0; slot[7 + clen] = 0; slot[8 + clen] = 0xff; slot[9 + clen] = 0xff;
+                chunk_bytes[gci] = (uint32_t)clen + 10u;
+            }
+            const uint8_t *sb = reinterpret_cast<const uint8_t *>(S.io);
+            for (int i = t; i < clen; i += DF_THREADS)
+                slot[5 + i] = sb[(i >> 6) * (DF_SEG_STRIDE * 4) + (i & 63)];
+        }
+        __syncthreads();
+        if (t == 0) chunk_adler[gci] = make_uint2(s_adler[0] % 65521u, s_adler[1] % 65521u);
         __syncthreads();
     }
 }
@@ -473,27 +508,33 @@ DeflateWs carve_deflate_ws(Carver &c, int n_streams, size_t max_chunks, bool nee
 }
 
 // encodes (wrap = 1) or sizes (wrap = 0, reduce-only mode) the chunks and finalizes per-stream totals
-int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, const uint8_t *in, const uint64_t *in_off,
-                           const uint32_t *in_bytes, int n_streams, const DeflateWs &w, cudaStream_t st)
+// shared_table: the streams are statistically alike (the frames of one batch): one sampled code for all of them
+int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, int shared_table, const uint8_t *in,
+                           const uint64_t *in_off, const uint32_t *in_bytes, int n_streams, const DeflateWs &w,
+                           cudaStream_t st)
 {
     if (n_streams <= 0) return 0;
     k_deflate_plan<<<1, 256, 0, st>>>(in_bytes, n_streams, w.chunk_base, w.counters, wrap ? w.ghist : nullptr);
     RC_LAUNCH_CHECK(ctx, "k_deflate_plan");
     if (wrap) {
-        size_t want = w.max_chunks < (size_t)ctx->sm_count * 8 ? w.max_chunks : (size_t)ctx->sm_count * 8;
-        if (want < 1) want = 1;
-        k_deflate_hist<<<(unsigned)want, DF_THREADS, 0, st>>>(in, in_off, in_bytes, n_streams, w.chunk_base, w.counters,
-                                                               level, w.ghist, w.chunk_adler);
-        RC_LAUNCH_CHECK(ctx, "k_deflate_hist");
+        size_t want;
         if (level > 0) {
-            k_deflate_tables<<<n_streams, DF_THREADS, 0, st>>>(w.ghist, w.chunk_base, in_bytes, (DeflateTable *)w.tables);
+            const size_t tasks = shared_table ? (w.max_chunks + DF_SAMPLE - 1) / DF_SAMPLE : w.max_chunks;
+            want = tasks < (size_t)ctx->sm_count * 8 ? tasks : (size_t)ctx->sm_count * 8;
+            if (want < 1) want = 1;
+            k_deflate_hist<<<(unsigned)want, DF_THREADS, 0, st>>>(in, in_off, in_bytes, n_streams, w.chunk_base,
+                                                                   w.counters, shared_table, w.ghist);
+            RC_LAUNCH_CHECK(ctx, "k_deflate_hist");
+            k_deflate_tables<<<shared_table ? 1 : n_streams, DF_THREADS, 0, st>>>(
+                w.ghist, w.chunk_base, in_bytes, w.counters, shared_table, n_streams, (DeflateTable *)w.tables);
             RC_LAUNCH_CHECK(ctx, "k_deflate_tables");
         }
         want = w.max_chunks < (size_t)ctx->sm_count * 6 ? w.max_chunks : (size_t)ctx->sm_count * 6;
         if (want < 1) want = 1;
         k_deflate_chunks<<<(unsigned)want, DF_THREADS, 0, st>>>(in, in_off, in_bytes, n_streams, w.chunk_base,
-                                                                 w.counters, level, (const DeflateTable *)w.tables,
-                                                                 w.scratch, w.chunk_bytes);
+                                                                 w.counters, level, shared_table,
+                                                                 (const DeflateTable *)w.tables, w.scratch,
+                                                                 w.chunk_bytes, w.chunk_adler);
         RC_LAUNCH_CHECK(ctx, "k_deflate_chunks");
     } else {
         k_raw_chunk_bytes<<<n_streams, 128, 0, st>>>(in_bytes, w.chunk_base, n_streams, w.chunk_bytes);

@@ -5,13 +5,16 @@
 // compressed bytes, so the encoder is designed for the GPU and for this data:
 //
 //   * input streams are cut into 16 KiB chunks; a chunk is encoded by one CTA of 256 threads, 64 input
-//     bytes per thread, all threads in lock step.
+//     bytes per thread.  A thread tokenizes its segment ONCE, writing the code bits into a private staging
+//     area; a block scan of the bit counts then places the 256 private bit strings (funnel shift + atomicOr).
 //   * LZ77 restricted to distance-1 matches (byte runs): binary maps are 85-99 % 0x00 bytes; a run costs one
 //     compare per byte, or one compare per 4 bytes on the all-equal-word fast path.
-//   * ONE dynamic-Huffman code per stream: k_deflate_hist sums the token histogram of all chunks of a
-//     stream, k_deflate_tables builds the code once (two-queue Huffman merge, zlib-style 15-bit length
-//     limiting, canonical codes, RFC 1951 code-length header) and every chunk of the stream re-uses the
-//     prebuilt header bits.  That removes all serial work from the per-chunk kernel.
+//   * the dynamic-Huffman code is built ONCE, not per chunk: k_deflate_hist sums a token histogram,
+//     k_deflate_tables builds the code (two-queue Huffman merge, zlib-style 15-bit length limiting, canonical
+//     codes, RFC 1951 code-length header) and every chunk re-uses the prebuilt header bits, which removes all
+//     serial work from the per-chunk kernel.  compression_level 1..5: one code per batch of streams from a
+//     1-in-8 sample of their chunks, every producible symbol smoothed to a non-zero count (frames of one
+//     acquisition share their statistics).  Levels 6..9: one code per stream from all of its chunks.
 //   * every chunk is its own deflate block, starts byte aligned, ends with an empty stored block (the
 //     Z_SYNC_FLUSH marker 00 00 FF FF) and never references bytes before its own start.  Chunks are therefore
 //     independent: encoded by different CTAs, concatenated by byte copies, and found and inflated in parallel
@@ -42,12 +45,15 @@ constexpr int DF_THREADS = 256;
 constexpr int DF_SEG = 64;                          // input bytes per thread
 constexpr int DF_CHUNK = DF_THREADS * DF_SEG;       // 16384
 constexpr int DF_SEG_WORDS = DF_SEG / 4;            // 16
+constexpr int DF_SEG_STRIDE = DF_SEG_WORDS + 1;     // staging stride in words: 17 -> bank-conflict free per-thread access
+constexpr int DF_STAGE_WORDS = DF_THREADS * DF_SEG_STRIDE;   // 4352 words = 17408 bytes
 constexpr int DF_NSYM = 288;                        // literal/length alphabet (286 used)
-constexpr int DF_OUT_WORDS = DF_CHUNK / 4 + 64;     // a compressed chunk never exceeds the stored form
+constexpr int DF_LEN_SYMS = 277;                    // symbols a chunk can produce: 0..255, 256, 257..276 (length <= 64)
 constexpr int DF_SLOT_BYTES = DF_CHUNK + 64;        // scratch slot per chunk (multiple of 16)
 constexpr int DF_HDR_WORDS = 136;                   // 17 + 57 + 288 * 14 bits worst case
+constexpr int DF_NTBL = DF_NSYM + DF_SEG + 1;       // token table: literals / EOB, then match lengths 0..64
 
-// per-stream code, built once by k_deflate_tables and read by every chunk of the stream
+// per-stream (or per-group) code, built once by k_deflate_tables and read by every chunk that uses it
 struct DeflateTable {
     uint16_t code[DF_NSYM];           // bit-reversed canonical codes
     uint8_t len[DF_NSYM];             // code lengths
@@ -56,9 +62,8 @@ struct DeflateTable {
     uint32_t pad[3];
 };
 
-// chunk staging: word k of thread t at [k*256 + (t ^ ((k>>2)<<3))] (transposed + swizzled: conflict-free both
-// for the coalesced 128-bit fill and for the per-thread word reads)
-DF_HD int df_in_index(int t, int k) { return k * DF_THREADS + (t ^ ((k >> 2) << 3)); }
+// chunk staging: thread t's 64-byte segment occupies words [17 t, 17 t + 16) (one pad word per segment)
+DF_HD int df_in_index(int t, int k) { return t * DF_SEG_STRIDE + k; }
 
 DF_HD void df_store_word(uint32_t *in32, int byte_off, uint32_t w)
 {
@@ -116,7 +121,7 @@ DF_HD uint32_t df_bitrev(uint32_t c, int n)
 // A run never crosses a segment, and the first byte of a chunk is always a literal (chunk independence).
 DF_HD uint32_t df_byte_at(const uint32_t *in32, int t, int pos)
 {
-    return (in32[df_in_index(t, pos >> 2)] >> (8 * (pos & 3))) & 0xffu;
+    return reinterpret_cast<const uint8_t *>(in32)[t * (DF_SEG_STRIDE * 4) + pos];   // little-endian words
 }
 
 // bit i (i < 4) set when byte i of x differs from byte i of y
@@ -206,33 +211,39 @@ DF_HD int df_seg_bytes(int t, int clen)
     return nbytes > DF_SEG ? DF_SEG : nbytes;
 }
 
-// ---- histogram + Adler-32 partials (k_deflate_hist) -----------------------------------------------------
-struct DfHistEmit {
-    uint32_t *hist;
-    uint32_t n0;                      // literal 0x00 is a third of all tokens on binary maps: count it privately
-    DF_HD void lit(uint32_t c)
-    {
-        if (c == 0) n0++;
-        else DF_ATOMIC_ADD(&hist[c], 1u);
-    }
-    DF_HD void match(int L)
-    {
-        int sym, eb, ev;
-        df_len_code(L, sym, eb, ev);
-        DF_ATOMIC_ADD(&hist[sym], 1u);
-    }
-};
-
-// hist: DF_NSYM counters (shared);  adler: {sum b_i, sum (clen - i) * b_i} mod 65521 (shared)
-DF_HD void df_phase_hist(const uint32_t *in32, uint32_t *hist, uint32_t *adler, int t, int clen, bool tokens)
+// ---- histogram (k_deflate_hist) -----------------------------------------------------------------------------
+// hist: DF_NSYM counters (shared).  Order does not matter here, so literals and matches are counted in two
+// loops whose bodies have no divergent branch.
+DF_HD void df_phase_hist(const uint32_t *in32, uint32_t *hist, int t, int clen)
 {
     const int nbytes = df_seg_bytes(t, clen);
     if (nbytes <= 0) return;
-    if (tokens) {
-        DfHistEmit em{hist, 0};
-        df_tokenize(in32, t, nbytes, em);
-        if (em.n0) DF_ATOMIC_ADD(&hist[0], em.n0);
+    const DfMasks m = df_token_masks(in32, t, nbytes);
+    uint32_t n0 = 0;                                 // literal 0x00 is frequent on binary maps: count it privately
+    uint64_t lit = m.lit;
+    while (lit) {
+        const int pos = df_ctz64(lit);
+        lit &= lit - 1;
+        const uint32_t c = df_byte_at(in32, t, pos);
+        if (c == 0) n0++;
+        else DF_ATOMIC_ADD(&hist[c], 1u);
     }
+    if (n0) DF_ATOMIC_ADD(&hist[0], n0);
+    uint64_t ms = m.ms;
+    while (ms) {
+        const int pos = df_ctz64(ms);
+        ms &= ms - 1;
+        const uint64_t r = ~(m.lng >> pos);
+        int sym, eb, ev;
+        df_len_code(r ? df_ctz64(r) : DF_SEG, sym, eb, ev);
+        DF_ATOMIC_ADD(&hist[sym], 1u);
+    }
+}
+
+// Adler-32 partials of thread t's segment: {sum b_i, sum (clen - i) * b_i}, i = position in the chunk
+DF_HD void df_adler_partial(const uint32_t *in32, int t, int clen, uint32_t &a_out, uint32_t &b_out)
+{
+    const int nbytes = df_seg_bytes(t, clen);
     uint32_t a = 0, b = 0;
     const int nw = (nbytes + 3) >> 2;
     for (int k = 0; k < nw; k++) {
@@ -247,10 +258,8 @@ DF_HD void df_phase_hist(const uint32_t *in32, uint32_t *hist, uint32_t *adler, 
             }
         }
     }
-    if (a) {
-        DF_ATOMIC_ADD(&adler[0], a % 65521u);
-        DF_ATOMIC_ADD(&adler[1], b % 65521u);
-    }
+    a_out = a;
+    b_out = b;
 }
 
 // ---- code construction (k_deflate_tables) ------------------------------------------------------------------
@@ -414,99 +423,91 @@ DF_HD void df_phase_build(DfBuildShared &B, int n_used)
 
 // ---- per-chunk emission (k_deflate_chunks) --------------------------------------------------------------------
 struct DfEmitShared {
-    uint32_t in32[DF_CHUNK / 4];
-    uint32_t out[DF_OUT_WORDS];       // bit stream, zero initialised
-    uint32_t cl[DF_NSYM];             // (length << 16) | bit-reversed code, literals and end-of-block
-    uint32_t mt[DF_SEG + 1];          // per match length 3..64: (total bits << 24) | length code + extra + distance bit
+    uint32_t io[DF_STAGE_WORDS];      // staged input; after the encode pass it is reused as the output bit stream
+    uint32_t priv[DF_STAGE_WORDS];    // private code bits of thread t at [17 t, 17 t + 17): 544 bits
+    uint32_t tbl[DF_NTBL];            // (bits << 24) | code: literals / EOB at [sym], matches of length L at [288 + L]
     uint32_t tbits[DF_THREADS];       // per-thread bit counts -> exclusive bit offsets
     uint32_t header_bits;
     uint32_t out_bytes;
+    uint32_t overflow;                // a thread's code bits did not fit its private area: store the chunk
 };
+constexpr int DF_PRIV_BITS = DF_SEG_STRIDE * 32;
 
-// fills S.cl / S.mt from the stream's table; thread i handles entries i, i + nthreads, ...
+// fills S.tbl from the code table; thread i handles entries i, i + nthreads, ...
 DF_HD void df_load_table(DfEmitShared &S, const DeflateTable &T, int i, int nthreads)
 {
-    for (int s = i; s < DF_NSYM; s += nthreads) S.cl[s] = ((uint32_t)T.len[s] << 16) | T.code[s];
-    for (int L = 3 + i; L <= DF_SEG; L += nthreads) {
-        int sym, eb, ev;
-        df_len_code(L, sym, eb, ev);
-        const uint32_t l = T.len[sym];
-        // length code, extra bits, then distance symbol 0 = code '0' (1 bit, distance 1 has no extra bits)
-        S.mt[L] = ((l + eb + 1) << 24) | (uint32_t)T.code[sym] | ((uint32_t)ev << l);
+    for (int s = i; s < DF_NSYM; s += nthreads) S.tbl[s] = ((uint32_t)T.len[s] << 24) | T.code[s];
+    for (int L = i; L <= DF_SEG; L += nthreads) {
+        uint32_t e = 0;
+        if (L >= 3) {
+            int sym, eb, ev;
+            df_len_code(L, sym, eb, ev);
+            const uint32_t l = T.len[sym];
+            // length code, extra bits, then distance symbol 0 = code '0' (1 bit, distance 1 has no extra bits)
+            e = ((l + eb + 1) << 24) | (uint32_t)T.code[sym] | ((uint32_t)ev << l);
+        }
+        S.tbl[DF_NSYM + L] = e;
     }
 }
 
-struct DfSizeEmit {
-    const uint32_t *cl, *mt;
-    uint32_t bits;
-    DF_HD void lit(uint32_t c) { bits += cl[c] >> 16; }
-    DF_HD void match(int L) { bits += mt[L] >> 24; }
-};
-
-// masks computed once per thread (k_deflate_chunks keeps them in registers for the size and the emit pass)
-DF_HD DfMasks df_phase_masks(const DfEmitShared &S, int t, int clen)
+// Tokenizes thread t's segment once: code bits go to the thread's private area, the bit count is returned.
+// The loop body is branch-free apart from the 32-bit flush, so lanes only diverge in the trip count.
+DF_HD uint32_t df_encode_segment(DfEmitShared &S, int t, int clen)
 {
     const int nbytes = df_seg_bytes(t, clen);
-    DfMasks m{0, 0, 0};
-    if (nbytes > 0) m = df_token_masks(S.in32, t, nbytes);
-    return m;
-}
-
-DF_HD void df_phase_size_m(DfEmitShared &S, int t, const DfMasks &m)
-{
-    DfSizeEmit em{S.cl, S.mt, 0};
-    df_for_tokens(S.in32, t, m, em);
-    S.tbits[t] = em.bits;
-}
-
-DF_HD void df_phase_size(DfEmitShared &S, int t, int clen)
-{
-    const DfMasks m = df_phase_masks(S, t, clen);
-    df_phase_size_m(S, t, m);
-}
-
-struct DfBitEmit {
-    uint32_t *out;
-    const uint32_t *cl, *mt;
-    uint64_t acc;
-    uint32_t nb, wpos;
-    DF_HD void add(uint32_t bits, int n)
-    {
-        acc |= (uint64_t)bits << nb;
-        nb += n;
+    if (nbytes <= 0) return 0;
+    const DfMasks m = df_token_masks(S.io, t, nbytes);
+    const uint8_t *seg = reinterpret_cast<const uint8_t *>(S.io) + t * (DF_SEG_STRIDE * 4);
+    uint32_t *priv = S.priv + t * DF_SEG_STRIDE;
+    uint64_t tk = m.lit | m.ms;
+    uint64_t acc = 0;
+    uint32_t nb = 0, w = 0, total = 0;
+    while (tk) {
+        const int pos = df_ctz64(tk);
+        tk &= tk - 1;
+        const uint64_t r = ~(m.lng >> pos);
+        const uint32_t L = r ? (uint32_t)df_ctz64(r) : (uint32_t)DF_SEG;
+        const uint32_t idx = ((m.lit >> pos) & 1) ? (uint32_t)seg[pos] : (uint32_t)DF_NSYM + L;
+        const uint32_t e = S.tbl[idx];
+        acc |= (uint64_t)(e & 0xffffffu) << nb;
+        nb += e >> 24;
+        total += e >> 24;
         if (nb >= 32) {
-            DF_ATOMIC_OR(&out[wpos], (uint32_t)acc);
+            if (w < (uint32_t)DF_SEG_STRIDE) priv[w] = (uint32_t)acc;
+            w++;
             acc >>= 32;
             nb -= 32;
-            wpos++;
         }
     }
-    DF_HD void lit(uint32_t c) { const uint32_t e = cl[c]; add(e & 0xffffu, e >> 16); }
-    DF_HD void match(int L) { const uint32_t e = mt[L]; add(e & 0xffffffu, e >> 24); }
-    DF_HD void flush() { if (nb) DF_ATOMIC_OR(&out[wpos], (uint32_t)acc); }
-};
-
-// S.tbits[t] must hold the exclusive prefix (bit offset relative to the header end)
-DF_HD void df_phase_emit_m(DfEmitShared &S, int t, const DfMasks &m)
-{
-    if (!(m.lit | m.ms)) return;
-    const uint32_t o = S.header_bits + S.tbits[t];
-    DfBitEmit em{S.out, S.cl, S.mt, 0, o & 31, o >> 5};
-    df_for_tokens(S.in32, t, m, em);
-    em.flush();
+    if (nb) {
+        if (w < (uint32_t)DF_SEG_STRIDE) priv[w] = (uint32_t)acc;
+        w++;
+    }
+    if (w > (uint32_t)DF_SEG_STRIDE) S.overflow = 1;
+    return total;
 }
 
-DF_HD void df_phase_emit(DfEmitShared &S, int t, int clen)
+// ORs thread t's private bit string into the output stream at bit offset S.header_bits + S.tbits[t] (exclusive scan)
+DF_HD void df_place_segment(DfEmitShared &S, int t, uint32_t nbits)
 {
-    const DfMasks m = df_phase_masks(S, t, clen);
-    df_phase_emit_m(S, t, m);
+    if (!nbits) return;
+    const uint32_t o = S.header_bits + S.tbits[t];
+    const uint32_t sh = o & 31;
+    uint32_t wpos = o >> 5;
+    const uint32_t *priv = S.priv + t * DF_SEG_STRIDE;
+    const uint32_t nw = (nbits + 31) >> 5;
+    for (uint32_t j = 0; j < nw; j++, wpos++) {
+        const uint32_t x = priv[j];
+        DF_ATOMIC_OR(&S.io[wpos], x << sh);
+        if (sh && (x >> (32 - sh))) DF_ATOMIC_OR(&S.io[wpos + 1], x >> (32 - sh));
+    }
 }
 
 // body_bits = header + all tokens.  Appends EOB and the sync-flush marker; sets out_bytes.  Single thread.
 DF_HD void df_phase_finish(DfEmitShared &S, uint32_t body_bits)
 {
-    DfBitWriter bw{S.out, body_bits};
-    bw.put(S.cl[256] & 0xffffu, S.cl[256] >> 16);      // end of block
+    DfBitWriter bw{S.io, body_bits};
+    bw.put(S.tbl[256] & 0xffffffu, S.tbl[256] >> 24);  // end of block
     bw.put(0, 3);                         // BFINAL=0, BTYPE=00: empty stored block
     bw.pos = (bw.pos + 7) & ~7u;          // pad to a byte boundary (zero bits)
     bw.put(0x0000, 16);                   // LEN = 0

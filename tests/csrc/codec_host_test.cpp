@@ -3,84 +3,108 @@
 // thread at a time, in exactly the order the kernels in deflate.cu / inflate.cu run them.  Lets the non-GPU
 // test suite check the codec logic against stock zlib.  Never linked into the product library.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 #include "../../pyrecode_b200/csrc/deflate_chunk.cuh"
 #include "../../pyrecode_b200/csrc/inflate_core.cuh"
 
-// mirrors k_deflate_hist / k_deflate_tables / k_deflate_chunks for one stream
+// mirrors k_deflate_hist / k_deflate_tables / k_deflate_chunks for one stream (a group of one stream)
 extern "C" long host_deflate_stream(const uint8_t *in, uint32_t n, int level, uint8_t *out, uint32_t cap)
 {
     static DfBuildShared B;
     static DfEmitShared S;
-    static uint32_t in32[DF_CHUNK / 4];
+    static uint32_t in32[DF_STAGE_WORDS];
     const uint32_t nchunks = (n + DF_CHUNK - 1) / DF_CHUNK;
-    std::vector<uint32_t> ghist(DF_NSYM, 0), ca(nchunks), cb(nchunks);
+    const bool shared_table = level < 6;
+    const uint32_t step = shared_table ? 8 : 1;
+    std::vector<uint32_t> ghist(DF_NSYM, 0);
     auto stage = [&](uint32_t *dst, uint32_t off, int clen) {
+        for (int i = 0; i < DF_STAGE_WORDS; i++) dst[i] = 0;
         for (int o = 0; o < DF_CHUNK; o += 4) {
             uint32_t w = 0;
             for (int b = 0; b < 4; b++) if (o + b < clen) w |= (uint32_t)in[off + o + b] << (8 * b);
             df_store_word(dst, o, w);
         }
     };
-    // pass 1
-    for (uint32_t c = 0; c < nchunks; c++) {
-        const int clen = (int)std::min<uint32_t>(DF_CHUNK, n - c * DF_CHUNK);
-        uint32_t hist[DF_NSYM] = {0}, adler[2] = {0, 0};
-        stage(in32, c * DF_CHUNK, clen);
-        for (int t = 0; t < DF_THREADS; t++) df_phase_hist(in32, hist, adler, t, clen, level > 0);
-        for (int i = 0; i < DF_NSYM; i++) ghist[i] += hist[i];
-        ca[c] = adler[0] % 65521u; cb[c] = adler[1] % 65521u;
-    }
-    // tables
-    if (level > 0 && nchunks) {
-        for (int i = 0; i < 512; i++) {
-            uint32_t c = i < DF_NSYM ? ghist[i] : 0;
-            if (i == 256) c = 1;
-            B.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
+    // histogram (sampled chunks when the table is shared)
+    uint32_t sampled = 0;
+    if (level > 0)
+        for (uint32_t c = 0; c < nchunks; c += step) {
+            const int clen = (int)std::min<uint32_t>(DF_CHUNK, n - c * DF_CHUNK);
+            uint32_t hist[DF_NSYM] = {0};
+            stage(in32, c * DF_CHUNK, clen);
+            for (int t = 0; t < DF_THREADS; t++) df_phase_hist(in32, hist, t, clen);
+            for (int i = 0; i < DF_NSYM; i++) ghist[i] += hist[i];
+            sampled += clen;
         }
-        std::sort(B.keys, B.keys + 512);
-        int n_used = 0;
-        while (n_used < 512 && B.keys[n_used] != 0xffffffffu) n_used++;
-        df_phase_build(B, n_used);
+    // tables
+    bool store_all = level == 0;
+    if (level > 0 && nchunks) {
+        double ntok = 0, bits = 0;
+        for (int i = 0; i < DF_NSYM; i++) ntok += ghist[i];
+        for (int i = 0; i < DF_NSYM; i++)
+            if (ghist[i]) bits += ghist[i] * (std::log2(ntok / ghist[i]) + (i > 264 ? 2. : (i > 256 ? 1. : 0.)));
+        store_all = bits * 0.125 + 128. >= 0.97 * sampled;
+        if (!store_all) {
+            for (int i = 0; i < 512; i++) {
+                uint32_t c = i < DF_NSYM ? ghist[i] : 0;
+                if (shared_table && i < DF_LEN_SYMS) c = c * 16u + 1u;
+                if (i == 256 && c == 0) c = 1;
+                B.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
+            }
+            std::sort(B.keys, B.keys + 512);
+            int n_used = 0;
+            while (n_used < 512 && B.keys[n_used] != 0xffffffffu) n_used++;
+            df_phase_build(B, n_used);
+        }
     }
-    // pass 2
+    // chunks
     uint32_t pos = 0;
     if (cap < 8) return -1;
     out[pos++] = 0x78; out[pos++] = 0x01;
     uint32_t s1 = 1, s2 = 0;
+    std::vector<uint32_t> bits_of(DF_THREADS);
     for (uint32_t c = 0; c < nchunks; c++) {
         const int clen = (int)std::min<uint32_t>(DF_CHUNK, n - c * DF_CHUNK);
-        stage(S.in32, c * DF_CHUNK, clen);
+        stage(S.io, c * DF_CHUNK, clen);
+        uint32_t ca = 0, cb = 0;
+        for (int t = 0; t < DF_THREADS; t++) {
+            uint32_t a, b;
+            df_adler_partial(S.io, t, clen, a, b);
+            ca = (ca + a % 65521u) % 65521u; cb = (cb + b % 65521u) % 65521u;
+        }
         uint32_t body_bits = 0;
-        bool stored = level == 0;
+        bool stored = store_all;
+        const DeflateTable &T = B.tab;
         if (!stored) {
-            const DeflateTable &T = B.tab;
-            const int hw = (int)((T.header_bits + 31) >> 5);
-            for (int i = 0; i < DF_OUT_WORDS; i++) S.out[i] = i < hw ? T.header[i] : 0;
             for (int i = 0; i < DF_THREADS; i++) df_load_table(S, T, i, DF_THREADS);
             S.header_bits = T.header_bits;
-            for (int t = 0; t < DF_THREADS; t++) df_phase_size(S, t, clen);
+            S.overflow = 0;
             uint32_t run = 0;
-            for (int t = 0; t < DF_THREADS; t++) { const uint32_t v = S.tbits[t]; S.tbits[t] = run; run += v; }
+            for (int t = 0; t < DF_THREADS; t++) bits_of[t] = df_encode_segment(S, t, clen);
+            for (int t = 0; t < DF_THREADS; t++) { S.tbits[t] = run; run += bits_of[t]; }
             body_bits = S.header_bits + run;
-            stored = df_dynamic_bytes(body_bits, (int)(S.cl[256] >> 16)) >= (uint32_t)clen + 10u;
+            stored = S.overflow || df_dynamic_bytes(body_bits, (int)(S.tbl[256] >> 24)) >= (uint32_t)clen + 10u;
         }
+        std::vector<uint8_t> piece;
         if (!stored) {
-            for (int t = 0; t < DF_THREADS; t++) df_phase_emit(S, t, clen);
+            const int hw = (int)((T.header_bits + 31) >> 5);
+            for (int i = 0; i < DF_STAGE_WORDS; i++) S.io[i] = i < hw ? T.header[i] : 0;
+            for (int t = 0; t < DF_THREADS; t++) df_place_segment(S, t, bits_of[t]);
             df_phase_finish(S, body_bits);
+            piece.assign(reinterpret_cast<uint8_t *>(S.io), reinterpret_cast<uint8_t *>(S.io) + S.out_bytes);
         } else {
-            uint8_t *ob = reinterpret_cast<uint8_t *>(S.out);
-            ob[0] = 0; ob[1] = clen & 0xff; ob[2] = clen >> 8; ob[3] = ~clen & 0xff; ob[4] = (~clen >> 8) & 0xff;
-            memcpy(ob + 5, in + c * DF_CHUNK, clen);
-            ob[5 + clen] = 0; ob[6 + clen] = 0; ob[7 + clen] = 0; ob[8 + clen] = 0xff; ob[9 + clen] = 0xff;
-            S.out_bytes = clen + 10;
+            piece.resize(clen + 10);
+            piece[0] = 0; piece[1] = clen & 0xff; piece[2] = clen >> 8; piece[3] = ~clen & 0xff; piece[4] = (~clen >> 8) & 0xff;
+            memcpy(piece.data() + 5, in + c * DF_CHUNK, clen);
+            piece[5 + clen] = 0; piece[6 + clen] = 0; piece[7 + clen] = 0; piece[8 + clen] = 0xff; piece[9 + clen] = 0xff;
         }
-        if (pos + S.out_bytes + 6 > cap) return -1;
-        memcpy(out + pos, S.out, S.out_bytes);
-        pos += S.out_bytes;
-        s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)clen * s1 + cb[c]) % 65521u);
-        s1 = (s1 + ca[c]) % 65521u;
+        if (pos + piece.size() + 6 > cap) return -1;
+        memcpy(out + pos, piece.data(), piece.size());
+        pos += (uint32_t)piece.size();
+        s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)clen * s1 + cb) % 65521u);
+        s1 = (s1 + ca) % 65521u;
     }
     out[pos++] = 0x03; out[pos++] = 0x00;
     const uint32_t ad = (s2 << 16) | s1;

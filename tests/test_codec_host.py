@@ -53,12 +53,15 @@ def cases():
     skew = np.concatenate([np.full(int(1.6 ** i) + 1, i, np.uint8) for i in range(24)])
     rng.shuffle(skew)
     c['skew'] = skew.tobytes()
+    # only chunks 0 and 8 are sampled for the level-1 code: the others hold symbols the sample never saw
+    c['unsampled'] = bytes(16384) + rng.integers(0, 256, 7 * 16384, dtype=np.uint8).tobytes() + bytes(16384) + \
+        np.packbits(rng.random(1 << 18) < 0.3, bitorder='little').tobytes()
     return c
 
 
 def test_encoder_output_inflates_with_stock_zlib(codec):
     for name, d in cases().items():
-        for level in (1, 0):
+        for level in (1, 0, 9):
             c = deflate(codec, d, level)
             assert zlib.decompress(c) == d, (name, level)
     m = cases()['map0.02']
