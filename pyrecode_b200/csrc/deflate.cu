@@ -166,31 +166,242 @@ k_deflate_tables(const uint32_t *__restrict__ ghist, const uint32_t *__restrict_
             return;
         }
     }
-    for (int i = t; i < 512; i += DF_THREADS) {
-        uint32_t c = i < DF_NSYM ? ghist[(size_t)s * DF_NSYM + i] : 0;
-        if (shared_table && i < DF_LEN_SYMS) c = c * 16u + 1u;   // smoothing (counts stay far below 2^23)
+    // ---- the code, built by the whole CTA; only the Huffman merge itself is serial (thread 0) ------------------
+    // (same result as the serial df_phase_build of deflate_chunk.cuh, which the CPU harness runs)
+    __shared__ uint32_t s_raw[DF_NSYM];         // unsorted keys
+    __shared__ uint32_t s_cnt[16], s_start[16], s_next[16];
+    __shared__ uint32_t s_misc[8];              // 0 n_used, 1 leaf overflow, 2 nlit, 3 nrl, 4 ncl, 5 header payload bits
+    __shared__ uint16_t s_pos[DF_NSYM + 4];     // per head: output position of its run-length symbols; then bit offsets
+    __shared__ uint8_t s_cllen[20];
+    __shared__ uint16_t s_clcode[20];
+    __shared__ uint32_t s_clfreq[20];
+    __shared__ uint32_t s_warp[9];
+    DeflateTable &T = B.tab;
+    // counts are scaled to < 2^21 so that (count << 9 | symbol) keys and all weight sums fit 32 bits
+    const uint32_t ntok = s_tok[0];
+    const int cshift = ntok >> 21 ? 32 - __clz(ntok >> 21) : 0;
+    for (int i = t; i < DF_NSYM; i += DF_THREADS) {
+        uint32_t c = ghist[(size_t)s * DF_NSYM + i];
+        if (c) c = max(c >> cshift, 1u);
+        if (shared_table && i < DF_LEN_SYMS) c = c * 2u + 1u; // smoothing: every producible symbol gets a code
         if (i == 256 && c == 0) c = 1;                        // end-of-block is used once per chunk; any count > 0 works
-        B.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
+        s_raw[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
+        T.len[i] = 0;
+        T.code[i] = 0;
     }
+    for (int i = t; i < DF_HDR_WORDS; i += DF_THREADS) T.header[i] = 0;
+    if (t < 16) s_cnt[t] = 0;
+    if (t < 20) s_clfreq[t] = 0;
+    if (t < 8) s_misc[t] = 0;
     __syncthreads();
-    for (int k = 2; k <= 512; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = t; i < 512; i += DF_THREADS) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const uint32_t a = B.keys[i], b = B.keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { B.keys[i] = b; B.keys[ixj] = a; }
-                }
-            }
-            __syncthreads();
+    // rank sort (keys are unique: the symbol is in the low bits)
+    for (int i = t; i < DF_NSYM; i += DF_THREADS) {
+        const uint32_t k = s_raw[i];
+        if (k != 0xffffffffu) {
+            uint32_t r = 0;
+            for (int j = 0; j < DF_NSYM; j++) r += s_raw[j] < k;
+            B.keys[r] = k;
+            atomicAdd(&s_misc[0], 1u);
         }
     }
-    if (t == 0) {
-        int lo = 0, hi = 512;                                 // used symbols = index of the first sentinel
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (B.keys[mid] != 0xffffffffu) lo = mid + 1; else hi = mid; }
-        df_phase_build(B, lo);
+    __syncthreads();
+    const int n_used = (int)s_misc[0];
+    if (n_used == 1) {
+        // a lone symbol still needs one bit; add a dummy sibling (as df_build_lengths does)
+        if (t == 0) {
+            const int sy = B.keys[0] & 511;
+            T.len[sy] = 1;
+            T.len[sy == 0 ? 1 : 0] = 1;
+        }
+    } else {
+        if (t == 0) {
+            // two-queue merge: leaves i (weight keys[i] >> 9), internal nodes j (weight node_w[j])
+            int li = 0, ii = 0, ni = 0;
+            uint32_t lw = B.keys[0] >> 9, iw = 0xffffffffu;
+            for (int k = 0; k < n_used - 1; k++) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int pick = 0; pick < 2; pick++) {
+                    if (li < n_used && (ii >= ni || lw <= iw)) {
+                        w += lw; B.node_parent[li] = (uint16_t)ni; li++;
+                        lw = li < n_used ? B.keys[li] >> 9 : 0xffffffffu;
+                    } else {
+                        w += iw; B.node_parent[DF_NSYM + ii] = (uint16_t)ni; ii++;
+                        iw = ii < ni ? B.node_w[ii] : 0xffffffffu;
+                    }
+                }
+                B.node_w[ni] = w;
+                if (ii == ni) iw = w;          // the new node is the head of the internal queue
+                ni++;
+            }
+            // depths of the internal nodes top-down with clamping; every clamped node counts (zlib gen_bitlen)
+            uint32_t overflow = 0;
+            B.node_depth[ni - 1] = 0;
+            for (int j = ni - 2; j >= 0; j--) {
+                int d = B.node_depth[B.node_parent[DF_NSYM + j]] + 1;
+                if (d > 15) { d = 15; overflow++; }
+                B.node_depth[j] = (uint8_t)d;
+            }
+            s_misc[1] = overflow;
+        }
+        __syncthreads();
+        for (int i = t; i < n_used; i += DF_THREADS) {
+            int d = B.node_depth[B.node_parent[i]] + 1;
+            if (d > 15) { d = 15; atomicAdd(&s_misc[1], 1u); }
+            atomicAdd(&s_cnt[d], 1u);
+        }
+        __syncthreads();
+        if (t == 0) {
+            int overflow = (int)s_misc[1];
+            while (overflow > 0) {
+                int bits = 14;
+                while (s_cnt[bits] == 0) bits--;
+                s_cnt[bits]--;
+                s_cnt[bits + 1] += 2;
+                s_cnt[15]--;
+                overflow -= 2;
+            }
+            uint32_t i = 0;                  // least frequent leaves (front of the sorted keys) get the longest codes
+            for (int bits = 15; bits >= 1; bits--) { s_start[bits] = i; i += s_cnt[bits]; }
+        }
+        __syncthreads();
+        for (int i = t; i < n_used; i += DF_THREADS) {
+            int bits = 15;
+            while (bits > 1 && !((uint32_t)i >= s_start[bits] && (uint32_t)i < s_start[bits] + s_cnt[bits])) bits--;
+            T.len[B.keys[i] & 511] = (uint8_t)bits;
+        }
     }
+    __syncthreads();
+    // canonical codes (RFC 1951 3.2.2): next_code per length, then rank among equal lengths by symbol order
+    if (t < 16) s_cnt[t] = 0;
+    __syncthreads();
+    for (int i = t; i < DF_NSYM; i += DF_THREADS) {
+        const int l = T.len[i];
+        if (l) atomicAdd(&s_cnt[l], 1u);
+        if (l && i < 286) atomicMax(&s_misc[2], (uint32_t)i + 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+        uint32_t c = 0;
+        s_next[0] = 0;
+        uint32_t prev = 0;
+        for (int bits = 1; bits <= 15; bits++) { c = (c + prev) << 1; s_next[bits] = c; prev = s_cnt[bits]; }
+        if (s_misc[2] < 257) s_misc[2] = 257;
+    }
+    __syncthreads();
+    for (int i = t; i < DF_NSYM; i += DF_THREADS) {
+        const int l = T.len[i];
+        if (l) {
+            uint32_t r = 0;
+            for (int j = 0; j < i; j++) r += T.len[j] == l;
+            T.code[i] = (uint16_t)df_bitrev(s_next[l] + r, l);
+        }
+    }
+    // ---- header: HLIT/HDIST/HCLEN, code-length code, run-length coded lengths (RFC 1951 3.2.7) ---------------
+    const int nlit = (int)s_misc[2];
+    const int nseq = nlit + 2;                  // like zlib: always two distance codes of one bit each
+    for (int i = t; i < nseq; i += DF_THREADS) B.seq[i] = i < nlit ? T.len[i] : 1;
+    __syncthreads();
+    // run heads -> number of run-length symbols each run emits
+    for (int i0 = 0; i0 < nseq; i0 += DF_THREADS) {
+        const int i = i0 + t;
+        uint32_t n = 0;
+        if (i < nseq && (i == 0 || B.seq[i] != B.seq[i - 1])) {
+            const int v = B.seq[i];
+            int R = 1;
+            while (i + R < nseq && B.seq[i + R] == v) R++;
+            if (v == 0) {
+                const int rem = R % 138;
+                n = R / 138 + (rem >= 3 ? 1 : rem);
+            } else {
+                const int left = R - 1, rem = left % 6;
+                n = 1 + left / 6 + (rem >= 3 ? 1 : rem);
+            }
+        }
+        uint32_t total;
+        const uint32_t e = block_excl_scan<8>(n, s_warp, &total);
+        if (i < nseq) s_pos[i] = (uint16_t)(s_misc[3] + e);
+        __syncthreads();
+        if (t == 0) s_misc[3] += total;
+        __syncthreads();
+    }
+    const int nrl = (int)s_misc[3];
+    for (int i = t; i < nseq; i += DF_THREADS) {
+        if (i == 0 || B.seq[i] != B.seq[i - 1]) {
+            const int v = B.seq[i];
+            int R = 1;
+            while (i + R < nseq && B.seq[i + R] == v) R++;
+            int o = s_pos[i];
+            if (v == 0) {
+                int left = R;
+                while (left >= 11) { const int r = left > 138 ? 138 : left; B.rl_sym[o] = 18; B.rl_ext[o++] = (uint8_t)(r - 11); left -= r; }
+                if (left >= 3) { B.rl_sym[o] = 17; B.rl_ext[o++] = (uint8_t)(left - 3); left = 0; }
+                while (left-- > 0) { B.rl_sym[o] = 0; B.rl_ext[o++] = 0; }
+            } else {
+                B.rl_sym[o] = (uint8_t)v; B.rl_ext[o++] = 0;
+                int left = R - 1;
+                while (left >= 3) { const int r = left > 6 ? 6 : left; B.rl_sym[o] = 16; B.rl_ext[o++] = (uint8_t)(r - 3); left -= r; }
+                while (left-- > 0) { B.rl_sym[o] = (uint8_t)v; B.rl_ext[o++] = 0; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = t; i < nrl; i += DF_THREADS) atomicAdd(&s_clfreq[B.rl_sym[i]], 1u);
+    __syncthreads();
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    if (t == 0) {
+        // code-length code: 19 symbols, 7 bits max; tiny insertion sort + the serial builder
+        uint32_t ckeys[19];
+        int cused = 0;
+        for (int sy = 0; sy < 19; sy++) if (s_clfreq[sy]) {
+            const uint32_t key = (s_clfreq[sy] << 9) | (uint32_t)sy;
+            int j = cused++;
+            while (j > 0 && ckeys[j - 1] > key) { ckeys[j] = ckeys[j - 1]; j--; }
+            ckeys[j] = key;
+        }
+        df_build_lengths(ckeys, cused, 7, s_cllen, 19, B.node_w, B.node_parent, B.node_depth);
+        df_assign_codes(s_cllen, 19, s_clcode);
+        int ncl = 19;
+        while (ncl > 4 && s_cllen[order[ncl - 1]] == 0) ncl--;
+        s_misc[4] = (uint32_t)ncl;
+        DfBitWriter bw{T.header, 0};
+        bw.put(0, 1);                 // BFINAL = 0 (the stream is closed by the assembler)
+        bw.put(2, 2);                 // BTYPE = 10 dynamic
+        bw.put((uint32_t)(nlit - 257), 5);
+        bw.put(1, 5);                 // HDIST = 2 - 1
+        bw.put((uint32_t)(ncl - 4), 4);
+    }
+    __syncthreads();
+    const int ncl = (int)s_misc[4];
+    if (t < ncl) {
+        const uint32_t pos = 17u + 3u * (uint32_t)t, v = s_cllen[order[t]];
+        atomicOr(&T.header[pos >> 5], v << (pos & 31));
+        if ((pos & 31) > 29) atomicOr(&T.header[(pos >> 5) + 1], v >> (32 - (pos & 31)));
+    }
+    // bit offset of every run-length symbol, then parallel emission
+    const uint32_t hbase = 17u + 3u * (uint32_t)ncl;
+    for (int i0 = 0; i0 < nrl; i0 += DF_THREADS) {
+        const int i = i0 + t;
+        uint32_t nb = 0, bits = 0;
+        if (i < nrl) {
+            const int sy = B.rl_sym[i];
+            const uint32_t l = s_cllen[sy];
+            const uint32_t eb = sy == 16 ? 2u : (sy == 17 ? 3u : (sy == 18 ? 7u : 0u));
+            bits = (uint32_t)s_clcode[sy] | ((uint32_t)B.rl_ext[i] << l);
+            nb = l + eb;
+        }
+        uint32_t total;
+        const uint32_t e = block_excl_scan<8>(nb, s_warp, &total);
+        if (nb) {
+            const uint32_t pos = hbase + s_misc[5] + e;
+            atomicOr(&T.header[pos >> 5], bits << (pos & 31));
+            if ((pos & 31) + nb > 32) atomicOr(&T.header[(pos >> 5) + 1], bits >> (32 - (pos & 31)));
+        }
+        __syncthreads();
+        if (t == 0) s_misc[5] += total;
+        __syncthreads();
+    }
+    if (t == 0) T.header_bits = hbase + s_misc[5];
     __syncthreads();
     const uint32_t *src = reinterpret_cast<const uint32_t *>(&B.tab);
     uint32_t *dst = reinterpret_cast<uint32_t *>(&tables[s]);

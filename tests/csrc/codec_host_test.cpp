@@ -47,9 +47,13 @@ extern "C" long host_deflate_stream(const uint8_t *in, uint32_t n, int level, ui
             if (ghist[i]) bits += ghist[i] * (std::log2(ntok / ghist[i]) + (i > 264 ? 2. : (i > 256 ? 1. : 0.)));
         store_all = bits * 0.125 + 128. >= 0.97 * sampled;
         if (!store_all) {
+            const uint32_t nt = (uint32_t)ntok;
+            int cshift = 0;
+            while ((nt >> 21) >> cshift) cshift++;
             for (int i = 0; i < 512; i++) {
                 uint32_t c = i < DF_NSYM ? ghist[i] : 0;
-                if (shared_table && i < DF_LEN_SYMS) c = c * 16u + 1u;
+                if (c) c = std::max(c >> cshift, 1u);
+                if (shared_table && i < DF_LEN_SYMS) c = c * 2u + 1u;
                 if (i == 256 && c == 0) c = 1;
                 B.keys[i] = c ? ((c << 9) | (uint32_t)i) : 0xffffffffu;
             }
