@@ -137,6 +137,7 @@ def main():
     ap.add_argument('--frames', type=int, default=32, help='frames per step per GPU')
     ap.add_argument('--distinct', type=int, default=4, help='distinct synthetic frames generated on the host')
     ap.add_argument('--cpu-frames-per-core', type=int, default=2)
+    ap.add_argument('--slots', type=int, default=2, help='batches in flight (each on its own CUDA stream)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -150,7 +151,8 @@ def main():
                 '(SURVEY 8d), %d frames per step per GPU, frame-sharded' % (level, BIT_DEPTH, KIND[level], args.frames))
     config = {'workload': workload, 'reduction_level': level, 'frames_per_step_per_gpu': args.frames,
               'frame_shape': [NY, NX], 'bit_depth': BIT_DEPTH, 'compression_level': 1,
-              'cache': 'inputs larger than L2 (%d MiB per step)' % (args.frames * frame_bytes >> 20)}
+              'cache': 'inputs larger than L2 (%d MiB per step)' % (args.frames * frame_bytes >> 20),
+              'batches_in_flight': args.slots}
     metric = 'frames/s, 4096x4096 L%d reduce+deflate' % level
 
     # ----------------------------------------------------------------------------------- reference arm
@@ -193,7 +195,7 @@ def main():
     dark, frames = make_inputs(level, args.distinct, seed=1234 + rank)
     F = args.frames
     eng = WriteEngine(NY, NX, 2, BIT_DEPTH, level, 1, 0, 0, 1, max_frames=F, device=local_rank,
-                      records_capacity=F * (frame_bytes // 4))
+                      records_capacity=F * (frame_bytes // 4), n_slots=args.slots)
     eng.set_threshold(dark, EPS)
     host = torch.empty((F, NY, NX), dtype=torch.uint16).pin_memory()
     hv = host.numpy()
@@ -210,27 +212,40 @@ def main():
     first_id = rank * F * (args.warmup + args.steps)
 
     # ---- device-resident timing (value) + dominant-kernel timing (roofline)
+    # Steps are issued round-robin on the engine's slots (one CUDA stream each), the way the writer keeps
+    # batches in flight; the timed region is bracketed by events on the default stream that all slot streams
+    # fork from / join to.
+    nsl = len(eng.slots)
+    cur = torch.cuda.current_stream()
+
+    def run_steps(n_steps, id0):
+        for sl in eng.slots:
+            sl.stream.wait_stream(cur)
+        for s in range(n_steps):
+            sl = eng.slots[s % nsl]
+            with torch.cuda.stream(sl.stream):
+                eng.launch(d_frames, F, id0 + s * F, s % nsl)
+        for sl in eng.slots:
+            cur.wait_stream(sl.stream)
+
     eng.ctx.profile_enable(True)
-    for s in range(args.warmup):
-        eng.launch(d_frames, F, first_id + s * F)
+    run_steps(args.warmup, first_id)
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     stage_ms = np.zeros(4)
-    launches0 = eng.ctx.launch_count()
+    launches0 = sum(sl.ctx.launch_count() for sl in eng.slots)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for s in range(args.steps):
-        eng.launch(d_frames, F, first_id + (args.warmup + s) * F)
-        if s % 4 == 3 or s == args.steps - 1:
-            pass
+    run_steps(args.steps, first_id + args.warmup * F)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = eng.ctx.launch_count() - launches0
-    # stage split: re-run a few steps with per-step readback of the stage marks (outside the timed region)
+    launches = sum(sl.ctx.launch_count() for sl in eng.slots) - launches0
+    # stage split: re-run a few steps one at a time on slot 0 with per-step readback of the stage marks
+    # (outside the timed region; the dominant kernel is timed alone here, which is what `roofline` reports)
     nprof = min(args.steps, 5)
     for s in range(nprof):
         eng.launch(d_frames, F, 0)
@@ -250,15 +265,23 @@ def main():
     # ---- end to end through host buffers
     e2e = None
     if not args.no_e2e:
-        for s in range(2):
-            eng.reduce_compress(host, first_frame_id=0)
+        # through the host-buffer API the writer uses: pinned host frames -> H2D -> kernels -> D2H of the records,
+        # every step, with `slots` batches in flight
+        def e2e_steps(n_steps, id0):
+            h2d = d2h = 0
+            pending = []
+            for s in range(n_steps):
+                pending.append(eng.submit(host, first_frame_id=id0 + s * F))
+                if len(pending) == nsl:
+                    _, _, _, h2d, d2h = eng.collect(pending.pop(0))
+            while pending:
+                _, _, _, h2d, d2h = eng.collect(pending.pop(0))
+            return h2d, d2h
+
+        e2e_steps(2, 0)
         barrier()
-        t0 = time.perf_counter()
         e0.record()
-        h2d = d2h = 0
-        for s in range(args.steps):
-            rec, offs2, counts, b_in, b_out = eng.reduce_compress(host, first_frame_id=first_id + s * F)
-            h2d, d2h = b_in, b_out
+        h2d, d2h = e2e_steps(args.steps, first_id)
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1)

@@ -14,11 +14,39 @@ from . import _native
 from ._native import Context, make_config
 
 
-class WriteEngine:
-    def __init__(self, ny, nx, itemsize, bit_depth, reduction_level, rc_operation_mode=1, l2_statistics=0,
-                 l4_centroiding=0, compression_level=1, max_frames=16, device=None, records_capacity=None):
+class _Slot:
+    """One in-flight batch of the write path: its own rc_ctx, CUDA stream, workspace and result buffers."""
+
+    def __init__(self, eng, device):
         self.ctx = Context(device)
-        self.dev = self.ctx.device
+        dev = self.ctx.device
+        with torch.cuda.device(dev):
+            self.stream = torch.cuda.Stream(device=dev)
+            self.ws = self.ctx.empty(self.ctx.workspace_bytes(eng.cfg))
+            self.records = self.ctx.empty(eng.records_cap)
+            self.offsets = self.ctx.zeros(eng.max_frames + 1, torch.int64)
+            self.counts = self.ctx.zeros(eng.max_frames, torch.int32)
+            self.status = self.ctx.zeros(1, torch.int32)
+            self.done = torch.cuda.Event()
+        self.frames_dev = None
+        self.pin_in = None
+        self.pin_off = torch.empty(eng.max_frames + 1, dtype=torch.int64).pin_memory()
+        self.pin_cnt = torch.empty(eng.max_frames, dtype=torch.int32).pin_memory()
+        self.pin_st = torch.empty(1, dtype=torch.int32).pin_memory()
+        self.pin_rec = None
+        self.n = 0
+        self.h2d = 0
+        self.busy = False
+
+
+class WriteEngine:
+    """Batches of frames -> finished part-file records.  `n_slots` batches can be in flight: submit() enqueues the
+    host-to-device copy and all kernels of a batch on the slot's stream and returns at once, collect() waits for
+    that batch and brings its records to the host, so the copies and the file write of one batch overlap the
+    kernels of the next."""
+
+    def __init__(self, ny, nx, itemsize, bit_depth, reduction_level, rc_operation_mode=1, l2_statistics=0,
+                 l4_centroiding=0, compression_level=1, max_frames=16, device=None, records_capacity=None, n_slots=1):
         self.ny, self.nx, self.itemsize, self.bit_depth = int(ny), int(nx), int(itemsize), int(bit_depth)
         self.level, self.mode = int(reduction_level), int(rc_operation_mode)
         self.max_frames = int(max_frames)
@@ -27,18 +55,16 @@ class WriteEngine:
         self.P = self.ny * self.nx
         self.np_dtype = _native.numpy_dtype(itemsize)
         self.t_dtype = _native.torch_dtype(itemsize)
-        with torch.cuda.device(self.dev):
-            self.ws = self.ctx.empty(self.ctx.workspace_bytes(self.cfg))
-            cap = self.ctx.records_capacity(self.cfg) if records_capacity is None else int(records_capacity)
-            self.records = self.ctx.empty(cap)
-            self.offsets = self.ctx.zeros(self.max_frames + 1, torch.int64)
-            self.counts = self.ctx.zeros(self.max_frames, torch.int32)
-            self.status = self.ctx.zeros(1, torch.int32)
-            self.frames_dev = None
+        probe = Context(device)
+        self.records_cap = probe.records_capacity(self.cfg) if records_capacity is None else int(records_capacity)
+        probe.close()
+        self.slots = [_Slot(self, device) for _ in range(max(1, int(n_slots)))]
+        self._next = 0
+        s0 = self.slots[0]
+        self.ctx, self.dev = s0.ctx, s0.ctx.device
+        # single-slot views used by the stage API and older callers
+        self.ws, self.records, self.offsets, self.counts, self.status = s0.ws, s0.records, s0.offsets, s0.counts, s0.status
         self.thr = None
-        self._pin_in = None
-        self._pin_meta = torch.empty(self.max_frames + 1, dtype=torch.int64).pin_memory()
-        self._pin_rec = None
 
     # ---- calibration -----------------------------------------------------------------------------
     def set_threshold(self, dark, eps):
@@ -46,59 +72,89 @@ class WriteEngine:
         d = torch.from_numpy(np.ascontiguousarray(dark, dtype=self.np_dtype)).to(self.dev)
         with torch.cuda.device(self.dev):
             self.thr = self.ctx.make_threshold(self.cfg, d, eps)
+            torch.cuda.current_stream().synchronize()
         return self.thr
 
     # ---- input staging ----------------------------------------------------------------------------
-    def _to_device(self, frames):
-        """frames: numpy [n, ny, nx], pinned/pageable torch CPU tensor, or CUDA tensor of the source dtype."""
+    def _to_device(self, frames, slot=None):
+        """frames: numpy [n, ny, nx], pinned/pageable torch CPU tensor, or CUDA tensor of the source dtype.
+        The copy is enqueued on the current stream."""
+        slot = slot or self.slots[0]
         if isinstance(frames, torch.Tensor) and frames.is_cuda:
             assert frames.dtype == self.t_dtype and frames.is_contiguous()
             return frames, 0
         if isinstance(frames, np.ndarray):
             a = np.ascontiguousarray(frames, dtype=self.np_dtype)
             n = a.shape[0]
-            if self._pin_in is None:
-                self._pin_in = torch.empty((self.max_frames, self.ny, self.nx), dtype=self.t_dtype).pin_memory()
-            self._pin_in[:n].numpy()[...] = a
-            src = self._pin_in[:n]
+            if slot.pin_in is None:
+                slot.pin_in = torch.empty((self.max_frames, self.ny, self.nx), dtype=self.t_dtype).pin_memory()
+            slot.pin_in[:n].numpy()[...] = a
+            src = slot.pin_in[:n]
         else:
             src = frames
             n = src.shape[0]
-        if self.frames_dev is None:
-            self.frames_dev = torch.empty((self.max_frames, self.ny, self.nx), dtype=self.t_dtype, device=self.dev)
-        dst = self.frames_dev[:n]
+        if slot.frames_dev is None:
+            slot.frames_dev = torch.empty((self.max_frames, self.ny, self.nx), dtype=self.t_dtype, device=self.dev)
+        dst = slot.frames_dev[:n]
         dst.copy_(src, non_blocking=True)
         return dst, src.numel() * src.element_size()
 
     # ---- the hot path ------------------------------------------------------------------------------
-    def launch(self, frames_dev, n, first_frame_id):
-        """Asynchronous: all kernels of one batch on the current stream."""
+    def launch(self, frames_dev, n, first_frame_id, slot=0):
+        """Asynchronous: all kernels of one batch on the CURRENT stream, using the buffers of `slot`."""
         if self.thr is None:
             raise RuntimeError('set_threshold() must be called first')
-        self.ctx.reduce_compress(self.cfg, frames_dev, n, self.thr, int(first_frame_id), self.ws, self.records,
-                                 self.offsets, self.counts, self.status)
+        s = self.slots[slot]
+        s.ctx.reduce_compress(self.cfg, frames_dev, n, self.thr, int(first_frame_id), s.ws, s.records, s.offsets,
+                              s.counts, s.status)
 
-    def reduce_compress(self, frames, first_frame_id=0):
-        """-> (records: np.uint8 [total], offsets: np.int64 [n+1], counts: np.int32 [n], h2d_bytes, d2h_bytes)."""
+    def submit(self, frames, first_frame_id=0):
+        """Enqueue one batch (copy in, kernels, copy of the record table out) on the next slot's stream.
+        Returns the slot index to pass to collect()."""
         n = int(frames.shape[0])
         if n > self.max_frames:
             raise ValueError('batch larger than max_frames')
+        k = self._next
+        s = self.slots[k]
+        if s.busy:
+            raise RuntimeError('slot %d still holds an uncollected batch' % k)
+        self._next = (k + 1) % len(self.slots)
         with torch.cuda.device(self.dev):
-            fd, h2d = self._to_device(frames)
-            self.launch(fd, n, first_frame_id)
-            meta = self._pin_meta
-            meta[:n + 1].copy_(self.offsets[:n + 1], non_blocking=True)
-            st = self.status.cpu()          # synchronizes the stream
-            counts = self.counts[:n].cpu().numpy()
-            offs = meta[:n + 1].numpy().copy()
-            total = int(offs[n])
-            if int(st[0]) & _native.RC_STATUS_RECORDS_OVERFLOW:
-                raise ValueError('Buffer size smaller than compressed data size')
-            if self._pin_rec is None or self._pin_rec.numel() < total:
-                self._pin_rec = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
-            self._pin_rec[:total].copy_(self.records[:total], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return self._pin_rec[:total].numpy(), offs, counts, h2d, total + (n + 1) * 8 + n * 4 + 4
+            if isinstance(frames, torch.Tensor) and frames.is_cuda:
+                s.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s.stream):
+                fd, s.h2d = self._to_device(frames, s)
+                self.launch(fd, n, first_frame_id, k)
+                s.pin_off[:n + 1].copy_(s.offsets[:n + 1], non_blocking=True)
+                s.pin_cnt[:n].copy_(s.counts[:n], non_blocking=True)
+                s.pin_st.copy_(s.status, non_blocking=True)
+                s.done.record(s.stream)
+        s.n = n
+        s.busy = True
+        return k
+
+    def collect(self, k):
+        """-> (records: np.uint8 [total] (valid until the slot is reused), offsets: np.int64 [n+1],
+        counts: np.int32 [n], h2d_bytes, d2h_bytes) of the batch submitted on slot k."""
+        s = self.slots[k]
+        n = s.n
+        s.done.synchronize()
+        s.busy = False
+        if int(s.pin_st[0]) & _native.RC_STATUS_RECORDS_OVERFLOW:
+            raise ValueError('Buffer size smaller than compressed data size')
+        offs = s.pin_off[:n + 1].numpy().copy()
+        counts = s.pin_cnt[:n].numpy().copy()
+        total = int(offs[n])
+        if s.pin_rec is None or s.pin_rec.numel() < total:
+            s.pin_rec = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
+        with torch.cuda.device(self.dev), torch.cuda.stream(s.stream):
+            s.pin_rec[:total].copy_(s.records[:total], non_blocking=True)
+            s.stream.synchronize()
+        return s.pin_rec[:total].numpy(), offs, counts, s.h2d, total + (n + 1) * 8 + n * 4 + 4
+
+    def reduce_compress(self, frames, first_frame_id=0):
+        """Synchronous submit + collect of one batch."""
+        return self.collect(self.submit(frames, first_frame_id))
 
     # ---- stage access (parity tests, c_recode shim) --------------------------------------------------
     def reduce(self, frames):

@@ -146,13 +146,14 @@ class ReCoDeWriter:
         cap = F * (frame_bytes + 64) + 4096
         eng = WriteEngine(ny, nx, itemsize, ip.source_bit_depth, ip.reduction_level, ip.rc_operation_mode,
                           ip.L2_statistics, ip.L4_centroiding, min(ip.compression_level, 9), max_frames=F,
-                          device=self._device, records_capacity=cap)
+                          device=self._device, records_capacity=cap, n_slots=2)
         if self._thr_host is not None:
             import torch
             eng.thr = torch.from_numpy(np.ascontiguousarray(self._thr_host)).to(eng.dev)
         else:
             eng.set_threshold(self._calibration_frame, ip.calibration_threshold_epsilon)
-        eng.ctx.profile_enable(True)
+        for slot in eng.slots:
+            slot.ctx.profile_enable(True)
         return eng
 
     # ------------------------------------------------------------------------------------------
@@ -251,16 +252,15 @@ class ReCoDeWriter:
         eng = self._engine
         F = eng.max_frames
         gap = self._init_params.validation_frame_gap
-        for b0 in range(0, available_frames, F):
-            n = min(F, available_frames - b0)
-            first_id = self._chunk_offset + frame_offset + b0
-            batch = data[b0:b0 + n]
-            rec, offs, counts, _, _ = eng.reduce_compress(batch, first_frame_id=first_id)
+        # two batches in flight: the copies and the file write of one batch overlap the kernels of the next
+        def finish(ticket):
+            slot, first_id, batch, n = ticket
+            rec, offs, counts, _, _ = eng.collect(slot)
             sizes = np.diff(offs)
             if sizes.size and int(sizes.max()) > self._frame_sz:
                 raise ValueError('Buffer size smaller than compressed data size')
             self._intermediate_file.write(rec)
-            st = eng.ctx.profile_read()
+            st = eng.slots[slot].ctx.profile_read()
             if len(st) >= 4:
                 gpu_ms['frame_thresholding_and_counting_time'] += st[0]
                 gpu_ms['frame_pixel_intensity_packing_time'] += st[1]
@@ -270,6 +270,18 @@ class ReCoDeWriter:
                 for i in range(n):
                     if (first_id + i) % gap == 0:
                         self._validation_frame(batch[i], run_metrics)
+
+        pending = None
+        for b0 in range(0, available_frames, F):
+            n = min(F, available_frames - b0)
+            first_id = self._chunk_offset + frame_offset + b0
+            batch = data[b0:b0 + n]
+            ticket = (eng.submit(batch, first_frame_id=first_id), first_id, batch, n)
+            if pending is not None:
+                finish(pending)
+            pending = ticket
+        if pending is not None:
+            finish(pending)
         self._intermediate_file.flush()
         for k in keys:
             run_metrics[k] = timedelta(milliseconds=gpu_ms[k])
