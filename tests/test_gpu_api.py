@@ -1,0 +1,244 @@
+"""GPU: the drop-in Python API end to end -- ReCoDeWriter -> part files -> ReCoDeReader / merge_parts, the way the
+reference's own test drives it (tests/minimal_read_write_test.py:15-124), for every reduction level and both
+operation modes, checked against the oracle and against the golden files the reference wrote."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def make_params(ny, nx, nz, level=1, mode=1, b=12, threads=1, eps=0, l2=0, l4=0, clevel=1):
+    from pyrecode_b200.params import InputParams
+    ip = InputParams()
+    vals = dict(l4_centroiding=l4, source_file_type=0, num_frames=nz, source_header_length=0,
+                calibration_frame_offset=0, compression_scheme=0, calibration_file_type=0, compression_level=clevel,
+                l2_statistics=l2, calibration_threshold_epsilon=eps, frame_offset=0, num_threads=threads,
+                rc_operation_mode=mode, num_calibration_frames=1, reduction_level=level, keep_calibration_data=1,
+                source_bit_depth=b, target_bit_depth=b, keep_part_files=0, num_rows=ny, num_cols=nx,
+                source_data_type=0, target_data_type=0)
+    for k, v in vals.items():
+        ip._param_map[k] = v
+    assert ip.validate()
+    return ip
+
+
+def reference_test_data(rng, nz=9, ny=512, nx=512):
+    """the data model of tests/minimal_read_write_test.py:15-25 (seeded here)"""
+    d = rng.integers(0, 4096, size=(nz, ny, nx)).astype(np.int64) - 3500
+    d[d < 0] = 0
+    return d.astype(np.uint16)
+
+
+def write_parts(tmp, name, data, dark, ip, n_nodes, **kw):
+    from pyrecode_b200.recode_writer import ReCoDeWriter
+    metrics = []
+    for node in range(n_nodes):
+        w = ReCoDeWriter(name, dark_data=dark, output_directory=str(tmp), input_params=ip, mode='batch', node_id=node,
+                         **kw)
+        w.start()
+        metrics.append(w.run(data))
+        w.close()
+    return metrics
+
+
+def test_minimal_read_write(tmp_path):
+    """tests/minimal_read_write_test.py: L1 / zlib 1 / 12 bit / 3 workers; part file, merged file, random access"""
+    from pyrecode_b200.recode_reader import ReCoDeReader, merge_parts
+    rng = np.random.default_rng(42)
+    data = reference_test_data(rng)
+    dark = np.zeros((1, 512, 512), np.uint16)
+    ip = make_params(512, 512, 9, threads=3)
+    metrics = write_parts(tmp_path, 'test_data', data, dark, ip, 3)
+    assert [m['run_frames'] for m in metrics] == [3, 3, 3]
+    assert 'frame_binary_image_compression_time' in metrics[0] and 'run_time' in metrics[0]
+
+    r = ReCoDeReader(str(tmp_path / 'test_data.rc1_part000'), is_intermediate=True)
+    r.open(print_header=False)
+    for i in range(3):
+        fd = r.get_next_frame()
+        (fid, fr), = fd.items()
+        assert fid == i
+        assert np.array_equal(np.asarray(fr['data'].todense()), data[fid])
+        assert fr['data'].dtype == np.uint16
+    assert r.get_next_frame() is None
+    r.close()
+
+    merge_parts(str(tmp_path), 'test_data.rc1', 3)
+    r = ReCoDeReader(str(tmp_path / 'test_data.rc1'), is_intermediate=False)
+    r.open(print_header=False)
+    assert r.get_shape() == (9, 512, 512)
+    for i in range(9):
+        (fid, fr), = r.get_next_frame().items()
+        assert fid == i and np.array_equal(np.asarray(fr['data'].todense()), data[i])
+    for z in (7, 0, 4):
+        (fid, fr), = r.get_frame(z).items()
+        assert fid == z and np.array_equal(fr['data'].toarray(), data[z])
+    with pytest.raises(ValueError):
+        r.get_frame(9)
+    r.close()
+
+
+@pytest.mark.parametrize('level', [1, 2, 3, 4])
+@pytest.mark.parametrize('mode', [1, 0])
+def test_levels_and_modes_roundtrip(tmp_path, level, mode):
+    """every (level, mode): record streams == oracle, and the reader returns what the format promises"""
+    from pyrecode_b200.recode_reader import ReCoDeReader
+    rng = np.random.default_rng(level * 10 + mode)
+    nz, ny, nx, b, eps = 5, 96, 160, 12, 3
+    dark = rng.integers(0, 6, size=(ny, nx)).astype(np.uint16)
+    frames = orc.synth_frames('l2' if level != 1 else 'l1', nz, ny, nx, dark + 20, seed=5 + level, bit_depth=b)
+    ip = make_params(ny, nx, nz, level=level, mode=mode, b=b, eps=eps)
+    write_parts(tmp_path, 'x', frames, dark[None], ip, 1)
+    path = str(tmp_path / ('x.rc%d_part000' % level))
+    thr = orc.make_threshold(dark, eps)
+    hdr, recs = orc.parse_part_file(path)
+    assert hdr['nz'] == nz and hdr['reduction_level'] == level and hdr['rc_operation_mode'] == mode
+    r = ReCoDeReader(path, is_intermediate=True)
+    r.open(print_header=False)
+    for f in range(nz):
+        m_ref, v_ref, n_ref = orc.reduce_frame(frames[f], thr, level, b)
+        rec = recs[f]
+        assert rec['frame_id'] == f
+        assert rec['map'] == m_ref                          # parse_part_file inflates with stock zlib
+        if level <= 2:
+            assert rec['vals'] == v_ref
+            assert rec['metadata'][orc.metadata_fields(level, mode)[-1]] == len(v_ref)
+        (fid, fr), = r.get_next_frame().items()
+        assert fid == f
+        dense = fr['data'].toarray()
+        binary = np.unpackbits(np.frombuffer(m_ref, np.uint8), bitorder='little')[:ny * nx].reshape(ny, nx)
+        if level == 1:
+            want = np.where(frames[f] > thr, frames[f] - thr, 0)
+            assert np.array_equal(dense, want)
+        else:
+            assert np.array_equal(dense, binary)            # value 1 at every map pixel (reader.h:39-41)
+        if level == 2:
+            assert np.array_equal(fr['summary_stats'], orc.bit_unpack(np.frombuffer(v_ref, np.uint8), n_ref, b))
+    assert r.get_next_frame() is None
+    r.close()
+
+
+def test_multi_batch_run_matches_single_frames(tmp_path):
+    """more frames than one launch batch, odd geometry, two batches in flight: records in order and identical
+    payloads to frame-at-a-time processing"""
+    from pyrecode_b200.recode_writer import ReCoDeWriter
+    rng = np.random.default_rng(3)
+    nz, ny, nx = 23, 37, 53
+    dark = rng.integers(0, 4, size=(ny, nx)).astype(np.uint16)
+    frames = (dark[None] + (rng.random((nz, ny, nx)) < 0.1) * rng.integers(1, 4000, size=(nz, ny, nx))).astype(np.uint16)
+    ip = make_params(ny, nx, nz, level=2, eps=1)
+    for tag, bf in (('a', 4), ('b', 1)):
+        w = ReCoDeWriter(tag, dark_data=dark[None], output_directory=str(tmp_path), input_params=ip, batch_frames=bf)
+        w.start()
+        w.run(frames)
+        w.close()
+    ha, ra = orc.parse_part_file(str(tmp_path / 'a.rc2_part000'))
+    hb, rb = orc.parse_part_file(str(tmp_path / 'b.rc2_part000'))
+    assert ha['nz'] == hb['nz'] == nz
+    for f in range(nz):
+        assert ra[f]['frame_id'] == rb[f]['frame_id'] == f
+        assert ra[f]['map'] == rb[f]['map'] and ra[f]['vals'] == rb[f]['vals']
+
+
+def test_cuda_tensor_input_and_stream_chunks(tmp_path):
+    """run() accepts a CUDA tensor (no host round trip) and successive run() calls continue the frame ids
+    (stream mode, recode_writer.py:385)"""
+    import torch
+    from pyrecode_b200.recode_reader import ReCoDeReader
+    from pyrecode_b200.recode_writer import ReCoDeWriter
+    rng = np.random.default_rng(8)
+    ny, nx = 64, 96
+    dark = np.zeros((1, ny, nx), np.uint16)
+    chunks = [reference_test_data(rng, 4, ny, nx) for _ in range(3)]
+    ip = make_params(ny, nx, 4)
+    w = ReCoDeWriter('', dark_data=dark, output_directory=str(tmp_path), input_params=ip, mode='stream', run_name='live')
+    w.start()
+    for c in chunks:
+        w.run(torch.from_numpy(c).cuda())
+    w.close()
+    r = ReCoDeReader(str(tmp_path / 'live.rc1_part000'), is_intermediate=True)
+    r.open(print_header=False)
+    assert r.get_shape()[0] == 12
+    allf = np.concatenate(chunks)
+    for i in range(12):
+        (fid, fr), = r.get_next_frame().items()
+        assert fid == i and np.array_equal(fr['data'].toarray(), allf[i])
+    r.close()
+
+
+def test_reads_reference_written_files(gold_dir):
+    """files written by the reference writer / merge_parts (tests/golden) decode to the reference's input"""
+    from pyrecode_b200.recode_reader import ReCoDeReader
+    z = np.load(os.path.join(gold_dir, 'gold_a_input.npz'))
+    data, dark, eps = z['data'], z['dark'], int(z['eps'])
+    thr = orc.make_threshold(dark, eps)
+    r = ReCoDeReader(os.path.join(gold_dir, 'gold_a.rc1'))
+    r.open(print_header=False)
+    nz = r.get_shape()[0]
+    for i in list(range(nz)) + [nz - 1, 0]:
+        fd = r.get_frame(i) if i in (nz - 1, 0) else r.get_next_frame()
+        (fid, fr), = fd.items()
+        want = np.where(data[fid] > thr, data[fid] - thr, 0)
+        assert np.array_equal(fr['data'].toarray(), want)
+    r.close()
+
+
+def test_dense_and_live_view_sum(tmp_path):
+    """batched read extras: dense frames on the device and the summed live-view image
+    (examples/ReCoDe_Live_View_MT.ipynb cell 1) equal the sum of the reconstructed frames"""
+    from pyrecode_b200.recode_reader import ReCoDeReader
+    rng = np.random.default_rng(11)
+    nz, ny, nx = 20, 128, 256
+    data = reference_test_data(rng, nz, ny, nx)
+    ip = make_params(ny, nx, nz)
+    write_parts(tmp_path, 'lv', data, np.zeros((1, ny, nx), np.uint16), ip, 1)
+    r = ReCoDeReader(str(tmp_path / 'lv.rc1_part000'), is_intermediate=True, batch_frames=8)
+    r.open(print_header=False)
+    ids, dense = r.read_frames_dense(7)
+    assert ids == list(range(7)) and np.array_equal(dense.cpu().numpy(), data[:7])
+    ids, total = r.sum_frames(100)
+    assert ids == list(range(7, nz))
+    assert np.array_equal(total.cpu().numpy().astype(np.int64).reshape(ny, nx), data[7:].astype(np.int64).sum(0))
+    r.close()
+
+
+def test_c_recode_shim(gold_dir):
+    """c_recode.Reader signatures (pyrecode.cpp:57-141) on the GPU, against the reference's recorded triples"""
+    from pyrecode_b200 import c_recode
+    z = np.load(os.path.join(gold_dir, 'gold_d_unpack.npz'))
+    ny, nx, b = int(z['ny']), int(z['nx']), int(z['b'])
+    rd = c_recode.Reader()
+    assert rd.create_buffers(ny, nx, b) == 1
+    out = np.zeros(ny * nx * 3, dtype=np.uint64)
+    n = rd.get_frame_sparse(1, z['map'].tobytes(), z['packed'].tobytes(), out)
+    assert n == z['triples_l1'].shape[0] and np.array_equal(out[:n * 3].reshape(n, 3), z['triples_l1'])
+    vals = z['triples_l1'][:, 2].astype(np.uint16)
+    packed = np.zeros((n * b + 7) // 8 + 8, dtype=np.uint8)
+    rd.bit_pack_pixel_intensities(len(packed), n, b, vals, packed)
+    assert packed[:(n * b + 7) // 8].tobytes() == z['packed'].tobytes()[:(n * b + 7) // 8]
+    back = np.zeros(n, dtype=np.uint64)
+    assert rd.bit_unpack_pixel_intensities(n, packed, back) == n
+    assert np.array_equal(back, vals)
+
+
+def test_writer_errors(tmp_path):
+    from pyrecode_b200.recode_writer import ReCoDeWriter
+    dark = np.zeros((1, 32, 32), np.uint16)
+    with pytest.raises(RuntimeError):                       # calibration frame shape mismatch (recode_writer.py:123-124)
+        ReCoDeWriter('x', dark_data=np.zeros((1, 16, 32), np.uint16), output_directory=str(tmp_path),
+                     input_params=make_params(32, 32, 2))
+    w = ReCoDeWriter('x', dark_data=dark, output_directory=str(tmp_path), input_params=make_params(32, 32, 2))
+    w.start()
+    with pytest.raises(RuntimeError):                       # frame shape mismatch (recode_writer.py:274-278)
+        w.run(np.zeros((2, 32, 48), np.uint16))
+    with pytest.raises(RuntimeError):                       # more frames requested than available (:283-284)
+        w.run(np.zeros((1, 32, 32), np.uint16))
+    w.close()
+    ip = make_params(32, 32, 2)
+    ip._param_map['compression_scheme'] = 1
+    with pytest.raises(NotImplementedError):                # no CPU fallback for other codecs
+        ReCoDeWriter('x', dark_data=dark, output_directory=str(tmp_path), input_params=ip)
