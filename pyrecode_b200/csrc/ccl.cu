@@ -110,36 +110,36 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
                 const uint32_t col = pow2 ? (gp & (unx - 1u)) : (gp % unx);
                 const bool hl = col > 0, hr = col + 1 < unx, up = gp >= unx;
                 const uint32_t e = p + HP;             // pixel index in the halo-extended map
-                const uint32_t q = e - unx;            // >= 0: the halo covers nx + 1 pixels
-                const uint32_t bw = (s_maskx[(e - 1) >> 5] >> ((e - 1) & 31)) & 1u;
-                const uint32_t bnw = (s_maskx[(q - 1) >> 5] >> ((q - 1) & 31)) & 1u;
-                const uint32_t bn = (s_maskx[q >> 5] >> (q & 31)) & 1u;
-                const uint32_t bne = (s_maskx[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u;
+                const uint32_t q = e - unx;            // >= 1: the halo covers nx + 1 pixels
+                const bool bw = (s_maskx[(e - 1) >> 5] >> ((e - 1) & 31)) & 1u;
+                const bool bnw = (s_maskx[(q - 1) >> 5] >> ((q - 1) & 31)) & 1u;
+                const bool bn = (s_maskx[q >> 5] >> (q & 31)) & 1u;
+                const bool bne = (s_maskx[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u;
                 // up to three links: W, and N or (NW, NE) -- NW / NE are implied when N is set
-                uint32_t c0 = 0xffffffffu, c1 = 0xffffffffu, c2 = 0xffffffffu;
-                if (bw && hl) c0 = e - 1;
-                if (up) {
-                    if (bn) c1 = q;
-                    else {
-                        if (bnw && hl) c1 = q - 1;
-                        if (bne && hr) c2 = q + 1;
-                    }
-                }
+                constexpr uint32_t NONE = 0xffffffffu;
+                const uint32_t c0 = (bw && hl) ? e - 1 : NONE;
+                const uint32_t c1 = !up ? NONE : (bn ? q : ((bnw && hl) ? q - 1 : NONE));
+                const uint32_t c2 = (up && !bn && bne && hr) ? q + 1 : NONE;
+                // candidates at or above HP are in this tile (branch-free slot lookups); the others are rare
+                const bool k0 = c0 != NONE && c0 >= HP, k1 = c1 != NONE && c1 >= HP, k2 = c2 != NONE && c2 >= HP;
+                const uint32_t q1 = k1 ? c1 - HP : 0u, q2 = k2 ? c2 - HP : 0u;
+                const uint32_t e0 = (i << 16) | (i - 1);
+                const uint32_t e1 = (i << 16) | (s_wpre[q1 >> 5] + __popc(s_mask[q1 >> 5] & ((1u << (q1 & 31)) - 1u)));
+                const uint32_t e2 = (i << 16) | (s_wpre[q2 >> 5] + __popc(s_mask[q2 >> 5] & ((1u << (q2 & 31)) - 1u)));
+                n = (uint32_t)k0 + (uint32_t)k1 + (uint32_t)k2;
+                l0 = k0 ? e0 : (k1 ? e1 : e2);
+                l1 = (k0 && k1) ? e1 : e2;
+                l2 = e2;
+                if ((c0 < HP) | (c1 < HP) | (c2 < HP)) {
+                    // neighbour in an earlier tile: (slot, neighbour PIXEL); k_ccl_border resolves its slot
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const uint32_t ce = c == 0 ? c0 : (c == 1 ? c1 : c2);
-                    if (ce == 0xffffffffu) continue;
-                    if (ce >= HP) {
-                        const uint32_t ql = ce - HP, w = ql >> 5;
-                        const uint32_t s = c == 0 ? i - 1 : s_wpre[w] + __popc(s_mask[w] & ((1u << (ql & 31)) - 1u));
-                        const uint32_t en = (i << 16) | s;
-                        if (n == 0) l0 = en; else if (n == 1) l1 = en; else l2 = en;
-                        n++;
-                    } else {
-                        // neighbour in an earlier tile: (slot, neighbour PIXEL); k_ccl_border resolves its slot
-                        const uint32_t k = atomicAdd(&s_nx, 1u);
-                        if (k < (uint32_t)CCL_XCAP) xl[k] = make_uint2(base + i, base - (HP - ce));
-                        else s_bad = 1;
+                    for (int c = 0; c < 3; c++) {
+                        const uint32_t ce = c == 0 ? c0 : (c == 1 ? c1 : c2);
+                        if (ce < HP) {
+                            const uint32_t k = atomicAdd(&s_nx, 1u);
+                            if (k < (uint32_t)CCL_XCAP) xl[k] = make_uint2(base + i, base - (HP - ce));
+                            else s_bad = 1;
+                        }
                     }
                 }
             }
@@ -370,18 +370,26 @@ k_ccl_roots(const uint32_t *__restrict__ tilecnt, int NT, int n_tiles_total, con
     const uint32_t tb = (uint32_t)tile * TILE_PX;
     const uint32_t cnt = tilecnt[gt];
     uint32_t carry = 0;
-    for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const uint32_t s = tb + i;
-        const bool is_root = i < cnt && parent_all[fs + s] == s;
-        const uint32_t b = __ballot_sync(0xffffffffu, is_root);
-        if (is_root) {
-            const uint32_t j = carry + __popc(b & ((1u << lane) - 1u));
-            if (PAYLOAD == 0) ord_all[fs + s] = j;
-            if (PAYLOAD == 1) out16[fs + tb + j] = (uint16_t)acc_all[fs + s];
-            if (PAYLOAD == 2) out64[fs + tb + j] = cent_all[fs + s];
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 128) {
+        // four independent parent loads in flight per lane
+        bool is_root[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = i0 + 32 * u + lane;
+            is_root[u] = i < cnt && parent_all[fs + tb + i] == tb + i;
         }
-        carry += __popc(b);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t s = tb + i0 + 32 * u + lane;
+            const uint32_t b = __ballot_sync(0xffffffffu, is_root[u]);
+            if (is_root[u]) {
+                const uint32_t j = carry + __popc(b & ((1u << lane) - 1u));
+                if (PAYLOAD == 0) ord_all[fs + s] = j;
+                if (PAYLOAD == 1) out16[fs + tb + j] = (uint16_t)acc_all[fs + s];
+                if (PAYLOAD == 2) out64[fs + tb + j] = cent_all[fs + s];
+            }
+            carry += __popc(b);
+        }
     }
     if (lane == 0) rootcnt[gt] = carry;
 }

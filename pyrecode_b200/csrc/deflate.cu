@@ -59,6 +59,15 @@ __device__ __forceinline__ int find_stream(const uint32_t *__restrict__ chunk_ba
 // coalesced 128-bit loads of one chunk -> per-thread segments in shared staging (zero padded past clen)
 __device__ __forceinline__ void stage_chunk(uint32_t *in32, const uint8_t *__restrict__ src, int clen, int t)
 {
+    if ((((uintptr_t)src & 15) == 0) && clen == DF_CHUNK) {          // uniform branch: the common case
+#pragma unroll
+        for (int u = t; u < DF_CHUNK / 16; u += DF_THREADS) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(src + u * 16);
+            uint32_t *d = in32 + df_in_index(u >> 2, (u & 3) * 4);
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        return;
+    }
     const bool aligned = ((uintptr_t)src & 15) == 0;
     for (int u = t; u < DF_CHUNK / 16; u += DF_THREADS) {
         const int o = u * 16;

@@ -133,22 +133,23 @@ DF_HD uint32_t df_ne_nibble(uint32_t x, uint32_t y)
     return ((z >> 7) * 0x00204081u >> 21) & 0xfu;     // gather bits 0, 8, 16, 24 -> bits 0..3
 }
 
-// Token masks of thread t's segment (bit i = byte i of the segment):
+// Token masks of thread t's segment (bit i = byte i of the segment; [0] = bytes 0..31, [1] = bytes 32..63):
 //   lit  bytes emitted as literals: bytes that differ from their predecessor, and members of runs shorter than 3
 //   lng  members of runs (>= 3 bytes equal to the byte before the run): covered by a distance-1 match
 //   ms   first byte of each such run = where the match token is emitted; its length is the run of lng bits
-// All of it is branch-free SIMD-in-register work on the 64-bit "same as predecessor" mask, so the 32 lanes of
-// a warp stay converged; the only data-dependent loop left is one iteration per TOKEN (df_for_tokens).
+// All of it is branch-free SIMD-in-register work on the "same as predecessor" mask, so the 32 lanes of a warp
+// stay converged; the only data-dependent loop left is one iteration per TOKEN.  Everything is kept in 32-bit
+// halves: 64-bit shifts and find-first-set cost several instructions each on the GPU.
 struct DfMasks {
-    uint64_t lit, ms, lng;
+    uint32_t lit[2], ms[2], lng[2];
 };
 
-DF_HD int df_ctz64(uint64_t x)
+DF_HD int df_ctz32(uint32_t x)                       // 32 for x == 0
 {
 #ifdef __CUDA_ARCH__
-    return __ffsll((long long)x) - 1;
+    return __clz(__brev(x));
 #else
-    return __builtin_ctzll(x);
+    return x ? __builtin_ctz(x) : 32;
 #endif
 }
 
@@ -168,31 +169,44 @@ DF_HD DfMasks df_token_masks(const uint32_t *in32, int t, int nbytes)
         if (k < 8) blo |= nz << (4 * k); else bhi |= nz << (4 * (k - 8));
         carry = x >> 24;
     }
-    uint64_t brk = ((uint64_t)bhi << 32) | blo;
-    if (prev == 0x100) brk |= 1;                     // chunk start: byte 0 is always a literal
-    const uint64_t valid = nbytes >= DF_SEG ? ~0ull : ((1ull << nbytes) - 1);
-    const uint64_t nb = ~brk & valid;                // same as predecessor
-    const uint64_t a = nb & (nb << 1) & (nb << 2);   // third or later member of a run
+    if (prev == 0x100) blo |= 1;                     // chunk start: byte 0 is always a literal
+    const uint32_t vlo = nbytes >= 32 ? 0xffffffffu : ((1u << nbytes) - 1u);
+    const uint32_t vhi = nbytes >= 64 ? 0xffffffffu : (nbytes > 32 ? ((1u << (nbytes - 32)) - 1u) : 0u);
+    const uint32_t nlo = ~blo & vlo, nhi = ~bhi & vhi;            // same as predecessor
+    // third or later member of a run: nb & (nb << 1) & (nb << 2) over the 64-bit mask
+    const uint32_t alo = nlo & (nlo << 1) & (nlo << 2);
+    const uint32_t ahi = nhi & ((nhi << 1) | (nlo >> 31)) & ((nhi << 2) | (nlo >> 30));
     DfMasks m;
-    m.lng = (a | (a >> 1) | (a >> 2)) & nb;          // every member of a run of >= 3
-    m.lit = valid & ~m.lng;
-    m.ms = m.lng & ~(m.lng << 1);
+    // every member of a run of >= 3: (a | a >> 1 | a >> 2) & nb
+    m.lng[0] = (alo | (alo >> 1) | (ahi << 31) | (alo >> 2) | (ahi << 30)) & nlo;
+    m.lng[1] = (ahi | (ahi >> 1) | (ahi >> 2)) & nhi;
+    m.lit[0] = vlo & ~m.lng[0];
+    m.lit[1] = vhi & ~m.lng[1];
+    m.ms[0] = m.lng[0] & ~(m.lng[0] << 1);
+    m.ms[1] = m.lng[1] & ~((m.lng[1] << 1) | (m.lng[0] >> 31));
     return m;
+}
+
+// Length of the run of lng bits that starts at bit pos of half h.  cont = number of lng bits at the bottom of
+// the upper half (a run that reaches the end of the lower half continues there).
+DF_HD uint32_t df_run_length(const DfMasks &m, int h, int pos, uint32_t cont)
+{
+    const uint32_t l0 = (uint32_t)df_ctz32(~(m.lng[h] >> pos));   // the NOT sets the pos vacated top bits
+    return l0 + ((h == 0 && (uint32_t)pos + l0 == 32u) ? cont : 0u);
 }
 
 // E.lit(c) / E.match(L) in stream order, one loop iteration per token
 template <typename E>
 DF_HD void df_for_tokens(const uint32_t *in32, int t, const DfMasks &m, E &em)
 {
-    uint64_t tk = m.lit | m.ms;
-    while (tk) {
-        const int pos = df_ctz64(tk);
-        tk &= tk - 1;
-        if ((m.lit >> pos) & 1) {
-            em.lit(df_byte_at(in32, t, pos));
-        } else {
-            const uint64_t r = ~(m.lng >> pos);
-            em.match(r ? df_ctz64(r) : DF_SEG);
+    const uint32_t cont = (uint32_t)df_ctz32(~m.lng[1]);
+    for (int h = 0; h < 2; h++) {
+        uint32_t tk = m.lit[h] | m.ms[h];
+        while (tk) {
+            const int pos = df_ctz32(tk);
+            tk &= tk - 1;
+            if ((m.lit[h] >> pos) & 1) em.lit(df_byte_at(in32, t, 32 * h + pos));
+            else em.match((int)df_run_length(m, h, pos, cont));
         }
     }
 }
@@ -219,43 +233,52 @@ DF_HD void df_phase_hist(const uint32_t *in32, uint32_t *hist, int t, int clen)
     const int nbytes = df_seg_bytes(t, clen);
     if (nbytes <= 0) return;
     const DfMasks m = df_token_masks(in32, t, nbytes);
+    const uint32_t cont = (uint32_t)df_ctz32(~m.lng[1]);
     uint32_t n0 = 0;                                 // literal 0x00 is frequent on binary maps: count it privately
-    uint64_t lit = m.lit;
-    while (lit) {
-        const int pos = df_ctz64(lit);
-        lit &= lit - 1;
-        const uint32_t c = df_byte_at(in32, t, pos);
-        if (c == 0) n0++;
-        else DF_ATOMIC_ADD(&hist[c], 1u);
+    for (int h = 0; h < 2; h++) {
+        uint32_t lit = m.lit[h];
+        while (lit) {
+            const int pos = df_ctz32(lit);
+            lit &= lit - 1;
+            const uint32_t c = df_byte_at(in32, t, 32 * h + pos);
+            if (c == 0) n0++;
+            else DF_ATOMIC_ADD(&hist[c], 1u);
+        }
     }
     if (n0) DF_ATOMIC_ADD(&hist[0], n0);
-    uint64_t ms = m.ms;
-    while (ms) {
-        const int pos = df_ctz64(ms);
-        ms &= ms - 1;
-        const uint64_t r = ~(m.lng >> pos);
-        int sym, eb, ev;
-        df_len_code(r ? df_ctz64(r) : DF_SEG, sym, eb, ev);
-        DF_ATOMIC_ADD(&hist[sym], 1u);
+    for (int h = 0; h < 2; h++) {
+        uint32_t ms = m.ms[h];
+        while (ms) {
+            const int pos = df_ctz32(ms);
+            ms &= ms - 1;
+            int sym, eb, ev;
+            df_len_code((int)df_run_length(m, h, pos, cont), sym, eb, ev);
+            DF_ATOMIC_ADD(&hist[sym], 1u);
+        }
     }
 }
 
 // Adler-32 partials of thread t's segment: {sum b_i, sum (clen - i) * b_i}, i = position in the chunk
 DF_HD void df_adler_partial(const uint32_t *in32, int t, int clen, uint32_t &a_out, uint32_t &b_out)
 {
-    const int nbytes = df_seg_bytes(t, clen);
+    const int nbytes = df_seg_bytes(t, clen);          // bytes past nbytes are staged as zeros
     uint32_t a = 0, b = 0;
-    const int nw = (nbytes + 3) >> 2;
-    for (int k = 0; k < nw; k++) {
-        const uint32_t x = in32[df_in_index(t, k)];
-        if (x == 0) continue;
-        for (int bi = 0; bi < 4; bi++) {
-            const int i = k * 4 + bi;
-            if (i < nbytes) {
-                const uint32_t c = (x >> (8 * bi)) & 0xffu;
-                a += c;
-                b += (uint32_t)(clen - (t * DF_SEG + i)) * c;   // <= 64 * 16384 * 255 < 2^32
-            }
+    if (nbytes > 0) {
+        const uint32_t w0 = (uint32_t)(clen - t * DF_SEG);          // weight of the segment's first byte
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < DF_SEG_WORDS; k++) {
+            const uint32_t x = in32[df_in_index(t, k)];
+#ifdef __CUDA_ARCH__
+            const uint32_t s = __dp4a(x, 0x01010101u, 0u);          // c0 + c1 + c2 + c3
+            const uint32_t w = __dp4a(x, 0x03020100u, 0u);          // 0 c0 + 1 c1 + 2 c2 + 3 c3
+#else
+            const uint32_t c0 = x & 0xff, c1 = (x >> 8) & 0xff, c2 = (x >> 16) & 0xff, c3 = x >> 24;
+            const uint32_t s = c0 + c1 + c2 + c3, w = c1 + 2 * c2 + 3 * c3;
+#endif
+            a += s;
+            b += (w0 - 4u * (uint32_t)k) * s - w;                   // <= 64 * 16384 * 255 < 2^32
         }
     }
     a_out = a;
@@ -459,28 +482,37 @@ DF_HD uint32_t df_encode_segment(DfEmitShared &S, int t, int clen)
     const DfMasks m = df_token_masks(S.io, t, nbytes);
     const uint8_t *seg = reinterpret_cast<const uint8_t *>(S.io) + t * (DF_SEG_STRIDE * 4);
     uint32_t *priv = S.priv + t * DF_SEG_STRIDE;
-    uint64_t tk = m.lit | m.ms;
-    uint64_t acc = 0;
+    const uint32_t cont = (uint32_t)df_ctz32(~m.lng[1]);
+    uint32_t lo = 0, hi = 0;                         // bit accumulator: lo is flushed when nb reaches 32
     uint32_t nb = 0, w = 0, total = 0;
-    while (tk) {
-        const int pos = df_ctz64(tk);
-        tk &= tk - 1;
-        const uint64_t r = ~(m.lng >> pos);
-        const uint32_t L = r ? (uint32_t)df_ctz64(r) : (uint32_t)DF_SEG;
-        const uint32_t idx = ((m.lit >> pos) & 1) ? (uint32_t)seg[pos] : (uint32_t)DF_NSYM + L;
-        const uint32_t e = S.tbl[idx];
-        acc |= (uint64_t)(e & 0xffffffu) << nb;
-        nb += e >> 24;
-        total += e >> 24;
-        if (nb >= 32) {
-            if (w < (uint32_t)DF_SEG_STRIDE) priv[w] = (uint32_t)acc;
-            w++;
-            acc >>= 32;
-            nb -= 32;
+    for (int h = 0; h < 2; h++) {
+        uint32_t tk = m.lit[h] | m.ms[h];
+        const uint32_t lit = m.lit[h];
+        while (tk) {
+            const int pos = df_ctz32(tk);
+            tk &= tk - 1;
+            const uint32_t L = df_run_length(m, h, pos, cont);
+            const uint32_t idx = ((lit >> pos) & 1) ? (uint32_t)seg[32 * h + pos] : (uint32_t)DF_NSYM + L;
+            const uint32_t e = S.tbl[idx];
+            const uint32_t code = e & 0xffffffu;
+            lo |= code << nb;
+#ifdef __CUDA_ARCH__
+            hi = __funnelshift_l(code, 0u, nb);      // bits of (code << nb) above bit 31; 0 for nb == 0
+#else
+            hi = nb ? code >> (32 - nb) : 0u;
+#endif
+            nb += e >> 24;
+            total += e >> 24;
+            if (nb >= 32) {
+                if (w < (uint32_t)DF_SEG_STRIDE) priv[w] = lo;
+                w++;
+                lo = hi;
+                nb -= 32;
+            }
         }
     }
     if (nb) {
-        if (w < (uint32_t)DF_SEG_STRIDE) priv[w] = (uint32_t)acc;
+        if (w < (uint32_t)DF_SEG_STRIDE) priv[w] = lo;
         w++;
     }
     if (w > (uint32_t)DF_SEG_STRIDE) S.overflow = 1;
