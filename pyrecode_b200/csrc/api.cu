@@ -146,6 +146,7 @@ extern "C" void rc_destroy(rc_ctx *ctx)
 {
     if (!ctx) return;
     if (ctx->profile) for (int i = 0; i < RC_MAX_MARKS; i++) cudaEventDestroy(ctx->marks[i]);
+    if (ctx->kept_tables) cudaFree(ctx->kept_tables);
     if (ctx->side_ready) {
         cudaStreamDestroy(ctx->side);
         cudaEventDestroy(ctx->ev_fork);
@@ -298,16 +299,43 @@ static int reduce_stage2(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const
     return launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, nullptr, 0, st);
 }
 
-// one deflate group (F streams): descriptors, then encode (wrap = 1) or size (wrap = 0) its chunks
-static int deflate_group(rc_ctx *ctx, const rc_config *cfg, const uint8_t *base, const uint8_t *first, size_t stride,
-                         const uint32_t *len, uint32_t uniform_len, int F, uint64_t *in_off, uint32_t *in_bytes,
-                         const DeflateWs &d, cudaStream_t st)
+// one deflate group (F streams; group 0 = maps, 1 = values): descriptors, then encode (wrap = 1) or size
+// (wrap = 0) its chunks
+static int deflate_group(rc_ctx *ctx, const rc_config *cfg, int group, const uint8_t *base, const uint8_t *first,
+                         size_t stride, const uint32_t *len, uint32_t uniform_len, int F, uint64_t *in_off,
+                         uint32_t *in_bytes, const DeflateWs &d, cudaStream_t st)
 {
     k_stream_desc<<<(F + 127) / 128, 128, 0, st>>>(base, first, stride, len, uniform_len, F, in_off, in_bytes);
     RC_LAUNCH_CHECK(ctx, "k_stream_desc");
-    // the frames of one batch are statistically alike: levels 1..5 share one sampled code per group
-    return launch_deflate_streams(ctx, cfg->compression_level, cfg->rc_operation_mode == 1, cfg->compression_level < 6,
-                                  base, in_off, in_bytes, F, d, st);
+    // The frames of one acquisition are statistically alike: levels 1..5 use one sampled code per group, kept in
+    // the context and rebuilt every RC_TABLE_REFRESH calls.  Any code encodes any data (all symbols are
+    // smoothed to non-zero counts, a chunk that would grow is stored), so staleness only costs ratio.
+    const int shared = cfg->compression_level >= 1 && cfg->compression_level < 6 && cfg->rc_operation_mode == 1;
+    void *kept = nullptr;
+    int build = 1;
+    if (shared) {
+        kept = (uint8_t *)ctx->kept_tables + (size_t)group * deflate_table_bytes();
+        build = ctx->table_age[group] == 0;
+        ctx->table_age[group] = (ctx->table_age[group] + 1) % RC_TABLE_REFRESH;
+    }
+    return launch_deflate_streams(ctx, cfg->compression_level, cfg->rc_operation_mode == 1, shared, kept, build, base,
+                                  in_off, in_bytes, F, d, st);
+}
+
+// the kept codes belong to one configuration: any change starts them afresh
+static int prepare_kept_tables(rc_ctx *ctx, const rc_config *cfg)
+{
+    if (!ctx->kept_tables) RC_CUDA(ctx, cudaMalloc(&ctx->kept_tables, 2 * deflate_table_bytes()));
+    const unsigned long long key = ((unsigned long long)cfg->ny << 40) ^ ((unsigned long long)cfg->nx << 20) ^
+                                   ((unsigned long long)cfg->bit_depth << 12) ^ ((unsigned long long)cfg->itemsize << 10) ^
+                                   ((unsigned long long)cfg->reduction_level << 7) ^
+                                   ((unsigned long long)cfg->l2_statistics << 5) ^
+                                   ((unsigned long long)cfg->l4_centroiding << 3) ^ (unsigned long long)cfg->compression_level;
+    if (key != ctx->table_key) {
+        ctx->table_key = key;
+        ctx->table_age[0] = ctx->table_age[1] = 0;
+    }
+    return 0;
 }
 
 static int ensure_side_stream(rc_ctx *ctx)
@@ -360,6 +388,7 @@ extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void 
     }
     const uint8_t *base = (const uint8_t *)d_workspace;
     const int level = cfg->reduction_level;
+    if ((rc = prepare_kept_tables(ctx, cfg))) return rc;
     // The map streams of L1 / L2 / L3 are final after stage 1: they are deflated on the side stream while the main
     // stream labels puddles and packs the values.  (L4's map is the last product of stage 2.)
     const bool fork = level != 4 && F > 0;
@@ -372,17 +401,17 @@ extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void 
         sm = ctx->side;
         RC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         RC_CUDA(ctx, cudaStreamWaitEvent(sm, ctx->ev_fork, 0));
-        if ((rc = deflate_group(ctx, cfg, base, (const uint8_t *)cw.maps, g.MS * 4, nullptr, (uint32_t)g.map_bytes, F,
+        if ((rc = deflate_group(ctx, cfg, 0, base, (const uint8_t *)cw.maps, g.MS * 4, nullptr, (uint32_t)g.map_bytes, F,
                                 cw.map_off, cw.map_len, cw.dm, sm))) return rc;
         RC_CUDA(ctx, cudaEventRecord(ctx->ev_join, sm));
     }
     if ((rc = reduce_stage2(ctx, cfg, g, w, F, cw.maps, cw.packed, cw.packed_stride, cw.packed_bytes, d_counts, st)))
         return rc;
     rc_mark(ctx, 2, st);
-    if (!fork && (rc = deflate_group(ctx, cfg, base, (const uint8_t *)cw.maps, g.MS * 4, nullptr, (uint32_t)g.map_bytes,
-                                     F, cw.map_off, cw.map_len, cw.dm, st))) return rc;
-    if (cw.spf == 2 && (rc = deflate_group(ctx, cfg, base, cw.packed, cw.packed_stride, cw.packed_bytes, 0, F, cw.val_off,
-                                           cw.val_len, cw.dv, st))) return rc;
+    if (!fork && (rc = deflate_group(ctx, cfg, 0, base, (const uint8_t *)cw.maps, g.MS * 4, nullptr,
+                                     (uint32_t)g.map_bytes, F, cw.map_off, cw.map_len, cw.dm, st))) return rc;
+    if (cw.spf == 2 && (rc = deflate_group(ctx, cfg, 1, base, cw.packed, cw.packed_stride, cw.packed_bytes, 0, F,
+                                           cw.val_off, cw.val_len, cw.dv, st))) return rc;
     if (fork) RC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     rc_mark(ctx, 3, st);
     const int wrap = cfg->rc_operation_mode == 1;
@@ -462,7 +491,7 @@ extern "C" int rc_deflate_zlib(rc_ctx *ctx, int compression_level, const uint8_t
     DeflateWs w = carve_deflate_ws(c, n_streams, deflate_max_chunks(n_streams, max_in_bytes), true);
     uint32_t *status = w.counters + 4;
     int rc;
-    if ((rc = launch_deflate_streams(ctx, compression_level, 1, 0, d_in, d_in_offsets, d_in_bytes, n_streams, w, st))) return rc;
+    if ((rc = launch_deflate_streams(ctx, compression_level, 1, 0, nullptr, 1, d_in, d_in_offsets, d_in_bytes, n_streams, w, st))) return rc;
     if ((rc = launch_layout_strided(ctx, w, n_streams, out_stride, d_out_bytes, st))) return rc;
     return launch_copy_pieces(ctx, w, 1, d_in, d_in_offsets, d_in_bytes, n_streams, d_out, (size_t)n_streams * out_stride,
                               status, st);

@@ -52,7 +52,15 @@ struct rc_ctx {
     cudaStream_t side;
     cudaEvent_t ev_fork, ev_join;
     int side_ready;
+    // Huffman codes kept across rc_reduce_compress calls (compression levels 1..5): [0] map streams, [1] value
+    // streams.  Frames of one acquisition share their statistics, so a code is rebuilt only every
+    // RC_TABLE_REFRESH calls (or when the configuration changes) instead of once per batch.
+    void *kept_tables;
+    int table_age[2];
+    unsigned long long table_key;
 };
+
+constexpr int RC_TABLE_REFRESH = 16;
 
 static inline void rc_mark(rc_ctx *ctx, int idx, cudaStream_t st)
 {

@@ -704,6 +704,8 @@ __global__ void k_raw_chunk_bytes(const uint32_t *__restrict__ in_bytes, const u
 }
 
 // ---- host side -------------------------------------------------------------------------------------
+size_t deflate_table_bytes() { return sizeof(DeflateTable); }
+
 size_t deflate_max_chunks(int n_streams, size_t max_in_bytes)
 {
     return (size_t)n_streams * ((max_in_bytes + DF_CHUNK - 1) / DF_CHUNK);
@@ -728,17 +730,21 @@ DeflateWs carve_deflate_ws(Carver &c, int n_streams, size_t max_chunks, bool nee
 }
 
 // encodes (wrap = 1) or sizes (wrap = 0, reduce-only mode) the chunks and finalizes per-stream totals
-// shared_table: the streams are statistically alike (the frames of one batch): one sampled code for all of them
-int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, int shared_table, const uint8_t *in,
-                           const uint64_t *in_off, const uint32_t *in_bytes, int n_streams, const DeflateWs &w,
-                           cudaStream_t st)
+// shared_table: the streams are statistically alike (the frames of one batch): one sampled code for all of them.
+// kept_table (shared_table only): a code in context-owned memory that survives the call; it is rebuilt from this
+// batch when build_table is set and re-used as it is otherwise (no histogram / table kernels at all).
+int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, int shared_table, void *kept_table, int build_table,
+                           const uint8_t *in, const uint64_t *in_off, const uint32_t *in_bytes, int n_streams,
+                           const DeflateWs &w, cudaStream_t st)
 {
     if (n_streams <= 0) return 0;
+    DeflateTable *tables = (shared_table && kept_table) ? (DeflateTable *)kept_table : (DeflateTable *)w.tables;
+    if (!(shared_table && kept_table)) build_table = 1;
     k_deflate_plan<<<1, 256, 0, st>>>(in_bytes, n_streams, w.chunk_base, w.counters, wrap ? w.ghist : nullptr);
     RC_LAUNCH_CHECK(ctx, "k_deflate_plan");
     if (wrap) {
         size_t want;
-        if (level > 0) {
+        if (level > 0 && build_table) {
             const size_t tasks = shared_table ? (w.max_chunks + DF_SAMPLE - 1) / DF_SAMPLE : w.max_chunks;
             want = tasks < (size_t)ctx->sm_count * 8 ? tasks : (size_t)ctx->sm_count * 8;
             if (want < 1) want = 1;
@@ -746,14 +752,14 @@ int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, int shared_table, c
                                                                    w.counters, shared_table, w.ghist);
             RC_LAUNCH_CHECK(ctx, "k_deflate_hist");
             k_deflate_tables<<<shared_table ? 1 : n_streams, DF_THREADS, 0, st>>>(
-                w.ghist, w.chunk_base, in_bytes, w.counters, shared_table, n_streams, (DeflateTable *)w.tables);
+                w.ghist, w.chunk_base, in_bytes, w.counters, shared_table, n_streams, tables);
             RC_LAUNCH_CHECK(ctx, "k_deflate_tables");
         }
         want = w.max_chunks < (size_t)ctx->sm_count * 6 ? w.max_chunks : (size_t)ctx->sm_count * 6;
         if (want < 1) want = 1;
         k_deflate_chunks<<<(unsigned)want, DF_THREADS, 0, st>>>(in, in_off, in_bytes, n_streams, w.chunk_base,
                                                                  w.counters, level, shared_table,
-                                                                 (const DeflateTable *)w.tables, w.scratch,
+                                                                 tables, w.scratch,
                                                                  w.chunk_bytes, w.chunk_adler);
         RC_LAUNCH_CHECK(ctx, "k_deflate_chunks");
     } else {

@@ -58,9 +58,10 @@ struct DeflateWs {
 };
 size_t deflate_max_chunks(int n_streams, size_t max_in_bytes);
 DeflateWs carve_deflate_ws(Carver &c, int n_streams, size_t max_chunks, bool need_scratch);
-int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, int shared_table, const uint8_t *in,
-                           const uint64_t *in_off, const uint32_t *in_bytes, int n_streams, const DeflateWs &w,
-                           cudaStream_t st);
+int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, int shared_table, void *kept_table, int build_table,
+                           const uint8_t *in, const uint64_t *in_off, const uint32_t *in_bytes, int n_streams,
+                           const DeflateWs &w, cudaStream_t st);
+size_t deflate_table_bytes();
 int launch_layout_strided(rc_ctx *ctx, const DeflateWs &w, int n_streams, size_t stride, uint32_t *out_bytes,
                           cudaStream_t st);
 int launch_layout_records(rc_ctx *ctx, const DeflateWs &wm, const DeflateWs &wv, const uint32_t *packed_bytes,
