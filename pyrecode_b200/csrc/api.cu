@@ -70,6 +70,7 @@ static ReduceWs carve_reduce(Carver &c, const rc_config *cfg, const Geom &g, int
         w.acc = c.take<uint32_t>(F * g.slots);
         w.stats16 = c.take<uint16_t>(F * g.slots);
     }
+    if ((what == 0 && level == 4) || what == 2) w.acc = c.take<uint32_t>(F * g.slots);    // L4: claim flags
     if ((what == 0 && level == 4) || what == 2) {
         w.bbox = c.take<uint32_t>(F * g.slots * 4);
         w.map1 = c.take<uint32_t>(F * g.MS + 16);
@@ -277,7 +278,8 @@ static int reduce_stage2(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const
     if (level == 2) {
         const int sum = cfg->l2_statistics == 2;
         if ((rc = launch_ccl_tiles(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf,
-                                   w.xcount, w.xlinks, w.parent, w.acc, F, st))) return rc;
+                                   w.xcount, w.xlinks, w.parent, w.acc, 0, nullptr, nullptr, nullptr, nullptr, F,
+                                   st))) return rc;
         if ((rc = launch_ccl_border(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, w.acc,
                                     F, st))) return rc;
         if ((rc = launch_ccl_roots(ctx, g, 1, w.tilecnt, w.parent, w.acc, nullptr, w.rootcnt, nullptr, w.stats16,
@@ -285,17 +287,16 @@ static int reduce_stage2(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const
         if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, packed_bytes, b, st))) return rc;
         return launch_bitpack(ctx, g, 2, w.stats16, w.rootpre, F, b, packed, packed_stride, st);
     }
-    if ((rc = launch_ccl_tiles(ctx, g, 0, w.map1, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf, w.xcount,
-                               w.xlinks, w.parent, nullptr, F, st))) return rc;
-    if ((rc = launch_ccl_border(ctx, g, 0, w.map1, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, nullptr, F,
-                                st))) return rc;
-    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, w.bbox, F, st))) return rc;
+    // level 4: puddles inside one tile are finished by k_ccl_tiles, the ones that cross tiles by k_l4_open
     RC_CUDA(ctx, cudaMemsetAsync(maps, 0, (size_t)F * g.MS * sizeof(uint32_t), st));
-    if ((rc = launch_l4_centroids(ctx, g, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox,
-                                  (const uint32_t *)w.vals, maps, nullptr, F, st))) return rc;
-    // puddle count = number of roots
-    if ((rc = launch_ccl_roots(ctx, g, 3, w.tilecnt, w.parent, nullptr, nullptr, w.rootcnt, nullptr, nullptr, nullptr,
-                               F, st))) return rc;
+    if ((rc = launch_ccl_tiles(ctx, g, 3, w.map1, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf, w.xcount,
+                               w.xlinks, w.parent, w.acc, cfg->l4_centroiding, w.bbox, maps, nullptr, w.rootcnt, F,
+                               st))) return rc;
+    if ((rc = launch_ccl_border(ctx, g, 3, w.map1, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, w.bbox, F,
+                                st))) return rc;
+    if ((rc = launch_l4_open(ctx, g, cfg->l4_centroiding, w.map1, w.wordpre, w.tilecnt, w.tileovf, w.xcount, w.xlinks,
+                             w.parent, w.acc, w.bbox, (const uint32_t *)w.vals, maps, nullptr, w.rootcnt, F, st)))
+        return rc;
     return launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, nullptr, 0, st);
 }
 
@@ -442,7 +443,7 @@ extern "C" int rc_ccl_label(rc_ctx *ctx, const rc_config *cfg, const uint32_t *d
     if ((rc = launch_map_counts(ctx, g, d_maps, F, w.tilecnt, w.wordpre, st))) return rc;
     if ((rc = launch_ccl_init(ctx, g, w.tilecnt, w.parent, F, st))) return rc;
     if ((rc = launch_ccl_union(ctx, g, d_maps, w.wordpre, w.parent, F, st))) return rc;
-    if ((rc = launch_ccl_flatten(ctx, g, 0, d_maps, w.wordpre, w.parent, nullptr, F, st))) return rc;
+    if ((rc = launch_ccl_flatten(ctx, g, d_maps, w.wordpre, w.parent, F, st))) return rc;
     if ((rc = launch_ccl_roots(ctx, g, 0, w.tilecnt, w.parent, nullptr, nullptr, w.rootcnt, w.ord, nullptr, nullptr, F, st))) return rc;
     if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, d_counts, nullptr, 0, st))) return rc;
     return launch_ccl_label_image(ctx, g, d_maps, w.wordpre, w.parent, w.ord, w.rootpre, d_labels, F, st);
@@ -463,13 +464,14 @@ extern "C" int rc_l4_centroids(rc_ctx *ctx, const rc_config *cfg, const void *d_
     const int F = n_frames, isz = cfg->itemsize;
     int rc;
     if ((rc = launch_reduce_tiles(ctx, g, isz, 2, d_frames, d_thr, F, w.map1, w.tilecnt, w.wordpre, w.vals, st))) return rc;
-    if ((rc = launch_ccl_tiles(ctx, g, 0, w.map1, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf, w.xcount,
-                               w.xlinks, w.parent, nullptr, F, st))) return rc;
-    if ((rc = launch_ccl_border(ctx, g, 0, w.map1, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, nullptr, F,
+    if ((rc = launch_ccl_tiles(ctx, g, 3, w.map1, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf, w.xcount,
+                               w.xlinks, w.parent, w.acc, cfg->l4_centroiding, w.bbox, nullptr, w.cent, w.rootcnt, F,
+                               st))) return rc;
+    if ((rc = launch_ccl_border(ctx, g, 3, w.map1, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, w.bbox, F,
                                 st))) return rc;
-    if ((rc = launch_ccl_flatten(ctx, g, 3, w.map1, w.wordpre, w.parent, w.bbox, F, st))) return rc;
-    if ((rc = launch_l4_centroids(ctx, g, cfg->l4_centroiding, w.map1, w.wordpre, w.parent, w.bbox, (const uint32_t *)w.vals, nullptr,
-                                  w.cent, F, st))) return rc;
+    if ((rc = launch_l4_open(ctx, g, cfg->l4_centroiding, w.map1, w.wordpre, w.tilecnt, w.tileovf, w.xcount, w.xlinks,
+                             w.parent, w.acc, w.bbox, (const uint32_t *)w.vals, nullptr, w.cent, w.rootcnt, F, st)))
+        return rc;
     if ((rc = launch_ccl_roots(ctx, g, 2, w.tilecnt, w.parent, nullptr, w.cent, w.rootcnt, nullptr, nullptr, w.cent_tiles,
                                F, st))) return rc;
     if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, d_counts, nullptr, 0, st))) return rc;

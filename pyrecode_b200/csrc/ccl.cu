@@ -17,12 +17,12 @@
 //   k_ccl_border    PASS 0 links pixels across tile boundaries with atomicMin unions; PASS 1 folds the L2
 //                   statistic of every tile-local root that was merged into an earlier tile's puddle.
 //   k_ccl_union     full-frame linking for maps that did not come from k_reduce_tiles (rc_ccl_label).
-//   k_ccl_flatten   parent[slot] = root; L4: grows the root's bounding box (row extent, left / right columns).
+//   k_ccl_flatten   parent[slot] = root (rc_ccl_label only).
 //   k_ccl_roots     one warp per tile: compacts per-root payloads (L2 statistics, centroids, ordinals) in
 //                   slot order == label order.
-//   k_l4_centroids  one thread per root: replays the puddle's pixels in raster order inside its bounding
-//                   box with the reference's float32-after-every-add accumulation, divides, rounds half to
-//                   even and sets the centroid bit.  Single-pixel puddles are their own centroid.
+//   k_l4_open       L4 puddles that cross tiles: one thread per puddle replays its pixels in raster order inside
+//                   its bounding box with the reference's float32-after-every-add accumulation, divides, rounds
+//                   half to even and sets the centroid bit.  (Puddles inside one tile: k_ccl_tiles<3>.)
 #include "common.cuh"
 #include "kernels.cuh"
 #include "ccl_core.cuh"
@@ -45,59 +45,109 @@ constexpr int CCL_XCAP = 256;          // cross-tile links per tile (global list
 constexpr int CCL_HALO = 264;          // map words kept in front of the tile (multiple of 4): nx <= 8447
 constexpr int CCL_THREADS = 256;
 
-// FOLD: 0 = labels only (L4), 1 = L2 max, 2 = L2 sum
+// Centroid of one puddle with the reference's arithmetic (pyrecode/utils/converters.py): members are added in
+// raster order, every += is float64 arithmetic rounded to float32 (numba: float32 element += float64 value).
+// mode: 0/1 weighted average (:167-197), 2 maximum pixel (:229-259), 3 unweighted (:200-226).
+struct CentAcc {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    bool first = true;
+    __device__ __forceinline__ void add(int mode, uint32_t r, uint32_t c, uint32_t val)
+    {
+        const double v = (double)val;
+        if (mode == 2) {
+            if (first || v > (double)a2) { a0 = (float)r; a1 = (float)c; a2 = (float)v; }
+        } else if (mode == 3) {
+            a0 = (float)((double)a0 + (double)r);
+            a1 = (float)((double)a1 + (double)c);
+            a2 = (float)((double)a2 + 1.0);
+        } else {
+            a0 = (float)((double)a0 + v * (double)r);
+            a1 = (float)((double)a1 + v * (double)c);
+            a2 = (float)((double)a2 + v);
+        }
+        first = false;
+    }
+    __device__ __forceinline__ void finish(int mode, float &fr, float &fc) const
+    {
+        if (mode == 2) { fr = a0; fc = a1; }
+        else { fr = __fdiv_rn(a0, a2); fc = __fdiv_rn(a1, a2); }
+    }
+};
+
+// centroid -> bit of the centroid map (make_binary_map intent, converters.py:300-309: round half to even)
+__device__ __forceinline__ bool centroid_pixel(float fr, float fc, int ny, int nx, uint32_t &q)
+{
+    const long rr = (long)rintf(fr), cc = (long)rintf(fc);
+    if (rr < 0 || rr >= ny || cc < 0 || cc >= nx) return false;
+    q = (uint32_t)rr * (uint32_t)nx + (uint32_t)cc;
+    return true;
+}
+
+// FOLD: 1 = L2 max, 2 = L2 sum, 3 = L4: centroids of the puddles that lie entirely inside the tile ("closed");
+// puddles that continue in another tile ("open") get a bounding box and are finished by k_l4_open.
 template <int FOLD>
 __global__ void __launch_bounds__(CCL_THREADS)
 k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
             const uint32_t *__restrict__ tilecnt, const uint32_t *__restrict__ vp_all, uint8_t *__restrict__ tileovf,
             uint32_t *__restrict__ xcount, uint2 *__restrict__ xlinks, uint32_t *__restrict__ parent_all,
-            uint32_t *__restrict__ acc_all, int ny, int nx)
+            uint32_t *__restrict__ acc_all, int ny, int nx, int l4mode, uint32_t *__restrict__ bbox_all,
+            uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all, uint32_t *__restrict__ rootcnt)
 {
+    constexpr bool L4 = FOLD == 3;
     // map words of the tile preceded by a halo: the CCL_HALO words before the tile (zeros before the frame),
     // so that the W / NW / N / NE probes of every pixel are plain shared-memory reads
     __shared__ __align__(16) uint32_t s_maskx[CCL_HALO + TILE_WORDS];
     __shared__ __align__(16) uint16_t s_wpre[TILE_WORDS];
     __shared__ uint32_t s_parent[CCL_CAP];
-    __shared__ uint32_t s_acc[FOLD ? CCL_CAP : 1];
+    __shared__ uint32_t s_acc[CCL_CAP];                // L2: statistic; L4: pixel value
     __shared__ uint16_t s_pos[CCL_CAP];
-    __shared__ uint32_t s_links[CCL_LINKS];            // (a << 16) | b, tile-local slots
-    __shared__ uint32_t s_nlinks, s_nx, s_bad;
+    __shared__ uint32_t s_links[CCL_LINKS];            // (a << 16) | b, tile-local slots; later: last member / root list
+    __shared__ __align__(16) uint32_t s_bot[L4 ? CCL_HALO : 4];     // first words of the next tile (zeros after the frame)
+    __shared__ uint8_t s_open[L4 ? CCL_CAP : 4];       // pixel, then root: its puddle continues in another tile
+    __shared__ uint32_t s_cmap[L4 ? TILE_WORDS : 4];   // centroid bits that fall inside the tile
+    __shared__ uint32_t s_nlinks, s_nx, s_bad, s_nlist, s_nclosed;
     const int tile = blockIdx.x, f = blockIdx.y, t = threadIdx.x, lane = t & 31;
     const size_t ti = (size_t)f * NT + tile;
     const uint32_t base = (uint32_t)tile << TILE_LOG2;
-    const size_t sbase = (size_t)f * ((size_t)NT * TILE_PX) + base;
+    const size_t slots = (size_t)NT * TILE_PX;
+    const size_t sbase = (size_t)f * slots + base;
     const size_t wo = (size_t)f * MS + (size_t)tile * TILE_WORDS;
     uint32_t *parent = parent_all + sbase;
     const uint32_t *vp = vp_all + sbase;
     const uint32_t *s_mask = s_maskx + CCL_HALO;
     // issue the tile's loads before the (dependent) per-pixel ones
     const uint4 r_map = reinterpret_cast<const uint4 *>(maps + wo)[t];
-    uint4 r_wpre = make_uint4(0, 0, 0, 0), r_halo = make_uint4(0, 0, 0, 0);
+    uint4 r_wpre = make_uint4(0, 0, 0, 0), r_halo = make_uint4(0, 0, 0, 0), r_bot = make_uint4(0, 0, 0, 0);
     if (t < TILE_WORDS / 8) r_wpre = reinterpret_cast<const uint4 *>(wordpre_all + wo)[t];
     if (t < CCL_HALO / 4 && tile > 0) r_halo = reinterpret_cast<const uint4 *>(maps + wo - CCL_HALO)[t];
+    if (L4 && t < CCL_HALO / 4 && tile + 1 < NT) r_bot = reinterpret_cast<const uint4 *>(maps + wo + TILE_WORDS)[t];
     const uint32_t total = tilecnt[ti];
     if (total == 0) {
-        if (t == 0) { tileovf[ti] = 0; xcount[ti] = 0; }
+        if (t == 0) { tileovf[ti] = 0; xcount[ti] = 0; if (L4) rootcnt[ti] = 0; }
         return;
     }
     const uint32_t unx = (uint32_t)nx;
     // the probes reach nx + 1 pixels back; wider frames than the halo covers take the global path
     bool overflow = total > (uint32_t)CCL_CAP || unx + 1 > (uint32_t)CCL_HALO * 32;
+    const bool pow2 = (unx & (unx - 1u)) == 0;
+    const uint32_t lg = 31 - __clz(unx);
     if (!overflow) {
         reinterpret_cast<uint4 *>(s_maskx + CCL_HALO)[t] = r_map;
         if (t < TILE_WORDS / 8) reinterpret_cast<uint4 *>(s_wpre)[t] = r_wpre;
         if (t < CCL_HALO / 4) reinterpret_cast<uint4 *>(s_maskx)[t] = r_halo;
+        if (L4 && t < CCL_HALO / 4) reinterpret_cast<uint4 *>(s_bot)[t] = r_bot;
         for (uint32_t i = t; i < total; i += CCL_THREADS) {
             const uint32_t v = vp[i];
             s_pos[i] = (uint16_t)v;
-            if (FOLD) s_acc[i] = v >> 16;
+            s_acc[i] = v >> 16;
             s_parent[i] = i;
+            if (L4) s_open[i] = 0;
         }
-        if (t == 0) { s_nlinks = 0; s_nx = 0; s_bad = 0; }
+        if (L4) for (int i = t; i < TILE_WORDS; i += CCL_THREADS) s_cmap[i] = 0;
+        if (t == 0) { s_nlinks = 0; s_nx = 0; s_bad = 0; s_nlist = 0; s_nclosed = 0; }
         __syncthreads();
 
         // ---- phase 1: link detection
-        const bool pow2 = (unx & (unx - 1u)) == 0;
         uint2 *xl = xlinks + ti * CCL_XCAP;
         constexpr uint32_t HP = CCL_HALO * 32;         // halo pixels
         for (uint32_t i0 = 0; i0 < total; i0 += CCL_THREADS) {
@@ -132,6 +182,7 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
                 l2 = e2;
                 if ((c0 < HP) | (c1 < HP) | (c2 < HP)) {
                     // neighbour in an earlier tile: (slot, neighbour PIXEL); k_ccl_border resolves its slot
+                    if (L4) s_open[i] = 1;
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
                         const uint32_t ce = c == 0 ? c0 : (c == 1 ? c1 : c2);
@@ -141,6 +192,20 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
                             else s_bad = 1;
                         }
                     }
+                }
+                if (L4 && p + unx + 1 >= (uint32_t)TILE_PX && gp + unx < (uint32_t)ny * unx) {
+                    // last rows of the tile: a SW / S / SE neighbour in the next tile also opens the puddle
+                    bool any = false;
+#pragma unroll
+                    for (int d = -1; d <= 1; d++) {
+                        if ((d < 0 && !hl) || (d > 0 && !hr)) continue;
+                        const uint32_t tq = p + unx + (uint32_t)d;
+                        if (tq >= (uint32_t)TILE_PX) {
+                            const uint32_t o = tq - TILE_PX;
+                            any |= (s_bot[o >> 5] >> (o & 31)) & 1u;
+                        }
+                    }
+                    if (any) s_open[i] = 1;
                 }
             }
             // warp-aggregated append of n in {0..3} entries per lane
@@ -161,10 +226,18 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     }
     if (overflow) {
         for (uint32_t i = t; i < total; i += CCL_THREADS) {
+            const uint32_t v = vp[i];
             parent[i] = base + i;
-            if (FOLD) acc_all[sbase + i] = vp[i] >> 16;
+            if (L4) {
+                // every pixel is its own puddle until k_ccl_border links the tile: box = the pixel, not claimed
+                const uint32_t gp = base + (v & 0x7fffu), r = gp / unx, c = gp - r * unx;
+                reinterpret_cast<uint4 *>(bbox_all)[sbase + i] = make_uint4(r, r, c, c);
+                acc_all[sbase + i] = 0;
+            } else {
+                acc_all[sbase + i] = v >> 16;
+            }
         }
-        if (t == 0) { tileovf[ti] = 1; xcount[ti] = 0; }
+        if (t == 0) { tileovf[ti] = 1; xcount[ti] = 0; if (L4) rootcnt[ti] = 0; }
         return;
     }
     if (t == 0) { tileovf[ti] = 0; xcount[ti] = s_nx; }
@@ -176,6 +249,15 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
         uf_union(s_parent, e >> 16, e & 0xffffu);
     }
     __syncthreads();
+    // L4: members of each root as a linked list (head per root, next per member); the link list and the map
+    // words are consumed, their shared memory is reused
+    constexpr uint32_t NIL = 0xffffu;
+    uint32_t *s_head = s_links;
+    uint16_t *s_next = reinterpret_cast<uint16_t *>(s_maskx);
+    if (L4) {
+        for (uint32_t i = t; i < total; i += CCL_THREADS) s_head[i] = NIL;
+        __syncthreads();
+    }
     // ---- phase 3: flatten; L2 folds every member's value into its root (non-roots are never written again)
     for (uint32_t i = t; i < total; i += CCL_THREADS) {
         const uint32_t r = uf_find_ro(s_parent, i);
@@ -183,6 +265,10 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
             s_parent[i] = r;
             if (FOLD == 1) atomicMax(&s_acc[r], s_acc[i]);
             if (FOLD == 2) atomicAdd(&s_acc[r], s_acc[i]);
+            if (L4) {
+                s_next[i] = (uint16_t)atomicExch(&s_head[r], i);
+                if (s_open[i]) s_open[r] = 1;
+            }
         }
     }
     __syncthreads();
@@ -190,8 +276,103 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     for (uint32_t i = t; i < total; i += CCL_THREADS) {
         const uint32_t r = s_parent[i];
         parent[i] = r == i ? base + i : ((base + r) | UF_FLAG);
-        if (FOLD) acc_all[sbase + i] = s_acc[i];
+        if (!L4) acc_all[sbase + i] = s_acc[i];
     }
+    if (!L4) return;
+
+    // ---- phase 5 (L4): one thread per root.  Single-pixel puddles are finished at once; the others go to a
+    // dense list first so that every lane of the second loop has a puddle to replay.  Members are visited in
+    // slot order = raster order.
+    uint32_t *cmap_g = map2_all ? map2_all + (size_t)f * MS : nullptr;
+    uint16_t *s_list = s_wpre;                        // the per-word prefixes are no longer needed
+    uint32_t nclosed = 0;
+    auto finish_root = [&](uint32_t i, bool open, const CentAcc &ca, uint4 box) {
+        if (open) {
+            reinterpret_cast<uint4 *>(bbox_all)[sbase + i] = box;
+            acc_all[sbase + i] = 0;                   // not yet claimed by k_l4_open
+            return;
+        }
+        float fr, fc;
+        ca.finish(l4mode, fr, fc);
+        nclosed++;
+        if (cent_all) cent_all[sbase + i] = (uint64_t)__float_as_uint(fr) | ((uint64_t)__float_as_uint(fc) << 32);
+        uint32_t q;
+        if (cmap_g && centroid_pixel(fr, fc, ny, nx, q)) {
+            const uint32_t ql = q - base;                             // wraps when q < base
+            if (ql < (uint32_t)TILE_PX) atomicOr(&s_cmap[ql >> 5], 1u << (ql & 31));
+            else atomicOr(&cmap_g[q >> 5], 1u << (q & 31));           // unaligned tiles only
+        }
+    };
+    for (uint32_t i0 = 0; i0 < total; i0 += CCL_THREADS) {
+        const uint32_t i = i0 + t;
+        const bool root = i < total && s_parent[i] == i;
+        const bool multi = root && s_head[i] != NIL;
+        if (root && !multi) {
+            const uint32_t gp = base + s_pos[i];
+            const uint32_t r = pow2 ? gp >> lg : gp / unx, c = gp - r * unx;
+            CentAcc ca;
+            ca.add(l4mode, r, c, s_acc[i]);
+            finish_root(i, s_open[i], ca, make_uint4(r, r, c, c));
+        }
+        const uint32_t bm = __ballot_sync(0xffffffffu, multi);
+        uint32_t wbase = 0;
+        if (lane == 0 && bm) wbase = atomicAdd(&s_nlist, __popc(bm));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (multi) s_list[wbase + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)i;
+    }
+    __syncthreads();
+    const uint32_t nlist = s_nlist;
+    // list entry k -> warp k % 8, lane k / 8: every warp gets its share of the replays
+    for (uint32_t k = (uint32_t)(t >> 5) + 8u * (uint32_t)lane; k < nlist; k += CCL_THREADS) {
+        const uint32_t i = s_list[k];
+        const bool open = s_open[i];
+        CentAcc ca;
+        uint32_t rmin = 0xffffffffu, rmax = 0, cmin = 0xffffffffu, cmax = 0;
+        auto visit = [&](uint32_t j) {
+            const uint32_t gp = base + s_pos[j];
+            const uint32_t r = pow2 ? gp >> lg : gp / unx, c = gp - r * unx;
+            if (open) {
+                rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+            } else {
+                ca.add(l4mode, r, c, s_acc[j]);
+            }
+        };
+        // up to 8 members besides the root: collect, sort (the list is in arrival order), replay in slot order
+        uint32_t m[8];
+        uint32_t p = s_head[i];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            m[u] = p;
+            if (p != NIL) p = s_next[p];
+        }
+        if (p == NIL) {
+#define RC_CSWAP(a, b) { const uint32_t lo_ = min(m[a], m[b]), hi_ = max(m[a], m[b]); m[a] = lo_; m[b] = hi_; }
+            // 19-comparator sorting network for 8 keys (NIL sorts last)
+            RC_CSWAP(0, 1) RC_CSWAP(2, 3) RC_CSWAP(4, 5) RC_CSWAP(6, 7)
+            RC_CSWAP(0, 2) RC_CSWAP(1, 3) RC_CSWAP(4, 6) RC_CSWAP(5, 7)
+            RC_CSWAP(1, 2) RC_CSWAP(5, 6) RC_CSWAP(0, 4) RC_CSWAP(3, 7)
+            RC_CSWAP(1, 5) RC_CSWAP(2, 6)
+            RC_CSWAP(1, 4) RC_CSWAP(3, 6)
+            RC_CSWAP(2, 4) RC_CSWAP(3, 5)
+            RC_CSWAP(3, 4)
+#undef RC_CSWAP
+            visit(i);
+#pragma unroll
+            for (int u = 0; u < 8; u++) if (m[u] != NIL) visit(m[u]);
+        } else {
+            // larger puddle: scan the slots after the root (members have larger slots than their root)
+            for (uint32_t j = i; j < total; j++) if (s_parent[j] == i) visit(j);
+        }
+        finish_root(i, open, ca, make_uint4(rmin, rmax, cmin, cmax));
+    }
+    if (nclosed) atomicAdd(&s_nclosed, nclosed);
+    __syncthreads();
+    if (cmap_g)
+        for (int i = t; i < TILE_WORDS; i += CCL_THREADS) {
+            const uint32_t w = s_cmap[i];
+            if (w) atomicOr(&cmap_g[(size_t)tile * TILE_WORDS + i], w);
+        }
+    if (t == 0) rootcnt[ti] = s_nclosed;
 }
 
 // full-frame union (maps that did not come from k_reduce_tiles: rc_ccl_label)
@@ -228,11 +409,32 @@ struct FoldAct {
     __device__ __forceinline__ void operator()(uint32_t a, uint32_t b) const { one(a); one(b); }
 };
 
+// L4: bounding box of a tile-local root that lost its root status -> merged into the box of its final root,
+// exactly once (same claim as FoldAct).  Boxes are {row min, row max, col min, col max}.
+struct BboxFoldAct {
+    uint32_t *parent, *bbox;
+    __device__ __forceinline__ void one(uint32_t x) const
+    {
+        const uint32_t px = parent[x];
+        const uint32_t r = (px & UF_FLAG) ? (px & ~UF_FLAG) : x;     // tile-local root of x
+        const uint32_t pr = parent[r];
+        if (pr == r || (pr & UF_FLAG)) return;                       // still a root, or already merged
+        if (atomicOr(&parent[r], UF_FLAG) & UF_FLAG) return;
+        const uint32_t g = uf_find_ro(parent, r);
+        const uint4 b = reinterpret_cast<const uint4 *>(bbox)[r];
+        atomicMin(&bbox[4 * (size_t)g + 0], b.x);
+        atomicMax(&bbox[4 * (size_t)g + 1], b.y);
+        atomicMin(&bbox[4 * (size_t)g + 2], b.z);
+        atomicMax(&bbox[4 * (size_t)g + 3], b.w);
+    }
+    __device__ __forceinline__ void operator()(uint32_t a, uint32_t b) const { one(a); one(b); }
+};
+
 // Links across tile boundaries.  k_ccl_tiles labelled every tile on its own and listed the links from its
 // first rows to pixels of earlier tiles; a tile that overflowed the shared-memory labelling (tileovf) has all
 // of its links made here instead, with the word-parallel global path.
 // PASS 0: union.  PASS 1: L2 fold of the re-parented tile-local roots (separate launch: needs final roots).
-// One warp per tile.
+// PASS 2: L4 merge of their bounding boxes (acc_all is then the box array).  One warp per tile.
 template <int PASS>
 __global__ void __launch_bounds__(256)
 k_ccl_border(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
@@ -255,7 +457,8 @@ k_ccl_border(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__res
             const uint2 e = xl[j];                       // (slot in this tile, neighbour pixel in an earlier tile)
             const uint32_t sq = slot_of(map, wordpre, e.y);
             if (PASS == 0) uf_union(parent, e.x, sq);
-            else FoldAct{parent, acc, sum}(e.x, sq);
+            else if (PASS == 1) FoldAct{parent, acc, sum}(e.x, sq);
+            else BboxFoldAct{parent, acc_all + (size_t)f * slots * 4}(e.x, sq);
         }
         return;
     }
@@ -268,15 +471,15 @@ k_ccl_border(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__res
         const uint32_t bits = map[w];
         if (!bits) continue;
         if (PASS == 0) link_word(sp, UnionAct{parent}, w, bits, ny, nx, 0xffffffffu);
-        else link_word(sp, FoldAct{parent, acc, sum}, w, bits, ny, nx, 0xffffffffu);
+        else if (PASS == 1) link_word(sp, FoldAct{parent, acc, sum}, w, bits, ny, nx, 0xffffffffu);
+        else link_word(sp, BboxFoldAct{parent, acc_all + (size_t)f * slots * 4}, w, bits, ny, nx, 0xffffffffu);
     }
 }
 
-// MODE 0: labels only.  MODE 3: L4 bounding boxes.  Afterwards every parent entry is the plain root slot.
-template <int MODE>
+// rc_ccl_label: afterwards every parent entry is the plain root slot
 __global__ void __launch_bounds__(256)
 k_ccl_flatten(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
-              uint32_t *__restrict__ parent_all, uint32_t *__restrict__ bbox_all, int ny, int nx, uint32_t MW)
+              uint32_t *__restrict__ parent_all, int ny, int nx, uint32_t MW)
 {
     const int f = blockIdx.y;
     const uint32_t w = blockIdx.x * 256 + threadIdx.x;
@@ -295,46 +498,12 @@ k_ccl_flatten(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__re
         if (!todo) return;
     }
     const uint32_t sb = word_slot_base(wordpre_all + (size_t)f * MS, w);
-    const uint32_t p0 = w << 5;
     while (todo) {
         const uint32_t k = __ffs(todo) - 1;
         todo &= todo - 1;
         const uint32_t s = sb + __popc(bits & ((1u << k) - 1u));
         const uint32_t root = uf_find_ro(parent, s);
-        if (root != s) {
-            parent[s] = root;
-            if (MODE == 3) {
-                // the root's pixel index was stored in bbox[3] by k_l4_init_bbox
-                const uint32_t p = p0 + k;
-                uint32_t *bb = bbox_all + ((size_t)f * slots + root) * 4;
-                const uint32_t rp = bb[3];
-                const uint32_t r = p / (uint32_t)nx, c = p - r * (uint32_t)nx;
-                const uint32_t rr = rp / (uint32_t)nx, rc = rp - rr * (uint32_t)nx;
-                atomicMax(&bb[0], r - rr);                       // rows below the root (root is the top row)
-                if (c < rc) atomicMax(&bb[1], rc - c);           // columns left of the root
-                if (c > rc) atomicMax(&bb[2], c - rc);           // columns right of the root
-            }
-        }
-    }
-}
-
-// L4: bbox[slot] = {0, 0, 0, pixel index} for every foreground slot (must precede k_ccl_flatten<3>)
-__global__ void __launch_bounds__(256)
-k_l4_init_bbox(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
-               uint32_t *__restrict__ bbox_all, uint32_t MW)
-{
-    const int f = blockIdx.y;
-    const uint32_t w = blockIdx.x * 256 + threadIdx.x;
-    if (w >= MW) return;
-    uint32_t bits = maps[(size_t)f * MS + w];
-    if (!bits) return;
-    const size_t slots = (size_t)NT * TILE_PX;
-    uint32_t s = word_slot_base(wordpre_all + (size_t)f * MS, w);
-    while (bits) {
-        const uint32_t k = __ffs(bits) - 1;
-        bits &= bits - 1;
-        reinterpret_cast<uint4 *>(bbox_all)[(size_t)f * slots + s] = make_uint4(0, 0, 0, (w << 5) + k);
-        s++;
+        if (root != s) parent[s] = root;
     }
 }
 
@@ -441,91 +610,59 @@ k_gather_centroids(const uint64_t *__restrict__ cent_tiles, const uint32_t *__re
     }
 }
 
-// ---- L4 centroids ------------------------------------------------------------------------------
-// One thread per root.  mode: 0/1 weighted (converters.py:167-197), 2 max pixel (:229-259), 3 unweighted (:200-226).
-// Each += of the reference is float64 arithmetic rounded to float32 (numba: float32 element += float64 value).
-__global__ void __launch_bounds__(128)
-k_l4_centroids(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
-               const uint32_t *__restrict__ parent_all, const uint32_t *__restrict__ bbox_all,
-               const uint32_t *__restrict__ vp_all, int ny, int nx, uint32_t MW, int mode,
-               uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all)
+// ---- L4: puddles that cross tile boundaries -----------------------------------------------------------
+// After k_ccl_border<0> (links) and <2> (boxes) every open puddle has a final root g with the box of all its
+// members.  It is reached through the cross-link lists (one warp per tile; all slots of an overflowed tile),
+// claimed once through claim[g] and replayed in raster order over its box with the reference's arithmetic.
+__global__ void __launch_bounds__(256)
+k_l4_open(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
+          const uint32_t *__restrict__ tilecnt, const uint8_t *__restrict__ tileovf,
+          const uint32_t *__restrict__ xcount, const uint2 *__restrict__ xlinks,
+          const uint32_t *__restrict__ parent_all, uint32_t *__restrict__ claim_all,
+          const uint32_t *__restrict__ bbox_all, const uint32_t *__restrict__ vp_all, int ny, int nx, int mode,
+          uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all, uint32_t *__restrict__ rootcnt)
 {
-    const int f = blockIdx.y;
-    const uint32_t w = blockIdx.x * 128 + threadIdx.x;
-    if (w >= MW) return;
-    const uint32_t *map = maps + (size_t)f * MS;
-    uint32_t bits = map[w];
-    if (!bits) return;
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5), f = blockIdx.y, lane = threadIdx.x & 31;
+    if (tile >= NT) return;
+    const size_t ti = (size_t)f * NT + tile;
     const size_t slots = (size_t)NT * TILE_PX;
+    const uint32_t *map = maps + (size_t)f * MS;
     const uint16_t *wordpre = wordpre_all + (size_t)f * MS;
     const uint32_t *parent = parent_all + (size_t)f * slots;
-    const uint32_t *vp = vp_all + (size_t)f * slots;            // (value << 16) | position, from k_reduce_tiles
-    uint32_t *map2 = map2_all + (size_t)f * MS;
-    uint32_t s = word_slot_base(wordpre, w);
-    const uint32_t p0 = w << 5;
-    for (; bits; s++) {
-        const uint32_t k = __ffs(bits) - 1;
-        bits &= bits - 1;
-        if (parent[s] != s) continue;
-        const uint32_t p = p0 + k;
-        const uint32_t r0 = p / (uint32_t)nx, c0 = p - r0 * (uint32_t)nx;
-        const uint4 bb = reinterpret_cast<const uint4 *>(bbox_all)[(size_t)f * slots + s];
-        float fr, fc;
-        if ((bb.x | bb.y | bb.z) == 0) {
-            // single-pixel puddle: the reference computes RN32(v*r) / RN32(v)
-            const float v = (float)(vp[s] >> 16);
-            if (mode == 2 || mode == 3) { fr = (float)r0; fc = (float)c0; }
-            else {
-                fr = __fdiv_rn((float)((double)v * (double)r0), v);
-                fc = __fdiv_rn((float)((double)v * (double)c0), v);
-            }
-        } else {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            bool first = true;
-            const uint32_t cl = c0 - bb.y, cr = c0 + bb.z;
-            for (uint32_t r = r0; r <= r0 + bb.x; r++) {
-                const uint32_t q0 = r * (uint32_t)nx + cl, q1 = r * (uint32_t)nx + cr;   // inclusive pixel range
-                for (uint32_t ww = q0 >> 5; ww <= (q1 >> 5); ww++) {
-                    uint32_t mb = map[ww];
-                    if (ww == (q0 >> 5)) mb &= 0xffffffffu << (q0 & 31);
-                    if (ww == (q1 >> 5)) mb &= 0xffffffffu >> (31 - (q1 & 31));
-                    while (mb) {
-                        const uint32_t kk = __ffs(mb) - 1;
-                        mb &= mb - 1;
-                        const uint32_t q = (ww << 5) + kk;
-                        const uint32_t sq = slot_of(map, wordpre, q);
-                        if (parent[sq] != s) continue;
-                        const double v = (double)(vp[sq] >> 16);
-                        const uint32_t c = q - r * (uint32_t)nx;
-                        if (mode == 2) {
-                            if (first || v > (double)a2) { a0 = (float)r; a1 = (float)c; a2 = (float)v; }
-                        } else if (mode == 3) {
-                            a0 = (float)((double)a0 + (double)r);
-                            a1 = (float)((double)a1 + (double)c);
-                            a2 = (float)((double)a2 + 1.0);
-                        } else {
-                            a0 = (float)((double)a0 + v * (double)r);
-                            a1 = (float)((double)a1 + v * (double)c);
-                            a2 = (float)((double)a2 + v);
-                        }
-                        first = false;
-                    }
+    const uint32_t *vp = vp_all + (size_t)f * slots;
+    uint32_t *claim = claim_all + (size_t)f * slots;
+    const bool ovf = tileovf[ti] != 0;
+    const uint32_t n = ovf ? tilecnt[ti] : xcount[ti];
+    const uint2 *xl = xlinks + ti * CCL_XCAP;
+    const uint32_t unx = (uint32_t)nx;
+    for (uint32_t j = lane; j < n; j += 32) {
+        const uint32_t a = ovf ? ((uint32_t)tile << TILE_LOG2) + j : xl[j].x;
+        const uint32_t g = uf_find_ro(parent, a);
+        if (atomicCAS(&claim[g], 0u, 1u) != 0u) continue;
+        const uint4 bb = reinterpret_cast<const uint4 *>(bbox_all)[(size_t)f * slots + g];
+        CentAcc ca;
+        for (uint32_t r = bb.x; r <= bb.y; r++) {
+            const uint32_t q0 = r * unx + bb.z, q1 = r * unx + bb.w;      // inclusive pixel range
+            for (uint32_t ww = q0 >> 5; ww <= (q1 >> 5); ww++) {
+                uint32_t mb = map[ww];
+                if (ww == (q0 >> 5)) mb &= 0xffffffffu << (q0 & 31);
+                if (ww == (q1 >> 5)) mb &= 0xffffffffu >> (31 - (q1 & 31));
+                while (mb) {
+                    const uint32_t kk = __ffs(mb) - 1;
+                    mb &= mb - 1;
+                    const uint32_t q = (ww << 5) + kk;
+                    const uint32_t sq = slot_of(map, wordpre, q);
+                    if (uf_find_ro(parent, sq) != g) continue;
+                    ca.add(mode, r, q - r * unx, vp[sq] >> 16);
                 }
             }
-            if (mode == 2) { fr = a0; fc = a1; }
-            else { fr = __fdiv_rn(a0, a2); fc = __fdiv_rn(a1, a2); }
         }
-        if (cent_all) {
-            const uint64_t pk = (uint64_t)__float_as_uint(fr) | ((uint64_t)__float_as_uint(fc) << 32);
-            cent_all[(size_t)f * slots + s] = pk;
-        }
-        if (map2_all) {
-            const long rr = (long)rintf(fr), cc = (long)rintf(fc);     // round half to even (np.round)
-            if (rr >= 0 && rr < ny && cc >= 0 && cc < nx) {
-                const uint32_t q = (uint32_t)rr * (uint32_t)nx + (uint32_t)cc;
-                atomicOr(&map2[q >> 5], 1u << (q & 31));
-            }
-        }
+        float fr, fc;
+        ca.finish(mode, fr, fc);
+        atomicAdd(&rootcnt[(size_t)f * NT + (g >> TILE_LOG2)], 1u);
+        if (cent_all) cent_all[(size_t)f * slots + g] = (uint64_t)__float_as_uint(fr) | ((uint64_t)__float_as_uint(fc) << 32);
+        uint32_t q;
+        if (map2_all && centroid_pixel(fr, fc, ny, nx, q)) atomicOr(&map2_all[(size_t)f * MS + (q >> 5)], 1u << (q & 31));
     }
 }
 
@@ -547,19 +684,21 @@ int launch_gather_centroids(rc_ctx *ctx, const Geom &g, const uint64_t *cent_til
     return 0;
 }
 
-// fold: 0 = labels only (L4), 1 = L2 max, 2 = L2 sum
+// fold: 1 = L2 max, 2 = L2 sum, 3 = L4 (l4mode = centroiding method; closed puddles -> map2 / cent / rootcnt)
 int launch_ccl_tiles(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps, const uint16_t *wordpre,
                      const uint32_t *tilecnt, const uint32_t *vp, uint8_t *tileovf, uint32_t *xcount, void *xlinks,
-                     uint32_t *parent, uint32_t *acc, int F, cudaStream_t st)
+                     uint32_t *parent, uint32_t *acc, int l4mode, uint32_t *bbox, uint32_t *map2, uint64_t *cent,
+                     uint32_t *rootcnt, int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
     dim3 grid((unsigned)g.NT, F);
 #define RC_CT(FO)                                                                                              \
     k_ccl_tiles<FO><<<grid, CCL_THREADS, 0, st>>>(maps, g.MS, wordpre, g.NT, tilecnt, vp, tileovf, xcount,       \
-                                                  (uint2 *)xlinks, parent, acc, g.ny, g.nx)
-    if (fold == 0) RC_CT(0);
-    else if (fold == 1) RC_CT(1);
-    else RC_CT(2);
+                                                  (uint2 *)xlinks, parent, acc, g.ny, g.nx, l4mode, bbox, map2,  \
+                                                  cent, rootcnt)
+    if (fold == 1) RC_CT(1);
+    else if (fold == 2) RC_CT(2);
+    else RC_CT(3);
 #undef RC_CT
     RC_LAUNCH_CHECK(ctx, "k_ccl_tiles");
     return 0;
@@ -577,7 +716,7 @@ int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uin
     return 0;
 }
 
-// fold: 0 = links only (L4), 1 = + L2 max fold, 2 = + L2 sum fold
+// fold: 1 = + L2 max fold, 2 = + L2 sum fold (acc = statistics), 3 = + L4 box merge (acc = boxes)
 int launch_ccl_border(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps, const uint16_t *wordpre,
                       const uint8_t *tileovf, const uint32_t *xcount, const void *xlinks, uint32_t *parent,
                       uint32_t *acc, int F, cudaStream_t st)
@@ -587,7 +726,11 @@ int launch_ccl_border(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps
     k_ccl_border<0><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, tileovf, xcount, (const uint2 *)xlinks, parent, acc,
                                           g.ny, g.nx, (uint32_t)g.MW, 0);
     RC_LAUNCH_CHECK(ctx, "k_ccl_border<0>");
-    if (fold) {
+    if (fold == 3) {
+        k_ccl_border<2><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, tileovf, xcount, (const uint2 *)xlinks, parent,
+                                              acc, g.ny, g.nx, (uint32_t)g.MW, 0);
+        RC_LAUNCH_CHECK(ctx, "k_ccl_border<2>");
+    } else if (fold) {
         k_ccl_border<1><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, tileovf, xcount, (const uint2 *)xlinks, parent,
                                               acc, g.ny, g.nx, (uint32_t)g.MW, fold == 2);
         RC_LAUNCH_CHECK(ctx, "k_ccl_border<1>");
@@ -595,19 +738,25 @@ int launch_ccl_border(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps
     return 0;
 }
 
-int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
-                       uint32_t *parent, uint32_t *bbox, int F, cudaStream_t st)
+int launch_l4_open(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
+                   const uint32_t *tilecnt, const uint8_t *tileovf, const uint32_t *xcount, const void *xlinks,
+                   const uint32_t *parent, uint32_t *claim, const uint32_t *bbox, const uint32_t *vp, uint32_t *map2,
+                   uint64_t *cent, uint32_t *rootcnt, int F, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    dim3 grid((unsigned)((g.NT + 7) / 8), F);
+    k_l4_open<<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, tilecnt, tileovf, xcount, (const uint2 *)xlinks, parent,
+                                    claim, bbox, vp, g.ny, g.nx, mode, map2, cent, rootcnt);
+    RC_LAUNCH_CHECK(ctx, "k_l4_open");
+    return 0;
+}
+
+int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre, uint32_t *parent,
+                       int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
     dim3 grid((unsigned)((g.MW + 255) / 256), F);
-    const uint32_t MW = (uint32_t)g.MW;
-    if (mode == 3) {
-        k_l4_init_bbox<<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, bbox, MW);
-        RC_LAUNCH_CHECK(ctx, "k_l4_init_bbox");
-        k_ccl_flatten<3><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, bbox, g.ny, g.nx, MW);
-    } else {
-        k_ccl_flatten<0><<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, bbox, g.ny, g.nx, MW);
-    }
+    k_ccl_flatten<<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, g.ny, g.nx, (uint32_t)g.MW);
     RC_LAUNCH_CHECK(ctx, "k_ccl_flatten");
     return 0;
 }
@@ -640,17 +789,5 @@ int launch_ccl_label_image(rc_ctx *ctx, const Geom &g, const uint32_t *maps, con
     k_ccl_label_image<<<grid, 256, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, ord, rootpre, labels, g.P,
                                             (uint32_t)g.MW);
     RC_LAUNCH_CHECK(ctx, "k_ccl_label_image");
-    return 0;
-}
-
-int launch_l4_centroids(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
-                        const uint32_t *parent, const uint32_t *bbox, const uint32_t *vp, uint32_t *map2,
-                        uint64_t *cent, int F, cudaStream_t st)
-{
-    if (F <= 0) return 0;
-    dim3 grid((unsigned)((g.MW + 127) / 128), F);
-    k_l4_centroids<<<grid, 128, 0, st>>>(maps, g.MS, wordpre, g.NT, parent, bbox, vp, g.ny, g.nx, (uint32_t)g.MW, mode,
-                                         map2, cent);
-    RC_LAUNCH_CHECK(ctx, "k_l4_centroids");
     return 0;
 }

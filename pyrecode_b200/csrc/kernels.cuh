@@ -22,22 +22,24 @@ int launch_ccl_union(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uin
                      int F, cudaStream_t st);
 int launch_ccl_tiles(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps, const uint16_t *wordpre,
                      const uint32_t *tilecnt, const uint32_t *vp, uint8_t *tileovf, uint32_t *xcount, void *xlinks,
-                     uint32_t *parent, uint32_t *acc, int F, cudaStream_t st);
+                     uint32_t *parent, uint32_t *acc, int l4mode, uint32_t *bbox, uint32_t *map2, uint64_t *cent,
+                     uint32_t *rootcnt, int F, cudaStream_t st);
 size_t ccl_xlinks_bytes(const Geom &g, size_t F);
 int launch_ccl_border(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps, const uint16_t *wordpre,
                       const uint8_t *tileovf, const uint32_t *xcount, const void *xlinks, uint32_t *parent,
                       uint32_t *acc, int F, cudaStream_t st);
-int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
-                       uint32_t *parent, uint32_t *bbox, int F, cudaStream_t st);
+int launch_l4_open(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
+                   const uint32_t *tilecnt, const uint8_t *tileovf, const uint32_t *xcount, const void *xlinks,
+                   const uint32_t *parent, uint32_t *claim, const uint32_t *bbox, const uint32_t *vp, uint32_t *map2,
+                   uint64_t *cent, uint32_t *rootcnt, int F, cudaStream_t st);
+int launch_ccl_flatten(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre, uint32_t *parent,
+                       int F, cudaStream_t st);
 int launch_ccl_roots(rc_ctx *ctx, const Geom &g, int payload, const uint32_t *tilecnt, const uint32_t *parent,
                      const uint32_t *acc, const uint64_t *cent, uint32_t *rootcnt, uint32_t *ord, uint16_t *out16,
                      uint64_t *out64, int F, cudaStream_t st);
 int launch_ccl_label_image(rc_ctx *ctx, const Geom &g, const uint32_t *maps, const uint16_t *wordpre,
                            const uint32_t *parent, const uint32_t *ord, const uint32_t *rootpre, int32_t *labels,
                            int F, cudaStream_t st);
-int launch_l4_centroids(rc_ctx *ctx, const Geom &g, int mode, const uint32_t *maps, const uint16_t *wordpre,
-                        const uint32_t *parent, const uint32_t *bbox, const uint32_t *vp, uint32_t *map2,
-                        uint64_t *cent, int F, cudaStream_t st);
 int launch_gather_centroids(rc_ctx *ctx, const Geom &g, const uint64_t *cent_tiles, const uint32_t *rootpre, int F,
                             float *out, size_t capacity, cudaStream_t st);
 
