@@ -38,6 +38,11 @@ EPS = 20
 KIND = {1: 'l1', 2: 'l2', 3: 'l1', 4: 'l4'}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of k_reduce_tiles per launch from the committed `ncu --set full`
+# capture (profiles/r01_ncu_k_reduce_tiles.txt): keyed by (level, frames per step)
+NCU_TRAFFIC = {(2, 32): 1107647000 + 89087744}
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -136,7 +141,9 @@ def main():
     ap.add_argument('--level', type=int, default=2)
     ap.add_argument('--frames', type=int, default=32, help='frames per step per GPU')
     ap.add_argument('--distinct', type=int, default=4, help='distinct synthetic frames generated on the host')
-    ap.add_argument('--cpu-frames-per-core', type=int, default=2)
+    ap.add_argument('--cpu-frames-per-core', type=int, default=96,
+                    help='frames per host core of the cpu_baseline sample (about 10 s of CPU work)')
+    ap.add_argument('--ref-frames-per-core', type=int, default=4, help='frames per core per step of --impl reference')
     ap.add_argument('--slots', type=int, default=2, help='batches in flight (each on its own CUDA stream)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -163,7 +170,7 @@ def main():
         best = None
         per_step = []
         for s in range(args.warmup + args.steps):
-            fps, cores, total, secs = cpu_run(level, dark, frames, args.cpu_frames_per_core)
+            fps, cores, total, secs = cpu_run(level, dark, frames, args.ref_frames_per_core)
             if s >= args.warmup:
                 per_step.append((total, secs))
         tot = sum(p[0] for p in per_step)
@@ -175,7 +182,7 @@ def main():
                 'config': config, 'input_gb_s': value * frame_bytes / 1e9,
                 'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                                  'sample': '%d frames per step (%d per core), oracle C port + stock zlib level 1; '
-                                           'the reference cannot execute L2/L4 (SURVEY 0.1)' % (total, args.cpu_frames_per_core)},
+                                           'the reference cannot execute L2/L4 (SURVEY 0.1)' % (total, args.ref_frames_per_core)},
                 'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'gpu_launches': 0}
         print(json.dumps(line))
@@ -306,7 +313,7 @@ def main():
             'hbm_roofline_frac_whole_path': value / world * frame_bytes / 1e9 / peak,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'kernel': 'k_reduce_tiles', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                         'frac': achieved / peak, 'traffic': NCU_TRAFFIC.get((level, F)), 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': F * frame_bytes, 'kernel_ms': k1_ms},
             'stage_ms_per_step': dict(zip(['threshold_pack_compact', 'reduce_rest', 'deflate', 'assemble'],
                                           [float(x) for x in stage_ms])),
