@@ -492,3 +492,14 @@ def test_read_reference_written_file(gold_dir):
     for i, r in enumerate(recs):
         f = r['frame_id']
         assert np.array_equal(dense[i], np.where(data[f] > thr, data[f] - thr, 0))
+
+
+def test_l4_synthetic_4096():
+    # BASELINE config 4 at full size: low-dose frame, centroid map and puddle count against the oracle
+    dark = orc.synth_dark(4096, 4096)
+    frames = orc.synth_frames('l4', 1, 4096, 4096, dark, seed=4321)
+    eng = engine(4096, 4096, 2, 12, 4, F=1)
+    eng.set_threshold(dark, 20)
+    maps, packed, counts = eng.reduce(frames)
+    m, v, n = orc.reduce_frame(frames[0], orc.make_threshold(dark, 20), 4, 12)
+    assert counts[0] == n and maps[0] == m
