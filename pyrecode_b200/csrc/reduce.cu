@@ -308,19 +308,55 @@ int launch_scan_tiles(rc_ctx *ctx, const Geom &g, const uint32_t *tilecnt, int F
 
 // ---- K3: bit packing -------------------------------------------------------------------------
 // Output word w of frame f gathers every value whose bit range [j*b, (j+1)*b) overlaps [32w, 32w+32).
+// The tile prefix table of the frame is staged in shared memory (when it fits) so that the per-word binary
+// search runs at shared-memory latency.
+constexpr int BP_SMEM_TILES = 4096;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_bitpack(const T *__restrict__ vals, const uint32_t *__restrict__ tilepre, int NT, int b,
           uint8_t *__restrict__ packed, size_t packed_stride)
 {
+    __shared__ uint32_t s_pre[BP_SMEM_TILES + 1];
     const int f = blockIdx.y;
-    const uint32_t *pre = tilepre + (size_t)f * (NT + 1);
+    const uint32_t *gpre = tilepre + (size_t)f * (NT + 1);
+    const bool staged = NT <= BP_SMEM_TILES;
+    if (staged) {
+        for (int i = threadIdx.x; i <= NT; i += 256) s_pre[i] = gpre[i];
+        __syncthreads();
+    }
+    const uint32_t *pre = staged ? s_pre : gpre;
     const T *v = vals + (size_t)f * ((size_t)NT * TILE_PX);
     uint32_t *out = reinterpret_cast<uint32_t *>(packed + (size_t)f * packed_stride);
     const uint64_t n = pre[NT];
     const uint64_t nbits = n * (uint64_t)b;
     const uint64_t nwords = (nbits + 31) / 32;
     const uint32_t vmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+    if (nbits < 0xffffffe0ull) {
+        // 32-bit indices (any frame up to 2^27 pixels): no 64-bit divisions in the loop
+        const uint32_t n32 = (uint32_t)n, nw32 = (uint32_t)nwords, ub = (uint32_t)b;
+        for (uint32_t w = blockIdx.x * 256 + threadIdx.x; w < nw32; w += gridDim.x * 256) {
+            const uint32_t bit0 = w * 32;
+            uint32_t j = bit0 / ub;
+            uint32_t jl = (bit0 + 31) / ub;
+            if (jl >= n32) jl = n32 - 1;
+            int lo = 0, hi = NT;                    // invariant: pre[lo] <= j < pre[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pre[mid] <= j) lo = mid; else hi = mid;
+            }
+            int tt = lo;
+            uint32_t acc = 0;
+            int sh = (int)(j * ub) - (int)bit0;     // bit position of value j relative to the word: (-b, 32)
+            for (; j <= jl; j++, sh += b) {
+                while (pre[tt + 1] <= j) tt++;
+                const uint32_t val = (uint32_t)v[(size_t)tt * TILE_PX + (j - pre[tt])] & vmask;
+                acc |= sh >= 0 ? (val << sh) : (val >> (-sh));
+            }
+            out[w] = acc;
+        }
+        return;
+    }
     for (uint64_t w = (uint64_t)blockIdx.x * 256 + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * 256) {
         const uint64_t bit0 = w * 32;
         uint64_t j = bit0 / (uint32_t)b;
@@ -348,7 +384,7 @@ int launch_bitpack(rc_ctx *ctx, const Geom &g, int val_itemsize, const void *val
                    int b, uint8_t *packed, size_t packed_stride, cudaStream_t st)
 {
     if (F <= 0) return 0;
-    dim3 grid(64, F);
+    dim3 grid(128, F);
     if (val_itemsize == 2)
         k_bitpack<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)vals, tilepre, g.NT, b, packed, packed_stride);
     else
