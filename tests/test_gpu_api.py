@@ -242,3 +242,63 @@ def test_writer_errors(tmp_path):
     ip._param_map['compression_scheme'] = 1
     with pytest.raises(NotImplementedError):                # no CPU fallback for other codecs
         ReCoDeWriter('x', dark_data=dark, output_directory=str(tmp_path), input_params=ip)
+
+
+@pytest.mark.parametrize('level', [1, 2, 3, 4])
+def test_degenerate_frames(tmp_path, level):
+    """empty frames, fully foreground frames (one puddle covering everything, far beyond the shared-memory
+    labelling capacity) and single-pixel events in the corners, through the whole writer / reader path"""
+    from pyrecode_b200.recode_reader import ReCoDeReader
+    ny, nx, b = 130, 192, 12
+    dark = np.zeros((ny, nx), np.uint16)
+    frames = np.zeros((5, ny, nx), np.uint16)
+    frames[1] = 4095
+    frames[2, 0, 0] = 7; frames[2, 0, nx - 1] = 9; frames[2, ny - 1, 0] = 11; frames[2, ny - 1, nx - 1] = 13
+    frames[3, ::2, :] = 100                                  # every other row: ny/2 long puddles
+    frames[4, :, ::2] = 200                                  # every other column: puddles crossing every tile
+    ip = make_params(ny, nx, 5, level=level, b=b)
+    write_parts(tmp_path, 'deg', frames, dark[None], ip, 1, batch_frames=2)
+    path = str(tmp_path / ('deg.rc%d_part000' % level))
+    hdr, recs = orc.parse_part_file(path)
+    assert hdr['nz'] == 5
+    r = ReCoDeReader(path, is_intermediate=True)
+    r.open(print_header=False)
+    for f in range(5):
+        m_ref, v_ref, n_ref = orc.reduce_frame(frames[f], dark, level, b)
+        assert recs[f]['map'] == m_ref, 'frame %d' % f
+        if level <= 2:
+            assert recs[f]['vals'] == v_ref, 'frame %d' % f
+        (fid, fr), = r.get_next_frame().items()
+        assert fid == f
+        if level == 1:
+            assert np.array_equal(fr['data'].toarray(), frames[f])
+        else:
+            bits = np.unpackbits(np.frombuffer(m_ref, np.uint8), bitorder='little')[:ny * nx].reshape(ny, nx)
+            assert np.array_equal(fr['data'].toarray(), bits)
+    r.close()
+
+
+def test_compression_levels_and_table_reuse(tmp_path):
+    """levels 0 (stored), 1 (shared sampled code, kept across batches), 9 (per-stream codes): same payloads.
+    The second half of the run has very different statistics from the batch the kept code was built from."""
+    rng = np.random.default_rng(21)
+    nz, ny, nx = 12, 256, 256
+    data = reference_test_data(rng, nz, ny, nx)
+    data[nz // 2:] = rng.integers(0, 4096, size=(nz - nz // 2, ny, nx)).astype(np.uint16)     # dense noise
+    dark = np.zeros((1, ny, nx), np.uint16)
+    ref = None
+    sizes = {}
+    for cl in (0, 1, 9):
+        ip = make_params(ny, nx, nz, clevel=cl)
+        write_parts(tmp_path, 'lv%d' % cl, data, dark, ip, 1, batch_frames=2)
+        p = str(tmp_path / ('lv%d.rc1_part000' % cl))
+        h, recs = orc.parse_part_file(p)
+        got = [(rr['map'], rr['vals']) for rr in recs]
+        if ref is None:
+            ref = got
+            for f in range(nz):
+                m, v, _ = orc.reduce_frame(data[f], dark[0], 1, 12)
+                assert got[f] == (m, v)
+        assert got == ref
+        sizes[cl] = os.path.getsize(p)
+    assert sizes[1] < sizes[0] and sizes[9] < sizes[0]
