@@ -302,3 +302,19 @@ def test_compression_levels_and_table_reuse(tmp_path):
         assert got == ref
         sizes[cl] = os.path.getsize(p)
     assert sizes[1] < sizes[0] and sizes[9] < sizes[0]
+
+
+def test_write_sharded_single_rank(tmp_path):
+    """pyrecode_b200.distributed on one rank (no process group): part file + merged file + live-view sum"""
+    from pyrecode_b200 import distributed as rd
+    rng = np.random.default_rng(5)
+    nz, ny, nx = 7, 64, 128
+    data = reference_test_data(rng, nz, ny, nx)
+    ip = make_params(ny, nx, nz, threads=1)
+    m = rd.write_sharded('one', data, np.zeros((1, ny, nx), np.uint16), str(tmp_path), ip, 0, 1)
+    assert m['run_frames'] == nz
+    h, recs = orc.parse_merged_file(str(tmp_path / 'one.rc1'))
+    assert h['nz'] == nz
+    ids, total = rd.live_view_sum(str(tmp_path / 'one.rc1_part000'), nz)
+    assert ids == list(range(nz))
+    assert np.array_equal(total.cpu().numpy().astype(np.int64), data.astype(np.int64).sum(0))
