@@ -44,6 +44,8 @@ constexpr int CCL_LINKS = 2560;        // tile-local links
 constexpr int CCL_XCAP = 256;          // cross-tile links per tile (global list)
 constexpr int CCL_HALO = 264;          // map words kept in front of the tile (multiple of 4): nx <= 8447
 constexpr int CCL_THREADS = 256;
+constexpr int CCL_WARPS = CCL_THREADS / 32;
+constexpr int CCL_MAPV = TILE_WORDS / 4 / CCL_THREADS;    // uint4 map loads per thread
 
 // Centroid of one puddle with the reference's arithmetic (pyrecode/utils/converters.py): members are added in
 // raster order, every += is float64 arithmetic rounded to float32 (numba: float32 element += float64 value).
@@ -116,7 +118,9 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     const uint32_t *vp = vp_all + sbase;
     const uint32_t *s_mask = s_maskx + CCL_HALO;
     // issue the tile's loads before the (dependent) per-pixel ones
-    const uint4 r_map = reinterpret_cast<const uint4 *>(maps + wo)[t];
+    uint4 r_map[CCL_MAPV];
+#pragma unroll
+    for (int u = 0; u < CCL_MAPV; u++) r_map[u] = reinterpret_cast<const uint4 *>(maps + wo)[t + u * CCL_THREADS];
     uint4 r_wpre = make_uint4(0, 0, 0, 0), r_halo = make_uint4(0, 0, 0, 0), r_bot = make_uint4(0, 0, 0, 0);
     if (t < TILE_WORDS / 8) r_wpre = reinterpret_cast<const uint4 *>(wordpre_all + wo)[t];
     if (t < CCL_HALO / 4 && tile > 0) r_halo = reinterpret_cast<const uint4 *>(maps + wo - CCL_HALO)[t];
@@ -132,7 +136,8 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     const bool pow2 = (unx & (unx - 1u)) == 0;
     const uint32_t lg = 31 - __clz(unx);
     if (!overflow) {
-        reinterpret_cast<uint4 *>(s_maskx + CCL_HALO)[t] = r_map;
+#pragma unroll
+        for (int u = 0; u < CCL_MAPV; u++) reinterpret_cast<uint4 *>(s_maskx + CCL_HALO)[t + u * CCL_THREADS] = r_map[u];
         if (t < TILE_WORDS / 8) reinterpret_cast<uint4 *>(s_wpre)[t] = r_wpre;
         if (t < CCL_HALO / 4) reinterpret_cast<uint4 *>(s_maskx)[t] = r_halo;
         if (L4 && t < CCL_HALO / 4) reinterpret_cast<uint4 *>(s_bot)[t] = r_bot;
@@ -322,8 +327,8 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     }
     __syncthreads();
     const uint32_t nlist = s_nlist;
-    // list entry k -> warp k % 8, lane k / 8: every warp gets its share of the replays
-    for (uint32_t k = (uint32_t)(t >> 5) + 8u * (uint32_t)lane; k < nlist; k += CCL_THREADS) {
+    // list entry k -> warp k % CCL_WARPS, lane k / CCL_WARPS: every warp gets its share of the replays
+    for (uint32_t k = (uint32_t)(t >> 5) + (uint32_t)CCL_WARPS * (uint32_t)lane; k < nlist; k += CCL_THREADS) {
         const uint32_t i = s_list[k];
         const bool open = s_open[i];
         CentAcc ca;
