@@ -101,9 +101,10 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     __shared__ __align__(16) uint32_t s_maskx[CCL_HALO + TILE_WORDS];
     __shared__ __align__(16) uint16_t s_wpre[TILE_WORDS];
     __shared__ uint32_t s_parent[CCL_CAP];
-    __shared__ uint32_t s_acc[CCL_CAP];                // L2: statistic; L4: pixel value
+    __shared__ uint32_t s_acc_l4[L4 ? CCL_CAP : 1];    // L4: pixel values (L2: the statistics reuse the link list)
     __shared__ uint16_t s_pos[CCL_CAP];
-    __shared__ uint32_t s_links[CCL_LINKS];            // (a << 16) | b, tile-local slots; later: last member / root list
+    __shared__ uint32_t s_links[CCL_LINKS];            // (a << 16) | b, tile-local slots; later: L2 statistics / L4 lists
+    uint32_t *s_acc = L4 ? s_acc_l4 : s_links;         // L2: loaded after the unions have consumed the links
     __shared__ __align__(16) uint32_t s_bot[L4 ? CCL_HALO : 4];     // first words of the next tile (zeros after the frame)
     __shared__ uint8_t s_open[L4 ? CCL_CAP : 4];       // pixel, then root: its puddle continues in another tile
     __shared__ uint32_t s_cmap[L4 ? TILE_WORDS : 4];   // centroid bits that fall inside the tile
@@ -144,7 +145,7 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
         for (uint32_t i = t; i < total; i += CCL_THREADS) {
             const uint32_t v = vp[i];
             s_pos[i] = (uint16_t)v;
-            s_acc[i] = v >> 16;
+            if (L4) s_acc[i] = v >> 16;
             s_parent[i] = i;
             if (L4) s_open[i] = 0;
         }
@@ -261,6 +262,10 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     uint16_t *s_next = reinterpret_cast<uint16_t *>(s_maskx);
     if (L4) {
         for (uint32_t i = t; i < total; i += CCL_THREADS) s_head[i] = NIL;
+        __syncthreads();
+    }
+    if (!L4) {
+        for (uint32_t i = t; i < total; i += CCL_THREADS) s_acc[i] = vp[i] >> 16;
         __syncthreads();
     }
     // ---- phase 3: flatten; L2 folds every member's value into its root (non-roots are never written again)
