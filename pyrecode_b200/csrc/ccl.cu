@@ -101,10 +101,10 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     __shared__ __align__(16) uint32_t s_maskx[CCL_HALO + TILE_WORDS];
     __shared__ __align__(16) uint16_t s_wpre[TILE_WORDS];
     __shared__ uint32_t s_parent[CCL_CAP];
-    __shared__ uint32_t s_acc_l4[L4 ? CCL_CAP : 1];    // L4: pixel values (L2: the statistics reuse the link list)
+
     __shared__ uint16_t s_pos[CCL_CAP];
     __shared__ uint32_t s_links[CCL_LINKS];            // (a << 16) | b, tile-local slots; later: L2 statistics / L4 lists
-    uint32_t *s_acc = L4 ? s_acc_l4 : s_links;         // L2: loaded after the unions have consumed the links
+    uint32_t *s_acc = s_links;                         // L2: loaded after the unions have consumed the links
     __shared__ __align__(16) uint32_t s_bot[L4 ? CCL_HALO : 4];     // first words of the next tile (zeros after the frame)
     __shared__ uint8_t s_open[L4 ? CCL_CAP : 4];       // pixel, then root: its puddle continues in another tile
     __shared__ uint32_t s_cmap[L4 ? TILE_WORDS : 4];   // centroid bits that fall inside the tile
@@ -145,7 +145,6 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
         for (uint32_t i = t; i < total; i += CCL_THREADS) {
             const uint32_t v = vp[i];
             s_pos[i] = (uint16_t)v;
-            if (L4) s_acc[i] = v >> 16;
             s_parent[i] = i;
             if (L4) s_open[i] = 0;
         }
@@ -321,7 +320,7 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
             const uint32_t gp = base + s_pos[i];
             const uint32_t r = pow2 ? gp >> lg : gp / unx, c = gp - r * unx;
             CentAcc ca;
-            ca.add(l4mode, r, c, s_acc[i]);
+            ca.add(l4mode, r, c, vp[i] >> 16);
             finish_root(i, s_open[i], ca, make_uint4(r, r, c, c));
         }
         const uint32_t bm = __ballot_sync(0xffffffffu, multi);
@@ -344,7 +343,7 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
             if (open) {
                 rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
             } else {
-                ca.add(l4mode, r, c, s_acc[j]);
+                ca.add(l4mode, r, c, vp[j] >> 16);       // L1 / L2-cache hit: loaded in phase 0
             }
         };
         // up to 8 members besides the root: collect, sort (the list is in arrival order), replay in slot order
