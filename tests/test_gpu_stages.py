@@ -503,3 +503,30 @@ def test_l4_synthetic_4096():
     maps, packed, counts = eng.reduce(frames)
     m, v, n = orc.reduce_frame(frames[0], orc.make_threshold(dark, 20), 4, 12)
     assert counts[0] == n and maps[0] == m
+
+
+def test_randomized_geometries_all_levels():
+    """seeded sweep over odd geometries (tile boundaries in the middle of rows, widths beyond the labelling halo,
+    single rows / columns), bit depths, occupancies and statistics, every level against the oracle"""
+    rng = np.random.default_rng(20261018)
+    shapes = [(1, 70000 // 7), (2049, 17), (33, 1025), (64, 8448), (5, 8449), (700, 257), (129, 255), (1, 40000),
+              (40000, 1), (96, 4096), (17, 33000)]
+    for case in range(26):
+        ny, nx = shapes[case % len(shapes)] if case < 16 else (int(rng.integers(1, 400)), int(rng.integers(1, 3000)))
+        b = int(rng.choice([9, 12, 16]))
+        occ = float(rng.choice([0.002, 0.02, 0.08, 0.3, 0.7]))
+        level = int(rng.choice([1, 2, 2, 4, 4, 3]))
+        l2 = int(rng.choice([0, 2]))
+        l4 = int(rng.choice([0, 2, 3]))
+        frames, dark = make_frames(rng, 2, ny, nx, np.uint16, (1 << b) - 1, occ)
+        eng = engine(ny, nx, 2, b, level, l2=l2, l4=l4, F=2)
+        eng.set_threshold(dark, 2)
+        maps, packed, counts = eng.reduce(frames)
+        thr = orc.make_threshold(dark, 2)
+        for f in range(2):
+            m, v, n = orc.reduce_frame(frames[f], thr, level, b, l2_statistics=l2, l4_centroiding=l4)
+            tag = 'case %d: %dx%d b=%d occ=%g level=%d l2=%d l4=%d frame %d' % (case, ny, nx, b, occ, level, l2, l4, f)
+            assert counts[f] == n, tag
+            assert maps[f] == m, tag + ' map ' + first_diff(maps[f], m)
+            if level <= 2:
+                assert packed[f] == v, tag + ' values ' + first_diff(packed[f], v)
