@@ -39,8 +39,8 @@ KIND = {1: 'l1', 2: 'l2', 3: 'l1', 4: 'l4'}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_reduce_tiles per launch from the committed `ncu --set full`
-# capture (profiles/r01_ncu_k_reduce_tiles.txt): keyed by (level, frames per step)
-NCU_TRAFFIC = {(2, 32): 1107647000 + 89087744}
+# capture (profiles/r01_ncu_k_reduce_tiles_bulk.txt): keyed by (level, frames per step)
+NCU_TRAFFIC = {(2, 32): 1107740000 + 133809408}
 
 
 def measured_peak():
@@ -320,7 +320,7 @@ def main():
             'input_gb_s': value * frame_bytes / 1e9,
             'hbm_roofline_frac_whole_path': value / world * frame_bytes / 1e9 / peak,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'kernel': 'k_reduce_tiles', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'roofline': {'bound': 'hbm', 'kernel': 'k_reduce_tiles_bulk' if level != 1 else 'k_reduce_tiles', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': NCU_TRAFFIC.get((level, F)), 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': F * frame_bytes, 'kernel_ms': k1_ms},
             'stage_ms_per_step': dict(zip(['threshold_pack_compact', 'reduce_rest', 'deflate', 'assemble'],
