@@ -50,7 +50,8 @@ template <> struct Px<uint16_t> {
             d[i] = __vmaxu2(f[i], t[i]) - t[i];
             e[i] = __vminu2(d[i], 0x00010001u);          // bit 0 / bit 16 = lane is foreground
         }
-        const uint32_t c = e[0] | (e[1] << 2) | (e[2] << 4) | (e[3] << 6);   // even pixels at bits 0..6, odd at 16..22
+        // even pixels at bits 0..6, odd at 16..22 (disjoint bits: the multiply-adds are ORs on the FMA pipe)
+        const uint32_t c = e[0] + 4u * e[1] + 16u * e[2] + 64u * e[3];
         return (c | (c >> 15)) & 0xffu;
     }
     static __device__ __forceinline__ void store_raw(uint16_t *dst, const uint32_t (&w)[4])
