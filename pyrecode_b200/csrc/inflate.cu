@@ -45,14 +45,29 @@ k_inflate_scan(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
     }
     if (t == 0) { status[s] = RC_STATUS_OK; c[0] = 2; }
     uint32_t carry = 1;
-    // a marker at byte q means a candidate block start at q + 4; the 6 trailer bytes can never hold a start
+    // a marker at byte q means a candidate block start at q + 4; the 6 trailer bytes can never hold a start.
+    // Every thread examines 16 consecutive positions per round (19 bytes, read as words when aligned), so a
+    // round covers 4096 bytes with one block scan.
     const uint32_t last = n - 6;
-    for (uint32_t q0 = 2; q0 + 4 <= last; q0 += 256) {
-        const uint32_t q = q0 + t;
-        const bool hit = q + 4 <= last && p[q] == 0 && p[q + 1] == 0 && p[q + 2] == 0xff && p[q + 3] == 0xff;
+    for (uint32_t q0 = 2; q0 + 4 <= last; q0 += 4096) {
+        const uint32_t q = q0 + (uint32_t)t * 16;
+        uint32_t hits = 0;                           // bit i: marker at q + i
+        if (q + 4 <= last) {
+            uint8_t b[19];
+#pragma unroll
+            for (int i = 0; i < 19; i++) b[i] = q + i < n ? p[q + i] : 0x55;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (q + i + 4 <= last && b[i] == 0 && b[i + 1] == 0 && b[i + 2] == 0xff && b[i + 3] == 0xff) hits |= 1u << i;
+        }
         uint32_t total;
-        const uint32_t e = block_excl_scan<8>(hit ? 1u : 0u, s_warp, &total);
-        if (hit && carry + e < cmax) c[carry + e] = q + 4;
+        uint32_t e = carry + block_excl_scan<8>(__popc(hits), s_warp, &total);
+        while (hits) {
+            const uint32_t i = __ffs(hits) - 1;
+            hits &= hits - 1;
+            if (e < cmax) c[e] = q + i + 4;
+            e++;
+        }
         carry += total;
         __syncthreads();
     }
@@ -100,12 +115,56 @@ k_inflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
         if (lane == 0) ti = atomicAdd(&counters[0], 1u);
         ti = __shfl_sync(0xffffffffu, ti, 0);
         if (ti >= total) break;
-        if (lane == 0) {
+        // stream / candidate of this task (all lanes)
+        int s;
+        {
             int lo = 0, hi = n_streams;
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (task_base[mid] <= ti) lo = mid; else hi = mid; }
-            const int s = lo;
-            const uint32_t j = ti - task_base[s];
-            const uint64_t ooff = (uint64_t)j * INF_CHUNK;
+            s = lo;
+        }
+        const uint32_t j = ti - task_base[s];
+        const uint64_t ooff = (uint64_t)j * INF_CHUNK;
+        // Fast path for the pieces our encoder stores: [00][LEN][~LEN][LEN bytes][00 00 00 FF FF], byte aligned.
+        // The 32 lanes copy the payload and sum its Adler-32 partials; anything else takes the serial decoder.
+        {
+            const uint8_t *p = in + in_off[s];
+            const uint32_t nb = in_bytes[s], st0 = cand[(size_t)s * cmax + j];
+            bool fast = false;
+            uint32_t len = 0;
+            if ((uint64_t)st0 + 10 <= nb && (p[st0] & 7) == 0) {
+                len = (uint32_t)p[st0 + 1] | ((uint32_t)p[st0 + 2] << 8);
+                const uint32_t nlen = (uint32_t)p[st0 + 3] | ((uint32_t)p[st0 + 4] << 8);
+                const uint64_t m = (uint64_t)st0 + 5 + len;
+                const uint64_t cap = ooff < out_stride ? out_stride - ooff : 0;
+                fast = len > 0 && (len ^ 0xffffu) == nlen && m + 5 <= nb && len <= cap && p[m] == 0 && p[m + 1] == 0 &&
+                       p[m + 2] == 0 && p[m + 3] == 0xff && p[m + 4] == 0xff;
+            }
+            if (fast) {
+                const uint8_t *src = p + st0 + 5;
+                uint8_t *dst = out + (size_t)s * out_stride + ooff;
+                uint32_t a = 0, b = 0;                          // sum c_i, sum (len - i) c_i
+                for (uint32_t i = lane; i < len; i += 32) {
+                    const uint32_t cc = src[i];
+                    dst[i] = (uint8_t)cc;
+                    a += cc;
+                    b = (b + (len - i) * cc) % 65521u;
+                }
+                a %= 65521u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    a += __shfl_down_sync(0xffffffffu, a, d);
+                    b += __shfl_down_sync(0xffffffffu, b, d);
+                }
+                if (lane == 0) {
+                    InfTask r;
+                    r.end = st0 + 5 + len + 5; r.out_len = len; r.s1 = a % 65521u; r.s2 = b % 65521u; r.code = IF_END_SYNC;
+                    tasks[ti] = r;
+                }
+                __syncwarp();
+                continue;
+            }
+        }
+        if (lane == 0) {
             IfOut O;
             O.out = out + (size_t)s * out_stride + ooff;
             O.cap = ooff < out_stride ? out_stride - ooff : 0;

@@ -247,7 +247,14 @@ IF_HD int if_inflate(const uint8_t *in, uint64_t nbytes, uint64_t start, IfOut &
                     const uint32_t dist = dbase[ds] + B.get(dext[ds]);
                     if (dist > O.n) return IF_ERR_DATA;          // reaches before this range's own output
                     if (O.n + len > O.cap) return IF_ERR_OUT;
-                    for (uint32_t i = 0; i < len; i++) O.put(O.out[O.n - dist]);
+                    if (dist == 1) {
+                        // byte run (the only match our own encoder emits): one read of the previous byte, then
+                        // stores only -- no store -> load round trip through memory per byte
+                        const uint8_t c = O.out[O.n - 1];
+                        for (uint32_t i = 0; i < len; i++) O.put(c);
+                    } else {
+                        for (uint32_t i = 0; i < len; i++) O.put(O.out[O.n - dist]);
+                    }
                 }
                 if (B.overrun()) return IF_ERR_IN;
             }
