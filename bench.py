@@ -144,7 +144,7 @@ def main():
     ap.add_argument('--cpu-frames-per-core', type=int, default=96,
                     help='frames per host core of the cpu_baseline sample (about 10 s of CPU work)')
     ap.add_argument('--ref-frames-per-core', type=int, default=4, help='frames per core per step of --impl reference')
-    ap.add_argument('--slots', type=int, default=2, help='batches in flight (each on its own CUDA stream)')
+    ap.add_argument('--slots', type=int, default=3, help='batches in flight (each on its own CUDA stream)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()

@@ -139,6 +139,10 @@ extern "C" int rc_create(rc_ctx **out, int device)
     if (!c) return -5;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    const char *e = getenv("RECODE_B200_PRIORITY");
+    c->use_priority = e ? (atoi(e) != 0) : -1;
+    e = getenv("RECODE_B200_CCL_CTAS");
+    c->ccl_ctas_per_sm = e ? atoi(e) : -1;
     *out = c;
     return 0;
 }
@@ -150,8 +154,11 @@ extern "C" void rc_destroy(rc_ctx *ctx)
     if (ctx->kept_tables) cudaFree(ctx->kept_tables);
     if (ctx->side_ready) {
         cudaStreamDestroy(ctx->side);
+        cudaStreamDestroy(ctx->post);
+        cudaStreamDestroy(ctx->side_hi);
         cudaEventDestroy(ctx->ev_fork);
         cudaEventDestroy(ctx->ev_join);
+        cudaEventDestroy(ctx->ev_post);
     }
     free(ctx);
 }
@@ -342,9 +349,14 @@ static int prepare_kept_tables(rc_ctx *ctx, const rc_config *cfg)
 static int ensure_side_stream(rc_ctx *ctx)
 {
     if (ctx->side_ready) return 0;
-    RC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    int lo = 0, hi = 0;                                   // numerically lower = higher priority
+    RC_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, lo));
+    RC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_hi, cudaStreamNonBlocking, hi));
+    RC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->post, cudaStreamNonBlocking, hi));
     RC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     RC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    RC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_post, cudaEventDisableTiming));
     ctx->side_ready = 1;
     return 0;
 }
@@ -393,36 +405,44 @@ extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void 
     // The map streams of L1 / L2 / L3 are final after stage 1: they are deflated on the side stream while the main
     // stream labels puddles and packs the values.  (L4's map is the last product of stage 2.)
     const bool fork = level != 4 && F > 0;
+    if ((rc = ensure_side_stream(ctx))) return rc;
     rc_mark(ctx, 0, st);
     if ((rc = reduce_stage1(ctx, cfg, g, w, d_frames, F, d_thr, cw.maps, st))) return rc;
     rc_mark(ctx, 1, st);
-    cudaStream_t sm = st;
+    // everything else on the context's high-priority stream(s); the caller's stream joins at the end
+    const bool prio = ctx->use_priority < 0 ? (level == 2 || level == 4) : ctx->use_priority != 0;
+    cudaStream_t sp = prio ? ctx->post : st;
+    RC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    if (sp != st) RC_CUDA(ctx, cudaStreamWaitEvent(sp, ctx->ev_fork, 0));
+    cudaStream_t sm = sp;
     if (fork) {
-        if ((rc = ensure_side_stream(ctx))) return rc;
-        sm = ctx->side;
-        RC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        sm = prio ? ctx->side_hi : ctx->side;
         RC_CUDA(ctx, cudaStreamWaitEvent(sm, ctx->ev_fork, 0));
         if ((rc = deflate_group(ctx, cfg, 0, base, (const uint8_t *)cw.maps, g.MS * 4, nullptr, (uint32_t)g.map_bytes, F,
                                 cw.map_off, cw.map_len, cw.dm, sm))) return rc;
         RC_CUDA(ctx, cudaEventRecord(ctx->ev_join, sm));
     }
-    if ((rc = reduce_stage2(ctx, cfg, g, w, F, cw.maps, cw.packed, cw.packed_stride, cw.packed_bytes, d_counts, st)))
+    if ((rc = reduce_stage2(ctx, cfg, g, w, F, cw.maps, cw.packed, cw.packed_stride, cw.packed_bytes, d_counts, sp)))
         return rc;
-    rc_mark(ctx, 2, st);
+    rc_mark(ctx, 2, sp);
     if (!fork && (rc = deflate_group(ctx, cfg, 0, base, (const uint8_t *)cw.maps, g.MS * 4, nullptr,
-                                     (uint32_t)g.map_bytes, F, cw.map_off, cw.map_len, cw.dm, st))) return rc;
+                                     (uint32_t)g.map_bytes, F, cw.map_off, cw.map_len, cw.dm, sp))) return rc;
     if (cw.spf == 2 && (rc = deflate_group(ctx, cfg, 1, base, cw.packed, cw.packed_stride, cw.packed_bytes, 0, F,
-                                           cw.val_off, cw.val_len, cw.dv, st))) return rc;
-    if (fork) RC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    rc_mark(ctx, 3, st);
+                                           cw.val_off, cw.val_len, cw.dv, sp))) return rc;
+    if (fork) RC_CUDA(ctx, cudaStreamWaitEvent(sp, ctx->ev_join, 0));
+    rc_mark(ctx, 3, sp);
     const int wrap = cfg->rc_operation_mode == 1;
     if ((rc = launch_layout_records(ctx, cw.dm, cw.dv, cw.packed_bytes, F, cw.spf, cfg->rc_operation_mode, first_frame_id,
-                                    d_records, records_capacity, d_record_offsets, d_status, st))) return rc;
+                                    d_records, records_capacity, d_record_offsets, d_status, sp))) return rc;
     if ((rc = launch_copy_pieces(ctx, cw.dm, wrap, base, cw.map_off, cw.map_len, F, d_records, records_capacity, d_status,
-                                 st))) return rc;
+                                 sp))) return rc;
     if (cw.spf == 2 && (rc = launch_copy_pieces(ctx, cw.dv, wrap, base, cw.val_off, cw.val_len, F, d_records,
-                                                records_capacity, d_status, st))) return rc;
-    rc_mark(ctx, 4, st);
+                                                records_capacity, d_status, sp))) return rc;
+    rc_mark(ctx, 4, sp);
+    if (sp != st) {
+        RC_CUDA(ctx, cudaEventRecord(ctx->ev_post, sp));
+        RC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_post, 0));
+    }
     return 0;
 }
 

@@ -88,12 +88,13 @@ __device__ __forceinline__ bool centroid_pixel(float fr, float fc, int ny, int n
 // FOLD: 1 = L2 max, 2 = L2 sum, 3 = L4: centroids of the puddles that lie entirely inside the tile ("closed");
 // puddles that continue in another tile ("open") get a bounding box and are finished by k_l4_open.
 template <int FOLD>
-__global__ void __launch_bounds__(CCL_THREADS)
-k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
-            const uint32_t *__restrict__ tilecnt, const uint32_t *__restrict__ vp_all, uint8_t *__restrict__ tileovf,
-            uint32_t *__restrict__ xcount, uint2 *__restrict__ xlinks, uint32_t *__restrict__ parent_all,
-            uint32_t *__restrict__ acc_all, int ny, int nx, int l4mode, uint32_t *__restrict__ bbox_all,
-            uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all, uint32_t *__restrict__ rootcnt)
+__device__ __forceinline__ void
+ccl_tile(const int tile, const int f,
+         const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
+         const uint32_t *__restrict__ tilecnt, const uint32_t *__restrict__ vp_all, uint8_t *__restrict__ tileovf,
+         uint32_t *__restrict__ xcount, uint2 *__restrict__ xlinks, uint32_t *__restrict__ parent_all,
+         uint32_t *__restrict__ acc_all, int ny, int nx, int l4mode, uint32_t *__restrict__ bbox_all,
+         uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all, uint32_t *__restrict__ rootcnt)
 {
     constexpr bool L4 = FOLD == 3;
     // map words of the tile preceded by a halo: the CCL_HALO words before the tile (zeros before the frame),
@@ -109,7 +110,7 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     __shared__ uint8_t s_open[L4 ? CCL_CAP : 4];       // pixel, then root: its puddle continues in another tile
     __shared__ uint32_t s_cmap[L4 ? TILE_WORDS : 4];   // centroid bits that fall inside the tile
     __shared__ uint32_t s_nlinks, s_nx, s_bad, s_nlist, s_nclosed;
-    const int tile = blockIdx.x, f = blockIdx.y, t = threadIdx.x, lane = t & 31;
+    const int t = threadIdx.x, lane = t & 31;
     const size_t ti = (size_t)f * NT + tile;
     const uint32_t base = (uint32_t)tile << TILE_LOG2;
     const size_t slots = (size_t)NT * TILE_PX;
@@ -382,6 +383,25 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
             if (w) atomicOr(&cmap_g[(size_t)tile * TILE_WORDS + i], w);
         }
     if (t == 0) rootcnt[ti] = s_nclosed;
+}
+
+// The grid is either one CTA per (tile, frame) or, when the launcher limits it to a few CTAs per SM, a
+// persistent one that walks the (tile, frame) pairs with a grid stride: the labelling then shares every SM with
+// the streaming kernel of the next batch (memory-bound next to issue-bound work) instead of displacing it.
+template <int FOLD>
+__global__ void __launch_bounds__(CCL_THREADS)
+k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT, int n_tiles_total,
+            const uint32_t *__restrict__ tilecnt, const uint32_t *__restrict__ vp_all, uint8_t *__restrict__ tileovf,
+            uint32_t *__restrict__ xcount, uint2 *__restrict__ xlinks, uint32_t *__restrict__ parent_all,
+            uint32_t *__restrict__ acc_all, int ny, int nx, int l4mode, uint32_t *__restrict__ bbox_all,
+            uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all, uint32_t *__restrict__ rootcnt)
+{
+    for (int gt = blockIdx.x; gt < n_tiles_total; gt += gridDim.x) {
+        const int f = gt / NT, tile = gt - f * NT;
+        ccl_tile<FOLD>(tile, f, maps, MS, wordpre_all, NT, tilecnt, vp_all, tileovf, xcount, xlinks, parent_all, acc_all,
+                       ny, nx, l4mode, bbox_all, map2_all, cent_all, rootcnt);
+        __syncthreads();                               // the next tile reuses the shared arrays
+    }
 }
 
 // full-frame union (maps that did not come from k_reduce_tiles: rc_ccl_label)
@@ -700,9 +720,13 @@ int launch_ccl_tiles(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps,
                      uint32_t *rootcnt, int F, cudaStream_t st)
 {
     if (F <= 0) return 0;
-    dim3 grid((unsigned)g.NT, F);
+    const int nt = F * g.NT;
+    unsigned grid = (unsigned)nt;
+    const int per_sm = ctx->ccl_ctas_per_sm >= 0 ? ctx->ccl_ctas_per_sm
+                                                 : (ctx->use_priority == 0 ? 0 : (fold == 3 ? 3 : 2));
+    if (per_sm > 0 && (unsigned)(per_sm * ctx->sm_count) < grid) grid = (unsigned)(per_sm * ctx->sm_count);
 #define RC_CT(FO)                                                                                              \
-    k_ccl_tiles<FO><<<grid, CCL_THREADS, 0, st>>>(maps, g.MS, wordpre, g.NT, tilecnt, vp, tileovf, xcount,       \
+    k_ccl_tiles<FO><<<grid, CCL_THREADS, 0, st>>>(maps, g.MS, wordpre, g.NT, nt, tilecnt, vp, tileovf, xcount,   \
                                                   (uint2 *)xlinks, parent, acc, g.ny, g.nx, l4mode, bbox, map2,  \
                                                   cent, rootcnt)
     if (fold == 1) RC_CT(1);

@@ -146,9 +146,9 @@ k_deflate_tables(const uint32_t *__restrict__ ghist, const uint32_t *__restrict_
         if (chunk_base[s + 1] == chunk_base[s]) return;      // empty stream: no chunk will ask for a table
         sampled_bytes = in_bytes[s];
     }
-    // Entropy estimate of the token stream: data that would shrink by < 3 % (bit-packed intensities are
-    // close to random bytes) is emitted as stored blocks, which skips the code construction and the
-    // tokenizer for all of its chunks.
+    // Entropy estimate of the token stream: data that would hardly shrink (bit-packed intensities are close to
+    // random bytes) is emitted as stored blocks, which skips the code construction and the tokenizer for all
+    // of its chunks -- and lets the reader copy them instead of decoding them.
     {
         uint32_t tok = 0;
         for (int i = t; i < DF_NSYM; i += DF_THREADS) tok += ghist[(size_t)s * DF_NSYM + i];
@@ -167,7 +167,9 @@ k_deflate_tables(const uint32_t *__restrict__ ghist, const uint32_t *__restrict_
         if (t == 0) {
             float b = 0.f;
             for (int i = 0; i < DF_THREADS; i++) b += s_bits[i];
-            s_skip = b * 0.125f + 128.f >= 0.97f * (float)sampled_bytes;
+            // levels 1..5 ("fast"): a group that would shrink by less than 10 % is stored -- bit-packed 12-bit
+            // values gain about 5 % but cost the reader a Huffman decode of every byte; levels 6..9: 3 %
+            s_skip = b * 0.125f + 128.f >= (shared_table ? 0.90f : 0.97f) * (float)sampled_bytes;
         }
         __syncthreads();
         if (s_skip) {

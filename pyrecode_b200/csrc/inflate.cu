@@ -22,7 +22,8 @@
 #include "inflate_core.cuh"
 
 constexpr int INF_CHUNK = 16384;
-constexpr int INF_WARPS = 4;
+constexpr int IF_RETRY = 100;           // task code: left to k_inflate_chunks by k_inflate_lanes
+constexpr int INF_WARPS = 2;             // decoding warps per CTA (about 21 KiB of shared memory each)
 
 __global__ void __launch_bounds__(256)
 k_inflate_scan(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
@@ -100,21 +101,34 @@ struct InfTask {
     int32_t code;        // IF_END_SYNC / IF_END_FINAL / error
 };
 
+// Per warp: a 16 KiB output buffer (one whole chunk of our encoder), a 2 KiB sliding window over the compressed
+// bytes and the decoding tables, all in shared memory.  Lane 0 decodes; the 32 lanes zero the buffer before and
+// copy it out -- and sum its Adler-32 partials -- afterwards, so global memory sees only coalesced 128-bit
+// accesses.  Output beyond 16 KiB (a foreign stream decoded from its only candidate) goes to global memory byte
+// by byte as before.
+struct InfWarpShared {
+    __align__(16) uint8_t out[INF_CHUNK];
+    __align__(16) uint32_t win[IF_WIN_BYTES / 4];
+    IfTables tab;
+};
+
 __global__ void __launch_bounds__(INF_WARPS * 32)
 k_inflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                  const uint32_t *__restrict__ in_bytes, int n_streams, uint32_t cmax,
                  const uint32_t *__restrict__ cand, const uint32_t *__restrict__ task_base,
                  uint32_t *__restrict__ counters, uint8_t *__restrict__ out, size_t out_stride,
-                 InfTask *__restrict__ tasks)
+                 InfTask *__restrict__ tasks, int retry_only)
 {
-    __shared__ IfTables s_tab[INF_WARPS];
+    __shared__ InfWarpShared s_w[INF_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    InfWarpShared &W = s_w[warp];
     const uint32_t total = task_base[n_streams];
     while (true) {
         uint32_t ti = 0;
         if (lane == 0) ti = atomicAdd(&counters[0], 1u);
         ti = __shfl_sync(0xffffffffu, ti, 0);
         if (ti >= total) break;
+        if (retry_only && tasks[ti].code != IF_RETRY) continue;      // finished by k_inflate_lanes
         // stream / candidate of this task (all lanes)
         int s;
         {
@@ -124,6 +138,8 @@ k_inflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
         }
         const uint32_t j = ti - task_base[s];
         const uint64_t ooff = (uint64_t)j * INF_CHUNK;
+        const uint64_t cap = ooff < out_stride ? out_stride - ooff : 0;
+        uint8_t *dst = out + (size_t)s * out_stride + ooff;
         // Fast path for the pieces our encoder stores: [00][LEN][~LEN][LEN bytes][00 00 00 FF FF], byte aligned.
         // The 32 lanes copy the payload and sum its Adler-32 partials; anything else takes the serial decoder.
         {
@@ -135,13 +151,11 @@ k_inflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
                 len = (uint32_t)p[st0 + 1] | ((uint32_t)p[st0 + 2] << 8);
                 const uint32_t nlen = (uint32_t)p[st0 + 3] | ((uint32_t)p[st0 + 4] << 8);
                 const uint64_t m = (uint64_t)st0 + 5 + len;
-                const uint64_t cap = ooff < out_stride ? out_stride - ooff : 0;
                 fast = len > 0 && (len ^ 0xffffu) == nlen && m + 5 <= nb && len <= cap && p[m] == 0 && p[m + 1] == 0 &&
                        p[m + 2] == 0 && p[m + 3] == 0xff && p[m + 4] == 0xff;
             }
             if (fast) {
                 const uint8_t *src = p + st0 + 5;
-                uint8_t *dst = out + (size_t)s * out_stride + ooff;
                 uint32_t a = 0, b = 0;                          // sum c_i, sum (len - i) c_i
                 for (uint32_t i = lane; i < len; i += 32) {
                     const uint32_t cc = src[i];
@@ -164,22 +178,293 @@ k_inflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
                 continue;
             }
         }
+        // zero the output buffer (runs of 0x00 are then not stored at all)
+#pragma unroll 4
+        for (int i = lane; i < INF_CHUNK / 16; i += 32) reinterpret_cast<uint4 *>(W.out)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        uint32_t o_n = 0, o_s1 = 0, o_s2 = 0, o_end = 0;
+        int code = 0;
         if (lane == 0) {
             IfOut O;
-            O.out = out + (size_t)s * out_stride + ooff;
-            O.cap = ooff < out_stride ? out_stride - ooff : 0;
-            O.n = 0; O.s1 = 0; O.s2 = 0;
+            O.init(dst, cap, W.out, (uint32_t)INF_CHUNK);
             uint64_t end = 0;
-            const int code = if_inflate(in + in_off[s], in_bytes[s], cand[(size_t)s * cmax + j], O, s_tab[warp], true, &end);
-            InfTask r;
-            r.end = (uint32_t)end; r.out_len = (uint32_t)O.n; r.s1 = O.s1 % 65521u; r.s2 = O.s2 % 65521u; r.code = code;
-            tasks[ti] = r;
+            code = if_inflate(in + in_off[s], in_bytes[s], cand[(size_t)s * cmax + j], O, W.tab, true, &end, W.win);
+            o_n = (uint32_t)O.n; o_s1 = O.s1 % 65521u; o_s2 = O.s2 % 65521u; o_end = (uint32_t)end;
 #ifdef RC_DEBUG
-            printf("[chunks] ti=%u s=%d j=%u start=%u code=%d end=%u out=%u\n", ti, s, j, cand[(size_t)s * cmax + j], code, r.end, r.out_len);
+            printf("[chunks] ti=%u s=%d j=%u start=%u code=%d end=%u out=%u\n", ti, s, j, cand[(size_t)s * cmax + j], code, o_end, o_n);
 #endif
         }
         __syncwarp();
+        o_n = __shfl_sync(0xffffffffu, o_n, 0);
+        code = __shfl_sync(0xffffffffu, code, 0);
+        if (code == IF_END_SYNC || code == IF_END_FINAL) {
+            // copy the buffered part out and sum its Adler-32 partials {sum c_i, sum (nsh - i) c_i}; the bytes of the
+            // buffer past nsh are still zero
+            const uint32_t nsh = o_n < (uint32_t)INF_CHUNK ? o_n : (uint32_t)INF_CHUNK;
+            const uint32_t nw = (nsh + 3) >> 2;
+            uint32_t a = 0, b = 0;
+            for (uint32_t k = lane; k < nw; k += 32) {
+                const uint32_t x = reinterpret_cast<const uint32_t *>(W.out)[k];
+                const uint32_t sm = __dp4a(x, 0x01010101u, 0u), wt = __dp4a(x, 0x03020100u, 0u);
+                a += sm;
+                b += (nsh - 4u * k) * sm - wt;          // per lane < 512 * 255 * 16384 < 2^32
+            }
+            a %= 65521u; b %= 65521u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                a += __shfl_down_sync(0xffffffffu, a, d);
+                b += __shfl_down_sync(0xffffffffu, b, d);
+            }
+            if (((uintptr_t)dst & 15) == 0) {
+                const uint32_t nv = nsh >> 4;
+                for (uint32_t k = lane; k < nv; k += 32) reinterpret_cast<uint4 *>(dst)[k] = reinterpret_cast<const uint4 *>(W.out)[k];
+                for (uint32_t k = (nv << 4) + lane; k < nsh; k += 32) dst[k] = W.out[k];
+            } else {
+                for (uint32_t k = lane; k < nsh; k += 32) dst[k] = W.out[k];
+            }
+            if (lane == 0) {
+                // buffered part A (nsh bytes) followed by the directly written part B (o_n - nsh bytes)
+                a %= 65521u; b %= 65521u;
+                const uint32_t nB = o_n - nsh;
+                InfTask r;
+                r.end = o_end; r.out_len = o_n; r.code = code;
+                r.s1 = (a + o_s1) % 65521u;
+                r.s2 = (uint32_t)(((uint64_t)b + (uint64_t)nB % 65521u * a + o_s2) % 65521u);
+                tasks[ti] = r;
+            }
+        } else if (lane == 0) {
+            InfTask r;
+            r.end = o_end; r.out_len = o_n; r.s1 = 0; r.s2 = 0; r.code = code;
+            tasks[ti] = r;
+        }
+        __syncwarp();
     }
+}
+
+// ---- lane-per-chunk decoding of our own streams -------------------------------------------------------------
+// Every chunk written by deflate.cu is one dynamic block, and all chunks of a stream carry the SAME code (one
+// code per group of streams at levels 1..5, one per stream at levels 6..9), i.e. bit-identical block headers.
+// k_inflate_tables parses the header of a stream's first chunk once and leaves the decoding tables in global
+// memory; k_inflate_lanes then gives every chunk whose header bits equal the first chunk's to ONE LANE: 32 chunks
+// decode per warp instead of one, which is what the latency-bound serial decoding needs to fill the machine.
+// A lane reads its compressed bytes through a preloaded 32-bit word (the load for the next refill is always in
+// flight), keeps the current output word in a register and stores only non-zero words into the zero-filled
+// output; distance-1 runs (the only matches our encoder emits) cost no memory access at all.  Anything a lane does
+// not understand -- another header, another distance, output beyond 16 KiB, a stored piece -- is left to
+// k_inflate_chunks (task code IF_RETRY).
+constexpr int INF_LANES = 64;            // chunks per CTA of k_inflate_lanes
+
+constexpr int INF_LUT_BITS = 15;         // k_inflate_lanes: every code of the stream in one table lookup (64 KiB)
+constexpr int INF_LUT_SIZE = 1 << INF_LUT_BITS;
+
+struct __align__(16) InfStreamTable {
+    uint16_t lut[INF_LUT_SIZE];   // literal / length code: (len << 12) | symbol, 0 = unused bit pattern
+    uint16_t dlut[IF_LUT_SIZE];   // distance code
+    uint32_t hdr_bits;       // bits from the chunk start to its first token; 0 = no lane decoding for this stream
+    uint32_t pad[3];
+};
+
+__global__ void __launch_bounds__(32)
+k_inflate_tables(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                 const uint32_t *__restrict__ in_bytes, const uint32_t *__restrict__ ncand, uint32_t cmax,
+                 InfStreamTable *__restrict__ tabs)
+{
+    __shared__ IfTables s_tab;
+    __shared__ uint32_t s_bits;
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const uint32_t nc = ncand[s];
+    if (lane == 0) {
+        s_bits = 0;
+        if (nc >= 2 && nc <= cmax) {
+            IfBits B;
+            B.init(in + in_off[s], in_bytes[s], 2);
+            const uint32_t bfinal = B.get(1), btype = B.get(2);
+            if (!bfinal && btype == 2) {
+                uint8_t lens[320];
+                int nl = 0, nd = 0;
+                if (if_dynamic_lengths(B, s_tab, lens, nl, nd) == IF_OK && !B.overrun() &&
+                    if_build(s_tab.ll, lens, nl) == 0 && if_build(s_tab.d, lens + 288, nd) == 0)
+                    s_bits = (uint32_t)(B.bitpos() - 16);
+            }
+        }
+    }
+    __syncwarp();
+    InfStreamTable &T = tabs[s];
+    if (lane == 0) T.hdr_bits = s_bits;
+    if (!s_bits) return;
+    // the wide LUT, all lanes: canonical code of the idx-th symbol in (length, value) order
+    for (int i = lane; i < INF_LUT_SIZE; i += 32) T.lut[i] = 0;
+    for (int i = lane; i < IF_LUT_SIZE; i += 32) T.dlut[i] = s_tab.d.lut[i];
+    __syncwarp();
+    uint32_t offs[17], first[17];
+    offs[1] = 0; first[1] = 0;
+    for (int l = 1; l <= 15; l++) {
+        offs[l + 1] = offs[l] + s_tab.ll.count[l];
+        first[l + 1] = (first[l] + s_tab.ll.count[l]) << 1;
+    }
+    for (uint32_t idx = lane; idx < offs[16]; idx += 32) {
+        int l = 1;
+        while (idx >= offs[l + 1]) l++;
+        if (l > INF_LUT_BITS) continue;
+        const uint32_t code = first[l] + (idx - offs[l]);
+        const uint32_t r = __brev(code) >> (32 - l);
+        const uint16_t e = (uint16_t)((l << 12) | s_tab.ll.symbol[idx]);
+        for (uint32_t x = r; x < (uint32_t)INF_LUT_SIZE; x += 1u << l) T.lut[x] = e;
+    }
+}
+
+__global__ void __launch_bounds__(INF_LANES)
+k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                const uint32_t *__restrict__ in_bytes, uint32_t cmax, const uint32_t *__restrict__ cand,
+                const uint32_t *__restrict__ ncand, const uint32_t *__restrict__ task_base,
+                const InfStreamTable *__restrict__ tabs, uint8_t *__restrict__ out, size_t out_stride,
+                InfTask *__restrict__ tasks)
+{
+    extern __shared__ __align__(16) uint16_t s_lanes[];
+    uint16_t *s_lut = s_lanes;                       // [INF_LUT_SIZE]
+    uint16_t *s_dlut = s_lanes + INF_LUT_SIZE;       // [IF_LUT_SIZE]
+    const int s = blockIdx.y, t = threadIdx.x;
+    const uint32_t nc = ncand[s];
+    const uint32_t j = blockIdx.x * INF_LANES + t;
+    if (nc > cmax || blockIdx.x * INF_LANES >= nc) return;
+    const InfStreamTable &T = tabs[s];
+    const uint32_t hdr_bits = T.hdr_bits;
+    const uint32_t tb = task_base[s];
+    if (hdr_bits == 0) {
+        if (j < nc) tasks[tb + j].code = IF_RETRY;
+        return;
+    }
+    for (int i = t; i < INF_LUT_SIZE / 8; i += INF_LANES)
+        reinterpret_cast<uint4 *>(s_lut)[i] = reinterpret_cast<const uint4 *>(T.lut)[i];
+    for (int i = t; i < IF_LUT_SIZE / 8; i += INF_LANES)
+        reinterpret_cast<uint4 *>(s_dlut)[i] = reinterpret_cast<const uint4 *>(T.dlut)[i];
+    __syncthreads();
+    if (j >= nc) return;
+    const uint8_t *p = in + in_off[s];
+    const uint32_t nb = in_bytes[s];
+    const uint32_t st0 = cand[(size_t)s * cmax + j];
+    InfTask r;
+    r.end = 0; r.out_len = 0; r.s1 = 0; r.s2 = 0; r.code = IF_RETRY;
+    // the stream's closing piece: an empty final fixed block (03 00) in front of the Adler-32 trailer
+    if ((uint64_t)st0 + 6 == nb && p[st0] == 0x03 && p[st0 + 1] == 0x00) {
+        r.end = st0 + 2; r.code = IF_END_FINAL;
+        tasks[tb + j] = r;
+        return;
+    }
+    const uint64_t ooff = (uint64_t)j * INF_CHUNK;
+    const uint64_t room = ooff < out_stride ? out_stride - ooff : 0;
+    const uint32_t cap = room < (uint64_t)INF_CHUNK ? (uint32_t)room : (uint32_t)INF_CHUNK;
+    const uint32_t hbytes = (hdr_bits + 7) >> 3;
+    bool ok = (uint64_t)st0 + hbytes + 8 <= nb;
+    if (ok && j > 0) {
+        // same header bits as the first chunk (whose tables these are)?
+        const uint8_t *a = p + 2, *b = p + st0;
+        uint32_t diff = 0;
+        for (uint32_t i = 0; i + 1 < hbytes; i++) diff |= (uint32_t)(a[i] ^ b[i]);
+        const uint32_t lastmask = (hdr_bits & 7) ? ((1u << (hdr_bits & 7)) - 1u) : 0xffu;
+        diff |= (uint32_t)(a[hbytes - 1] ^ b[hbytes - 1]) & lastmask;
+        ok = diff == 0;
+    }
+    if (!ok) { tasks[tb + j] = r; return; }
+
+    // ---- bit reader: 64-bit buffer fed by aligned 32-bit words, the next word always preloaded
+    const uint8_t *first = p + st0 + (hdr_bits >> 3);
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>((uintptr_t)first & ~(uintptr_t)3);
+    const uint32_t *wend = reinterpret_cast<const uint32_t *>(((uintptr_t)(p + nb) + 3) & ~(uintptr_t)3);
+    const uint32_t *wfirst = wp;
+    const uint32_t skip = (uint32_t)((uintptr_t)first & 3) * 8u + (hdr_bits & 7u);
+    uint64_t buf = (uint64_t)(wp < wend ? __ldg(wp) : 0u);
+    wp++;
+    buf |= (uint64_t)(wp < wend ? __ldg(wp) : 0u) << 32;
+    wp++;
+    buf >>= skip;
+    int cnt = 64 - (int)skip;
+    uint32_t nxt = wp < wend ? __ldg(wp) : 0u;
+    wp++;
+#define LN_REFILL()                                                      \
+    if (cnt <= 32) {                                                     \
+        buf |= (uint64_t)nxt << cnt;                                     \
+        cnt += 32;                                                       \
+        nxt = wp < wend ? __ldg(wp) : 0u;                                \
+        wp++;                                                            \
+    }
+    // bits consumed since `first`'s word: 32 * (words moved into buf) - cnt
+#define LN_BITPOS() ((uint64_t)((wp - wfirst) - 1) * 32u - (uint64_t)cnt)
+
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(out + (size_t)s * out_stride + ooff);
+    uint32_t n = 0, w = 0, last = 0, s1 = 0;
+    uint64_t s2 = 0;
+    int code = IF_OK;
+    while (true) {
+        LN_REFILL();
+        // literal / length symbol
+        const uint32_t e = s_lut[(uint32_t)buf & (INF_LUT_SIZE - 1)];
+        if (e == 0) { code = IF_RETRY; break; }      // not a code of this stream
+        buf >>= (e >> 12); cnt -= (int)(e >> 12);
+        const uint32_t sym = e & 0xfffu;
+        if (sym == 256) break;
+        // one straight-line path for literals and matches: a literal is a "run" of one byte; a match reads its
+        // length bits and distance code, a literal reads nothing (zero bits)
+        const bool is_match = sym > 256;
+        const uint32_t li = is_match ? sym - 257 : 0u;
+        if (li >= 29) { code = IF_RETRY; break; }
+        const uint32_t eb = (li < 8 || li == 28) ? 0u : (li - 4) >> 2;
+        const uint32_t lb = li < 8 ? li + 3 : (li == 28 ? 258u : ((4u + (li & 3u)) << eb) + 3u);
+        const uint32_t L = is_match ? lb + ((uint32_t)buf & ((1u << eb) - 1u)) : 1u;
+        buf >>= eb; cnt -= (int)eb;
+        // (at least 33 bits were there: 15 code + 5 length bits + 9 distance code bits never run dry)
+        const uint32_t d = s_dlut[(uint32_t)buf & (IF_LUT_SIZE - 1)];
+        // only distance 1 (symbol 0, a run of the previous byte) is decoded here
+        if (is_match && (d == 0 || (d & 0xfffu) != 0 || n == 0)) { code = IF_RETRY; break; }
+        const uint32_t dl = is_match ? d >> 12 : 0u;
+        buf >>= dl; cnt -= (int)dl;
+        const uint32_t c = is_match ? last : sym;
+        if (n + L > cap) { code = IF_RETRY; break; }
+        // Adler-32 partials of L copies of c in closed form
+        s2 += (uint64_t)L * s1 + (uint64_t)(c * ((L * (L + 1)) >> 1));
+        s1 += c * L;
+        if (c == 0) {
+            const uint32_t nn = n + L;
+            if ((n ^ nn) >> 2) {
+                if (w) out32[n >> 2] = w;
+                w = 0;
+            }
+            n = nn;
+        } else {
+            for (uint32_t i = 0; i < L; i++) {
+                w |= c << ((n & 3u) * 8u);
+                n++;
+                if ((n & 3u) == 0) { out32[(n >> 2) - 1] = w; w = 0; }
+            }
+        }
+        last = c;
+    }
+    if (code == IF_OK) {
+        // the chunk's block is followed by the sync marker: 000 (stored, not final), pad to the byte, 00 00 FF FF
+        LN_REFILL();
+        const uint32_t hb = (uint32_t)buf & 7u;
+        buf >>= 3; cnt -= 3;
+        const uint64_t bp = LN_BITPOS();
+        const uint32_t pad = (uint32_t)((8u - (bp & 7u)) & 7u);
+        buf >>= pad; cnt -= (int)pad;
+        LN_REFILL();
+        if (hb == 0 && (uint32_t)buf == 0xffff0000u) {
+            const uint64_t endbit = LN_BITPOS() + 32u;
+            const uint64_t endbyte = (uint64_t)((const uint8_t *)wfirst - p) + (endbit >> 3);
+            if (endbyte <= nb) {
+                if (w) {
+                    // trailing partial word: byte stores, the bytes after it belong to someone else
+                    uint8_t *o8 = reinterpret_cast<uint8_t *>(out32);
+                    for (uint32_t k = n & ~3u; k < n; k++) o8[k] = (uint8_t)(w >> ((k & 3u) * 8u));
+                }
+                r.end = (uint32_t)endbyte; r.out_len = n; r.s1 = s1 % 65521u; r.s2 = (uint32_t)(s2 % 65521u);
+                r.code = IF_END_SYNC;
+            }
+        }
+    }
+#undef LN_REFILL
+#undef LN_BITPOS
+    tasks[tb + j] = r;
 }
 
 __global__ void k_inflate_validate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
@@ -229,7 +514,7 @@ k_inflate_serial(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
     const int s = blockIdx.x;
     if (!need_serial[s] || threadIdx.x != 0) return;
     IfOut O;
-    O.out = out + (size_t)s * out_stride; O.cap = out_stride; O.n = 0; O.s1 = 0; O.s2 = 0;
+    O.init(out + (size_t)s * out_stride, out_stride);
     uint64_t end = 0;
     const int code = if_inflate(in + in_off[s], in_bytes[s], 2, O, s_tab, false, &end);
     uint32_t st = RC_STATUS_OK;
@@ -262,6 +547,7 @@ size_t inflate_workspace_bytes(int n_streams, size_t out_stride)
     c.take<uint32_t>(8);
     c.take<InfTask>((size_t)n_streams * cmax + 1);
     c.take<uint32_t>((size_t)n_streams + 1);
+    c.take<InfStreamTable>((size_t)n_streams);
     return c.used();
 }
 
@@ -277,16 +563,33 @@ int launch_inflate(rc_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const
     uint32_t *counters = c.take<uint32_t>(8);
     InfTask *tasks = c.take<InfTask>((size_t)n_streams * cmax + 1);
     uint32_t *need_serial = c.take<uint32_t>((size_t)n_streams + 1);
+    InfStreamTable *tabs = c.take<InfStreamTable>((size_t)n_streams);
 
     k_inflate_scan<<<n_streams, 256, 0, st>>>(in, in_off, in_bytes, cmax, cand, ncand, status);
     RC_LAUNCH_CHECK(ctx, "k_inflate_scan");
     k_scan_u32<<<1, 256, 0, st>>>(ncand, n_streams, cmax, task_base, counters);
     RC_LAUNCH_CHECK(ctx, "k_scan_u32");
+    // lane-per-chunk pass over the streams of our own encoder (word stores into a zero-filled output)
+    const int lanes = (((uintptr_t)out | (uintptr_t)out_stride) & 3) == 0;
+    if (lanes) {
+        RC_CUDA(ctx, cudaMemsetAsync(out, 0, (size_t)n_streams * out_stride, st));
+        k_inflate_tables<<<n_streams, 32, 0, st>>>(in, in_off, in_bytes, ncand, cmax, tabs);
+        RC_LAUNCH_CHECK(ctx, "k_inflate_tables");
+        dim3 grid((cmax + INF_LANES - 1) / INF_LANES, (unsigned)n_streams);
+        constexpr int lanes_smem = (INF_LUT_SIZE + IF_LUT_SIZE) * (int)sizeof(uint16_t);
+        if (!ctx->inflate_attr_set) {
+            RC_CUDA(ctx, cudaFuncSetAttribute(k_inflate_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, lanes_smem));
+            ctx->inflate_attr_set = true;
+        }
+        k_inflate_lanes<<<grid, INF_LANES, lanes_smem, st>>>(in, in_off, in_bytes, cmax, cand, ncand, task_base, tabs, out,
+                                                   out_stride, tasks);
+        RC_LAUNCH_CHECK(ctx, "k_inflate_lanes");
+    }
     size_t blocks = ((size_t)n_streams * cmax + INF_WARPS - 1) / INF_WARPS;
-    const size_t cap = (size_t)ctx->sm_count * 12;
+    const size_t cap = (size_t)ctx->sm_count * 5;            // 5 CTAs of 43 KiB fit one SM
     if (blocks > cap) blocks = cap;
     k_inflate_chunks<<<(unsigned)blocks, INF_WARPS * 32, 0, st>>>(in, in_off, in_bytes, n_streams, cmax, cand, task_base,
-                                                                 counters, out, out_stride, tasks);
+                                                                 counters, out, out_stride, tasks, lanes);
     RC_LAUNCH_CHECK(ctx, "k_inflate_chunks");
     k_inflate_validate<<<(n_streams + 127) / 128, 128, 0, st>>>(in, in_off, in_bytes, n_streams, cmax, cand, ncand,
                                                                task_base, tasks, out_bytes, status, need_serial);

@@ -34,18 +34,72 @@ struct IfTables {
 
 enum { IF_OK = 0, IF_END_SYNC = 1, IF_END_FINAL = 2, IF_ERR_DATA = -1, IF_ERR_OUT = -2, IF_ERR_IN = -3 };
 
+constexpr int IF_WIN_BYTES = 2048;        // shared-memory input window of a decoding lane (device)
+
 struct IfBits {
     const uint8_t *in;
     uint64_t nbytes;     // bytes available
     uint64_t pos;        // next byte to load
     uint64_t buf;
     int cnt;             // valid bits in buf
-    IF_HD void init(const uint8_t *p, uint64_t n, uint64_t start_byte)
+    // Device: a shared-memory window over the compressed bytes.  Window byte k mirrors the 16-byte aligned global
+    // address `in + win_lo + k`; the decoding lane slides it forward itself with 128-bit loads (many in flight)
+    // instead of paying one global-memory latency per input byte.
+    uint32_t *win;       // IF_WIN_BYTES / 4 words, or nullptr (host, serial fallback)
+    int64_t win_lo, win_hi;   // stream offsets covered by the window: [win_lo, win_hi)
+    IF_HD void init(const uint8_t *p, uint64_t n, uint64_t start_byte, uint32_t *window = nullptr)
     {
         in = p; nbytes = n; pos = start_byte; buf = 0; cnt = 0;
+        win = window; win_lo = 0; win_hi = 0;
     }
+#ifdef __CUDA_ARCH__
+    __device__ __forceinline__ bool slide()
+    {
+        // whole 16-byte units that lie inside the stream's buffer, starting at the unit that holds `pos`
+        const uintptr_t a0 = (uintptr_t)(in + pos) & ~(uintptr_t)15;
+        const uintptr_t a1 = (uintptr_t)(in + nbytes) & ~(uintptr_t)15;
+        if (a0 + 16 > a1) return false;
+        uint32_t units = (uint32_t)((a1 - a0) >> 4);
+        if (units > IF_WIN_BYTES / 16) units = IF_WIN_BYTES / 16;
+        const uint4 *src = reinterpret_cast<const uint4 *>(a0);
+        uint4 *dst = reinterpret_cast<uint4 *>(win);
+        uint32_t u = 0;
+        for (; u + 8 <= units; u += 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = src[u + k];
+#pragma unroll
+            for (int k = 0; k < 8; k++) dst[u + k] = v[k];
+        }
+        for (; u < units; u++) dst[u] = src[u];
+        win_lo = (int64_t)pos - (int64_t)((uintptr_t)(in + pos) - a0);
+        win_hi = win_lo + (int64_t)units * 16;
+        return true;
+    }
+#endif
     IF_HD void refill()
     {
+#ifdef __CUDA_ARCH__
+        if (win) {
+            if (!((int64_t)pos >= win_lo && (int64_t)pos + 12 <= win_hi)) {
+                if (pos + 12 <= nbytes) slide();
+            }
+            if ((int64_t)pos >= win_lo && (int64_t)pos + 12 <= win_hi) {
+                // 8 stream bytes at `pos` from three aligned words; the bytes above `cnt` that are ORed in early
+                // are the same bytes a later refill puts there again
+                const uint32_t o = (uint32_t)((int64_t)pos - win_lo);
+                const uint32_t *w = win + (o >> 2);
+                const uint32_t sh = (o & 3u) * 8u;
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+                buf |= (((uint64_t)hi << 32) | lo) << cnt;
+                const int nb = (63 - cnt) >> 3;
+                pos += (uint64_t)nb;
+                cnt += nb * 8;
+                return;
+            }
+        }
+#endif
         while (cnt <= 56) {
             const uint64_t b = pos < nbytes ? in[pos] : 0;    // zeros past the end; overrun is checked by callers
             pos++;
@@ -147,14 +201,82 @@ struct IfOut {
     uint8_t *out;
     uint64_t cap;
     uint64_t n;          // bytes produced
-    uint32_t s1, s2;     // Adler-32 partials of the produced bytes, started from (0, 0)
+    uint32_t s1, s2;     // Adler-32 partials, started from (0, 0), of the bytes produced at index >= sh_cap
+    // Device: the first sh_cap bytes (a whole chunk of our own encoder) are produced in a shared-memory buffer,
+    // zero-filled beforehand, that the warp copies out -- and checksums -- together afterwards.  Runs of 0x00, most of
+    // a binary map, then need no stores at all, and the byte before a run is read back from shared memory.
+    uint8_t *sh;
+    uint32_t sh_cap;
+    IF_HD void init(uint8_t *o, uint64_t capacity, uint8_t *shared = nullptr, uint32_t shared_cap = 0)
+    {
+        out = o; cap = capacity; n = 0; s1 = 0; s2 = 0; sh = shared; sh_cap = shared_cap;
+    }
+    IF_HD uint8_t at(uint64_t i) const { return i < sh_cap ? sh[i] : out[i]; }
     IF_HD void put(uint8_t c)
     {
+        if (n < sh_cap) { sh[n++] = c; return; }
         out[n++] = c;
         s1 += c; s2 += s1;
         if ((n & 2047) == 0) { s1 %= 65521u; s2 %= 65521u; }
     }
+    // len copies of c (a distance-1 match): Adler-32 in closed form, s1' = s1 + len c,
+    // s2' = s2 + len s1 + c len (len + 1) / 2
+    IF_HD void put_run(uint8_t c, uint32_t len)
+    {
+        if (n < sh_cap) {
+            const uint32_t k = (uint64_t)len < sh_cap - n ? len : (uint32_t)(sh_cap - n);
+            if (c != 0)
+                for (uint32_t i = 0; i < k; i++) sh[n + i] = c;
+            n += k;
+            len -= k;
+            if (len == 0) return;
+        }
+        for (uint32_t i = 0; i < len; i++) out[n + i] = c;
+        n += len;
+        s1 %= 65521u;
+        s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)len * s1 + (uint64_t)c * (len * (len + 1) / 2)) % 65521u);
+        s1 = (s1 + len * (uint32_t)c) % 65521u;
+    }
 };
+
+// Reads the code description of a dynamic block (RFC 1951 3.2.7) that follows the 3 block-header bits:
+// lens[0..nlen_codes) literal/length code lengths, lens[288..288 + ndist_codes) distance code lengths.
+// T.d is used as scratch for the code-length code.
+IF_HD int if_dynamic_lengths(IfBits &B, IfTables &T, uint8_t *lens, int &nlen_codes, int &ndist_codes)
+{
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    nlen_codes = (int)B.get(5) + 257;
+    ndist_codes = (int)B.get(5) + 1;
+    const int ncl = (int)B.get(4) + 4;
+    if (nlen_codes > 286 || ndist_codes > 30) return IF_ERR_DATA;
+    uint8_t cl[19];
+    for (int i = 0; i < 19; i++) cl[i] = 0;
+    for (int i = 0; i < ncl; i++) cl[order[i]] = (uint8_t)B.get(3);
+    if (if_build(T.d, cl, 19) != 0) return IF_ERR_DATA;     // T.d reused as the code-length table
+    int idx = 0;
+    while (idx < nlen_codes + ndist_codes) {
+        const int sym = if_decode(B, T.d);
+        if (sym < 0) return IF_ERR_DATA;
+        if (sym < 16) lens[idx++] = (uint8_t)sym;
+        else {
+            int rep, val = 0;
+            if (sym == 16) {
+                if (idx == 0) return IF_ERR_DATA;
+                val = lens[idx - 1];
+                rep = 3 + (int)B.get(2);
+            } else if (sym == 17) rep = 3 + (int)B.get(3);
+            else rep = 11 + (int)B.get(7);
+            if (idx + rep > nlen_codes + ndist_codes) return IF_ERR_DATA;
+            while (rep--) lens[idx++] = (uint8_t)val;
+        }
+    }
+    if (lens[256] == 0) return IF_ERR_DATA;
+    // move distance lengths to a fixed place
+    uint8_t dl[30];
+    for (int i = 0; i < ndist_codes; i++) dl[i] = lens[nlen_codes + i];
+    for (int i = 0; i < ndist_codes; i++) lens[288 + i] = dl[i];
+    return IF_OK;
+}
 
 // Decodes blocks starting at byte `start` of in[0..nbytes).  Stops after the final block (IF_END_FINAL) or,
 // if stop_at_sync, right after an empty stored block (IF_END_SYNC).  *end_byte receives the byte offset
@@ -162,16 +284,15 @@ struct IfOut {
 // block does not: it is rounded up).  Window = everything written to O.out so far (O.n); a distance reaching
 // before O.out[0] is an error, i.e. independent chunks only.
 IF_HD int if_inflate(const uint8_t *in, uint64_t nbytes, uint64_t start, IfOut &O, IfTables &T, bool stop_at_sync,
-                     uint64_t *end_byte)
+                     uint64_t *end_byte, uint32_t *window = nullptr)
 {
     const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
     const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
     const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
     const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
     IfBits B;
-    B.init(in, nbytes, start);
+    B.init(in, nbytes, start, window);
     while (true) {
         const uint32_t bfinal = B.get(1);
         const uint32_t btype = B.get(2);
@@ -196,36 +317,8 @@ IF_HD int if_inflate(const uint8_t *in, uint64_t nbytes, uint64_t start, IfOut &
                 for (int i = 0; i < 32; i++) lens[288 + i] = 5;     // 30 and 31 never occur in valid data
                 nlen_codes = 288; ndist_codes = 32;
             } else {
-                nlen_codes = (int)B.get(5) + 257;
-                ndist_codes = (int)B.get(5) + 1;
-                const int ncl = (int)B.get(4) + 4;
-                if (nlen_codes > 286 || ndist_codes > 30) return IF_ERR_DATA;
-                uint8_t cl[19];
-                for (int i = 0; i < 19; i++) cl[i] = 0;
-                for (int i = 0; i < ncl; i++) cl[order[i]] = (uint8_t)B.get(3);
-                if (if_build(T.d, cl, 19) != 0) return IF_ERR_DATA;     // T.d reused as the code-length table
-                int idx = 0;
-                while (idx < nlen_codes + ndist_codes) {
-                    const int sym = if_decode(B, T.d);
-                    if (sym < 0) return IF_ERR_DATA;
-                    if (sym < 16) lens[idx++] = (uint8_t)sym;
-                    else {
-                        int rep, val = 0;
-                        if (sym == 16) {
-                            if (idx == 0) return IF_ERR_DATA;
-                            val = lens[idx - 1];
-                            rep = 3 + (int)B.get(2);
-                        } else if (sym == 17) rep = 3 + (int)B.get(3);
-                        else rep = 11 + (int)B.get(7);
-                        if (idx + rep > nlen_codes + ndist_codes) return IF_ERR_DATA;
-                        while (rep--) lens[idx++] = (uint8_t)val;
-                    }
-                }
-                if (lens[256] == 0) return IF_ERR_DATA;
-                // move distance lengths to a fixed place
-                uint8_t dl[30];
-                for (int i = 0; i < ndist_codes; i++) dl[i] = lens[nlen_codes + i];
-                for (int i = 0; i < ndist_codes; i++) lens[288 + i] = dl[i];
+                const int hrc = if_dynamic_lengths(B, T, lens, nlen_codes, ndist_codes);
+                if (hrc != IF_OK) return hrc;
             }
             if (B.overrun()) return IF_ERR_IN;
             if (if_build(T.ll, lens, nlen_codes) != 0) return IF_ERR_DATA;
@@ -250,10 +343,9 @@ IF_HD int if_inflate(const uint8_t *in, uint64_t nbytes, uint64_t start, IfOut &
                     if (dist == 1) {
                         // byte run (the only match our own encoder emits): one read of the previous byte, then
                         // stores only -- no store -> load round trip through memory per byte
-                        const uint8_t c = O.out[O.n - 1];
-                        for (uint32_t i = 0; i < len; i++) O.put(c);
+                        O.put_run(O.at(O.n - 1), len);
                     } else {
-                        for (uint32_t i = 0; i < len; i++) O.put(O.out[O.n - dist]);
+                        for (uint32_t i = 0; i < len; i++) O.put(O.at(O.n - dist));
                     }
                 }
                 if (B.overrun()) return IF_ERR_IN;

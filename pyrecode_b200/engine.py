@@ -339,6 +339,66 @@ class ReadEngine:
         self.has_vals = has_vals
         return h2d
 
+    # ---- block staging: the reader reads a batch of records from the file straight into pinned memory
+    def block_buffer(self, nbytes, keep=0):
+        """-> numpy uint8 view of at least nbytes of pinned host memory (the first `keep` bytes survive a regrow)"""
+        cur = getattr(self, '_h_block', None)
+        if cur is None or cur.numel() < nbytes:
+            cap = max(int(nbytes), 2 * (cur.numel() if cur is not None else 0), 16 << 20)
+            new = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            if cur is not None and keep:
+                new[:keep].copy_(cur[:keep])
+            self._h_block = new
+            with torch.cuda.device(self.dev):
+                self._d_block = self.ctx.empty(cap + 64)
+        return self._h_block.numpy()
+
+    def wait_block_free(self):
+        """the pinned block may be overwritten again once its host-to-device copy has finished"""
+        ev = getattr(self, '_h2d_done', None)
+        if ev is not None:
+            ev.synchronize()
+
+    def load_block(self, nbytes, map_off, map_sz, val_off=None, val_sz=None):
+        """Inflate n frames whose compressed streams lie in the pinned block (block_buffer) at the given byte
+        offsets.  Everything is enqueued on the current CUDA stream; nothing synchronizes."""
+        if self.mode != 1:
+            raise ValueError('load_block handles compressed records (rc_operation_mode 1) only')
+        n = len(map_off)
+        if n > self.max_frames:
+            raise ValueError('batch larger than max_frames')
+        has_vals = val_off is not None and self.level <= 2
+        F = self.max_frames
+        with torch.cuda.device(self.dev):
+            meta = getattr(self, '_h_meta', None)
+            if meta is None:
+                self._h_meta = meta = torch.empty(2 * F * 3, dtype=torch.int32).pin_memory()
+                self._d_meta = self.ctx.empty(2 * F * 3 * 4).view(torch.int32)
+            mv = meta.numpy()
+            offs = mv[:4 * F].view(np.int64)           # [2F] stream offsets, then [2F] int32 stream sizes
+            sizes = mv[4 * F:]
+            offs[:n] = map_off
+            sizes[:n] = map_sz
+            if has_vals:
+                offs[F:F + n] = val_off
+                sizes[F:F + n] = val_sz
+            d_blk = self._d_block
+            d_blk[:nbytes].copy_(self._h_block[:nbytes], non_blocking=True)
+            self._d_meta.copy_(meta, non_blocking=True)
+            self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record()
+            d_off = self._d_meta[:4 * F].view(torch.int64)
+            d_sz = self._d_meta[4 * F:]
+            self._inf_ws = self.ctx.inflate_zlib(d_blk, d_off, d_sz, n, self.inflated, self.stride,
+                                                 self.out_bytes, self.status, self._inf_ws)
+            if has_vals:
+                self._inf_ws2 = self.ctx.inflate_zlib(d_blk, d_off[F:], d_sz[F:], n, self.inflated[F * self.stride:],
+                                                      self.stride, self.out_bytes[F:], self.status[F:],
+                                                      getattr(self, '_inf_ws2', None))
+        self.n = n
+        self.has_vals = has_vals
+        return int(nbytes) + meta.numel() * 4
+
     def _views(self):
         F = self.max_frames
         maps = self.inflated[:F * self.stride]

@@ -21,12 +21,14 @@ from .structures import ReCoDeStructures
 
 class ReCoDeReader:
 
-    def __init__(self, file, is_intermediate=False, device=None, batch_frames=16):
+    def __init__(self, file, is_intermediate=False, device=None, batch_frames=16, bulk_frames=64):
         self._source_filename = file
         self._current_frame_index = 0
         self._is_intermediate = 1 if is_intermediate else 0
         self._device = device
         self._batch_frames = batch_frames
+        self._bulk_frames = bulk_frames          # frames per batch of read_frames_dense / sum_frames
+        self._bulk = None
         self._file_size = None
         self._header = None
         self._frame_metadata = None
@@ -124,6 +126,9 @@ class ReCoDeReader:
         raise NotImplementedError
 
     def close(self):
+        if getattr(self, '_pool', None) is not None:
+            self._pool.shutdown()
+            self._pool = None
         self._fp.close()
 
     def seek_to_frame_data(self):
@@ -267,8 +272,182 @@ class ReCoDeReader:
             self._current_frame_index += 1
         return ids, mds, raws
 
+    # Bulk decoding keeps several batches in flight, one ReadEngine + CUDA stream each: the records of a batch are
+    # read from the file straight into the engine's pinned block (one readinto per frame of a part file, one per
+    # batch of a merged file), copied to the device in one piece and inflated / unpacked asynchronously while the
+    # host already stages the next batch.  (The serial inflate of a 16 KiB chunk takes milliseconds whatever the
+    # batch size, so throughput comes from the number of chunks in flight.)
+    def _bulk_engines(self, n_inflight=3):
+        if getattr(self, '_bulk', None) is None:
+            from .engine import ReadEngine
+            import torch
+            h = self._header
+            if h['target_dtype'] != 0 or not 1 <= h['target_bit_depth'] <= 16:
+                raise NotImplementedError('only unsigned targets of 1..16 bits are supported on the GPU path')
+            itemsize = 1 if h['target_bit_depth'] <= 8 else 2
+            self._bulk = []
+            for _ in range(n_inflight):
+                e = ReadEngine(h['ny'], h['nx'], itemsize, h['target_bit_depth'], h['reduction_level'],
+                               h['rc_operation_mode'], max_frames=self._bulk_frames, device=self._device)
+                e.stream = torch.cuda.Stream(device=e.dev)
+                self._bulk.append(e)
+        return self._bulk
+
+    def _read_block(self, n, eng):
+        """Reads the records of up to n frames into eng's pinned block.
+        -> (frame ids, nbytes, map_off, map_sz, val_off, val_sz); val_* are None for levels 3 / 4."""
+        h = self._header
+        level = h['reduction_level']
+        two = level in (1, 2)
+        vname = 'bytes_in_compressed_' + ('pixvals' if level == 1 else 'summary_stats')
+        if self._current_frame_index == 0:
+            self._fp.seek(self._frame_data_start_position, 0)
+        ids, moff, msz, voff, vsz = [], [], [], [], []
+        pos = 0
+        fd = self._fp.fileno()
+        if self._is_intermediate:
+            # records are [frame_id][sizes...][map stream][value stream], back to back: walk the small headers with
+            # preads, then fetch the whole byte range of the batch at once (in parallel slices)
+            nf = len(self._sm)
+            names = [f['name'] for f in self._sm]
+            i_map = names.index('bytes_in_compressed_binary_map')
+            i_val = names.index(vname) if two else -1
+            hlen = 4 + 4 * nf
+            start = fpos = self._fp.tell()
+            while len(ids) < n:
+                hdr = os.pread(fd, hlen, fpos)
+                if len(hdr) < hlen:
+                    break
+                rec = np.frombuffer(hdr, dtype='<u4')
+                n_map = int(rec[1 + i_map])
+                n_val = int(rec[1 + i_val]) if two else 0
+                if fpos + hlen + n_map + n_val > self._file_size:
+                    raise ValueError('truncated record of frame %d' % int(rec[0]))
+                ids.append(int(rec[0]))
+                moff.append(fpos - start + hlen); msz.append(n_map)
+                if two:
+                    voff.append(fpos - start + hlen + n_map); vsz.append(n_val)
+                fpos += hlen + n_map + n_val
+            pos = fpos - start
+            if ids:
+                self._pread_parallel(fd, eng.block_buffer(pos + 16), start, pos)
+                self._fp.seek(fpos, 0)
+                self._current_frame_index += len(ids)
+        else:
+            z0 = self._current_frame_index
+            z1 = min(h['nz'], z0 + n)
+            if z1 > z0:
+                sizes = self._seek_table[z0:z1, 0].astype(np.int64)
+                start = int(self._seek_table[z0, 1])
+                total = int(sizes.sum())
+                self._pread_parallel(fd, eng.block_buffer(total + 16), self._frame_data_start_position + start, total)
+                rel = (self._seek_table[z0:z1, 1].astype(np.int64) - start)
+                for k, z in enumerate(range(z0, z1)):
+                    md = self._frame_metadata[z]
+                    n_map = int(md['bytes_in_compressed_binary_map'])
+                    ids.append(z)
+                    moff.append(int(rel[k])); msz.append(n_map)
+                    if two:
+                        voff.append(int(rel[k]) + n_map); vsz.append(int(md[vname]))
+                pos = total
+                self._current_frame_index = z1
+        if not two:
+            voff = vsz = None
+        return ids, pos, moff, msz, voff, vsz
+
+    def _pread_parallel(self, fd, buf, offset, nbytes, n_threads=4):
+        """file[offset : offset + nbytes] -> buf[:nbytes] (pinned), in slices read by a few threads (preadv releases
+        the GIL; one thread copies out of the page cache at only a few GB/s)"""
+        mv = memoryview(buf)
+
+        def rd(a, b):
+            while a < b:
+                k = os.preadv(fd, [mv[a:b]], offset + a)
+                if k <= 0:
+                    raise ValueError('truncated file')
+                a += k
+
+        if nbytes < (8 << 20):
+            rd(0, nbytes)
+            return
+        if getattr(self, '_pool', None) is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(n_threads)
+        step = (nbytes + n_threads - 1) // n_threads
+        step = (step + 4095) // 4096 * 4096
+        futs = [self._pool.submit(rd, a, min(nbytes, a + step)) for a in range(0, nbytes, step)]
+        for f in futs:
+            f.result()
+
+    def _bulk_run(self, n, consume):
+        """Pipelined decode of the next n frames; consume(engine) enqueues the unpack of a loaded batch on the
+        engine's stream.  -> frame ids (in file order)"""
+        import torch
+        if self._header['rc_operation_mode'] != 1:
+            raise ValueError('bulk decoding handles compressed files (rc_operation_mode 1) only')
+        import time
+        engs = self._bulk_engines()
+        pending = []                                   # engines whose batch has not been checked yet
+        ids = []
+        k = 0
+        st = self.bulk_stats = {'file_read_s': 0.0, 'enqueue_s': 0.0, 'wait_s': 0.0, 'bytes': 0}
+        while len(ids) < n:
+            eng = engs[k % len(engs)]
+            t0 = time.perf_counter()
+            if eng in pending:                         # its previous batch: validate before reusing the buffers
+                eng.stream.synchronize()
+                eng.check()
+                pending.remove(eng)
+            eng.wait_block_free()
+            t1 = time.perf_counter()
+            bi, nbytes, moff, msz, voff, vsz = self._read_block(min(eng.max_frames, n - len(ids)), eng)
+            t2 = time.perf_counter()
+            st['wait_s'] += t1 - t0
+            st['file_read_s'] += t2 - t1
+            if not bi:
+                break
+            eng.stream.wait_stream(torch.cuda.current_stream(eng.dev))
+            with torch.cuda.stream(eng.stream):
+                eng.load_block(nbytes, moff, msz, voff, vsz)
+                consume(eng)
+            st['enqueue_s'] += time.perf_counter() - t2
+            st['bytes'] += nbytes
+            pending.append(eng)
+            ids += bi
+            k += 1
+        t0 = time.perf_counter()
+        for eng in pending:
+            eng.stream.synchronize()
+            eng.check()
+            torch.cuda.current_stream(eng.dev).wait_stream(eng.stream)
+        st['wait_s'] += time.perf_counter() - t0
+        return ids
+
     def read_frames_dense(self, n):
         """next n frames -> (frame ids, CUDA tensor [k, ny, nx] of the target dtype); k <= n at EOF"""
+        import torch
+        if self._header['rc_operation_mode'] != 1:
+            return self._read_frames_dense_serial(n)
+        out = []
+        ids = self._bulk_run(n, lambda eng: out.append(eng.dense()))
+        if not out:
+            return ids, None
+        return ids, (out[0] if len(out) == 1 else torch.cat(out, 0))
+
+    def sum_frames(self, n, total=None):
+        """live view: adds the next n frames into `total` (uint32 CUDA tensor [ny*nx], created if None) without
+        materialising dense frames (examples/ReCoDe_Live_View_MT.ipynb cell 1) -> (frame ids, total)"""
+        import torch
+        if self._header['rc_operation_mode'] != 1:
+            return self._sum_frames_serial(n, total)
+        engs = self._bulk_engines()
+        if total is None:
+            total = torch.zeros(self._header['ny'] * self._header['nx'], dtype=torch.int32, device=engs[0].dev)
+        # the unpack kernel accumulates with atomics, so batches on different streams may share `total`
+        ids = self._bulk_run(n, lambda eng: eng.dense(total=total, want_dense=False))
+        return ids, total
+
+    def _read_frames_dense_serial(self, n):
         eng = self._get_engine()
         import torch
         ids, out = [], []
@@ -285,9 +464,7 @@ class ReCoDeReader:
             return ids, None
         return ids, torch.cat(out, 0)
 
-    def sum_frames(self, n, total=None):
-        """live view: adds the next n frames into `total` (uint32 CUDA tensor [ny*nx], created if None) without
-        materialising dense frames (examples/ReCoDe_Live_View_MT.ipynb cell 1) -> (frame ids, total)"""
+    def _sum_frames_serial(self, n, total=None):
         eng = self._get_engine()
         import torch
         if total is None:

@@ -45,7 +45,7 @@ extern "C" long host_deflate_stream(const uint8_t *in, uint32_t n, int level, ui
         for (int i = 0; i < DF_NSYM; i++) ntok += ghist[i];
         for (int i = 0; i < DF_NSYM; i++)
             if (ghist[i]) bits += ghist[i] * (std::log2(ntok / ghist[i]) + (i > 264 ? 2. : (i > 256 ? 1. : 0.)));
-        store_all = bits * 0.125 + 128. >= 0.97 * sampled;
+        store_all = bits * 0.125 + 128. >= (shared_table ? 0.90 : 0.97) * sampled;
         if (!store_all) {
             const uint32_t nt = (uint32_t)ntok;
             int cshift = 0;
@@ -124,7 +124,8 @@ extern "C" long host_inflate_stream(const uint8_t *in, uint32_t n, uint8_t *out,
     if (n < 8) return -1;
     if ((in[0] & 0x0f) != 8 || ((in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) return -1;
     if (serial) {
-        IfOut O{out, cap, 0, 0, 0};
+        IfOut O;
+        O.init(out, cap);
         uint64_t end = 0;
         const int code = if_inflate(in, n, 2, O, T, false, &end);
         if (code != IF_END_FINAL || end + 4 > n) return code == IF_ERR_OUT ? -2 : -1;
@@ -142,7 +143,8 @@ extern "C" long host_inflate_stream(const uint8_t *in, uint32_t n, uint8_t *out,
     bool finished = false;
     for (size_t j = 0; j < cand.size(); j++) {
         const uint64_t ooff = (uint64_t)j * 16384;
-        IfOut O{out + ooff, ooff < cap ? cap - ooff : 0, 0, 0, 0};
+        IfOut O;
+        O.init(out + ooff, ooff < cap ? cap - ooff : 0);
         uint64_t end = 0;
         const int code = if_inflate(in, n, cand[j], O, T, true, &end);
         if (cand[j] != pos) return -100;

@@ -16,7 +16,7 @@ from oracle import oracle as orc
 from pyrecode_b200.engine import ReadEngine, WriteEngine
 
 NY = NX = 4096
-F = 16
+F = int(os.environ.get('RB_FRAMES', '16'))
 for level, kind in ((1, 'l1'), (2, 'l2')):
     dark = orc.synth_dark(NY, NX)
     frames = orc.synth_frames(kind, 2, NY, NX, dark, seed=1234)
@@ -48,3 +48,51 @@ for level, kind in ((1, 'l1'), (2, 'l2')):
     torch.cuda.synchronize(); t0 = time.perf_counter(); re_.load(zm, zv); torch.cuda.synchronize(); t1 = time.perf_counter()
     print('   foreign (stock zlib) streams: load + inflate %.2f ms' % ((t1 - t0) * 1e3))
     del re_
+
+# ---- through the reader API: an L2 part file on tmpfs -> dense frames / live-view sum (bulk path)
+import tempfile
+from pyrecode_b200.recode_reader import ReCoDeReader
+from pyrecode_b200.recode_writer import ReCoDeWriter
+from pyrecode_b200.params import InputParams
+
+NZ = int(os.environ.get('RB_FILE_FRAMES', '256'))
+tmp = tempfile.mkdtemp(dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
+ip = InputParams()
+for k, v in dict(l4_centroiding=0, source_file_type=0, num_frames=NZ, source_header_length=0, calibration_frame_offset=0,
+                 compression_scheme=0, calibration_file_type=0, compression_level=1, l2_statistics=0,
+                 calibration_threshold_epsilon=20, frame_offset=0, num_threads=1, rc_operation_mode=1,
+                 num_calibration_frames=1, reduction_level=2, keep_calibration_data=1, source_bit_depth=12,
+                 target_bit_depth=12, keep_part_files=0, num_rows=NY, num_cols=NX, source_data_type=0,
+                 target_data_type=0).items():
+    ip._param_map[k] = v
+dark = orc.synth_dark(NY, NX)
+fr = orc.synth_frames('l2', 4, NY, NX, dark, seed=1234)
+w = ReCoDeWriter('rb', dark_data=dark[None], output_directory=tmp, input_params=ip, mode='batch', node_id=0)
+w.start()
+w.run(np.stack([fr[i % 4] for i in range(NZ)]))
+w.close()
+path = os.path.join(tmp, 'rb.rc2_part000')
+print('L2 part file: %d frames, %.1f MB' % (NZ, os.path.getsize(path) / 1e6))
+for bulk in (32, 64, 128):
+    for what in ('sum', 'dense'):
+        best = 0
+        for it in range(3):
+            r = ReCoDeReader(path, is_intermediate=True, bulk_frames=bulk)
+            r.open(print_header=False)
+            r._bulk_engines()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            if what == 'sum':
+                ids, total = r.sum_frames(NZ)
+            else:
+                ids, dense = r.read_frames_dense(min(NZ, 128))
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            if len(ids) / (t1 - t0) > best:
+                best, stats = len(ids) / (t1 - t0), dict(r.bulk_stats)
+            r.close()
+            del r
+            if what == 'dense':
+                del dense
+        print('reader API, bulk_frames=%d, %s: %.0f frames/s  (file read %.1f ms, enqueue %.1f ms, GPU wait %.1f ms, %.0f MB)'
+              % (bulk, what, best, stats['file_read_s'] * 1e3, stats['enqueue_s'] * 1e3, stats['wait_s'] * 1e3,
+                 stats['bytes'] / 1e6))
+os.remove(path)

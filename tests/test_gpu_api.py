@@ -206,6 +206,35 @@ def test_dense_and_live_view_sum(tmp_path):
     r.close()
 
 
+@pytest.mark.parametrize('level', [1, 2, 3])
+def test_bulk_read_pipeline(tmp_path, level):
+    """read_frames_dense / sum_frames with several small batches in flight (records staged through the engines'
+    pinned blocks), part file and merged file, equal the frame-by-frame reader"""
+    from pyrecode_b200.recode_reader import ReCoDeReader, merge_parts
+    rng = np.random.default_rng(5 + level)
+    nz, ny, nx = 23, 96, 160
+    data = reference_test_data(rng, nz, ny, nx)
+    ip = make_params(ny, nx, nz, level=level, threads=2)
+    write_parts(tmp_path, 'bulk', data, np.zeros((1, ny, nx), np.uint16), ip, 2)
+    merge_parts(str(tmp_path), 'bulk.rc%d' % level, 2)
+    r = ReCoDeReader(str(tmp_path / ('bulk.rc%d' % level)))
+    r.open(print_header=False)
+    want = np.stack([r.get_next_frame().popitem()[1]['data'].toarray() for _ in range(nz)])
+    r.close()
+    for name, inter, n_expect in (('bulk.rc%d' % level, False, nz), ('bulk.rc%d_part001' % level, True, nz - 12)):
+        r = ReCoDeReader(str(tmp_path / name), is_intermediate=inter, bulk_frames=3)
+        r.open(print_header=False)
+        ids, dense = r.read_frames_dense(8)
+        first = 12 if inter else 0
+        assert ids == list(range(first, first + 8))
+        assert np.array_equal(dense.cpu().numpy(), want[first:first + 8])
+        ids2, total = r.sum_frames(1000)
+        assert ids2 == list(range(first + 8, first + n_expect))
+        assert np.array_equal(total.cpu().numpy().astype(np.int64).reshape(ny, nx),
+                              want[first + 8:first + n_expect].astype(np.int64).sum(0))
+        r.close()
+
+
 def test_c_recode_shim(gold_dir):
     """c_recode.Reader signatures (pyrecode.cpp:57-141) on the GPU, against the reference's recorded triples"""
     from pyrecode_b200 import c_recode
