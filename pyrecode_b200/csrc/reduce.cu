@@ -266,9 +266,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 
 constexpr int BULK_STAGES = 2;                 // sub-tiles in flight per warp (ring)
 template <typename T>
-constexpr size_t bulk_smem_bytes() { return (size_t)BULK_STAGES * SUB_PX * sizeof(T); }
+constexpr size_t bulk_smem_bytes(bool thr_bulk) { return (size_t)BULK_STAGES * SUB_PX * sizeof(T) * (thr_bulk ? 2 : 1); }
 
-template <typename T, int VALMODE>
+// THRB: the threshold tile travels through the ring as well (second region of every stage) instead of being
+// loaded just in time with cached 128-bit loads (which wait for L2 once per sub-tile).
+template <typename T, int VALMODE, bool THRB>
 __global__ void __launch_bounds__(256)
 k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, size_t P, int NT, size_t MS,
                     uint32_t *__restrict__ maps, uint32_t *__restrict__ tilecnt, uint16_t *__restrict__ wordpre,
@@ -277,7 +279,8 @@ k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, siz
     constexpr int W = Px<T>::W;
     constexpr uint32_t REGION_BYTES = 1024 * sizeof(T);         // one warp's pixels of one sub-tile
     extern __shared__ __align__(128) uint8_t s_dyn[];
-    T *s_ring = reinterpret_cast<T *>(s_dyn);                   // [BULK_STAGES][8 warps][1024 pixels]
+    T *s_ring = reinterpret_cast<T *>(s_dyn);                   // [BULK_STAGES][8 warps][1024 pixels] (x 2: frame, thr)
+    constexpr int RS = THRB ? 2048 : 1024;                      // ring pixels per (stage, warp)
     __shared__ __align__(16) uint32_t s_mask[TILE_WORDS];
     __shared__ __align__(16) uint16_t s_wpre[TILE_WORDS];
     __shared__ __align__(16) uint32_t s_wsum[2][8];
@@ -298,8 +301,10 @@ k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, siz
     auto issue = [&](int sub) {
         const int stg = sub % BULK_STAGES;
         const uint32_t bar = smem_u32(&s_bar[stg][warp]);
-        mbar_expect_tx(bar, REGION_BYTES);
-        bulk_g2s(smem_u32(s_ring + (stg * 8 + warp) * 1024), fr + sub * SUB_PX + warp * 1024, REGION_BYTES, bar);
+        mbar_expect_tx(bar, THRB ? 2 * REGION_BYTES : REGION_BYTES);
+        bulk_g2s(smem_u32(s_ring + (stg * 8 + warp) * RS), fr + sub * SUB_PX + warp * 1024, REGION_BYTES, bar);
+        if (THRB)
+            bulk_g2s(smem_u32(s_ring + (stg * 8 + warp) * RS + 1024), th + sub * SUB_PX + warp * 1024, REGION_BYTES, bar);
     };
     if (lane == 0) {
 #pragma unroll
@@ -311,13 +316,19 @@ k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, siz
     for (int sub = 0; sub < NSUB; sub++) {
         const int wpx0 = sub * SUB_PX + warp * 1024;
         uint32_t fw[4][W], tw[4][W];
+        if (!THRB) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) Px<T>::load_cached(th + wpx0 + j * 256 + lane * 8, tw[j]);
+            for (int j = 0; j < 4; j++) Px<T>::load_cached(th + wpx0 + j * 256 + lane * 8, tw[j]);
+        }
         const int stg = sub % BULK_STAGES;
-        T *region = s_ring + (stg * 8 + warp) * 1024;            // this warp's 1024 pixels of the sub-tile
+        T *region = s_ring + (stg * 8 + warp) * RS;              // this warp's 1024 pixels of the sub-tile
         mbar_wait(smem_u32(&s_bar[stg][warp]), (uint32_t)(sub / BULK_STAGES) & 1u);
 #pragma unroll
         for (int j = 0; j < 4; j++) Px<T>::load_shared(region + j * 256 + lane * 8, fw[j]);
+        if (THRB) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) Px<T>::load_shared(region + 1024 + j * 256 + lane * 8, tw[j]);
+        }
         uint8_t *mb = reinterpret_cast<uint8_t *>(s_mask + sub * SUB_WORDS + warp * 32);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -387,12 +398,17 @@ static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, const 
     // the staged tile (measured 0.234 vs 0.224 ms per 32 frames).
     static const bool force_generic = getenv("RC_K1_GENERIC") != nullptr;
     const bool bulk = vec_ok && g.P % TILE_PX == 0 && !force_generic && valmode != 1;
+    static const bool thr_bulk = getenv("RC_K1_THR_BULK") ? atoi(getenv("RC_K1_THR_BULK")) != 0 : false;
+#define RC_K1B(VM, TB)                                                                                     \
+    {                                                                                                      \
+        cudaFuncSetAttribute(k_reduce_tiles_bulk<T, VM, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             (int)bulk_smem_bytes<T>(TB));                                                 \
+        k_reduce_tiles_bulk<T, VM, TB><<<grid, block, bulk_smem_bytes<T>(TB), st>>>(                       \
+            (const T *)frames, (const T *)thr, g.P, g.NT, g.MS, maps, tilecnt, wordpre, vals);             \
+    }
 #define RC_K1(VM)                                                                                          \
     if (bulk) {                                                                                            \
-        cudaFuncSetAttribute(k_reduce_tiles_bulk<T, VM>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                             (int)bulk_smem_bytes<T>());                                                   \
-        k_reduce_tiles_bulk<T, VM><<<grid, block, bulk_smem_bytes<T>(), st>>>(                             \
-            (const T *)frames, (const T *)thr, g.P, g.NT, g.MS, maps, tilecnt, wordpre, vals);             \
+        if (thr_bulk) RC_K1B(VM, true) else RC_K1B(VM, false)                                              \
     } else {                                                                                               \
         k_reduce_tiles<T, VM><<<grid, block, 0, st>>>((const T *)frames, (const T *)thr, g.P, g.NT, g.MS,  \
                                                       maps, tilecnt, wordpre, vals, vec_ok);               \
@@ -401,6 +417,7 @@ static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, const 
     else if (valmode == 1) { RC_K1(1) }
     else { RC_K1(2) }
 #undef RC_K1
+#undef RC_K1B
     RC_LAUNCH_CHECK(ctx, "k_reduce_tiles");
     return 0;
 }

@@ -51,7 +51,12 @@ k_unpack_sparse(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__r
     }
 }
 
-// One warp per 256-pixel segment, lane l owns pixels [8l, 8l+8) of the segment.
+// One warp per UD_SEGS consecutive 256-pixel segments; lane l owns pixels [8l, 8l+8) of each, so every store
+// instruction of the warp writes 512 contiguous bytes (uint16).  The rank of a lane's first foreground pixel comes
+// from the per-word prefix that k_map_counts left (tile prefix + word prefix + popc of the word's lower bytes): no
+// scan, and the UD_SEGS map words of a lane are loaded up front, so their latencies overlap.
+constexpr int UD_SEGS = 8;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_unpack_dense(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__restrict__ packed, size_t packed_stride,
@@ -60,44 +65,58 @@ k_unpack_dense(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__re
 {
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const uint32_t seg = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint32_t seg0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * UD_SEGS;
     const uint32_t nseg = (uint32_t)NT * SEGS_PER_TILE;
-    if (seg >= nseg) return;
-    const size_t p_base = (size_t)seg * SEG_PX + (size_t)lane * 8;
-    if ((size_t)seg * SEG_PX >= P) return;
-    const uint8_t *mapb = reinterpret_cast<const uint8_t *>(maps + (size_t)f * MS);
-    const uint32_t m = mapb[(size_t)seg * 32 + lane];
-    const uint32_t pc = __popc(m);
-    const uint32_t incl = warp_incl_scan(pc);
-    uint64_t rank = (uint64_t)tilepre_all[(size_t)f * (NT + 1) + (seg >> SEGS_PER_TILE_LOG2)] +
-                    wordpre_all[(size_t)f * MS + (size_t)seg * SEG_WORDS] + (incl - pc);
+    if (seg0 >= nseg) return;
+    const uint32_t *map = maps + (size_t)f * MS;
     const uint32_t *pk = reinterpret_cast<const uint32_t *>(packed + (size_t)f * packed_stride);
-    uint32_t v[8];
+    uint32_t mw[UD_SEGS];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        v[k] = 0;
-        if (m & (1u << k)) {
-            v[k] = level == 1 ? fetch_bits(pk, rank * (uint32_t)b, b) : 1u;
-            rank++;
-            if (sum) atomicAdd(&sum[p_base + k], v[k]);
-        }
+    for (int u = 0; u < UD_SEGS; u++) {
+        const uint32_t seg = seg0 + u;
+        mw[u] = seg < nseg ? map[(size_t)seg * SEG_WORDS + (lane >> 2)] : 0u;    // 4 lanes share a word
     }
-    if (dense) {
-        T *o = dense + (size_t)f * P + p_base;
-        if (vec_ok && p_base + 8 <= P) {
-            if (sizeof(T) == 2) {
-                uint4 q;
-                q.x = v[0] | (v[1] << 16); q.y = v[2] | (v[3] << 16); q.z = v[4] | (v[5] << 16); q.w = v[6] | (v[7] << 16);
-                *reinterpret_cast<uint4 *>(o) = q;
-            } else {
-                uint2 q;
-                q.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-                q.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
-                *reinterpret_cast<uint2 *>(o) = q;
-            }
-        } else {
+    const uint32_t bsh = (uint32_t)(lane & 3) * 8u;
 #pragma unroll
-            for (int k = 0; k < 8; k++) if (p_base + k < P) o[k] = (T)v[k];
+    for (int u = 0; u < UD_SEGS; u++) {
+        const uint32_t seg = seg0 + u;
+        const size_t p_base = (size_t)seg * SEG_PX + (size_t)lane * 8;
+        if (seg >= nseg || (size_t)seg * SEG_PX >= P) break;
+        const uint32_t m = (mw[u] >> bsh) & 0xffu;
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (m >> k) & 1u;
+        if (m && (level == 1 || sum)) {
+            uint64_t rank = 0;
+            if (level == 1)
+                rank = (uint64_t)tilepre_all[(size_t)f * (NT + 1) + (seg >> SEGS_PER_TILE_LOG2)] +
+                       wordpre_all[(size_t)f * MS + (size_t)seg * SEG_WORDS + (lane >> 2)] +
+                       __popc(mw[u] & ((1u << bsh) - 1u));
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (m & (1u << k)) {
+                    if (level == 1) { v[k] = fetch_bits(pk, rank * (uint32_t)b, b); rank++; }
+                    if (sum) atomicAdd(&sum[p_base + k], v[k]);
+                }
+            }
+        }
+        if (dense) {
+            T *o = dense + (size_t)f * P + p_base;
+            if (vec_ok && p_base + 8 <= P) {
+                if (sizeof(T) == 2) {
+                    uint4 q;
+                    q.x = v[0] | (v[1] << 16); q.y = v[2] | (v[3] << 16); q.z = v[4] | (v[5] << 16); q.w = v[6] | (v[7] << 16);
+                    __stcs(reinterpret_cast<uint4 *>(o), q);
+                } else {
+                    uint2 q;
+                    q.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+                    q.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+                    __stcs(reinterpret_cast<uint2 *>(o), q);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (p_base + k < P) o[k] = (T)v[k];
+            }
         }
     }
 }
@@ -120,7 +139,7 @@ int launch_unpack_dense(rc_ctx *ctx, const Geom &g, int itemsize, int level, int
 {
     if (F <= 0) return 0;
     const uint32_t nseg = (uint32_t)g.NT * SEGS_PER_TILE;
-    dim3 grid((nseg + 7) / 8, F);
+    dim3 grid((nseg + 8 * UD_SEGS - 1) / (8 * UD_SEGS), F);
     const int vec_ok = dense && ((g.P * itemsize) % 16 == 0) && ((uintptr_t)dense % 16 == 0);
     if (itemsize == 2)
         k_unpack_dense<uint16_t><<<grid, 256, 0, st>>>(maps, g.MS, packed, packed_stride, wordpre, tilepre, g.NT, g.P,
