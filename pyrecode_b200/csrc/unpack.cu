@@ -83,21 +83,32 @@ k_unpack_dense(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__re
         const size_t p_base = (size_t)seg * SEG_PX + (size_t)lane * 8;
         if (seg >= nseg || (size_t)seg * SEG_PX >= P) break;
         const uint32_t m = (mw[u] >> bsh) & 0xffu;
-        uint32_t v[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = (m >> k) & 1u;
+        // 8 pixel values as two 64-bit halves of 16-bit slots (pixels 0..3, 4..7); levels 2..4: the map bit itself
+        uint64_t qlo = 0, qhi = 0;
+        if (level != 1) {
+            const uint32_t a = m & 0xfu, c = m >> 4;
+            qlo = (uint64_t)((a & 1u) | ((a & 2u) << 15)) | ((uint64_t)(((a >> 2) & 1u) | ((a & 8u) << 13)) << 32);
+            qhi = (uint64_t)((c & 1u) | ((c & 2u) << 15)) | ((uint64_t)(((c >> 2) & 1u) | ((c & 8u) << 13)) << 32);
+        }
         if (m && (level == 1 || sum)) {
+            // one iteration per foreground pixel (a few per hundred pixels)
             uint64_t rank = 0;
             if (level == 1)
                 rank = (uint64_t)tilepre_all[(size_t)f * (NT + 1) + (seg >> SEGS_PER_TILE_LOG2)] +
                        wordpre_all[(size_t)f * MS + (size_t)seg * SEG_WORDS + (lane >> 2)] +
                        __popc(mw[u] & ((1u << bsh) - 1u));
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (m & (1u << k)) {
-                    if (level == 1) { v[k] = fetch_bits(pk, rank * (uint32_t)b, b); rank++; }
-                    if (sum) atomicAdd(&sum[p_base + k], v[k]);
+            uint32_t todo = m;
+            while (todo) {
+                const uint32_t k = __ffs(todo) - 1;
+                todo &= todo - 1;
+                uint32_t val = 1u;
+                if (level == 1) {
+                    val = fetch_bits(pk, rank * (uint32_t)b, b);
+                    rank++;
+                    const uint64_t x = (uint64_t)val << ((k & 3u) * 16u);
+                    if (k & 4u) qhi |= x; else qlo |= x;
                 }
+                if (sum) atomicAdd(&sum[p_base + k], val);
             }
         }
         if (dense) {
@@ -105,17 +116,20 @@ k_unpack_dense(const uint32_t *__restrict__ maps, size_t MS, const uint8_t *__re
             if (vec_ok && p_base + 8 <= P) {
                 if (sizeof(T) == 2) {
                     uint4 q;
-                    q.x = v[0] | (v[1] << 16); q.y = v[2] | (v[3] << 16); q.z = v[4] | (v[5] << 16); q.w = v[6] | (v[7] << 16);
+                    q.x = (uint32_t)qlo; q.y = (uint32_t)(qlo >> 32); q.z = (uint32_t)qhi; q.w = (uint32_t)(qhi >> 32);
                     __stcs(reinterpret_cast<uint4 *>(o), q);
                 } else {
+                    // 8-bit targets: squeeze the 16-bit slots to bytes
+                    const uint32_t l0 = (uint32_t)qlo, l1 = (uint32_t)(qlo >> 32), h0 = (uint32_t)qhi, h1 = (uint32_t)(qhi >> 32);
                     uint2 q;
-                    q.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-                    q.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+                    q.x = (l0 & 0xffu) | ((l0 >> 8) & 0xff00u) | ((l1 & 0xffu) << 16) | ((l1 & 0xff0000u) << 8);
+                    q.y = (h0 & 0xffu) | ((h0 >> 8) & 0xff00u) | ((h1 & 0xffu) << 16) | ((h1 & 0xff0000u) << 8);
                     __stcs(reinterpret_cast<uint2 *>(o), q);
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 8; k++) if (p_base + k < P) o[k] = (T)v[k];
+                for (int k = 0; k < 8; k++)
+                    if (p_base + k < P) o[k] = (T)(((k < 4 ? qlo : qhi) >> ((k & 3) * 16)) & 0xffffu);
             }
         }
     }

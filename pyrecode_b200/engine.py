@@ -299,6 +299,10 @@ class ReadEngine:
             self.status = self.ctx.zeros(2 * F, torch.int32)
             self.counts = self.ctx.zeros(F, torch.int32)
             self._inf_ws = None
+            if self.mode == 1:
+                need = self.ctx._lib.rc_inflate_workspace_bytes(F, self.stride)
+                self._inf_ws = self.ctx.empty(need)
+                self._inf_ws2 = self.ctx.empty(need) if self.level <= 2 else None
 
     def load(self, map_streams, val_streams):
         """Stage n frames' streams (compressed when mode 1, raw when mode 0) -> device maps / packed values."""

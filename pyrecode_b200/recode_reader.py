@@ -290,6 +290,8 @@ class ReCoDeReader:
                 e = ReadEngine(h['ny'], h['nx'], itemsize, h['target_bit_depth'], h['reduction_level'],
                                h['rc_operation_mode'], max_frames=self._bulk_frames, device=self._device)
                 e.stream = torch.cuda.Stream(device=e.dev)
+                # pinned staging for one batch, sized from the file's average record (it grows on demand)
+                e.block_buffer(int(self._file_size / max(1, h['nz']) * self._bulk_frames * 1.25) + (1 << 20))
                 self._bulk.append(e)
         return self._bulk
 

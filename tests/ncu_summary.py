@@ -1,0 +1,32 @@
+"""Print the judged subset of an `ncu --set full` report (first kernel): python tests/ncu_summary.py x.ncu-rep"""
+import csv
+import subprocess
+import sys
+
+KEYS = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+        'launch__shared_mem_per_block_static', 'launch__shared_mem_per_block_dynamic', 'gpu__time_duration.sum',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'launch__waves_per_multiprocessor',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio']
+
+
+def main(path):
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units, r = rows[0], rows[1], rows[2]
+    d = dict(zip(h, zip(r, units)))
+    for k in KEYS:
+        if k in d:
+            print('%-90s %s %s' % (k, d[k][0][:110], d[k][1]))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])
