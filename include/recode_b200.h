@@ -166,6 +166,13 @@ int rc_bit_unpack(rc_ctx *ctx, int bit_depth, const uint8_t *d_packed, uint64_t 
 int rc_bit_pack(rc_ctx *ctx, int bit_depth, const uint16_t *d_vals, uint64_t n_values, uint8_t *d_packed,
                 void *stream);
 
+/* offline recalibration of reconstructed L1 frames: replaces the per-frame numpy arithmetic of recalibrate_l1
+ * (pyrecode/utils/converters.py:15-57): d_out = (T) clamp(float64(frame) + d_diff, 0, max(T)), d_diff[n_pixels] =
+ * original_calibration - (new_calibration + epsilon) as float64.  Buffers 16-byte aligned, n_pixels * itemsize a
+ * multiple of 16.  d_out must not overlap d_frames. */
+int rc_recalibrate(rc_ctx *ctx, int itemsize, const void *d_frames, const double *d_diff, size_t n_pixels,
+                   int n_frames, void *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

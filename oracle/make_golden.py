@@ -120,7 +120,46 @@ def check_oracle_vs_part(files, data, dark, eps, base):
                 assert rec['metadata']['bytes_in_packed_pixvals'] == len(v)
 
 
+def make_converters_golden():
+    """gold_e_converters.npz: the reference's recalibrate_l1 / l1_to_l4_converter (pyrecode/utils/converters.py)
+    run live on seeded L1 frame dictionaries; the oracle restatement is asserted equal first."""
+    from scipy.sparse import coo_matrix
+    with contextlib.redirect_stdout(io.StringIO()):
+        from pyrecode.utils.converters import recalibrate_l1, l1_to_l4_converter
+    rng = np.random.default_rng(777)
+    nz, ny, nx = 4, 80, 80
+    # puddle-like L1 frames: event centres with random E / S / SE neighbours, 12-bit dark-subtracted values
+    fr = np.zeros((nz, ny, nx), dtype=np.uint16)
+    for z in range(nz):
+        c = rng.random((ny, nx)) < 0.03
+        v = np.where(c, rng.integers(50, 1000, (ny, nx)), 0)
+        for dy, dx in ((0, 1), (1, 0), (1, 1)):
+            m = np.roll(np.roll(c, dy, 0), dx, 1) & (rng.random((ny, nx)) < 0.5)
+            v = np.where(m & (v == 0), rng.integers(25, 500, (ny, nx)), v)
+        fr[z] = v
+    fr[3] = 0                                                   # an empty frame
+    frames = {10 + z: {'metadata': {'n': z}, 'data': coo_matrix(fr[z])} for z in range(nz)}
+    orig = rng.integers(90, 110, (ny, nx)).astype(np.uint16)
+    new = rng.integers(80, 125, (ny, nx)).astype(np.uint16)
+    eps = 2.5
+    with contextlib.redirect_stdout(io.StringIO()):
+        rec = recalibrate_l1(frames, original_calibration_frame=orig, new_calibration_frame=new, epsilon=eps)
+        l4 = l1_to_l4_converter(frames, (ny, nx))
+    rec_d = np.stack([np.asarray(rec[k]['data'].todense()) for k in frames])
+    l4_d = np.stack([np.asarray(l4[k]['data'].todense()) for k in frames])
+    for i, k in enumerate(frames):
+        assert np.array_equal(rec_d[i], orc.recalibrate_l1_frame(fr[i], orig, new, eps)), 'recalibrate oracle'
+        assert np.array_equal(l4_d[i], orc.l1_to_l4_frame(fr[i], 0, True)), 'l1_to_l4 oracle'
+    np.savez_compressed(os.path.join(GOLD, 'gold_e_converters.npz'), frames=fr, ids=np.array(list(frames)), orig=orig,
+                        new=new, eps=eps, recalibrated=rec_d, l4=l4_d)
+    return 'gold_e_converters.npz: recalibrate_l1 and l1_to_l4_converter (weighted_average) on %d frames of %dx%d' % (
+        nz, ny, nx)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'converters':      # add this fixture without regenerating the others
+        print(make_converters_golden())
+        return
     if os.path.isdir(GOLD):
         shutil.rmtree(GOLD)
     os.makedirs(GOLD)
@@ -257,6 +296,7 @@ def main():
                   'c_recode triples: oracle == reference')
 
     shutil.rmtree(tmp)
+    report.append(make_converters_golden())
     with open(os.path.join(GOLD, 'README.md'), 'w') as f:
         f.write('# Golden fixtures\n\nGenerated by `python oracle/make_golden.py` in the build container from the '
                 'unmodified reference at `/root/reference` (numpy %s, scipy %s). Every line below was asserted '

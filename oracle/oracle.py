@@ -162,6 +162,31 @@ def centroid_map(centroids, ny, nx):
     return b
 
 
+def recalibrate_l1_frame(frame, original_calibration, new_calibration, epsilon=0.0):
+    """converters.py:18-45 for one dense frame: float64 add of the calibration difference, clamp, cast back"""
+    diff = original_calibration.astype(np.float64) - (new_calibration.astype(np.float64) + epsilon)
+    info = np.iinfo(frame.dtype)
+    f = frame.astype(np.float64) + diff
+    f[f < info.min] = info.min
+    f[f > info.max] = info.max
+    return f.astype(frame.dtype)
+
+
+def l1_to_l4_frame(frame, mode=0, transpose=True):
+    """converters.py:84-100 for one dense dark-subtracted frame -> bool [ny, nx] centroid image.
+    The reference stores centroid [row_c, col_c] at (col_c, row_c) (:100): transpose=True reproduces that."""
+    ny, nx = frame.shape
+    labels, k = label8(frame > 0)
+    out = np.zeros((ny, nx), dtype=bool)
+    if k:
+        c = np.round(l4_centroids(labels, frame, k, mode)).astype(np.int64)
+        if transpose:
+            out[c[:, 1], c[:, 0]] = True
+        else:
+            out[c[:, 0], c[:, 1]] = True
+    return out
+
+
 def unpack_sparse(ny, nx, b, map_bytes, val_bytes, level):
     """reader.h:10-68; returns uint64 [n, 3] (row, col, value)"""
     m = np.frombuffer(bytes(map_bytes), dtype=np.uint8)

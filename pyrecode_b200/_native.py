@@ -58,6 +58,7 @@ _SIGNATURES = {
     'rc_unpack_sparse': (ctypes.c_int, [_vp, _cfgp, _vp, _vp, _sz, ctypes.c_int, _vp, _sz, _vp, _sz, _vp, _vp]),
     'rc_unpack_dense': (ctypes.c_int, [_vp, _cfgp, _vp, _vp, _sz, ctypes.c_int, _vp, _sz, _vp, _vp, _vp, _vp]),
     'rc_bit_unpack': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint64, _vp, _vp]),
+    'rc_recalibrate': (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_int, _vp, _vp]),
     'rc_bit_pack': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint64, _vp, _vp]),
 }
 
@@ -224,6 +225,10 @@ class Context:
     def bit_unpack(self, bit_depth, packed, n_values, out):
         self._check(self._lib.rc_bit_unpack(self._h, bit_depth, _ptr(packed), n_values, _ptr(out), _stream()),
                     'rc_bit_unpack')
+
+    def recalibrate(self, itemsize, frames, diff, n_pixels, n_frames, out):
+        self._check(self._lib.rc_recalibrate(self._h, itemsize, _ptr(frames), _ptr(diff), n_pixels, n_frames, _ptr(out),
+                                             _stream()), 'rc_recalibrate')
 
     def bit_pack(self, bit_depth, vals, n_values, packed):
         self._check(self._lib.rc_bit_pack(self._h, bit_depth, _ptr(vals), n_values, _ptr(packed), _stream()),

@@ -611,3 +611,12 @@ extern "C" int rc_bit_pack(rc_ctx *ctx, int bit_depth, const uint16_t *d_vals, u
     if ((uintptr_t)d_packed % 4) RC_FAIL(ctx, -1, "d_packed must be 4-byte aligned");
     return launch_bitpack_flat(ctx, bit_depth, d_vals, n_values, d_packed, (cudaStream_t)stream);
 }
+
+extern "C" int rc_recalibrate(rc_ctx *ctx, int itemsize, const void *d_frames, const double *d_diff, size_t n_pixels,
+                              int n_frames, void *d_out, void *stream)
+{
+    if (!ctx) return -1;
+    if (itemsize != 1 && itemsize != 2) RC_FAIL(ctx, -1, "itemsize must be 1 or 2 (got %d)", itemsize);
+    if (n_frames < 0) RC_FAIL(ctx, -1, "n_frames must be >= 0");
+    return launch_recalibrate(ctx, itemsize, d_frames, d_diff, n_pixels, n_frames, d_out, (cudaStream_t)stream);
+}

@@ -85,3 +85,5 @@ int launch_unpack_sparse(rc_ctx *ctx, const Geom &g, int level, int b, const uin
 int launch_unpack_dense(rc_ctx *ctx, const Geom &g, int itemsize, int level, int b, const uint32_t *maps,
                         const uint8_t *packed, size_t packed_stride, const uint16_t *wordpre, const uint32_t *tilepre,
                         int F, void *dense, uint32_t *sum, cudaStream_t st);
+int launch_recalibrate(rc_ctx *ctx, int itemsize, const void *frames, const double *diff, size_t P, int F, void *out,
+                       cudaStream_t st);

@@ -164,3 +164,59 @@ int launch_unpack_dense(rc_ctx *ctx, const Geom &g, int itemsize, int level, int
     RC_LAUNCH_CHECK(ctx, "k_unpack_dense");
     return 0;
 }
+
+// ---- offline recalibration of L1 frames (pyrecode/utils/converters.py:15-57, recalibrate_l1) --------------------
+// out = (T) clamp(float64(frame) + diff, 0, max(T)) per pixel, diff = original_calibration - (new_calibration + eps)
+// as float64 [P] (shared by all frames, L2-resident).  float64 -> integer conversion truncates, like numpy's astype.
+// HBM-bound: itemsize read + itemsize written per pixel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_recalibrate(const T *__restrict__ frames, const double *__restrict__ diff, size_t P, int F, T *__restrict__ out)
+{
+    constexpr int V = 16 / sizeof(T);                       // pixels per 128-bit access
+    const double tmax = (double)((1u << (8 * sizeof(T))) - 1u);
+    const size_t nvec = P / V;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        double d[V];
+#pragma unroll
+        for (int k = 0; k < V; k += 2) {
+            const double2 dd = reinterpret_cast<const double2 *>(diff)[(i * V + k) / 2];
+            d[k] = dd.x; d[k + 1] = dd.y;
+        }
+        for (int f = 0; f < F; f++) {
+            const uint4 q = ld_stream_u4(frames + (size_t)f * P + i * V);
+            const T *x = reinterpret_cast<const T *>(&q);
+            uint4 r;
+            T *y = reinterpret_cast<T *>(&r);
+#pragma unroll
+            for (int k = 0; k < V; k++) {
+                double v = (double)x[k] + d[k];
+                v = v < 0.0 ? 0.0 : (v > tmax ? tmax : v);
+                y[k] = (T)v;
+            }
+            __stcs(reinterpret_cast<uint4 *>(out + (size_t)f * P + i * V), r);
+        }
+    }
+    // ragged tail (P not a multiple of the vector width)
+    const size_t t0 = nvec * V;
+    for (size_t i = t0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x)
+        for (int f = 0; f < F; f++) {
+            double v = (double)frames[(size_t)f * P + i] + diff[i];
+            v = v < 0.0 ? 0.0 : (v > tmax ? tmax : v);
+            out[(size_t)f * P + i] = (T)v;
+        }
+}
+
+int launch_recalibrate(rc_ctx *ctx, int itemsize, const void *frames, const double *diff, size_t P, int F, void *out,
+                       cudaStream_t st)
+{
+    if (F <= 0 || P == 0) return 0;
+    const int vec_ok = ((P * itemsize) % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                       ((uintptr_t)diff % 16 == 0);
+    if (!vec_ok) RC_FAIL(ctx, -1, "rc_recalibrate needs 16-byte aligned buffers and frames of a multiple of 16 bytes");
+    const unsigned grid = (unsigned)ctx->sm_count * 8;
+    if (itemsize == 2) k_recalibrate<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)frames, diff, P, F, (uint16_t *)out);
+    else k_recalibrate<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)frames, diff, P, F, (uint8_t *)out);
+    RC_LAUNCH_CHECK(ctx, "k_recalibrate");
+    return 0;
+}

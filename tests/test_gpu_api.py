@@ -235,6 +235,56 @@ def test_bulk_read_pipeline(tmp_path, level):
         r.close()
 
 
+def test_converters_golden(gold_dir):
+    """utils.converters.recalibrate_l1 / l1_to_l4_converter on the GPU == the live reference's outputs"""
+    from scipy.sparse import coo_matrix
+    from pyrecode_b200.utils.converters import recalibrate_l1, l1_to_l4_converter
+    z = np.load(os.path.join(gold_dir, 'gold_e_converters.npz'))
+    fr, ids = z['frames'], [int(i) for i in z['ids']]
+    frames = {k: {'metadata': {'n': i}, 'data': coo_matrix(fr[i])} for i, k in enumerate(ids)}
+    rec = recalibrate_l1(frames, original_calibration_frame=z['orig'], new_calibration_frame=z['new'],
+                         epsilon=float(z['eps']), batch_frames=3)
+    l4 = l1_to_l4_converter(frames, fr.shape[1:], batch_frames=3)
+    assert list(rec) == ids and list(l4) == ids
+    for i, k in enumerate(ids):
+        assert rec[k]['metadata'] == {'n': i} and rec[k]['data'].dtype == np.uint16
+        assert np.array_equal(np.asarray(rec[k]['data'].todense()), z['recalibrated'][i])
+        assert l4[k]['data'].dtype == bool and l4[k]['data'].shape == fr.shape[1:]
+        assert np.array_equal(np.asarray(l4[k]['data'].todense()), z['l4'][i])
+    assert frames[ids[0]]['data'].dtype == np.uint16                # inputs untouched (in_place=False)
+
+
+@pytest.mark.parametrize('method,mode', [('weighted_average', 0), ('max', 2), ('unweighted', 3)])
+def test_converters_random(method, mode):
+    """larger, non-square frames (transpose=False) and every centroiding method against the oracle; the device-
+    resident recalibration; uint8 frames"""
+    import torch
+    from scipy.sparse import coo_matrix
+    from pyrecode_b200.utils.converters import recalibrate_l1, recalibrate_dense, l1_to_l4_converter
+    rng = np.random.default_rng(99 + mode)
+    nz, ny, nx = 5, 200, 328
+    fr = np.where(rng.random((nz, ny, nx)) < 0.08, rng.integers(1, 4096, (nz, ny, nx)), 0).astype(np.uint16)
+    frames = {i: {'data': coo_matrix(fr[i])} for i in range(nz)}
+    l4 = l1_to_l4_converter(frames, (ny, nx), method=method, transpose=False)
+    for i in range(nz):
+        assert np.array_equal(np.asarray(l4[i]['data'].todense()), orc.l1_to_l4_frame(fr[i], mode, False))
+    with pytest.raises(NotImplementedError):
+        l1_to_l4_converter(frames, (ny, nx), area_threshold=2)
+    orig = rng.integers(0, 300, (ny, nx)).astype(np.uint16)
+    new = rng.integers(0, 300, (ny, nx)).astype(np.uint16)
+    out = recalibrate_dense(torch.from_numpy(fr).cuda(), orig, new, epsilon=-0.75)
+    want = np.stack([orc.recalibrate_l1_frame(fr[i], orig, new, -0.75) for i in range(nz)])
+    assert np.array_equal(out.cpu().numpy(), want)
+    # saturation at both ends, uint8
+    f8 = rng.integers(0, 256, (2, 64, 64)).astype(np.uint8)
+    o8 = rng.integers(0, 256, (64, 64)).astype(np.uint8)
+    n8 = rng.integers(0, 256, (64, 64)).astype(np.uint8)
+    r8 = recalibrate_l1({i: {'data': coo_matrix(f8[i])} for i in range(2)}, original_calibration_frame=o8,
+                        new_calibration_frame=n8, epsilon=0.5)
+    for i in range(2):
+        assert np.array_equal(np.asarray(r8[i]['data'].todense()), orc.recalibrate_l1_frame(f8[i], o8, n8, 0.5))
+
+
 def test_c_recode_shim(gold_dir):
     """c_recode.Reader signatures (pyrecode.cpp:57-141) on the GPU, against the reference's recorded triples"""
     from pyrecode_b200 import c_recode

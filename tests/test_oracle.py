@@ -128,3 +128,14 @@ def test_partition_rule():
     assert [orc.partition(9, 3, i) for i in range(3)] == [(0, 3), (3, 3), (6, 3)]
     assert [orc.partition(8, 3, i) for i in range(3)] == [(0, 3), (3, 3), (6, 2)]
     assert [orc.partition(2, 4, i) for i in range(4)] == [(0, 1), (1, 1), (2, 0), (3, 0)]
+
+
+def test_converters_against_reference(gold_dir):
+    """oracle restatement of recalibrate_l1 / l1_to_l4_converter (pyrecode/utils/converters.py:15-123) against
+    the outputs the live reference produced (oracle/make_golden.py converters)"""
+    z = np.load(os.path.join(gold_dir, 'gold_e_converters.npz'))
+    fr = z['frames']
+    for i in range(fr.shape[0]):
+        assert np.array_equal(orc.recalibrate_l1_frame(fr[i], z['orig'], z['new'], float(z['eps'])), z['recalibrated'][i])
+        assert np.array_equal(orc.l1_to_l4_frame(fr[i], 0, True), z['l4'][i])
+    assert not z['l4'][3].any() and z['l4'][:3].any()
