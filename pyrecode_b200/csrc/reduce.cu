@@ -274,7 +274,7 @@ template <typename T, int VALMODE, bool THRB>
 __global__ void __launch_bounds__(256)
 k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, size_t P, int NT, size_t MS,
                     uint32_t *__restrict__ maps, uint32_t *__restrict__ tilecnt, uint16_t *__restrict__ wordpre,
-                    void *__restrict__ vals_out)
+                    void *__restrict__ vals_out, int k1_prefetch)
 {
     constexpr int W = Px<T>::W;
     constexpr uint32_t REGION_BYTES = 1024 * sizeof(T);         // one warp's pixels of one sub-tile
@@ -312,13 +312,17 @@ k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, siz
     }
 
     uint32_t run = 0;
-#pragma unroll 1
+#pragma unroll 2
     for (int sub = 0; sub < NSUB; sub++) {
         const int wpx0 = sub * SUB_PX + warp * 1024;
         uint32_t fw[4][W], tw[4][W];
         if (!THRB) {
 #pragma unroll
             for (int j = 0; j < 4; j++) Px<T>::load_cached(th + wpx0 + j * 256 + lane * 8, tw[j]);
+            // the threshold pixels of the NEXT sub-tile: one 128-byte line per lane into L1, so that the loads above
+            // find them there one iteration later instead of waiting for L2
+            if (k1_prefetch && sub + 1 < NSUB && lane * (128 / (int)sizeof(T)) < 1024)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(th + wpx0 + SUB_PX + lane * (128 / (int)sizeof(T))));
         }
         const int stg = sub % BULK_STAGES;
         T *region = s_ring + (stg * 8 + warp) * RS;              // this warp's 1024 pixels of the sub-tile
@@ -354,19 +358,26 @@ k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, siz
                 total += ws[i];
             }
         }
-        uint32_t rank = run + before + incl - pc;
+        const uint32_t rank = run + before + incl - pc;
         s_wpre[sub * SUB_WORDS + t] = (uint16_t)rank;
         if (VALMODE) {
             const T *src = region + lane * 32;                  // this thread's word = 32 consecutive pixels
             uint32_t bits = word;
-            while (bits) {
-                const uint32_t k = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const T v = src[k];
-                if (VALMODE == 1) reinterpret_cast<T *>(vals_out)[sbase + rank] = v;
-                else reinterpret_cast<uint32_t *>(vals_out)[sbase + rank] =
-                         ((uint32_t)v << 16) | (uint32_t)(sub * SUB_PX + t * 32) | k;
-                rank++;
+            if (VALMODE == 1) {
+                T *o = reinterpret_cast<T *>(vals_out) + sbase + rank;
+                while (bits) {
+                    const uint32_t k = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    *o++ = src[k];
+                }
+            } else {
+                uint32_t *o = reinterpret_cast<uint32_t *>(vals_out) + sbase + rank;
+                const uint32_t posbase = (uint32_t)(sub * SUB_PX + t * 32);
+                while (bits) {
+                    const uint32_t k = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    *o++ = ((uint32_t)src[k] << 16) | posbase | k;
+                }
             }
         }
         // the warp is done with this stage: refill it with the sub-tile BULK_STAGES ahead
@@ -404,8 +415,9 @@ static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, const 
         cudaFuncSetAttribute(k_reduce_tiles_bulk<T, VM, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                              (int)bulk_smem_bytes<T>(TB));                                                 \
         k_reduce_tiles_bulk<T, VM, TB><<<grid, block, bulk_smem_bytes<T>(TB), st>>>(                       \
-            (const T *)frames, (const T *)thr, g.P, g.NT, g.MS, maps, tilecnt, wordpre, vals);             \
+            (const T *)frames, (const T *)thr, g.P, g.NT, g.MS, maps, tilecnt, wordpre, vals, k1_prefetch); \
     }
+    static const int k1_prefetch = getenv("RC_K1_PREFETCH") ? atoi(getenv("RC_K1_PREFETCH")) : 1;
 #define RC_K1(VM)                                                                                          \
     if (bulk) {                                                                                            \
         if (thr_bulk) RC_K1B(VM, true) else RC_K1B(VM, false)                                              \
