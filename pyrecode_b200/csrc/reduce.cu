@@ -152,6 +152,9 @@ k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P
             for (int j = 0; j < 4; j++) Px<T>::load_stream(fr + wpx0 + j * 256 + lane * 8, fw[j]);
 #pragma unroll
             for (int j = 0; j < 4; j++) Px<T>::load_cached(th + wpx0 + j * 256 + lane * 8, tw[j]);
+            // next sub-tile's threshold lines into L1 (see k_reduce_tiles_bulk)
+            if (vec_ok > 1 && sub_px0 + 2 * SUB_PX <= npx && lane * (128 / (int)sizeof(T)) < 1024)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(th + wpx0 + SUB_PX + lane * (128 / (int)sizeof(T))));
         } else {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -405,10 +408,11 @@ static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, const 
     const int vec_ok = ((g.P * sizeof(T)) % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)thr % 16 == 0);
     dim3 grid(F, g.NT), block(256);
     // full tiles + aligned frames: the bulk-copy variant (RC_K1_GENERIC=1 in the environment forces the other).
-    // L1 stays on the register path: its values are frame - thr, which the bulk variant has to write back into
-    // the staged tile (measured 0.234 vs 0.224 ms per 32 frames).
+    // L1 writes frame - thr back into the staged tile; alone it is as fast as the register path (0.224 vs 0.228 ms
+    // per 32 frames), inside the pipeline it leaves more of every SM to the other kernels (81.0 vs 76.9 k frames/s).
     static const bool force_generic = getenv("RC_K1_GENERIC") != nullptr;
-    const bool bulk = vec_ok && g.P % TILE_PX == 0 && !force_generic && valmode != 1;
+    static const bool l1_bulk = getenv("RC_K1_L1_BULK") ? atoi(getenv("RC_K1_L1_BULK")) != 0 : true;
+    const bool bulk = vec_ok && g.P % TILE_PX == 0 && !force_generic && (valmode != 1 || l1_bulk);
     static const bool thr_bulk = getenv("RC_K1_THR_BULK") ? atoi(getenv("RC_K1_THR_BULK")) != 0 : false;
 #define RC_K1B(VM, TB)                                                                                     \
     {                                                                                                      \
@@ -423,7 +427,8 @@ static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, const 
         if (thr_bulk) RC_K1B(VM, true) else RC_K1B(VM, false)                                              \
     } else {                                                                                               \
         k_reduce_tiles<T, VM><<<grid, block, 0, st>>>((const T *)frames, (const T *)thr, g.P, g.NT, g.MS,  \
-                                                      maps, tilecnt, wordpre, vals, vec_ok);               \
+                                                      maps, tilecnt, wordpre, vals,                        \
+                                                      vec_ok ? (k1_prefetch ? 2 : 1) : 0);                 \
     }
     if (valmode == 0) { RC_K1(0) }
     else if (valmode == 1) { RC_K1(1) }
