@@ -320,7 +320,7 @@ def main():
             'input_gb_s': value * frame_bytes / 1e9,
             'hbm_roofline_frac_whole_path': value / world * frame_bytes / 1e9 / peak,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'kernel': 'k_reduce_tiles_bulk' if level != 1 else 'k_reduce_tiles', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'roofline': {'bound': 'hbm', 'kernel': 'k_reduce_tiles_bulk', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': NCU_TRAFFIC.get((level, F)), 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': F * frame_bytes, 'kernel_ms': k1_ms},
             'stage_ms_per_step': dict(zip(['threshold_pack_compact', 'reduce_rest', 'deflate', 'assemble'],

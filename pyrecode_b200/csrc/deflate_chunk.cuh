@@ -482,17 +482,24 @@ DF_HD uint32_t df_encode_segment(DfEmitShared &S, int t, int clen)
     const DfMasks m = df_token_masks(S.io, t, nbytes);
     const uint8_t *seg = reinterpret_cast<const uint8_t *>(S.io) + t * (DF_SEG_STRIDE * 4);
     uint32_t *priv = S.priv + t * DF_SEG_STRIDE;
-    const uint32_t cont = (uint32_t)df_ctz32(~m.lng[1]);
+    // Every byte of the segment belongs to exactly one token (a literal, or a match that covers a run up to the
+    // literal that ends it), so a token's length is the distance to the next token start -- which the loop needs
+    // anyway -- or to the end of the segment: no run-length scan per token.
+    const uint32_t tk0 = m.lit[0] | m.ms[0], tk1 = m.lit[1] | m.ms[1];
+    const uint32_t end = (uint32_t)nbytes;
+    const uint32_t first1 = tk1 ? 32u + (uint32_t)df_ctz32(tk1) : end;     // first token start of the upper half
     uint32_t lo = 0, hi = 0;                         // bit accumulator: lo is flushed when nb reaches 32
     uint32_t nb = 0, w = 0, total = 0;
     for (int h = 0; h < 2; h++) {
-        uint32_t tk = m.lit[h] | m.ms[h];
+        uint32_t tk = h ? tk1 : tk0;
+        if (!tk) continue;
         const uint32_t lit = m.lit[h];
-        while (tk) {
-            const int pos = df_ctz32(tk);
+        const uint32_t lim = h ? end - 32u : first1; // where the half's last token ends (relative to the half)
+        uint32_t pos = (uint32_t)df_ctz32(tk);
+        while (true) {
             tk &= tk - 1;
-            const uint32_t L = df_run_length(m, h, pos, cont);
-            const uint32_t idx = ((lit >> pos) & 1) ? (uint32_t)seg[32 * h + pos] : (uint32_t)DF_NSYM + L;
+            const uint32_t nxt = tk ? (uint32_t)df_ctz32(tk) : lim;
+            const uint32_t idx = ((lit >> pos) & 1) ? (uint32_t)seg[32 * h + pos] : (uint32_t)DF_NSYM + (nxt - pos);
             const uint32_t e = S.tbl[idx];
             const uint32_t code = e & 0xffffffu;
             lo |= code << nb;
@@ -509,6 +516,8 @@ DF_HD uint32_t df_encode_segment(DfEmitShared &S, int t, int clen)
                 lo = hi;
                 nb -= 32;
             }
+            if (!tk) break;
+            pos = nxt;
         }
     }
     if (nb) {
