@@ -47,6 +47,15 @@ constexpr int CCL_THREADS = 256;
 constexpr int CCL_WARPS = CCL_THREADS / 32;
 constexpr int CCL_MAPV = TILE_WORDS / 4 / CCL_THREADS;    // uint4 map loads per thread
 
+// shared-memory atomic add issued as is: around an atomicAdd() that only one lane executes the compiler still emits
+// its warp-aggregation sequence (vote, leader election, shuffle)
+__device__ __forceinline__ uint32_t atom_add_shared(uint32_t *p, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
+
 // Centroid of one puddle with the reference's arithmetic (pyrecode/utils/converters.py): members are added in
 // raster order, every += is float64 arithmetic rounded to float32 (numba: float32 element += float64 value).
 // mode: 0/1 weighted average (:167-197), 2 maximum pixel (:229-259), 3 unweighted (:200-226).
@@ -168,9 +177,10 @@ ccl_tile(const int tile, const int f,
                 const uint32_t e = p + HP;             // pixel index in the halo-extended map
                 const uint32_t q = e - unx;            // >= 1: the halo covers nx + 1 pixels
                 const bool bw = (s_maskx[(e - 1) >> 5] >> ((e - 1) & 31)) & 1u;
-                const bool bnw = (s_maskx[(q - 1) >> 5] >> ((q - 1) & 31)) & 1u;
-                const bool bn = (s_maskx[q >> 5] >> (q & 31)) & 1u;
-                const bool bne = (s_maskx[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u;
+                // NW, N, NE = three consecutive map bits from q - 1: one funnel shift over two words
+                const uint32_t uw = (q - 1) >> 5;
+                const uint32_t up3 = __funnelshift_r(s_maskx[uw], s_maskx[uw + 1], (q - 1) & 31);
+                const bool bnw = up3 & 1u, bn = up3 & 2u, bne = up3 & 4u;
                 // up to three links: W, and N or (NW, NE) -- NW / NE are implied when N is set
                 constexpr uint32_t NONE = 0xffffffffu;
                 const uint32_t c0 = (bw && hl) ? e - 1 : NONE;
@@ -220,7 +230,7 @@ ccl_tile(const int tile, const int f,
             const uint32_t pre = __popc(b0 & lt) + 2u * __popc(b1 & lt);
             const uint32_t tot = __popc(b0) + 2u * __popc(b1);
             uint32_t wbase = 0;
-            if (lane == 0 && tot) wbase = atomicAdd(&s_nlinks, tot);
+            if (lane == 0 && tot) wbase = atom_add_shared(&s_nlinks, tot);
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
             const uint32_t o = wbase + pre;
             if (n > 0 && o < (uint32_t)CCL_LINKS) s_links[o] = l0;
@@ -326,7 +336,7 @@ ccl_tile(const int tile, const int f,
         }
         const uint32_t bm = __ballot_sync(0xffffffffu, multi);
         uint32_t wbase = 0;
-        if (lane == 0 && bm) wbase = atomicAdd(&s_nlist, __popc(bm));
+        if (lane == 0 && bm) wbase = atom_add_shared(&s_nlist, __popc(bm));
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
         if (multi) s_list[wbase + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)i;
     }
