@@ -39,8 +39,8 @@ KIND = {1: 'l1', 2: 'l2', 3: 'l1', 4: 'l4'}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_reduce_tiles per launch from the committed `ncu --set full`
-# capture (profiles/r01_ncu_k_reduce_tiles_bulk.txt): keyed by (level, frames per step)
-NCU_TRAFFIC = {(2, 32): 1107740000 + 133809408}
+# capture (profiles/r01_ncu_k_reduce_tiles_bulk_v6.txt): keyed by (level, frames per step)
+NCU_TRAFFIC = {(2, 32): 1107738000 + 131561216}
 
 
 def measured_peak():
