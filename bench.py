@@ -262,6 +262,7 @@ def main():
     # stage split: re-run a few steps one at a time on slot 0 with per-step readback of the stage marks
     # (outside the timed region; the dominant kernel is timed alone here, which is what `roofline` reports)
     nprof = min(args.steps, 5)
+    eng.ctx.set_pipelined(False)              # one batch at a time: every kernel gets the whole GPU
     for s in range(nprof):
         eng.launch(d_frames, F, 0)
         stage_ms += np.array(eng.ctx.profile_read()[:4])

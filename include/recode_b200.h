@@ -63,6 +63,11 @@ int          rc_sm_count(const rc_ctx *ctx);
 int                 rc_profile_enable(rc_ctx *ctx, int on);
 int                 rc_profile_read(rc_ctx *ctx, float *ms, int capacity);   /* returns number of stages (4) */
 unsigned long long  rc_launch_count(const rc_ctx *ctx);
+/* Tell the context that several contexts keep batches in flight on this GPU (one stream each).  rc_reduce_compress
+ * then runs everything after the streaming kernel on context-owned high-priority streams and labels puddles with a
+ * few persistent CTAs per SM, so that the batches share the SMs instead of queueing behind each other (L2 / L4).  Off
+ * (the default) every kernel gets the whole GPU, which is what a single stream wants. */
+int                 rc_set_pipelined(rc_ctx *ctx, int on);
 
 /* ---- sizes ----------------------------------------------------------------------------- */
 size_t rc_map_stride_words(size_t n_pixels);                 /* uint32 words per frame map on device      */

@@ -38,6 +38,7 @@ _SIGNATURES = {
     'rc_profile_enable': (ctypes.c_int, [_vp, ctypes.c_int]),
     'rc_profile_read': (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
     'rc_launch_count': (ctypes.c_ulonglong, [_vp]),
+    'rc_set_pipelined': (ctypes.c_int, [_vp, ctypes.c_int]),
     'rc_map_stride_words': (_sz, [_sz]),
     'rc_packed_stride_bytes': (_sz, [_cfgp]),
     'rc_workspace_bytes': (_sz, [_cfgp]),
@@ -136,6 +137,9 @@ class Context:
 
     # ---- instrumentation -----------------------------------------------------------------------
     STAGES = ('threshold_pack_compact', 'reduce_rest', 'deflate', 'assemble')
+
+    def set_pipelined(self, on=True):
+        self._check(self._lib.rc_set_pipelined(self._h, 1 if on else 0), 'rc_set_pipelined')
 
     def profile_enable(self, on=True):
         self._check(self._lib.rc_profile_enable(self._h, 1 if on else 0), 'rc_profile_enable')

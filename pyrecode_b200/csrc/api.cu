@@ -190,6 +190,13 @@ extern "C" int rc_profile_read(rc_ctx *ctx, float *ms, int capacity)
     return n;
 }
 
+extern "C" int rc_set_pipelined(rc_ctx *ctx, int on)
+{
+    if (!ctx) return -1;
+    ctx->pipelined = on != 0;
+    return 0;
+}
+
 extern "C" unsigned long long rc_launch_count(const rc_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" const char *rc_last_error(const rc_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" int rc_version(void) { return RC_VERSION; }
@@ -410,7 +417,7 @@ extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void 
     if ((rc = reduce_stage1(ctx, cfg, g, w, d_frames, F, d_thr, cw.maps, st))) return rc;
     rc_mark(ctx, 1, st);
     // everything else on the context's high-priority stream(s); the caller's stream joins at the end
-    const bool prio = ctx->use_priority < 0 ? (level == 2 || level == 4) : ctx->use_priority != 0;
+    const bool prio = ctx->use_priority < 0 ? (ctx->pipelined && (level == 2 || level == 4)) : ctx->use_priority != 0;
     cudaStream_t sp = prio ? ctx->post : st;
     RC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     if (sp != st) RC_CUDA(ctx, cudaStreamWaitEvent(sp, ctx->ev_fork, 0));

@@ -733,7 +733,7 @@ int launch_ccl_tiles(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps,
     const int nt = F * g.NT;
     unsigned grid = (unsigned)nt;
     const int per_sm = ctx->ccl_ctas_per_sm >= 0 ? ctx->ccl_ctas_per_sm
-                                                 : (ctx->use_priority == 0 ? 0 : (fold == 3 ? 3 : 2));
+                                                 : ((ctx->use_priority == 0 || !ctx->pipelined) ? 0 : (fold == 3 ? 3 : 2));
     if (per_sm > 0 && (unsigned)(per_sm * ctx->sm_count) < grid) grid = (unsigned)(per_sm * ctx->sm_count);
 #define RC_CT(FO)                                                                                              \
     k_ccl_tiles<FO><<<grid, CCL_THREADS, 0, st>>>(maps, g.MS, wordpre, g.NT, nt, tilecnt, vp, tileovf, xcount,   \

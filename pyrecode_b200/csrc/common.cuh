@@ -60,9 +60,10 @@ struct rc_ctx {
     // has no such chain of small kernels, loses 3 % and keeps the caller's stream.)
     cudaStream_t post, side_hi;
     cudaEvent_t ev_post;
-    int use_priority;                  // RECODE_B200_PRIORITY: 0 = never, 1 = always, unset = levels 2 and 4
+    int pipelined;                     // rc_set_pipelined: several contexts keep batches in flight on this GPU
+    int use_priority;                  // RECODE_B200_PRIORITY: 0 = never, 1 = always, unset = pipelined levels 2 and 4
     int ccl_ctas_per_sm;               // RECODE_B200_CCL_CTAS: n > 0 = persistent k_ccl_tiles with n CTAs per SM,
-                                       // 0 = one CTA per tile, unset = 2 (L2) / 3 (L4)
+                                       // 0 = one CTA per tile, unset = 2 (L2) / 3 (L4) when pipelined, else 0
     // Huffman codes kept across rc_reduce_compress calls (compression levels 1..5): [0] map streams, [1] value
     // streams.  Frames of one acquisition share their statistics, so a code is rebuilt only every
     // RC_TABLE_REFRESH calls (or when the configuration changes) instead of once per batch.

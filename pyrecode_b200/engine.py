@@ -59,6 +59,9 @@ class WriteEngine:
         self.records_cap = probe.records_capacity(self.cfg) if records_capacity is None else int(records_capacity)
         probe.close()
         self.slots = [_Slot(self, device) for _ in range(max(1, int(n_slots)))]
+        if len(self.slots) > 1:
+            for sl in self.slots:                 # several batches in flight: let them share the SMs (rc_set_pipelined)
+                sl.ctx.set_pipelined(True)
         self._next = 0
         s0 = self.slots[0]
         self.ctx, self.dev = s0.ctx, s0.ctx.device
