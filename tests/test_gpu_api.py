@@ -285,6 +285,33 @@ def test_converters_random(method, mode):
         assert np.array_equal(np.asarray(r8[i]['data'].todense()), orc.recalibrate_l1_frame(f8[i], o8, n8, 0.5))
 
 
+@pytest.mark.parametrize('level', [2, 4])
+def test_pipelined_contexts_match_single(level):
+    """three batches in flight (rc_set_pipelined: post-streaming work on the contexts' high-priority streams, persistent
+    labelling grid) produce byte-identical records to one context running one batch at a time"""
+    from pyrecode_b200.engine import WriteEngine
+    ny, nx, F = 256, 512, 6
+    dark = orc.synth_dark(ny, nx)
+    frames = np.stack(orc.synth_frames('l2' if level == 2 else 'l4', 3 * F, ny, nx, dark, seed=77))
+    piped = WriteEngine(ny, nx, 2, 12, level, 1, 0, 0, 1, max_frames=F, n_slots=3)
+    piped.set_threshold(dark, 20)
+    want = []
+    for b in range(3):
+        # a fresh context per batch, like the slot that will see this batch: the Huffman code a context keeps across
+        # calls is built from the first batch it sees
+        single = WriteEngine(ny, nx, 2, 12, level, 1, 0, 0, 1, max_frames=F, n_slots=1)
+        single.set_threshold(dark, 20)
+        rec, offs, counts, _, _ = single.reduce_compress(frames[b * F:(b + 1) * F], first_frame_id=b * F)
+        want.append((bytes(rec[:int(offs[F])]), offs.copy(), counts.copy()))
+        del single
+    for rep in range(3):                               # slots are reused: the joins between the streams must hold
+        ks = [piped.submit(frames[b * F:(b + 1) * F], first_frame_id=b * F) for b in range(3)]
+        for b, k in enumerate(ks):
+            rec, offs, counts, _, _ = piped.collect(k)
+            assert np.array_equal(offs, want[b][1]) and np.array_equal(counts, want[b][2])
+            assert bytes(rec[:int(offs[F])]) == want[b][0]
+
+
 def test_c_recode_shim(gold_dir):
     """c_recode.Reader signatures (pyrecode.cpp:57-141) on the GPU, against the reference's recorded triples"""
     from pyrecode_b200 import c_recode
