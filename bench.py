@@ -132,6 +132,96 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
 
 
+def run_read(args, rank, world, local_rank, dev):
+    """BASELINE config 5: every rank decodes its own L2 part file (frame-sharded stream) to the summed live-view image,
+    the images are all-reduced over NCCL; then the same file to dense frames.  File reads are inside the timed region."""
+    import shutil
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from pyrecode_b200.params import InputParams
+    from pyrecode_b200.recode_reader import ReCoDeReader
+    from pyrecode_b200.recode_writer import ReCoDeWriter
+    from pyrecode_b200 import distributed as rcd
+    nz = args.read_frames
+    dark, frames = make_inputs(2, args.distinct, seed=1234 + rank)
+    tmp = tempfile.mkdtemp(prefix='recode_bench_', dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
+    try:
+        ip = InputParams()
+        for k, v in dict(l4_centroiding=0, source_file_type=0, num_frames=nz, source_header_length=0,
+                         calibration_frame_offset=0, compression_scheme=0, calibration_file_type=0, compression_level=1,
+                         l2_statistics=0, calibration_threshold_epsilon=EPS, frame_offset=0, num_threads=1,
+                         rc_operation_mode=1, num_calibration_frames=1, reduction_level=2, keep_calibration_data=1,
+                         source_bit_depth=BIT_DEPTH, target_bit_depth=BIT_DEPTH, keep_part_files=0, num_rows=NY,
+                         num_cols=NX, source_data_type=0, target_data_type=0).items():
+            ip._param_map[k] = v
+        w = ReCoDeWriter('rb', dark_data=dark[None], output_directory=tmp, input_params=ip, mode='batch', node_id=0,
+                         device=local_rank)
+        w.start()
+        w.run(np.stack([frames[i % len(frames)] for i in range(nz)]))
+        w.close()
+        path = os.path.join(tmp, 'rb.rc2_part000')
+        fsize = os.path.getsize(path)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # one reader for the whole run, rewound every step: its engines (contexts, device buffers, pinned staging)
+        # are set up once, as for a long acquisition decoded batch after batch
+        r = ReCoDeReader(path, is_intermediate=True, device=local_rank)
+        r.open(print_header=False)
+
+        def one(what):
+            r.rewind()
+            if what == 'sum':
+                ids, total = r.sum_frames(nz)
+                rcd.allreduce_view(total)
+                out = int(total[:1024].sum().item())          # device -> host read of the result
+            else:
+                ids, dense = r.read_frames_dense(min(nz, 128))
+                out = int(dense[0, 0, :8].sum().item())
+                del dense
+            return len(ids), dict(r.bulk_stats)
+
+        res = {}
+        for what in ('sum', 'dense'):
+            for _ in range(max(1, args.warmup)):
+                one(what)
+            barrier()
+            t0 = time.perf_counter()
+            n = 0
+            for _ in range(args.steps):
+                k, st = one(what)
+                n += k
+            barrier()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[what] = (world * n / float(t[0]), float(t[0]) / args.steps, st)
+        if rank == 0:
+            line = {'metric': 'frames/s, 4096x4096 L2 part file -> live-view sum (NCCL all-reduce across ranks)',
+                    'value': res['sum'][0], 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+                    'warmup': max(1, args.warmup), 'ms_per_step': 1e3 * res['sum'][1], 'higher_is_better': True,
+                    'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u16', 'data': 'synthetic',
+                    'config': {'workload': 'read path (BASELINE config 5): %d-frame L2 part file per GPU on tmpfs, '
+                                           '%d-bit, file reads inside the timed region' % (nz, BIT_DEPTH),
+                               'file_bytes': fsize, 'frames_per_step_per_gpu': nz},
+                    'dense_frames_per_s': res['dense'][0],
+                    'dense_output_gb_s': res['dense'][0] * NY * NX * 2 / 1e9,
+                    'host_time_split_ms_last_step': {k: (1e3 * v if k.endswith('_s') else v)
+                                                     for k, v in res['sum'][2].items()},
+                    'e2e': {'value': res['sum'][0], 'unit': 'frames/s', 'h2d_bytes_per_step': fsize,
+                            'd2h_bytes_per_step': 8},
+                    'roofline': None, 'cpu_baseline': None}
+            print(json.dumps(line))
+        r.close()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -147,7 +237,14 @@ def main():
     ap.add_argument('--slots', type=int, default=3, help='batches in flight (each on its own CUDA stream)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--bit-depth', type=int, default=12, help='source / target bit depth (SURVEY 8d: 8, 12, 16)')
+    ap.add_argument('--mode', default='write', choices=['write', 'read'],
+                    help="read: BASELINE config 5 -- an L2 part file per GPU -> live-view sum (+ NCCL all-reduce) and "
+                         "dense frames through ReCoDeReader's bulk calls; an auxiliary line, not the headline")
+    ap.add_argument('--read-frames', type=int, default=256, help='frames in the part file of --mode read')
     args = ap.parse_args()
+    global BIT_DEPTH
+    BIT_DEPTH = args.bit_depth
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -198,6 +295,11 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    if args.mode == 'read':
+        run_read(args, rank, world, local_rank, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # every rank generates its own frame range of the stream (seed offset = rank: different frames per GPU)
     dark, frames = make_inputs(level, args.distinct, seed=1234 + rank)

@@ -138,6 +138,11 @@ class ReCoDeReader:
         if self._frame_data_start_position <= self._fp.tell():
             self._fp.seek(self._frame_data_start_position, 0)
 
+    def rewind(self):
+        """back to the first frame (sequential reads start over; the bulk engines and their buffers are kept)"""
+        self._current_frame_index = 0
+        self.seek_to_frame_data()
+
     def get_file_position(self):
         return self._fp.tell()
 

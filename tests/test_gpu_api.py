@@ -232,6 +232,11 @@ def test_bulk_read_pipeline(tmp_path, level):
         assert ids2 == list(range(first + 8, first + n_expect))
         assert np.array_equal(total.cpu().numpy().astype(np.int64).reshape(ny, nx),
                               want[first + 8:first + n_expect].astype(np.int64).sum(0))
+        r.rewind()                                     # the same engines again, from the first frame
+        ids3, total3 = r.sum_frames(5)
+        assert ids3 == list(range(first, first + 5))
+        assert np.array_equal(total3.cpu().numpy().astype(np.int64).reshape(ny, nx),
+                              want[first:first + 5].astype(np.int64).sum(0))
         r.close()
 
 
