@@ -348,6 +348,7 @@ class ReCoDeReader:
                 start = int(self._seek_table[z0, 1])
                 total = int(sizes.sum())
                 self._pread_parallel(fd, eng.block_buffer(total + 16), self._frame_data_start_position + start, total)
+                self._fp.seek(self._frame_data_start_position + start + total, 0)     # sequential reads continue here
                 rel = (self._seek_table[z0:z1, 1].astype(np.int64) - start)
                 for k, z in enumerate(range(z0, z1)):
                     md = self._frame_metadata[z]

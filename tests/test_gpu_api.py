@@ -237,6 +237,9 @@ def test_bulk_read_pipeline(tmp_path, level):
         assert ids3 == list(range(first, first + 5))
         assert np.array_equal(total3.cpu().numpy().astype(np.int64).reshape(ny, nx),
                               want[first:first + 5].astype(np.int64).sum(0))
+        # frame-by-frame reads continue where the bulk call stopped
+        (fid, fr), = r.get_next_frame().items()
+        assert fid == first + 5 and np.array_equal(fr['data'].toarray(), want[first + 5])
         r.close()
 
 
