@@ -139,7 +139,9 @@ int rc_deflate_zlib(rc_ctx *ctx, int compression_level, const uint8_t *d_in, con
 /* Batched zlib-format inflate: replaces zlib.decompress (recode_compressors.py:42-43).  Accepts stored,
  * fixed and dynamic blocks (reference-written files are multi-block dynamic streams).
  * Output stream s at d_out + s * out_stride (capacity out_stride); d_out_bytes[s] = inflated length;
- * d_status[s] = RC_STATUS_* per stream. */
+ * d_status[s] = RC_STATUS_* per stream.  The input is read in aligned 16-byte units: d_in must be readable from
+ * the 16-byte boundary below each stream's first byte to the one above its last byte.  The bytes of d_out past a
+ * stream's inflated length are unspecified (zero when d_out and out_stride are multiples of 4). */
 size_t rc_inflate_workspace_bytes(int n_streams, size_t out_stride);
 int rc_inflate_zlib(rc_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_offsets, const uint32_t *d_in_bytes,
                     int n_streams, void *d_workspace, size_t workspace_bytes,
