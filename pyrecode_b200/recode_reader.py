@@ -29,6 +29,7 @@ class ReCoDeReader:
         self._batch_frames = batch_frames
         self._bulk_frames = bulk_frames          # frames per batch of read_frames_dense / sum_frames
         self._bulk = None
+        self._ahead = []                         # decoded read-ahead frames of get_next_frame
         self._file_size = None
         self._header = None
         self._frame_metadata = None
@@ -132,6 +133,7 @@ class ReCoDeReader:
         self._fp.close()
 
     def seek_to_frame_data(self):
+        self._ahead = []
         self._frame_data_start_position = self._rc_header.get_frame_data_offset(self._is_intermediate,
                                                                                 self._sz_frame_metadata)
         self._fp.seek(0, 2)
@@ -144,9 +146,10 @@ class ReCoDeReader:
         self.seek_to_frame_data()
 
     def get_file_position(self):
-        return self._fp.tell()
+        return self._ahead[0][3] if self._ahead else self._fp.tell()
 
     def copy_headers_to(self, target_fp, source_header_length):
+        self._ahead = []
         self._fp.seek(0, 0)
         target_fp.write(self._fp.read(self._rc_header.recode_header_length))
         target_fp.write(self._fp.read(source_header_length))
@@ -219,6 +222,7 @@ class ReCoDeReader:
             raise ValueError("Random acceess is not available for intermediate files")
         if z >= self._header['nz']:
             raise ValueError('Requested frame index is greater than number of frames in dataset')
+        self._ahead = []
         self._fp.seek(self._frame_data_start_position + int(self._seek_table[z, 1]), 0)
         if self._file_size - self._fp.tell() == 0:
             self._header['nz'] = self._current_frame_index
@@ -247,16 +251,40 @@ class ReCoDeReader:
         raw = self._get_frame_raw(md, read_data=read_data)
         return frame_id, md, raw
 
+    def _drop_ahead(self):
+        """forget the decoded read-ahead of get_next_frame and put the file back where the next frame starts"""
+        if self._ahead:
+            self._fp.seek(self._ahead[0][3], 0)
+            self._ahead = []
+
     def get_next_frame(self):
-        r = self._next_raw()
-        if r is None:
-            return None
-        frame_id, md, raw = r
-        d = self._decode([raw], [md])[0]
+        # Frames are decoded `batch_frames` at a time (one GPU round trip) and handed out one by one; the frame index
+        # and the file position callers can observe stay those of the next frame not yet handed out.
+        if not self._ahead:
+            first = self._current_frame_index
+            batch = []
+            while len(batch) < max(1, int(self._batch_frames)):
+                if batch and not self._is_intermediate and self._current_frame_index >= self._header['nz']:
+                    break                              # end of a merged file: only the caller's own request may raise
+                if self._current_frame_index == 0:
+                    self._fp.seek(self._frame_data_start_position, 0)
+                pos = self._fp.tell()
+                r = self._next_raw()
+                if r is None:
+                    break
+                batch.append((r[0], r[1], r[2], pos))
+                self._current_frame_index += 1
+            self._current_frame_index = first
+            if not batch:
+                return None
+            dec = self._decode([b[2] for b in batch], [b[1] for b in batch])
+            self._ahead = [(b[0], b[1], d, b[3]) for b, d in zip(batch, dec)]
+        frame_id, md, d, _ = self._ahead.pop(0)
         self._current_frame_index += 1
         return {frame_id: self._frame_dict(md, d)}
 
     def get_next_frame_raw(self, read_data=True):
+        self._drop_ahead()
         r = self._next_raw(read_data=read_data)
         if r is None:
             return None
@@ -266,6 +294,7 @@ class ReCoDeReader:
 
     # ---- batched extras (device resident results) ------------------------------------------------
     def _next_batch_raw(self, n):
+        self._drop_ahead()
         ids, mds, raws = [], [], []
         while len(raws) < n:
             r = self._next_raw()
@@ -303,6 +332,7 @@ class ReCoDeReader:
     def _read_block(self, n, eng):
         """Reads the records of up to n frames into eng's pinned block.
         -> (frame ids, nbytes, map_off, map_sz, val_off, val_sz); val_* are None for levels 3 / 4."""
+        self._drop_ahead()
         h = self._header
         level = h['reduction_level']
         two = level in (1, 2)

@@ -320,6 +320,39 @@ def test_pipelined_contexts_match_single(level):
             assert bytes(rec[:int(offs[F])]) == want[b][0]
 
 
+def test_read_ahead_is_invisible(tmp_path):
+    """get_next_frame decodes batch_frames frames per GPU round trip; frame order, the observable file position,
+    get_next_frame_raw / get_frame in between and the end of file behave as with one frame at a time"""
+    from pyrecode_b200.recode_reader import ReCoDeReader, merge_parts
+    rng = np.random.default_rng(21)
+    nz, ny, nx = 11, 64, 96
+    data = reference_test_data(rng, nz, ny, nx)
+    ip = make_params(ny, nx, nz, threads=1)
+    write_parts(tmp_path, 'ra', data, np.zeros((1, ny, nx), np.uint16), ip, 1)
+    merge_parts(str(tmp_path), 'ra.rc1', 1)
+    for name, inter in (('ra.rc1_part000', True), ('ra.rc1', False)):
+        one = ReCoDeReader(str(tmp_path / name), is_intermediate=inter, batch_frames=1)
+        many = ReCoDeReader(str(tmp_path / name), is_intermediate=inter, batch_frames=4)
+        one.open(print_header=False)
+        many.open(print_header=False)
+        for i in range(nz):
+            if i == 5:                                  # a raw read in the middle of a read-ahead batch
+                a, b = one.get_next_frame_raw(), many.get_next_frame_raw()
+                assert list(a) == list(b) == [5] and a[5]['data']['binary_map'] == b[5]['data']['binary_map']
+                continue
+            a, b = one.get_next_frame(), many.get_next_frame()
+            assert list(a) == list(b) == [i]
+            assert np.array_equal(a[i]['data'].toarray(), data[i]) and np.array_equal(b[i]['data'].toarray(), data[i])
+            assert one.get_file_position() == many.get_file_position()
+        assert one.get_next_frame() is None and many.get_next_frame() is None      # end of file (recode_reader.py:229-230)
+        if not inter:
+            fr = many.get_frame(3)
+            assert np.array_equal(fr[3]['data'].toarray(), data[3])
+            assert list(many.get_next_frame()) == [4]
+        one.close()
+        many.close()
+
+
 def test_c_recode_shim(gold_dir):
     """c_recode.Reader signatures (pyrecode.cpp:57-141) on the GPU, against the reference's recorded triples"""
     from pyrecode_b200 import c_recode
