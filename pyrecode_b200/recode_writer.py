@@ -32,7 +32,7 @@ class ReCoDeWriter:
     def __init__(self, image_filename, dark_data=None, dark_filename='', output_directory='', input_params=None,
                  params_filename='', mode='batch', validation_frame_gap=-1, log_filename='recode.log', run_name='run',
                  verbosity=0, use_c=False, max_count=-1, chunk_time_in_sec=0, node_id=0, buffer_size_in_frames=10.0,
-                 device=None, batch_frames=None):
+                 device=None, batch_frames=None, merged=False):
         self._init_params = InitParams(mode, output_directory, image_filename=image_filename,
                                        calibration_filename=dark_filename, params_filename=params_filename,
                                        validation_frame_gap=validation_frame_gap, log_filename=log_filename,
@@ -88,6 +88,13 @@ class ReCoDeWriter:
         else:
             self._thr_host = None
 
+        # merged=True (an extension): a single batch-mode writer emits the random-access layout of
+        # merge_parts directly -- header, nz x metadata table, payloads -- instead of a part file to be merged later
+        self._merged = bool(merged)
+        if self._merged and (mode != 'batch' or ip.num_threads != 1 or node_id != 0):
+            raise ValueError("merged=True needs mode='batch', num_threads = 1 and node_id = 0")
+        self._merged_table = []
+        self._merged_table_pos = None
         self._node_id = node_id
         self._device = device
         self._batch_frames = batch_frames
@@ -165,7 +172,8 @@ class ReCoDeWriter:
             base_filename = self._init_params.run_name
         self._intermediate_file_name = os.path.join(
             self._init_params.output_directory,
-            base_filename + '.rc' + str(self._input_params.reduction_level) + '_part' + '{0:03d}'.format(self._node_id))
+            base_filename + '.rc' + str(self._input_params.reduction_level) +
+            ('' if self._merged else '_part' + '{0:03d}'.format(self._node_id)))
         self._intermediate_file = open(self._intermediate_file_name, 'wb')
         self._rc_header.serialize_to(self._intermediate_file)
         self._intermediate_file.flush()
@@ -259,7 +267,20 @@ class ReCoDeWriter:
             sizes = np.diff(offs)
             if sizes.size and int(sizes.max()) > self._frame_sz:
                 raise ValueError('Buffer size smaller than compressed data size')
-            self._intermediate_file.write(rec)
+            if self._merged:
+                # payloads only; the [sizes...] of every record go to the metadata table written by close()
+                hl = 4 + 4 * n_meta
+                table = np.empty((n, n_meta), dtype='<u4')
+                mv = memoryview(rec)
+                parts = []
+                for i in range(n):
+                    o = int(offs[i])
+                    table[i] = np.frombuffer(mv[o + 4:o + hl], dtype='<u4')
+                    parts.append(mv[o + hl:int(offs[i + 1])])
+                self._merged_table.append(table)
+                self._intermediate_file.writelines(parts)
+            else:
+                self._intermediate_file.write(rec)
             st = eng.slots[slot].ctx.profile_read()
             if len(st) >= 4:
                 gpu_ms['frame_thresholding_and_counting_time'] += st[0]
@@ -271,6 +292,14 @@ class ReCoDeWriter:
                     if (first_id + i) % gap == 0:
                         self._validation_frame(batch[i], run_metrics)
 
+        n_meta = len(self._structures.standard_frame_metadata_structure_for(self._header['reduction_level'],
+                                                                            self._header['rc_operation_mode']))
+        if self._merged:
+            if self._merged_table_pos is not None:
+                raise RuntimeError('merged=True writes the whole dataset in one run()')
+            # the table comes first in the file: reserve it now that the frame count is known
+            self._merged_table_pos = self._intermediate_file.tell()
+            self._intermediate_file.write(bytes(4 * n_meta * available_frames))
         pending = None
         for b0 in range(0, available_frames, F):
             n = min(F, available_frames - b0)
@@ -315,6 +344,9 @@ class ReCoDeWriter:
     def close(self):
         """rewrite the header with the true frame count and close the part file (recode_writer.py:589-603)"""
         self._rc_header.update('nz', self._num_frames_in_part)
+        if self._merged and self._merged_table:
+            self._intermediate_file.seek(self._merged_table_pos)
+            self._intermediate_file.write(np.concatenate(self._merged_table).tobytes())
         self._intermediate_file.seek(0)
         self._rc_header.serialize_to(self._intermediate_file)
         self._intermediate_file.close()

@@ -353,6 +353,41 @@ def test_read_ahead_is_invisible(tmp_path):
         many.close()
 
 
+@pytest.mark.parametrize('level,mode', [(1, 1), (2, 1), (4, 1), (1, 0), (3, 0)])
+def test_merged_writer_equals_merge_parts(tmp_path, level, mode):
+    """ReCoDeWriter(merged=True) emits byte for byte the file merge_parts makes from the part file of the same run
+    (header, metadata table, payloads: pyrecode/recode_reader.py:513-591)"""
+    from pyrecode_b200.recode_reader import ReCoDeReader, merge_parts
+    from pyrecode_b200.recode_writer import ReCoDeWriter
+    rng = np.random.default_rng(40 + level)
+    nz, ny, nx = 13, 72, 104
+    data = reference_test_data(rng, nz, ny, nx)
+    dark = np.zeros((1, ny, nx), np.uint16)
+    ip = make_params(ny, nx, nz, level=level, mode=mode)
+    (tmp_path / 'a').mkdir()
+    (tmp_path / 'b').mkdir()
+    write_parts(tmp_path / 'a', 'm', data, dark, ip, 1, batch_frames=4)
+    merge_parts(str(tmp_path / 'a'), 'm.rc%d' % level, 1)
+    w = ReCoDeWriter('m', dark_data=dark, output_directory=str(tmp_path / 'b'), input_params=ip, mode='batch',
+                     batch_frames=4, merged=True)
+    w.start()
+    w.run(data)
+    w.close()
+    a = (tmp_path / 'a' / ('m.rc%d' % level)).read_bytes()
+    b = (tmp_path / 'b' / ('m.rc%d' % level)).read_bytes()
+    assert a == b
+    r = ReCoDeReader(str(tmp_path / 'b' / ('m.rc%d' % level)))
+    r.open(print_header=False)
+    assert r.get_true_shape()[0] == nz
+    fr = r.get_frame(nz - 2)
+    if level == 1:
+        assert np.array_equal(fr[nz - 2]['data'].toarray(), data[nz - 2])
+    r.close()
+    with pytest.raises(ValueError):
+        ReCoDeWriter('m', dark_data=dark, output_directory=str(tmp_path / 'b'), input_params=ip, mode='batch', node_id=1,
+                     merged=True)
+
+
 def test_c_recode_shim(gold_dir):
     """c_recode.Reader signatures (pyrecode.cpp:57-141) on the GPU, against the reference's recorded triples"""
     from pyrecode_b200 import c_recode
