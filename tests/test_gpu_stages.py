@@ -341,10 +341,12 @@ def test_inflate_own_streams_and_errors(ctx):
     from pyrecode_b200.engine import deflate_batch, inflate_batch
     cases = payload_cases()
     names = list(cases)
-    comp = deflate_batch(ctx, [cases[k] for k in names], 1)
-    out, st = inflate_batch(ctx, comp, max(len(v) for v in cases.values()))
-    for k, o, s in zip(names, out, st):
-        assert s == 0 and o == cases[k], k
+    # level 1: one code per batch (identical chunk headers across streams); 9: one code per stream; 0: stored pieces
+    for level in (9, 0, 1):
+        comp = deflate_batch(ctx, [cases[k] for k in names], level)
+        out, st = inflate_batch(ctx, comp, max(len(v) for v in cases.values()))
+        for k, o, s in zip(names, out, st):
+            assert s == 0 and o == cases[k], (level, k)
     bad = bytearray(comp[names.index('map0.02')])
     bad[len(bad) // 2] ^= 0x55
     trunc = comp[names.index('map0.5')][:1000]
@@ -530,3 +532,34 @@ def test_randomized_geometries_all_levels():
             assert maps[f] == m, tag + ' map ' + first_diff(maps[f], m)
             if level <= 2:
                 assert packed[f] == v, tag + ' values ' + first_diff(packed[f], v)
+
+
+def test_read_path_full_frames_4096():
+    """full-size property test of the read path: L1 records of 4096 x 4096 frames (129 chunks per map stream, decoded
+    one chunk per lane) -> dense frames == where(frame > thr, frame - thr, 0); live-view sum == their sum"""
+    import torch
+    from pyrecode_b200.engine import ReadEngine, WriteEngine
+    ny = nx = 4096
+    F = 3
+    dark = orc.synth_dark(ny, nx)
+    frames = np.stack(orc.synth_frames('l1', F, ny, nx, dark, seed=99))
+    thr = orc.make_threshold(dark, 20)
+    we = WriteEngine(ny, nx, 2, 12, 1, 1, 0, 0, 1, max_frames=F, records_capacity=F * (ny * nx // 2))
+    we.set_threshold(dark, 20)
+    rec, offs, counts, _, _ = we.reduce_compress(frames)
+    rec = bytes(rec)
+    maps, vals = [], []
+    for f in range(F):
+        r = rec[int(offs[f]):int(offs[f + 1])]
+        h = np.frombuffer(r[:16], '<u4')
+        maps.append(r[16:16 + h[1]])
+        vals.append(r[16 + h[1]:16 + h[1] + h[2]])
+    del we
+    re_ = ReadEngine(ny, nx, 2, 12, 1, 1, max_frames=F)
+    re_.load(maps, vals)
+    re_.check()
+    total = torch.zeros(ny * nx, dtype=torch.int32, device='cuda')
+    dense = re_.dense(total=total).cpu().numpy()
+    want = np.where(frames > thr, frames - thr, 0).astype(np.uint16)
+    assert np.array_equal(dense, want)
+    assert np.array_equal(total.cpu().numpy().reshape(ny, nx).astype(np.int64), want.astype(np.int64).sum(0))
