@@ -180,6 +180,14 @@ int rc_bit_pack(rc_ctx *ctx, int bit_depth, const uint16_t *d_vals, uint64_t n_v
 int rc_recalibrate(rc_ctx *ctx, int itemsize, const void *d_frames, const double *d_diff, size_t n_pixels,
                    int n_frames, void *d_out, void *stream);
 
+/* per-pixel median and population standard deviation over a stack of n_frames frames (d_stack: n_frames x n_pixels of
+ * the source dtype), as float32: replaces _median_std_nb (pyrecode/utils/calibration.py:48-57), the heavy step of
+ * make_calibration_frames (:87-138).  The median is exact (np.median); the standard deviation comes from exact
+ * integer sums, rounded once in float64 and once to float32. */
+size_t rc_median_std_workspace_bytes(size_t n_pixels);
+int rc_median_std(rc_ctx *ctx, int itemsize, const void *d_stack, int n_frames, size_t n_pixels, float *d_median,
+                  float *d_std, void *d_workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -156,7 +156,47 @@ def make_converters_golden():
         nz, ny, nx)
 
 
+def make_calibration_golden():
+    """gold_f_calibration.npz: the reference's make_calibration_frames (pyrecode/utils/calibration.py:87-138) and its
+    numba _median_std_nb run live on a seeded dark stack.  The module imports pims (absent here) only to open the .seq
+    file: a stand-in module whose open() returns the in-memory stack lets everything else run unmodified."""
+    import types
+    stack = []
+    pims = types.ModuleType('pims')
+    pims.open = lambda path: stack
+    sys.modules['pims'] = pims
+    with contextlib.redirect_stdout(io.StringIO()):
+        from pyrecode.utils import calibration as cal
+    rng = np.random.default_rng(4242)
+    nF, ny, nx = 41, 40, 40                               # odd and (below) even frame counts
+    dark = rng.integers(95, 110, (ny, nx))
+    d = dark[None] + np.round(rng.normal(0, 3, (nF + 1, ny, nx)))
+    ev = rng.random((nF + 1, ny, nx)) < 0.01
+    d = np.where(ev, d + rng.integers(50, 1000, (nF + 1, ny, nx)), d)
+    d[:, 3, 5] = rng.integers(0, 4000, nF + 1)            # a hot pixel: median outside any narrow window
+    d[:, 7, 7] = 0
+    d = d.astype(np.uint16)
+    out = {}
+    for tag, n in (('odd', nF), ('even', nF + 1)):
+        m, s_ = cal._median_std_nb(d[:n], ny, nx)
+        om, os_ = orc.median_std(d[:n])
+        assert np.array_equal(m, om) and np.allclose(s_, os_, rtol=1e-6, atol=0), 'median/std oracle'
+        out['med_' + tag], out['std_' + tag] = m, s_
+    tmp = tempfile.mkdtemp(prefix='recode_cal_')
+    stack.extend(list(d[:nF]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        cal.make_calibration_frames('x.seq', np.uint16, nF, 10, 4, savepath=tmp, filename_prefix='c')
+    thr = np.stack([np.fromfile(os.path.join(tmp, 'c__dark_ref_%d.bin' % i), dtype=np.uint16).reshape(ny, nx)
+                    for i in range(4)])
+    shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(GOLD, 'gold_f_calibration.npz'), stack=d, n_odd=nF, thresholds=thr, **out)
+    return 'gold_f_calibration.npz: _median_std_nb (odd / even frame counts) and make_calibration_frames thresholds'
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'calibration':
+        print(make_calibration_golden())
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'converters':      # add this fixture without regenerating the others
         print(make_converters_golden())
         return
@@ -297,6 +337,7 @@ def main():
 
     shutil.rmtree(tmp)
     report.append(make_converters_golden())
+    report.append(make_calibration_golden())
     with open(os.path.join(GOLD, 'README.md'), 'w') as f:
         f.write('# Golden fixtures\n\nGenerated by `python oracle/make_golden.py` in the build container from the '
                 'unmodified reference at `/root/reference` (numpy %s, scipy %s). Every line below was asserted '

@@ -187,6 +187,12 @@ def l1_to_l4_frame(frame, mode=0, transpose=True):
     return out
 
 
+def median_std(stack):
+    """_median_std_nb (pyrecode/utils/calibration.py:48-57): per-pixel np.median / np.std over the frames, as float32"""
+    d = np.asarray(stack)
+    return np.median(d, axis=0).astype(np.float32), np.std(d.astype(np.float64), axis=0).astype(np.float32)
+
+
 def unpack_sparse(ny, nx, b, map_bytes, val_bytes, level):
     """reader.h:10-68; returns uint64 [n, 3] (row, col, value)"""
     m = np.frombuffer(bytes(map_bytes), dtype=np.uint8)

@@ -60,6 +60,8 @@ _SIGNATURES = {
     'rc_unpack_dense': (ctypes.c_int, [_vp, _cfgp, _vp, _vp, _sz, ctypes.c_int, _vp, _sz, _vp, _vp, _vp, _vp]),
     'rc_bit_unpack': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint64, _vp, _vp]),
     'rc_recalibrate': (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_int, _vp, _vp]),
+    'rc_median_std_workspace_bytes': (_sz, [_sz]),
+    'rc_median_std': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _sz, _vp, _vp, _vp, _sz, _vp]),
     'rc_bit_pack': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint64, _vp, _vp]),
 }
 
@@ -233,6 +235,12 @@ class Context:
     def recalibrate(self, itemsize, frames, diff, n_pixels, n_frames, out):
         self._check(self._lib.rc_recalibrate(self._h, itemsize, _ptr(frames), _ptr(diff), n_pixels, n_frames, _ptr(out),
                                              _stream()), 'rc_recalibrate')
+
+    def median_std(self, itemsize, stack, n_frames, n_pixels, median, std):
+        ws = self.empty(self._lib.rc_median_std_workspace_bytes(n_pixels))
+        self._check(self._lib.rc_median_std(self._h, itemsize, _ptr(stack), n_frames, n_pixels, _ptr(median), _ptr(std),
+                                            _ptr(ws), ws.numel(), _stream()), 'rc_median_std')
+        return ws
 
     def bit_pack(self, bit_depth, vals, n_values, packed):
         self._check(self._lib.rc_bit_pack(self._h, bit_depth, _ptr(vals), n_values, _ptr(packed), _stream()),

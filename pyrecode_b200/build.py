@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'librecode_b200.so')
-SOURCES = ['api.cu', 'reduce.cu', 'ccl.cu', 'deflate.cu', 'inflate.cu', 'unpack.cu']
+SOURCES = ['api.cu', 'reduce.cu', 'ccl.cu', 'deflate.cu', 'inflate.cu', 'unpack.cu', 'calibrate.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Wno-deprecated-gpu-targets']
 

@@ -627,3 +627,16 @@ extern "C" int rc_recalibrate(rc_ctx *ctx, int itemsize, const void *d_frames, c
     if (n_frames < 0) RC_FAIL(ctx, -1, "n_frames must be >= 0");
     return launch_recalibrate(ctx, itemsize, d_frames, d_diff, n_pixels, n_frames, d_out, (cudaStream_t)stream);
 }
+
+extern "C" size_t rc_median_std_workspace_bytes(size_t n_pixels) { return median_std_workspace_bytes(n_pixels); }
+
+extern "C" int rc_median_std(rc_ctx *ctx, int itemsize, const void *d_stack, int n_frames, size_t n_pixels,
+                             float *d_median, float *d_std, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (!ctx) return -1;
+    if (itemsize != 1 && itemsize != 2) RC_FAIL(ctx, -1, "itemsize must be 1 or 2 (got %d)", itemsize);
+    if (n_frames < 1 || n_frames > (1 << 20)) RC_FAIL(ctx, -1, "n_frames must be 1..2^20");
+    if (workspace_bytes < median_std_workspace_bytes(n_pixels)) RC_FAIL(ctx, -1, "workspace too small");
+    return launch_median_std(ctx, itemsize, d_stack, n_pixels, n_frames, d_median, d_std, d_workspace,
+                             (cudaStream_t)stream);
+}

@@ -87,3 +87,6 @@ int launch_unpack_dense(rc_ctx *ctx, const Geom &g, int itemsize, int level, int
                         int F, void *dense, uint32_t *sum, cudaStream_t st);
 int launch_recalibrate(rc_ctx *ctx, int itemsize, const void *frames, const double *diff, size_t P, int F, void *out,
                        cudaStream_t st);
+size_t median_std_workspace_bytes(size_t P);
+int launch_median_std(rc_ctx *ctx, int itemsize, const void *stack, size_t P, int N, float *med, float *sd, void *ws,
+                      cudaStream_t st);

@@ -388,6 +388,43 @@ def test_merged_writer_equals_merge_parts(tmp_path, level, mode):
                      merged=True)
 
 
+def test_calibration_golden(gold_dir, tmp_path):
+    """utils.calibration on the GPU == the live reference: per-pixel median (exact) and std (float32, 1e-6 relative:
+    the reference sums float64 deviations, the kernel exact integers), and the threshold frames
+    make_calibration_frames writes (pyrecode/utils/calibration.py:87-138)"""
+    from pyrecode_b200.utils.calibration import median_std, make_calibration_frames
+    z = np.load(os.path.join(gold_dir, 'gold_f_calibration.npz'))
+    n = int(z['n_odd'])
+    for tag, k in (('odd', n), ('even', n + 1)):
+        m, s = median_std(z['stack'][:k])
+        assert m.dtype == np.float32 and np.array_equal(m, z['med_' + tag])
+        assert np.allclose(s, z['std_' + tag], rtol=1e-6, atol=0)
+    res = make_calibration_frames('unused.seq', np.uint16, n, 10, 4, savepath=str(tmp_path), filename_prefix='c',
+                                  data=z['stack'][:n])
+    for i in range(4):
+        t = np.fromfile(str(tmp_path / ('c__dark_ref_%d.bin' % i)), dtype=np.uint16).reshape(z['thresholds'][i].shape)
+        assert np.array_equal(t, z['thresholds'][i]), i
+        assert np.array_equal(res['thresholds'][i], t)
+    with pytest.raises(NotImplementedError):
+        make_calibration_frames('unused.seq', np.uint16, n, 10, 4, data=z['stack'][:n], use_acc=True)
+
+
+@pytest.mark.parametrize('dtype,n', [(np.uint16, 64), (np.uint16, 257), (np.uint8, 33)])
+def test_calibration_median_std_random(dtype, n):
+    """wider distributions (most medians outside the 64-count window: the bisection kernel), uint8 stacks, ragged
+    pixel counts, against the oracle"""
+    from pyrecode_b200.utils.calibration import median_std
+    rng = np.random.default_rng(n)
+    ny, nx = 37, 53
+    hi = 250 if dtype == np.uint8 else 60000
+    stack = rng.integers(0, hi, (n, ny, nx)).astype(dtype)
+    stack[:, :10] = (100 + rng.integers(0, 6, (n, 10, nx))).astype(dtype)      # narrow rows: the window path
+    m, s = median_std(stack)
+    om, os_ = orc.median_std(stack)
+    assert np.array_equal(m, om)
+    assert np.allclose(s, os_, rtol=1e-6, atol=0)
+
+
 def test_c_recode_shim(gold_dir):
     """c_recode.Reader signatures (pyrecode.cpp:57-141) on the GPU, against the reference's recorded triples"""
     from pyrecode_b200 import c_recode

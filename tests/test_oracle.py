@@ -139,3 +139,14 @@ def test_converters_against_reference(gold_dir):
         assert np.array_equal(orc.recalibrate_l1_frame(fr[i], z['orig'], z['new'], float(z['eps'])), z['recalibrated'][i])
         assert np.array_equal(orc.l1_to_l4_frame(fr[i], 0, True), z['l4'][i])
     assert not z['l4'][3].any() and z['l4'][:3].any()
+
+
+def test_calibration_median_std_against_reference(gold_dir):
+    """oracle restatement of _median_std_nb (pyrecode/utils/calibration.py:48-57) against the live reference's output"""
+    z = np.load(os.path.join(gold_dir, 'gold_f_calibration.npz'))
+    n = int(z['n_odd'])
+    for tag, k in (('odd', n), ('even', n + 1)):
+        m, s = orc.median_std(z['stack'][:k])
+        assert np.array_equal(m, z['med_' + tag])
+        assert np.allclose(s, z['std_' + tag], rtol=1e-6, atol=0)
+    assert z['thresholds'].shape[0] == 4 and np.array_equal(z['thresholds'][0], np.floor(z['med_odd']).astype(np.uint16))
