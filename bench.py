@@ -52,9 +52,9 @@ def measured_peak():
 
 
 def make_inputs(level, n_distinct, seed=1234):
-    from oracle import oracle as orc
-    dark = orc.synth_dark(NY, NX)
-    frames = orc.synth_frames(KIND[level], n_distinct, NY, NX, dark, seed=seed, bit_depth=BIT_DEPTH)
+    from pyrecode_b200.synth import synth_dark, synth_frames
+    dark = synth_dark(NY, NX)
+    frames = synth_frames(KIND[level], n_distinct, NY, NX, dark, seed=seed, bit_depth=BIT_DEPTH)
     return dark, frames
 
 
