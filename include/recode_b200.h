@@ -65,7 +65,7 @@ int                 rc_profile_read(rc_ctx *ctx, float *ms, int capacity);   /* 
 unsigned long long  rc_launch_count(const rc_ctx *ctx);
 /* Tell the context that several contexts keep batches in flight on this GPU (one stream each).  rc_reduce_compress
  * then runs everything after the streaming kernel on context-owned high-priority streams and labels puddles with a
- * few persistent CTAs per SM, so that the batches share the SMs instead of queueing behind each other (L2 / L4).  Off
+ * few persistent CTAs per SM, so that the batches share the SMs instead of queueing behind each other.  Off
  * (the default) every kernel gets the whole GPU, which is what a single stream wants. */
 int                 rc_set_pipelined(rc_ctx *ctx, int on);
 

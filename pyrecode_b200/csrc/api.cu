@@ -417,7 +417,7 @@ extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void 
     if ((rc = reduce_stage1(ctx, cfg, g, w, d_frames, F, d_thr, cw.maps, st))) return rc;
     rc_mark(ctx, 1, st);
     // everything else on the context's high-priority stream(s); the caller's stream joins at the end
-    const bool prio = ctx->use_priority < 0 ? (ctx->pipelined && (level == 2 || level == 4)) : ctx->use_priority != 0;
+    const bool prio = ctx->use_priority < 0 ? ctx->pipelined != 0 : ctx->use_priority != 0;
     cudaStream_t sp = prio ? ctx->post : st;
     RC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     if (sp != st) RC_CUDA(ctx, cudaStreamWaitEvent(sp, ctx->ev_fork, 0));
