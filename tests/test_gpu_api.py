@@ -293,14 +293,14 @@ def test_converters_random(method, mode):
         assert np.array_equal(np.asarray(r8[i]['data'].todense()), orc.recalibrate_l1_frame(f8[i], o8, n8, 0.5))
 
 
-@pytest.mark.parametrize('level', [2, 4])
+@pytest.mark.parametrize('level', [1, 2, 4])
 def test_pipelined_contexts_match_single(level):
     """three batches in flight (rc_set_pipelined: post-streaming work on the contexts' high-priority streams, persistent
     labelling grid) produce byte-identical records to one context running one batch at a time"""
     from pyrecode_b200.engine import WriteEngine
     ny, nx, F = 256, 512, 6
     dark = orc.synth_dark(ny, nx)
-    frames = np.stack(orc.synth_frames('l2' if level == 2 else 'l4', 3 * F, ny, nx, dark, seed=77))
+    frames = np.stack(orc.synth_frames({1: 'l1', 2: 'l2', 4: 'l4'}[level], 3 * F, ny, nx, dark, seed=77))
     piped = WriteEngine(ny, nx, 2, 12, level, 1, 0, 0, 1, max_frames=F, n_slots=3)
     piped.set_threshold(dark, 20)
     want = []
