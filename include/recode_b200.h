@@ -188,6 +188,14 @@ size_t rc_median_std_workspace_bytes(size_t n_pixels);
 int rc_median_std(rc_ctx *ctx, int itemsize, const void *d_stack, int n_frames, size_t n_pixels, float *d_median,
                   float *d_std, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* per-pixel "accurate" thresholds: replaces _get_pixel_thresh_2 (pyrecode/utils/calibration.py:27-45).  For every
+ * pixel, of the stack values above d_thr[pixel] the expected_n_events + 1 largest are kept (missing ones count as the
+ * float32 minimum, as in the reference); d_out = mean of the two smallest of them, float32.  as_run != 0: what the
+ * reference computes when actually run (its removal of a found maximum is an out-of-range float -> unsigned store that
+ * changes nothing): the largest value above d_thr[pixel], whatever expected_n_events. */
+int rc_pixel_thresholds(rc_ctx *ctx, int itemsize, const void *d_stack, int n_frames, size_t n_pixels,
+                        const float *d_thr, int expected_n_events, int as_run, float *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,7 +189,27 @@ def make_calibration_golden():
     thr = np.stack([np.fromfile(os.path.join(tmp, 'c__dark_ref_%d.bin' % i), dtype=np.uint16).reshape(ny, nx)
                     for i in range(4)])
     shutil.rmtree(tmp)
-    np.savez_compressed(os.path.join(GOLD, 'gold_f_calibration.npz'), stack=d, n_odd=nF, thresholds=thr, **out)
+    # "accurate" per-pixel thresholds: a busier stack so that more than one event per pixel is expected
+    ev2 = rng.random((nF, ny, nx)) < 0.08
+    d2 = np.where(ev2, d[:nF].astype(np.int64) + rng.integers(50, 1000, (nF, ny, nx)), d[:nF]).astype(np.uint16)
+    m2, _ = cal._median_std_nb(d2, ny, nx)
+    for k in (2, 5):
+        a = cal._get_pixel_thresh_2(d2, ny, nx, k, m2)
+        with np.errstate(all='ignore'):
+            assert np.array_equal(a, orc.pixel_thresholds(d2, m2, k), equal_nan=True), 'pixel thresholds oracle'
+        out['acc_k%d' % k] = a
+    del stack[:]
+    stack.extend(list(d2))
+    tmp = tempfile.mkdtemp(prefix='recode_cal_')
+    with contextlib.redirect_stdout(io.StringIO()):
+        cal.make_calibration_frames('x.seq', np.uint16, nF, 10, 4, savepath=tmp, filename_prefix='c', use_acc=True,
+                                    sigma_acc=2)
+    assert os.path.exists(os.path.join(tmp, 'c__dark_ref_2A.bin')), 'the busy stack should reach expected_n_events >= 2'
+    out['acc_file'] = np.fromfile(os.path.join(tmp, 'c__dark_ref_2A.bin'), dtype=np.uint16).reshape(ny, nx)
+    out['thresholds2'] = np.stack([np.fromfile(os.path.join(tmp, 'c__dark_ref_%d.bin' % i), dtype=np.uint16).reshape(ny, nx)
+                                   for i in range(4)])
+    shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(GOLD, 'gold_f_calibration.npz'), stack=d, stack2=d2, n_odd=nF, thresholds=thr, **out)
     return 'gold_f_calibration.npz: _median_std_nb (odd / even frame counts) and make_calibration_frames thresholds'
 
 

@@ -193,6 +193,28 @@ def median_std(stack):
     return np.median(d, axis=0).astype(np.float32), np.std(d.astype(np.float64), axis=0).astype(np.float32)
 
 
+def pixel_thresholds(stack, thr, k, as_run=True):
+    """_get_pixel_thresh_2 (pyrecode/utils/calibration.py:27-45): of the values above thr the k + 1 largest (float32
+    minimum where there are fewer), ascending; (top[0] + top[1]) / 2 with a float32 sum.  as_run: the live reference
+    never removes a found maximum (:42 stores a float32 minimum into an unsigned list: no effect), so all k + 1 kept
+    values are the maximum."""
+    d = np.asarray(stack)
+    n, ny, nx = d.shape
+    fmin = np.finfo(np.float32).min
+    out = np.empty((ny, nx), dtype=np.float32)
+    with np.errstate(over='ignore'):
+        for r in range(ny):
+            for c in range(nx):
+                v = np.sort(d[:, r, c][d[:, r, c] > thr[r, c]].astype(np.float32))[::-1][:k + 1]
+                top = np.full(k + 1, fmin, dtype=np.float32)
+                top[:v.size] = v
+                if as_run and v.size:
+                    top[:] = v[0]
+                top.sort()
+                out[r, c] = np.float32(np.float64(np.float32(top[0] + top[1])) / 2)
+    return out
+
+
 def unpack_sparse(ny, nx, b, map_bytes, val_bytes, level):
     """reader.h:10-68; returns uint64 [n, 3] (row, col, value)"""
     m = np.frombuffer(bytes(map_bytes), dtype=np.uint8)

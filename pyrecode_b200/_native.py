@@ -60,6 +60,8 @@ _SIGNATURES = {
     'rc_unpack_dense': (ctypes.c_int, [_vp, _cfgp, _vp, _vp, _sz, ctypes.c_int, _vp, _sz, _vp, _vp, _vp, _vp]),
     'rc_bit_unpack': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint64, _vp, _vp]),
     'rc_recalibrate': (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_int, _vp, _vp]),
+    'rc_pixel_thresholds': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _sz, _vp, ctypes.c_int, ctypes.c_int, _vp,
+                                           _vp]),
     'rc_median_std_workspace_bytes': (_sz, [_sz]),
     'rc_median_std': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _sz, _vp, _vp, _vp, _sz, _vp]),
     'rc_bit_pack': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint64, _vp, _vp]),
@@ -241,6 +243,11 @@ class Context:
         self._check(self._lib.rc_median_std(self._h, itemsize, _ptr(stack), n_frames, n_pixels, _ptr(median), _ptr(std),
                                             _ptr(ws), ws.numel(), _stream()), 'rc_median_std')
         return ws
+
+    def pixel_thresholds(self, itemsize, stack, n_frames, n_pixels, thr, expected_n_events, as_run, out):
+        self._check(self._lib.rc_pixel_thresholds(self._h, itemsize, _ptr(stack), n_frames, n_pixels, _ptr(thr),
+                                                  expected_n_events, 1 if as_run else 0, _ptr(out), _stream()),
+                    'rc_pixel_thresholds')
 
     def bit_pack(self, bit_depth, vals, n_values, packed):
         self._check(self._lib.rc_bit_pack(self._h, bit_depth, _ptr(vals), n_values, _ptr(packed), _stream()),

@@ -640,3 +640,13 @@ extern "C" int rc_median_std(rc_ctx *ctx, int itemsize, const void *d_stack, int
     return launch_median_std(ctx, itemsize, d_stack, n_pixels, n_frames, d_median, d_std, d_workspace,
                              (cudaStream_t)stream);
 }
+
+extern "C" int rc_pixel_thresholds(rc_ctx *ctx, int itemsize, const void *d_stack, int n_frames, size_t n_pixels,
+                                   const float *d_thr, int expected_n_events, int as_run, float *d_out, void *stream)
+{
+    if (!ctx) return -1;
+    if (itemsize != 1 && itemsize != 2) RC_FAIL(ctx, -1, "itemsize must be 1 or 2 (got %d)", itemsize);
+    if (n_frames < 1) RC_FAIL(ctx, -1, "n_frames must be >= 1");
+    return launch_cal_topk(ctx, itemsize, d_stack, n_pixels, n_frames, d_thr, expected_n_events, as_run, d_out,
+                           (cudaStream_t)stream);
+}

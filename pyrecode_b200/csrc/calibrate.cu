@@ -191,6 +191,54 @@ k_cal_bisect(const T *__restrict__ stack, size_t P, int N, const uint32_t *__res
     }
 }
 
+// ---- per-pixel "accurate" thresholds (pyrecode/utils/calibration.py:27-45, _get_pixel_thresh_2) -------------------
+// Of the values of a pixel that lie above its threshold t (the float32 median), the k + 1 largest are kept (with
+// multiplicity); the result is the mean of the two smallest of those, i.e. of the (k + 1)-th and k-th largest value.
+// Missing values count as the float32 minimum, exactly like the reference's initial fill, so a pixel with fewer than
+// k + 1 values above t yields the same -inf / -1.7e38 the reference stores.  One thread per pixel, the k + 1 largest
+// values in a small sorted register / local array (k is the expected number of events per pixel: a handful).
+// as_run = 1 reproduces what the reference actually computes when run (numba 0.65): its "remove the maximum found"
+// step stores the float32 minimum into a list of unsigned integers, an out-of-range conversion that leaves the list
+// unchanged, so every round finds the same maximum and the result is the largest value above t, whatever k.
+constexpr int CAL_TOPK_MAX = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(CAL_THREADS)
+k_cal_topk(const T *__restrict__ stack, size_t P, int N, const float *__restrict__ thr, int k, int as_run,
+           float *__restrict__ out)
+{
+    const size_t p = (size_t)blockIdx.x * CAL_THREADS + threadIdx.x;
+    if (p >= P) return;
+    const float t = thr[p];
+    const float FMIN = -3.4028234663852886e38f;          // np.finfo(np.float32).min
+    float top[CAL_TOPK_MAX + 1];                         // ascending: top[0] is the smallest of the kept values
+    const int m = k + 1;
+    for (int i = 0; i < m; i++) top[i] = FMIN;
+    for (int f = 0; f < N; f++) {
+        const float v = (float)stack[(size_t)f * P + p];
+        if (v > t && v > top[0]) {
+            // replace the smallest kept value and restore the order
+            int i = 0;
+            while (i + 1 < m && top[i + 1] < v) { top[i] = top[i + 1]; i++; }
+            top[i] = v;
+        }
+    }
+    if (as_run) top[0] = top[1] = top[m - 1];            // k + 1 copies of the maximum
+    out[p] = (float)(((double)(top[0] + top[1])) / 2.0);  // float32 sum (may overflow to -inf), then the halving
+}
+
+int launch_cal_topk(rc_ctx *ctx, int itemsize, const void *stack, size_t P, int N, const float *thr, int k, int as_run,
+                    float *out, cudaStream_t st)
+{
+    if (N <= 0 || P == 0) return 0;
+    if (k < 1 || k > CAL_TOPK_MAX - 1) RC_FAIL(ctx, -1, "expected_n_events must be 1..%d (got %d)", CAL_TOPK_MAX - 1, k);
+    const unsigned grid = (unsigned)((P + CAL_THREADS - 1) / CAL_THREADS);
+    if (itemsize == 2) k_cal_topk<uint16_t><<<grid, CAL_THREADS, 0, st>>>((const uint16_t *)stack, P, N, thr, k, as_run, out);
+    else k_cal_topk<uint8_t><<<grid, CAL_THREADS, 0, st>>>((const uint8_t *)stack, P, N, thr, k, as_run, out);
+    RC_LAUNCH_CHECK(ctx, "k_cal_topk");
+    return 0;
+}
+
 size_t median_std_workspace_bytes(size_t P) { return round_up(P * 4, 256) * 2 + 256; }
 
 template <typename T>

@@ -90,3 +90,5 @@ int launch_recalibrate(rc_ctx *ctx, int itemsize, const void *frames, const doub
 size_t median_std_workspace_bytes(size_t P);
 int launch_median_std(rc_ctx *ctx, int itemsize, const void *stack, size_t P, int N, float *med, float *sd, void *ws,
                       cudaStream_t st);
+int launch_cal_topk(rc_ctx *ctx, int itemsize, const void *stack, size_t P, int N, const float *thr, int k, int as_run,
+                    float *out, cudaStream_t st);

@@ -9,7 +9,8 @@ foreground fractions of the stats frames against each threshold frame).
 
 The reference reads the stack with pims (a .seq file); pims is not a dependency here: pass the frames as `data`
 ([nFrames, ny, nx] numpy array) or point `filepath` at a raw binary stack of `dtype` together with `shape=(ny, nx)`.
-`use_acc=True` (the per-pixel top-k thresholds of _get_pixel_thresh_2) is not implemented.  No CPU fallback.
+`use_acc=True` adds the per-pixel thresholds of _get_pixel_thresh_2 (:27-45) for sigma index `sigma_acc`
+(rc_pixel_thresholds).  No CPU fallback.
 """
 import os
 from datetime import datetime
@@ -62,11 +63,31 @@ def median_std(data, device=None, frames_per_upload=None):
         return med.cpu().numpy().reshape(ny, nx), sd.cpu().numpy().reshape(ny, nx)
 
 
+def pixel_thresholds(data, thr, expected_n_events, device=None, as_run=True):
+    """_get_pixel_thresh_2 (calibration.py:27-45) -> float32 [ny, nx].  As written: per pixel, the mean of the (k + 1)-th
+    and k-th largest of the stack values above thr[pixel] (k = expected_n_events; missing values count as the float32
+    minimum) -- as_run=False.  As it runs (numba 0.65; as_run=True, the default, bit-exact with the live reference): the
+    "remove the maximum" store of a float32 minimum into a list of unsigned integers changes nothing, so the result is
+    the largest value above thr[pixel] whatever k."""
+    import torch
+    from .._native import Context
+    ctx = Context(device)
+    a = np.ascontiguousarray(data)
+    if a.dtype not in (np.dtype(np.uint8), np.dtype(np.uint16)):
+        raise NotImplementedError('the GPU path handles uint8 / uint16 stacks (got %s)' % a.dtype)
+    n, ny, nx = a.shape
+    with torch.cuda.device(ctx.device):
+        stack = torch.from_numpy(a).to(ctx.device)
+        t = torch.from_numpy(np.ascontiguousarray(thr, dtype=np.float32).reshape(-1)).to(ctx.device)
+        out = torch.empty(ny * nx, dtype=torch.float32, device=ctx.device)
+        ctx.pixel_thresholds(a.dtype.itemsize, stack, n, ny * nx, t, int(expected_n_events), as_run, out)
+        torch.cuda.synchronize()
+        return out.cpu().numpy().reshape(ny, nx)
+
+
 def make_calibration_frames(filepath, dtype, nFrames, n_stats_frames, n_sigmas, savepath='', filename_prefix='',
-                            use_acc=False, sigma_acc=-1, data=None, shape=None, device=None):
+                            use_acc=False, sigma_acc=-1, data=None, shape=None, device=None, acc_as_run=True):
     from ..engine import WriteEngine
-    if use_acc:
-        raise NotImplementedError('use_acc (per-pixel top-k thresholds) is not implemented on the GPU path')
     if not filename_prefix.endswith('_'):
         filename_prefix += '_'
     start = datetime.now()
@@ -89,6 +110,7 @@ def make_calibration_frames(filepath, dtype, nFrames, n_stats_frames, n_sigmas, 
     stats = d[nFrames - n_stats_frames:nFrames]
     eng = None
     out = []
+    acc = None
     for i in range(n_sigmas):
         t = np.floor(_m + _fit_std * i).astype(dtype)
         t.tofile(os.path.join(savepath, filename_prefix + "_dark_ref_" + str(i) + ".bin"))
@@ -110,4 +132,15 @@ def make_calibration_frames(filepath, dtype, nFrames, n_stats_frames, n_sigmas, 
         print("Avg. electron count for sigma=" + str(i) + " is: " + str(avg_n_events))
         print("Avg. dose rate for sigma=" + str(i) + " is: " + str(avg_n_events / n_pixels_in_frame))
         print("")
-    return {'median': _m, 'std': _stds, 'sigma': _fit_std, 'thresholds': out}
+        if use_acc and i == sigma_acc:
+            expected_n_events = int(np.ceil(nFrames * (avg_n_events / n_pixels_in_frame)))
+            print(expected_n_events)
+            if expected_n_events < 2:
+                print("Unable to compute accurate thresholds: too few events in dataset")
+            else:
+                acc_t = pixel_thresholds(d, _m, expected_n_events, device=device, as_run=acc_as_run)
+                with np.errstate(invalid='ignore'):
+                    acc_t.astype(dtype).tofile(os.path.join(savepath, filename_prefix + "_dark_ref_" + str(i) + "A.bin"))
+                print(acc_t)
+                acc = acc_t
+    return {'median': _m, 'std': _stds, 'sigma': _fit_std, 'thresholds': out, 'accurate_thresholds': acc}

@@ -405,8 +405,22 @@ def test_calibration_golden(gold_dir, tmp_path):
         t = np.fromfile(str(tmp_path / ('c__dark_ref_%d.bin' % i)), dtype=np.uint16).reshape(z['thresholds'][i].shape)
         assert np.array_equal(t, z['thresholds'][i]), i
         assert np.array_equal(res['thresholds'][i], t)
-    with pytest.raises(NotImplementedError):
-        make_calibration_frames('unused.seq', np.uint16, n, 10, 4, data=z['stack'][:n], use_acc=True)
+    # the per-pixel "accurate" thresholds: as the live reference computes them (as_run) and as written (oracle)
+    from pyrecode_b200.utils.calibration import pixel_thresholds
+    d2 = z['stack2']
+    m2, _ = median_std(d2)
+    for k in (2, 5):
+        a = pixel_thresholds(d2, m2, k)
+        assert a.dtype == np.float32 and np.array_equal(a, z['acc_k%d' % k])
+        with np.errstate(all='ignore'):
+            assert np.array_equal(pixel_thresholds(d2, m2, k, as_run=False), orc.pixel_thresholds(d2, m2, k, as_run=False))
+    make_calibration_frames('unused.seq', np.uint16, n, 10, 4, savepath=str(tmp_path), filename_prefix='d', data=d2,
+                            use_acc=True, sigma_acc=2)
+    acc = np.fromfile(str(tmp_path / 'd__dark_ref_2A.bin'), dtype=np.uint16).reshape(z['acc_file'].shape)
+    assert np.array_equal(acc, z['acc_file'])
+    for i in range(4):
+        t = np.fromfile(str(tmp_path / ('d__dark_ref_%d.bin' % i)), dtype=np.uint16).reshape(z['acc_file'].shape)
+        assert np.array_equal(t, z['thresholds2'][i]), i
 
 
 @pytest.mark.parametrize('dtype,n', [(np.uint16, 64), (np.uint16, 257), (np.uint8, 33)])

@@ -150,3 +150,7 @@ def test_calibration_median_std_against_reference(gold_dir):
         assert np.array_equal(m, z['med_' + tag])
         assert np.allclose(s, z['std_' + tag], rtol=1e-6, atol=0)
     assert z['thresholds'].shape[0] == 4 and np.array_equal(z['thresholds'][0], np.floor(z['med_odd']).astype(np.uint16))
+    m2 = orc.median_std(z['stack2'])[0]
+    with np.errstate(all='ignore'):
+        for k in (2, 5):
+            assert np.array_equal(orc.pixel_thresholds(z['stack2'], m2, k), z['acc_k%d' % k])
