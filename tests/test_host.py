@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 import shutil
+import zlib
 
 import numpy as np
 import pytest
@@ -207,3 +208,66 @@ def test_no_gpu_means_loud_failure():
     from pyrecode_b200.engine import WriteEngine
     with pytest.raises(RuntimeError):
         WriteEngine(64, 64, 2, 12, 1)
+
+
+class _FakeEngine:
+    """stands in for a ReadEngine in the host-side staging code: a plain buffer instead of pinned memory"""
+    max_frames = 64
+
+    def __init__(self):
+        self.buf = np.zeros(1 << 16, dtype=np.uint8)
+
+    def block_buffer(self, nbytes, keep=0):
+        if self.buf.size < nbytes:
+            new = np.zeros(max(nbytes, 2 * self.buf.size), dtype=np.uint8)
+            new[:keep] = self.buf[:keep]
+            self.buf = new
+        return self.buf
+
+
+@pytest.mark.parametrize('name,inter', [('gold_a.rc1_part001', True), ('gold_a.rc1', False), ('gold_c_l3m1.rc3_part000', True)])
+def test_bulk_read_staging_offsets(gold_dir, name, inter):
+    """ReCoDeReader._read_block (the host half of read_frames_dense / sum_frames): the records of a batch land in the
+    staging block and the stream offsets / sizes it reports address exactly the reference-written streams"""
+    path = os.path.join(gold_dir, name)
+    if inter:
+        _, recs = orc.parse_part_file(path)
+    else:
+        _, recs = orc.parse_merged_file(path)
+    r = ReCoDeReader(path, is_intermediate=inter)
+    r.open(print_header=False)
+    eng = _FakeEngine()
+    got = 0
+    for n in (2, 64):                                    # two calls: the second continues where the first stopped
+        ids, nbytes, moff, msz, voff, vsz = r._read_block(n, eng)
+        for k, fid in enumerate(ids):
+            want = recs[got + k]
+            assert fid == want['frame_id']
+            # (the oracle's merged-file walker keeps the inflated payloads only)
+            assert zlib.decompress(bytes(eng.buf[moff[k]:moff[k] + msz[k]])) == want['map']
+            if 'cmap' in want:
+                assert bytes(eng.buf[moff[k]:moff[k] + msz[k]]) == want['cmap']
+            if voff is not None:
+                assert zlib.decompress(bytes(eng.buf[voff[k]:voff[k] + vsz[k]])) == want['vals']
+            assert moff[k] + msz[k] <= nbytes
+        got += len(ids)
+    assert got == len(recs)
+    assert r._read_block(4, eng)[0] == []                # end of file
+    r.rewind()
+    assert r._read_block(1, eng)[0] == [recs[0]['frame_id']]
+    r.close()
+
+
+def test_offline_utilities_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from scipy.sparse import coo_matrix
+    from pyrecode_b200.utils.calibration import median_std
+    from pyrecode_b200.utils.converters import recalibrate_l1
+    with pytest.raises(RuntimeError):
+        median_std(np.zeros((3, 8, 8), np.uint16))
+    frames = {0: {'data': coo_matrix(np.ones((8, 8), np.uint16))}}
+    with pytest.raises(RuntimeError):
+        recalibrate_l1(frames, original_calibration_frame=np.zeros((8, 8), np.uint16),
+                       new_calibration_frame=np.zeros((8, 8), np.uint16))
