@@ -30,17 +30,20 @@
 // ---- tile-local labelling ----------------------------------------------------------------------
 // One CTA per (tile, frame).  A tile of an electron-counting frame holds a few hundred foreground pixels in
 // puddles of a few pixels, so the work is organised per foreground pixel, not per map word:
-//   phase 1  every foreground pixel (position from k_reduce_tiles) tests its W / NW / N / NE neighbours on
-//            the shared-memory copy of the tile's map and appends the links it finds to a dense list
-//            (warp-aggregated).  Links to pixels of earlier tiles go to the tile's global cross-link list.
-//   phase 2  the dense list is processed with atomicMin unions in shared memory (all lanes busy).
+//   phase 1  every foreground pixel (value and position from k_reduce_tiles) probes its W / NW / N / NE
+//            neighbours on the shared-memory copy of the tile's map and takes ONE of them as its parent with a
+//            plain store (all of them precede it in raster order, so the parent entries form a forest).  The four
+//            earlier neighbours of a pixel are pairwise adjacent except NE with NW / W: only a pixel that has
+//            NE and (NW or W) but not N can join two trees, and only such pixels append a link to a short list.
+//            Links to pixels of earlier tiles go to the tile's global cross-link list.
+//   phase 2  the (few) listed links are united with atomicMin on the roots.
 //   phase 3  flatten; L2 folds each member's value into its root (max or sum).
 //   phase 4  parent[slot] = slot of the tile-local root (| UF_FLAG for non-roots), acc[slot].
 // A tile with more than CCL_CAP foreground pixels (> 6 % occupancy), or whose link lists overflow, is not
 // labelled here: it gets parent[slot] = slot, acc[slot] = value, tileovf = 1 and k_ccl_border links all of
 // its pixels with the global word-parallel path.
 constexpr int CCL_CAP = 2048;          // foreground pixels per tile handled in shared memory
-constexpr int CCL_LINKS = 2560;        // tile-local links
+constexpr int CCL_LINKS = 512;         // tile-local tree-joining links
 constexpr int CCL_XCAP = 256;          // cross-tile links per tile (global list)
 constexpr int CCL_HALO = 264;          // map words kept in front of the tile (multiple of 4): nx <= 8447
 constexpr int CCL_THREADS = 256;
@@ -54,6 +57,17 @@ __device__ __forceinline__ uint32_t atom_add_shared(uint32_t *p, uint32_t v)
     uint32_t old;
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
     return old;
+}
+
+// root of x in a shared-memory forest whose entries only ever decrease (any value read is a valid ancestor)
+__device__ __forceinline__ uint32_t find_shared(const uint32_t *parent, uint32_t x)
+{
+    uint32_t p = ((const volatile uint32_t *)parent)[x];
+    while (p != x) {
+        x = p;
+        p = ((const volatile uint32_t *)parent)[x];
+    }
+    return x;
 }
 
 // Centroid of one puddle with the reference's arithmetic (pyrecode/utils/converters.py): members are added in
@@ -111,10 +125,9 @@ ccl_tile(const int tile, const int f,
     __shared__ __align__(16) uint32_t s_maskx[CCL_HALO + TILE_WORDS];
     __shared__ __align__(16) uint16_t s_wpre[TILE_WORDS];
     __shared__ uint32_t s_parent[CCL_CAP];
-
-    __shared__ uint16_t s_pos[CCL_CAP];
-    __shared__ uint32_t s_links[CCL_LINKS];            // (a << 16) | b, tile-local slots; later: L2 statistics / L4 lists
-    uint32_t *s_acc = s_links;                         // L2: loaded after the unions have consumed the links
+    __shared__ uint16_t s_pos[L4 ? CCL_CAP : 4];
+    __shared__ uint32_t s_acc[CCL_CAP];                // L2: statistic per slot; L4: member-list heads
+    __shared__ uint32_t s_links[CCL_LINKS];            // (a << 16) | b, tile-local slots
     __shared__ __align__(16) uint32_t s_bot[L4 ? CCL_HALO : 4];     // first words of the next tile (zeros after the frame)
     __shared__ uint8_t s_open[L4 ? CCL_CAP : 4];       // pixel, then root: its puddle continues in another tile
     __shared__ uint32_t s_cmap[L4 ? TILE_WORDS : 4];   // centroid bits that fall inside the tile
@@ -147,95 +160,86 @@ ccl_tile(const int tile, const int f,
     const bool pow2 = (unx & (unx - 1u)) == 0;
     const uint32_t lg = 31 - __clz(unx);
     if (!overflow) {
+        // the first pixel values are requested before the barrier that publishes the map
+        uint32_t v_next = (uint32_t)t < total ? vp[t] : 0u;
 #pragma unroll
         for (int u = 0; u < CCL_MAPV; u++) reinterpret_cast<uint4 *>(s_maskx + CCL_HALO)[t + u * CCL_THREADS] = r_map[u];
         if (t < TILE_WORDS / 8) reinterpret_cast<uint4 *>(s_wpre)[t] = r_wpre;
         if (t < CCL_HALO / 4) reinterpret_cast<uint4 *>(s_maskx)[t] = r_halo;
         if (L4 && t < CCL_HALO / 4) reinterpret_cast<uint4 *>(s_bot)[t] = r_bot;
-        for (uint32_t i = t; i < total; i += CCL_THREADS) {
-            const uint32_t v = vp[i];
-            s_pos[i] = (uint16_t)v;
-            s_parent[i] = i;
-            if (L4) s_open[i] = 0;
-        }
         if (L4) for (int i = t; i < TILE_WORDS; i += CCL_THREADS) s_cmap[i] = 0;
         if (t == 0) { s_nlinks = 0; s_nx = 0; s_bad = 0; s_nlist = 0; s_nclosed = 0; }
         __syncthreads();
 
-        // ---- phase 1: link detection
+        // ---- phase 1: one parent per pixel, tree-joining links to the list
         uint2 *xl = xlinks + ti * CCL_XCAP;
         constexpr uint32_t HP = CCL_HALO * 32;         // halo pixels
-        for (uint32_t i0 = 0; i0 < total; i0 += CCL_THREADS) {
-            const uint32_t i = i0 + t;
-            uint32_t l0 = 0, l1 = 0, l2 = 0;           // local links found by this pixel: (i << 16) | other
-            uint32_t n = 0;
-            if (i < total) {
-                const uint32_t p = s_pos[i];
-                const uint32_t gp = base + p;
-                const uint32_t col = pow2 ? (gp & (unx - 1u)) : (gp % unx);
-                const bool hl = col > 0, hr = col + 1 < unx, up = gp >= unx;
-                const uint32_t e = p + HP;             // pixel index in the halo-extended map
-                const uint32_t q = e - unx;            // >= 1: the halo covers nx + 1 pixels
-                const bool bw = (s_maskx[(e - 1) >> 5] >> ((e - 1) & 31)) & 1u;
-                // NW, N, NE = three consecutive map bits from q - 1: one funnel shift over two words
-                const uint32_t uw = (q - 1) >> 5;
-                const uint32_t up3 = __funnelshift_r(s_maskx[uw], s_maskx[uw + 1], (q - 1) & 31);
-                const bool bnw = up3 & 1u, bn = up3 & 2u, bne = up3 & 4u;
-                // up to three links: W, and N or (NW, NE) -- NW / NE are implied when N is set
-                constexpr uint32_t NONE = 0xffffffffu;
-                const uint32_t c0 = (bw && hl) ? e - 1 : NONE;
-                const uint32_t c1 = !up ? NONE : (bn ? q : ((bnw && hl) ? q - 1 : NONE));
-                const uint32_t c2 = (up && !bn && bne && hr) ? q + 1 : NONE;
-                // candidates at or above HP are in this tile (branch-free slot lookups); the others are rare
-                const bool k0 = c0 != NONE && c0 >= HP, k1 = c1 != NONE && c1 >= HP, k2 = c2 != NONE && c2 >= HP;
-                const uint32_t q1 = k1 ? c1 - HP : 0u, q2 = k2 ? c2 - HP : 0u;
-                const uint32_t e0 = (i << 16) | (i - 1);
-                const uint32_t e1 = (i << 16) | (s_wpre[q1 >> 5] + __popc(s_mask[q1 >> 5] & ((1u << (q1 & 31)) - 1u)));
-                const uint32_t e2 = (i << 16) | (s_wpre[q2 >> 5] + __popc(s_mask[q2 >> 5] & ((1u << (q2 & 31)) - 1u)));
-                n = (uint32_t)k0 + (uint32_t)k1 + (uint32_t)k2;
-                l0 = k0 ? e0 : (k1 ? e1 : e2);
-                l1 = (k0 && k1) ? e1 : e2;
-                l2 = e2;
-                if ((c0 < HP) | (c1 < HP) | (c2 < HP)) {
-                    // neighbour in an earlier tile: (slot, neighbour PIXEL); k_ccl_border resolves its slot
-                    if (L4) s_open[i] = 1;
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const uint32_t ce = c == 0 ? c0 : (c == 1 ? c1 : c2);
-                        if (ce < HP) {
-                            const uint32_t k = atomicAdd(&s_nx, 1u);
-                            if (k < (uint32_t)CCL_XCAP) xl[k] = make_uint2(base + i, base - (HP - ce));
-                            else s_bad = 1;
-                        }
-                    }
+        constexpr uint32_t NONE = 0xffffffffu;
+        for (uint32_t i = t; i < total; i += CCL_THREADS) {
+            const uint32_t v = v_next;
+            if (i + CCL_THREADS < total) v_next = vp[i + CCL_THREADS];
+            const uint32_t p = v & 0xffffu;
+            if (L4) { s_pos[i] = (uint16_t)p; s_open[i] = 0; }
+            else s_acc[i] = v >> 16;
+            const uint32_t gp = base + p;
+            const uint32_t col = pow2 ? (gp & (unx - 1u)) : (gp % unx);
+            const bool hl = col > 0, hr = col + 1 < unx, up = gp >= unx;
+            const uint32_t e = p + HP;             // pixel index in the halo-extended map
+            const uint32_t q = e - unx;            // >= 1: the halo covers nx + 1 pixels
+            const bool bw = (s_maskx[(e - 1) >> 5] >> ((e - 1) & 31)) & 1u;
+            // NW, N, NE = three consecutive map bits from q - 1: one funnel shift over two words
+            const uint32_t uw = (q - 1) >> 5;
+            const uint32_t up3 = __funnelshift_r(s_maskx[uw], s_maskx[uw + 1], (q - 1) & 31);
+            const bool bnw = up3 & 1u, bn = up3 & 2u, bne = up3 & 4u;
+            // candidates: W; N, else NW; NE when N is clear (NW / NE next to a set N are linked through N's own W link)
+            const uint32_t c0 = (bw && hl) ? e - 1 : NONE;
+            const uint32_t c1 = !up ? NONE : (bn ? q : ((bnw && hl) ? q - 1 : NONE));
+            const uint32_t c2 = (up && !bn && bne && hr) ? q + 1 : NONE;
+            // candidates at or above HP are in this tile; the others (rare) lie in an earlier tile
+            const bool k0 = c0 != NONE && c0 >= HP, k1 = c1 != NONE && c1 >= HP, k2 = c2 != NONE && c2 >= HP;
+            uint32_t par = k0 ? i - 1 : i;
+            if (k1 | k2) {
+                const uint32_t qq = (k1 ? c1 : c2) - HP;
+                par = s_wpre[qq >> 5] + __popc(s_mask[qq >> 5] & ((1u << (qq & 31)) - 1u));
+            }
+            s_parent[i] = par;
+            // NE joins another tree than the parent's: with NW as parent, or as parent itself next to W
+            if (k2 & (k1 | k0)) {
+                uint32_t other = i - 1;
+                if (k1) {
+                    const uint32_t qq = c2 - HP;
+                    other = s_wpre[qq >> 5] + __popc(s_mask[qq >> 5] & ((1u << (qq & 31)) - 1u));
                 }
-                if (L4 && p + unx + 1 >= (uint32_t)TILE_PX && gp + unx < (uint32_t)ny * unx) {
-                    // last rows of the tile: a SW / S / SE neighbour in the next tile also opens the puddle
-                    bool any = false;
+                const uint32_t k = atom_add_shared(&s_nlinks, 1u);
+                if (k < (uint32_t)CCL_LINKS) s_links[k] = (i << 16) | other;
+            }
+            if ((c0 < HP) | (c1 < HP) | (c2 < HP)) {
+                // neighbour in an earlier tile: (slot, neighbour PIXEL); k_ccl_border resolves its slot
+                if (L4) s_open[i] = 1;
 #pragma unroll
-                    for (int d = -1; d <= 1; d++) {
-                        if ((d < 0 && !hl) || (d > 0 && !hr)) continue;
-                        const uint32_t tq = p + unx + (uint32_t)d;
-                        if (tq >= (uint32_t)TILE_PX) {
-                            const uint32_t o = tq - TILE_PX;
-                            any |= (s_bot[o >> 5] >> (o & 31)) & 1u;
-                        }
+                for (int c = 0; c < 3; c++) {
+                    const uint32_t ce = c == 0 ? c0 : (c == 1 ? c1 : c2);
+                    if (ce < HP) {
+                        const uint32_t k = atom_add_shared(&s_nx, 1u);
+                        if (k < (uint32_t)CCL_XCAP) xl[k] = make_uint2(base + i, base - (HP - ce));
+                        else s_bad = 1;
                     }
-                    if (any) s_open[i] = 1;
                 }
             }
-            // warp-aggregated append of n in {0..3} entries per lane
-            const uint32_t b0 = __ballot_sync(0xffffffffu, n & 1u), b1 = __ballot_sync(0xffffffffu, n & 2u);
-            const uint32_t lt = (1u << lane) - 1u;
-            const uint32_t pre = __popc(b0 & lt) + 2u * __popc(b1 & lt);
-            const uint32_t tot = __popc(b0) + 2u * __popc(b1);
-            uint32_t wbase = 0;
-            if (lane == 0 && tot) wbase = atom_add_shared(&s_nlinks, tot);
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            const uint32_t o = wbase + pre;
-            if (n > 0 && o < (uint32_t)CCL_LINKS) s_links[o] = l0;
-            if (n > 1 && o + 1 < (uint32_t)CCL_LINKS) s_links[o + 1] = l1;
-            if (n > 2 && o + 2 < (uint32_t)CCL_LINKS) s_links[o + 2] = l2;
+            if (L4 && p + unx + 1 >= (uint32_t)TILE_PX && gp + unx < (uint32_t)ny * unx) {
+                // last rows of the tile: a SW / S / SE neighbour in the next tile also opens the puddle
+                bool any = false;
+#pragma unroll
+                for (int d = -1; d <= 1; d++) {
+                    if ((d < 0 && !hl) || (d > 0 && !hr)) continue;
+                    const uint32_t tq = p + unx + (uint32_t)d;
+                    if (tq >= (uint32_t)TILE_PX) {
+                        const uint32_t o = tq - TILE_PX;
+                        any |= (s_bot[o >> 5] >> (o & 31)) & 1u;
+                    }
+                }
+                if (any) s_open[i] = 1;
+            }
         }
         __syncthreads();
         overflow = s_bad || s_nlinks > (uint32_t)CCL_LINKS;
@@ -258,29 +262,27 @@ ccl_tile(const int tile, const int f,
     }
     if (t == 0) { tileovf[ti] = 0; xcount[ti] = s_nx; }
 
-    // ---- phase 2: unions
+    // ---- phase 2: the tree-joining links (block-uniform count: no barrier when there is none)
     const uint32_t nl = s_nlinks;
-    for (uint32_t j = t; j < nl; j += CCL_THREADS) {
-        const uint32_t e = s_links[j];
-        uf_union(s_parent, e >> 16, e & 0xffffu);
+    if (nl) {
+        for (uint32_t j = t; j < nl; j += CCL_THREADS) {
+            const uint32_t e = s_links[j];
+            uf_union(s_parent, e >> 16, e & 0xffffu);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    // L4: members of each root as a linked list (head per root, next per member); the link list and the map
-    // words are consumed, their shared memory is reused
+    // L4: members of each root as a linked list (head per root, next per member); the map words are consumed,
+    // their shared memory is reused
     constexpr uint32_t NIL = 0xffffu;
-    uint32_t *s_head = s_links;
+    uint32_t *s_head = s_acc;
     uint16_t *s_next = reinterpret_cast<uint16_t *>(s_maskx);
     if (L4) {
         for (uint32_t i = t; i < total; i += CCL_THREADS) s_head[i] = NIL;
         __syncthreads();
     }
-    if (!L4) {
-        for (uint32_t i = t; i < total; i += CCL_THREADS) s_acc[i] = vp[i] >> 16;
-        __syncthreads();
-    }
     // ---- phase 3: flatten; L2 folds every member's value into its root (non-roots are never written again)
     for (uint32_t i = t; i < total; i += CCL_THREADS) {
-        const uint32_t r = uf_find_ro(s_parent, i);
+        const uint32_t r = find_shared(s_parent, i);
         if (r != i) {
             s_parent[i] = r;
             if (FOLD == 1) atomicMax(&s_acc[r], s_acc[i]);

@@ -113,6 +113,7 @@ class ReCoDeWriter:
         self._vc_n_pixels = None
         self._vc_dose_rate = 0.0
         self._vc_engine = None
+        self._val_engine = None
         self._source_shape = None
 
     # ------------------------------------------------------------------------------------------
@@ -330,7 +331,13 @@ class ReCoDeWriter:
         from .engine import WriteEngine
         fh = frame.cpu().numpy() if isinstance(frame, torch.Tensor) else np.asarray(frame)
         self._validation_file.write(fh.tobytes())
-        maps, _, _ = self._engine.reduce(fh[None])
+        # a private one-frame engine (own context, workspace, pinned staging and device buffers): the batch engine's
+        # slots hold the batches that are still in flight while a finished batch is validated
+        if self._val_engine is None:
+            be = self._engine
+            self._val_engine = WriteEngine(be.ny, be.nx, be.itemsize, be.bit_depth, 3, max_frames=1, device=self._device)
+            self._val_engine.thr = be.thr
+        maps, _, _ = self._val_engine.reduce(fh[None])
         ny, nx = self._header['ny'], self._header['nx']
         bits = np.unpackbits(np.frombuffer(maps[0], dtype=np.uint8), bitorder='little')[:ny * nx].reshape(ny, nx)
         roi = self._vc_roi

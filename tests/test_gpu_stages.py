@@ -174,6 +174,26 @@ def test_l2_reduce(ny, nx, b, occ, stat):
         assert packed[f] == v, first_diff(packed[f], v)
 
 
+
+@pytest.mark.parametrize('stat', [0, 2])
+@pytest.mark.parametrize('ny,nx,b,occ', [(37, 53, 8, 0.2), (128, 256, 5, 0.1), (512, 512, 8, 0.03), (300, 1000, 5, 0.15),
+                                         (257, 4096, 8, 0.02)])
+def test_l2_reduce_uint8_source(ny, nx, b, occ, stat):
+    """itemsize-1 sources (what misc.map_dtype selects for bit depths <= 8, pyrecode/misc.py:41-71): raw values and
+    thresholds are bytes; the per-puddle sum is kept modulo 2^b by the packer"""
+    rng = np.random.default_rng(ny + b + stat + 77)
+    frames, dark = make_frames(rng, 2, ny, nx, np.uint8, (1 << b) - 1, occ)
+    eng = engine(ny, nx, 1, b, 2, l2=stat, F=2)
+    eng.set_threshold(dark, 3)
+    maps, packed, counts = eng.reduce(frames)
+    thr = orc.make_threshold(dark, 3, dtype=np.uint8)
+    for f in range(2):
+        m, v, n = orc.reduce_frame(frames[f].astype(np.uint16), thr.astype(np.uint16), 2, b, l2_statistics=stat)
+        assert counts[f] == n
+        assert maps[f] == m
+        assert packed[f] == v, first_diff(packed[f], v)
+
+
 def _cross_tile_frames(ny, nx, rng, vmax):
     """Frames whose puddles cross the 32768-pixel tile boundaries of the labelling kernel in every way:
     full-height vertical lines, diagonals, U shapes closed only in a later tile, combs, one tile dense enough
@@ -238,6 +258,24 @@ def test_l4_cross_tile_puddles(ny, nx):
         m, v, n = orc.reduce_frame(frames[f], dark, 4, 12)
         assert counts[f] == n == k
         assert maps[f] == m, first_diff(maps[f], m)
+
+
+
+@pytest.mark.parametrize('level,stat', [(2, 0), (2, 2), (4, 0)])
+@pytest.mark.parametrize('ny,nx,b', [(512, 512, 8), (300, 1000, 5), (257, 4096, 8)])
+def test_cross_tile_puddles_uint8_source(ny, nx, b, level, stat):
+    rng = np.random.default_rng(ny * 13 + nx + stat + level)
+    frames = _cross_tile_frames(ny, nx, rng, (1 << b) - 1).astype(np.uint8)
+    dark = np.zeros((ny, nx), np.uint8)
+    eng = engine(ny, nx, 1, b, level, l2=stat, F=4)
+    eng.set_threshold(dark, 0)
+    maps, packed, counts = eng.reduce(frames)
+    for f in range(4):
+        m, v, n = orc.reduce_frame(frames[f].astype(np.uint16), dark.astype(np.uint16), level, b, l2_statistics=stat)
+        assert counts[f] == n, 'frame %d: %d puddles, expected %d' % (f, counts[f], n)
+        assert maps[f] == m, 'frame %d: %s' % (f, first_diff(maps[f], m))
+        if level == 2:
+            assert packed[f] == v, 'frame %d: %s' % (f, first_diff(packed[f], v))
 
 
 def test_l2_synthetic_4096():
@@ -513,20 +551,21 @@ def test_randomized_geometries_all_levels():
     rng = np.random.default_rng(20261018)
     shapes = [(1, 70000 // 7), (2049, 17), (33, 1025), (64, 8448), (5, 8449), (700, 257), (129, 255), (1, 40000),
               (40000, 1), (96, 4096), (17, 33000)]
-    for case in range(26):
+    for case in range(40):
         ny, nx = shapes[case % len(shapes)] if case < 16 else (int(rng.integers(1, 400)), int(rng.integers(1, 3000)))
-        b = int(rng.choice([9, 12, 16]))
+        b = int(rng.choice([9, 12, 16, 8, 5]))
+        isz, dt = (1, np.uint8) if b <= 8 else (2, np.uint16)
         occ = float(rng.choice([0.002, 0.02, 0.08, 0.3, 0.7]))
         level = int(rng.choice([1, 2, 2, 4, 4, 3]))
         l2 = int(rng.choice([0, 2]))
         l4 = int(rng.choice([0, 2, 3]))
-        frames, dark = make_frames(rng, 2, ny, nx, np.uint16, (1 << b) - 1, occ)
-        eng = engine(ny, nx, 2, b, level, l2=l2, l4=l4, F=2)
+        frames, dark = make_frames(rng, 2, ny, nx, dt, (1 << b) - 1, occ)
+        eng = engine(ny, nx, isz, b, level, l2=l2, l4=l4, F=2)
         eng.set_threshold(dark, 2)
         maps, packed, counts = eng.reduce(frames)
-        thr = orc.make_threshold(dark, 2)
+        thr = orc.make_threshold(dark, 2, dtype=dt).astype(np.uint16)
         for f in range(2):
-            m, v, n = orc.reduce_frame(frames[f], thr, level, b, l2_statistics=l2, l4_centroiding=l4)
+            m, v, n = orc.reduce_frame(frames[f].astype(np.uint16), thr, level, b, l2_statistics=l2, l4_centroiding=l4)
             tag = 'case %d: %dx%d b=%d occ=%g level=%d l2=%d l4=%d frame %d' % (case, ny, nx, b, occ, level, l2, l4, f)
             assert counts[f] == n, tag
             assert maps[f] == m, tag + ' map ' + first_diff(maps[f], m)
