@@ -14,7 +14,10 @@ import numpy as np
 
 class Reader:
 
-    def __init__(self):
+    def __init__(self, device=None):
+        """device: CUDA device index of this Reader's context and buffers (an extension; the reference takes no
+        arguments, pyrecode.cpp:41-55); None = the current device"""
+        self._device = device
         self.ny = 0
         self.nx = 0
         self.bit_depth = 0
@@ -28,7 +31,7 @@ class Reader:
     def _context(self):
         if self._ctx is None:
             from ._native import Context
-            self._ctx = Context()
+            self._ctx = Context(self._device)
         return self._ctx
 
     def _engine(self, level):
@@ -36,14 +39,18 @@ class Reader:
             from .engine import ReadEngine
             itemsize = 1 if self.bit_depth <= 8 else 2
             self._engines[level] = ReadEngine(self.ny, self.nx, itemsize, self.bit_depth, level,
-                                              rc_operation_mode=0, max_frames=1)
+                                              rc_operation_mode=0, max_frames=1, device=self._device)
         return self._engines[level]
 
     def get_frame_sparse(self, reduction_level, binary_map, packed_vals, out):
-        """fills `out` (writable buffer viewed as uint64) with (row, col, value) triples, returns n foreground"""
+        """fills `out` (writable buffer viewed as uint64) with (row, col, value) triples, returns n foreground.
+        As in the reference, only level 1 reads `packed_vals`; every other level emits value 1 for each set map bit
+        and ignores the second stream (reader.h:39-41) -- L2 statistics are unpacked by
+        bit_unpack_pixel_intensities."""
         level = 1 if reduction_level == 1 else 3
         eng = self._engine(level)
         eng.load([bytes(binary_map)], [bytes(packed_vals)] if level == 1 and packed_vals is not None else None)
+        eng.check()                                   # a map of the wrong length raises instead of reading zeros
         tri = eng.sparse()[0]
         dst = np.frombuffer(out, dtype=np.uint64)
         dst[:tri.size] = tri.ravel()

@@ -592,11 +592,15 @@ k_layout_records(const uint32_t *__restrict__ map_bytes, const uint32_t *__restr
         if (f < n_frames) {
             l0 = map_bytes[f];
             l1 = spf == 2 ? val_bytes[f] : 0;
-            len = hdr + l0 + l1;        // < 2^32: bounded by the records capacity check below
+            len = hdr + l0 + l1;        // one record: < 2^32 (two streams of < 2^31 bytes each)
         }
-        uint32_t total;
-        const uint32_t e = block_excl_scan<8>(len, s_warp, &total);
-        const uint64_t off = s_carry + e;
+        // the sum over a group of 256 records can pass 2^32: scan 16 MiB units and remainders separately
+        uint32_t total_hi, total_lo;
+        const uint32_t e_hi = block_excl_scan<8>(len >> 24, s_warp, &total_hi);
+        __syncthreads();
+        const uint32_t e_lo = block_excl_scan<8>(len & 0xffffffu, s_warp, &total_lo);
+        const uint64_t off = s_carry + ((uint64_t)e_hi << 24) + e_lo;
+        const uint64_t total = ((uint64_t)total_hi << 24) + total_lo;
         if (f < n_frames) {
             record_off[f] = off;
             map_dst[f] = off + hdr;

@@ -412,8 +412,10 @@ class ReadEngine:
         packed = self.inflated[F * self.stride:]
         return maps, packed
 
-    def check(self):
-        """Host-side validation after load(): stream status and sizes (raises ValueError like zlib.error would)."""
+    def check(self, packed_sizes=None):
+        """Host-side validation after load(): stream status and sizes (raises ValueError like zlib.error would).
+        packed_sizes: the bytes_in_packed_* metadata of the n frames -- the value stream must inflate to exactly that
+        many bytes (a valid but short stream would otherwise read as zeros out of the cleared output buffer)."""
         F, n = self.max_frames, self.n
         st = self.status.cpu().numpy()
         ob = self.out_bytes.cpu().numpy()
@@ -422,6 +424,9 @@ class ReadEngine:
                 raise ValueError('corrupt compressed stream in frame %d (status %d/%d)' % (f, st[f], st[F + f]))
             if ob[f] != self.map_bytes:
                 raise ValueError('binary map of frame %d inflates to %d bytes, expected %d' % (f, ob[f], self.map_bytes))
+            if self.has_vals and packed_sizes is not None and int(ob[F + f]) != int(packed_sizes[f]):
+                raise ValueError('value stream of frame %d inflates to %d bytes, the record says %d'
+                                 % (f, ob[F + f], int(packed_sizes[f])))
         return ob
 
     def sparse(self):

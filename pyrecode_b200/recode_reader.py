@@ -199,7 +199,11 @@ class ReCoDeReader:
         for i0 in range(0, len(raws), eng.max_frames):
             part = raws[i0:i0 + eng.max_frames]
             eng.load([r['binary_map'] for r in part], [r['pixvals'] for r in part] if level in (1, 2) else None)
-            sizes = eng.check()
+            pk = None
+            if level in (1, 2) and h['rc_operation_mode'] == 1:
+                name = 'bytes_in_packed_' + ('pixvals' if level == 1 else 'summary_stats')
+                pk = [int(mds[i0 + j][name]) for j in range(len(part))]
+            sizes = eng.check(pk)
             tri = eng.sparse()
             stats = eng.summary_stats(sizes) if level == 2 else [None] * len(part)
             for j, t in enumerate(tri):
@@ -337,6 +341,8 @@ class ReCoDeReader:
         level = h['reduction_level']
         two = level in (1, 2)
         vname = 'bytes_in_compressed_' + ('pixvals' if level == 1 else 'summary_stats')
+        pname = 'bytes_in_packed_' + ('pixvals' if level == 1 else 'summary_stats')
+        self._block_packed = pk = []                  # bytes the value streams must inflate to (ReadEngine.check)
         if self._current_frame_index == 0:
             self._fp.seek(self._frame_data_start_position, 0)
         ids, moff, msz, voff, vsz = [], [], [], [], []
@@ -349,6 +355,7 @@ class ReCoDeReader:
             names = [f['name'] for f in self._sm]
             i_map = names.index('bytes_in_compressed_binary_map')
             i_val = names.index(vname) if two else -1
+            i_pk = names.index(pname) if two else -1
             hlen = 4 + 4 * nf
             start = fpos = self._fp.tell()
             while len(ids) < n:
@@ -364,6 +371,7 @@ class ReCoDeReader:
                 moff.append(fpos - start + hlen); msz.append(n_map)
                 if two:
                     voff.append(fpos - start + hlen + n_map); vsz.append(n_val)
+                    pk.append(int(rec[1 + i_pk]))
                 fpos += hlen + n_map + n_val
             pos = fpos - start
             if ids:
@@ -387,6 +395,7 @@ class ReCoDeReader:
                     moff.append(int(rel[k])); msz.append(n_map)
                     if two:
                         voff.append(int(rel[k]) + n_map); vsz.append(int(md[vname]))
+                        pk.append(int(md[pname]))
                 pos = total
                 self._current_frame_index = z1
         if not two:
@@ -434,7 +443,7 @@ class ReCoDeReader:
             t0 = time.perf_counter()
             if eng in pending:                         # its previous batch: validate before reusing the buffers
                 eng.stream.synchronize()
-                eng.check()
+                eng.check(eng.expect_packed)
                 pending.remove(eng)
             eng.wait_block_free()
             t1 = time.perf_counter()
@@ -444,6 +453,7 @@ class ReCoDeReader:
             st['file_read_s'] += t2 - t1
             if not bi:
                 break
+            eng.expect_packed = self._block_packed or None
             eng.stream.wait_stream(torch.cuda.current_stream(eng.dev))
             with torch.cuda.stream(eng.stream):
                 eng.load_block(nbytes, moff, msz, voff, vsz)
@@ -456,7 +466,7 @@ class ReCoDeReader:
         t0 = time.perf_counter()
         for eng in pending:
             eng.stream.synchronize()
-            eng.check()
+            eng.check(eng.expect_packed)
             torch.cuda.current_stream(eng.dev).wait_stream(eng.stream)
         st['wait_s'] += time.perf_counter() - t0
         return ids
