@@ -102,6 +102,16 @@ class WriteEngine:
         dst.copy_(src, non_blocking=True)
         return dst, src.numel() * src.element_size()
 
+    def pinned_input(self, n):
+        """-> pinned CPU tensor [n, ny, nx] of the slot the next submit() will use: a source that can fill it in place
+        (a file read) saves the staging copy.  The slot must have been collected."""
+        s = self.slots[self._next]
+        if s.busy:
+            raise RuntimeError('slot %d still holds an uncollected batch' % self._next)
+        if s.pin_in is None:
+            s.pin_in = torch.empty((self.max_frames, self.ny, self.nx), dtype=self.t_dtype).pin_memory()
+        return s.pin_in[:n]
+
     # ---- the hot path ------------------------------------------------------------------------------
     def launch(self, frames_dev, n, first_frame_id, slot=0):
         """Asynchronous: all kernels of one batch on the CURRENT stream, using the buffers of `slot`."""

@@ -198,8 +198,17 @@ class ReCoDeWriter:
             ft = self._input_params.source_file_type
             if ft == rc.FILE_TYPE_BINARY:
                 self._source_shape = (self._header['nz'], self._header['ny'], self._header['nx'])
-            elif ft in (rc.FILE_TYPE_MRC, rc.FILE_TYPE_SEQ):
-                raise NotImplementedError('MRC / SEQ sources need mrcfile / pims; pass data= instead')
+            elif ft == rc.FILE_TYPE_SEQ:
+                # frames present in the chunk right now (the header's count may be ahead of the file while the
+                # acquisition is writing: recode_writer.py:330-347 falls back to frame-by-frame reads for that)
+                from .em_reader import SEQReader
+                with SEQReader(self._init_params.image_filename) as f:
+                    self._source_shape = tuple(f.shape)
+                    if np.dtype(f.dtype).itemsize != np.dtype(self._src_dtype).itemsize:
+                        raise RuntimeError('Sequence file holds %s pixels, the params say %s'
+                                           % (np.dtype(f.dtype).name, np.dtype(self._src_dtype).name))
+            elif ft == rc.FILE_TYPE_MRC:
+                raise NotImplementedError('MRC sources need mrcfile; pass data= instead')
             else:
                 raise NotImplementedError("No implementation available for loading calibration file of type 'Other'")
         else:
@@ -221,6 +230,11 @@ class ReCoDeWriter:
         import torch
         run_metrics = {}
         self._do_sanity_checks(data)
+        if self._is_first_chunk and data is None and self._input_params.source_file_type == rc.FILE_TYPE_SEQ:
+            # the source header follows the ReCoDe header (recode_writer.py:267-270); for SEQ sources the reference
+            # stores 1024 zero bytes (em_reader.py:296-300)
+            self._intermediate_file.write(bytes(1024))
+            self._intermediate_file.flush()
         self._is_first_chunk = False
 
         if self._init_params.mode == 'batch':
@@ -235,7 +249,13 @@ class ReCoDeWriter:
         available_frames = min(n_frames_per_thread, max(n_frames_in_chunk - frame_offset, 0))
 
         stt = datetime.now()
-        if data is None:
+        seq = None
+        if data is None and self._input_params.source_file_type == rc.FILE_TYPE_SEQ:
+            # read batch by batch straight into the engine's pinned staging buffers (below)
+            from .em_reader import SEQReader
+            seq = SEQReader(self._init_params.image_filename)
+            available_frames = min(available_frames, max(seq.shape[0] - frame_offset, 0))
+        elif data is None:
             itemsize = np.dtype(self._src_dtype).itemsize
             off = self._input_params.source_header_length + \
                 (self._input_params.frame_offset + frame_offset) * self._frame_sz
@@ -248,7 +268,7 @@ class ReCoDeWriter:
         else:
             data = data[frame_offset:frame_offset + available_frames]
         on_device = isinstance(data, torch.Tensor) and data.is_cuda
-        if not on_device and isinstance(data, np.ndarray) and data.dtype != self._src_dtype:
+        if seq is None and not on_device and isinstance(data, np.ndarray) and data.dtype != self._src_dtype:
             warnings.warn('Source data type either not as specified or does not match params specs. Attempting to cast.')
             data = data.astype(self._src_dtype)
         run_metrics['run_data_read_time'] = datetime.now() - stt
@@ -305,13 +325,19 @@ class ReCoDeWriter:
         for b0 in range(0, available_frames, F):
             n = min(F, available_frames - b0)
             first_id = self._chunk_offset + frame_offset + b0
-            batch = data[b0:b0 + n]
+            if seq is not None:
+                batch = eng.pinned_input(n)                   # the next slot's staging buffer (its last batch is done)
+                seq.read_into(batch.numpy().view(self._src_dtype), frame_offset + b0, frame_offset + b0 + n)
+            else:
+                batch = data[b0:b0 + n]
             ticket = (eng.submit(batch, first_frame_id=first_id), first_id, batch, n)
             if pending is not None:
                 finish(pending)
             pending = ticket
         if pending is not None:
             finish(pending)
+        if seq is not None:
+            seq.close()
         self._intermediate_file.flush()
         for k in keys:
             run_metrics[k] = timedelta(milliseconds=gpu_ms[k])
