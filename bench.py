@@ -206,6 +206,8 @@ def parity_check(eng, level, dark, frames, F, ids_of_slot):
     thr = orc.make_threshold(dark.astype(np.uint16), eps_of()).astype(np.uint16)
     expect = [orc.reduce_frame(np.ascontiguousarray(f, dtype=np.uint16), thr, level, BIT_DEPTH) for f in frames]
     checked = 0
+    ours_bytes = zlib1_bytes = 0
+    z1 = [len(zlib.compress(m, 1)) + (len(zlib.compress(v, 1)) if level <= 2 else 0) for m, v, _ in expect]
     for k, sl in enumerate(eng.slots):
         if ids_of_slot[k] is None:
             continue
@@ -222,7 +224,9 @@ def parity_check(eng, level, dark, frames, F, ids_of_slot):
             if level <= 2 and zlib.decompress(cv) != v:
                 return False, 'slot %d frame %d: value stream' % (k, i)
             checked += 1
-    return True, '%d records of %d slots' % (checked, len(eng.slots))
+            ours_bytes += len(cm) + (len(cv) if cv is not None else 0)
+            zlib1_bytes += z1[i % len(z1)]
+    return True, '%d records of %d slots' % (checked, len(eng.slots)), ours_bytes / max(zlib1_bytes, 1)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -612,6 +616,7 @@ def main():
             'ms_per_launch': ms_total / (args.steps * M),
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'parity_checked': bool(parity[0]) if parity else False, 'parity_detail': parity[1] if parity else 'skipped',
+            'compressed_bytes_vs_zlib1': parity[2] if parity and len(parity) > 2 else None,
             'roofline': {'bound': 'hbm', 'kernel': 'k_reduce_tiles_bulk', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': ncu_traffic(level, F), 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': F * frame_bytes, 'kernel_ms': k1_ms},

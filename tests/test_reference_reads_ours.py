@@ -1,0 +1,100 @@
+"""CPU, build container only: files written by the GPU ReCoDeWriter (tests/golden/ours_*, produced on the B200 box by
+tests/make_ours_golden.py) are opened by the UNMODIFIED reference ReCoDeReader (pyrecode/recode_reader.py:39-61,
+223-273, 188-221) and every frame is compared with the input -- the reverse direction of the on-disk contract
+(SURVEY Appendix A).  Skipped where /root/reference does not exist (the GPU box)."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+REF = '/root/reference'
+REF_EXT = os.path.join(ROOT, 'oracle', '_ref')
+
+pytestmark = pytest.mark.skipif(
+    not os.path.isdir(os.path.join(REF, 'pyrecode')) or not os.path.isdir(REF_EXT) or not any(
+        f.startswith('c_recode') for f in os.listdir(REF_EXT)) or not os.path.exists(os.path.join(GOLD, 'ours_a.rc1')),
+    reason='needs the reference tree, its compiled extension (oracle/_ref) and the GPU-written fixtures')
+
+
+@pytest.fixture(scope='module')
+def ref_reader():
+    sys.dont_write_bytecode = True
+    np.int = int                                      # SURVEY B-8: alias removed from numpy >= 1.24
+    for p in (REF, REF_EXT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    with contextlib.redirect_stdout(io.StringIO()):
+        from pyrecode.recode_reader import ReCoDeReader
+    return ReCoDeReader
+
+
+def _inputs():
+    g = np.load(os.path.join(GOLD, 'gold_a_input.npz'))
+    data, dark, eps = g['data'], g['dark'], int(g['eps'])
+    thr = (dark + np.uint16(eps)).astype(np.uint16)
+    return data, thr
+
+
+def _read_all(ReCoDeReader, path, intermediate):
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = ReCoDeReader(path, is_intermediate=intermediate)
+        r.open(print_header=False)
+        for _ in range(r.get_shape()[0]):
+            f = r.get_next_frame()
+            if f is None:
+                break
+            fid = int(list(f.keys())[0])
+            out[fid] = np.asarray(f[fid]['data'].todense())
+        r.close()
+    return out
+
+
+@pytest.mark.parametrize('name', ['ours_a.rc1', 'ours_m.rc1'])
+def test_reference_reads_our_merged_l1(ref_reader, name):
+    data, thr = _inputs()
+    frames = _read_all(ref_reader, os.path.join(GOLD, name), False)
+    assert sorted(frames) == list(range(data.shape[0]))
+    for z, d in frames.items():
+        assert np.array_equal(d, np.where(data[z] > thr, data[z] - thr, 0)), 'frame %d' % z
+
+
+def test_reference_random_access_on_our_merged_file(ref_reader):
+    data, thr = _inputs()
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = ref_reader(os.path.join(GOLD, 'ours_m.rc1'), is_intermediate=False)
+        r.open(print_header=False)
+        for z in (5, 0, 7, 3):
+            f = r.get_frame(z)
+            assert np.array_equal(np.asarray(f[z]['data'].todense()), np.where(data[z] > thr, data[z] - thr, 0))
+        r.close()
+
+
+@pytest.mark.parametrize('name', ['ours_a.rc1_part000', 'ours_a.rc1_part001', 'ours_a.rc1_part002', 'ours_c9.rc1_part000',
+                                  'ours_m0.rc1_part000'])
+def test_reference_reads_our_part_files_l1(ref_reader, name):
+    data, thr = _inputs()
+    frames = _read_all(ref_reader, os.path.join(GOLD, name), True)
+    assert frames
+    for z, d in frames.items():
+        assert np.array_equal(d, np.where(data[z] > thr, data[z] - thr, 0)), 'frame %d' % z
+    if name.startswith('ours_a'):
+        node = int(name[-3:])
+        per = -(-data.shape[0] // 3)
+        assert sorted(frames) == list(range(node * per, min((node + 1) * per, data.shape[0])))
+    else:
+        assert sorted(frames) == list(range(data.shape[0]))
+
+
+@pytest.mark.parametrize('name,inter', [('ours_l3.rc3_part000', True), ('ours_l3_mg.rc3', False)])
+def test_reference_reads_our_l3(ref_reader, name, inter):
+    data, thr = _inputs()
+    frames = _read_all(ref_reader, os.path.join(GOLD, name), inter)
+    assert sorted(frames) == list(range(data.shape[0]))
+    for z, d in frames.items():
+        assert np.array_equal(d != 0, data[z] > thr), 'frame %d' % z
