@@ -525,10 +525,16 @@ def main():
     # (outside the timed region; the dominant kernel is timed alone here, which is what `roofline` reports)
     nprof = 5
     eng.ctx.set_pipelined(False)              # one batch at a time: every kernel gets the whole GPU
+    eng.ctx.profile_enable(2)
+    detail = None
     for s in range(nprof):
         eng.launch(d_frames, F, 0)
         stage_ms += np.array(eng.ctx.profile_read()[:4])
+        d = np.array(eng.ctx.profile_read_detail())
+        detail = d if detail is None else detail + d
     stage_ms /= nprof
+    detail = [float(x) / nprof for x in detail] if detail is not None else None
+    eng.ctx.profile_enable(1)
     eng.ctx.set_pipelined(nsl > 1)
     st = int(eng.status.cpu()[0])
     offs = eng.offsets.cpu().numpy()
@@ -622,6 +628,7 @@ def main():
                          'algorithmic_bytes_per_launch': F * frame_bytes, 'kernel_ms': k1_ms},
             'stage_ms_per_launch': dict(zip(['threshold_pack_compact', 'reduce_rest', 'deflate', 'assemble'],
                                             [float(x) for x in stage_ms])),
+            'stage2_kernel_ms_per_launch': detail,
             'record_bytes_per_frame': rec_bytes / F, 'status': st}
     if rd is not None:
         line['read'] = rd

@@ -62,6 +62,10 @@ int          rc_sm_count(const rc_ctx *ctx);
  * timing of the last rc_reduce_compress call and a count of kernels launched through the context */
 int                 rc_profile_enable(rc_ctx *ctx, int on);
 int                 rc_profile_read(rc_ctx *ctx, float *ms, int capacity);   /* returns number of stages (4) */
+/* rc_profile_enable(ctx, 2) additionally records one event after every kernel (group) of the reduction's second stage
+ * (labelling, cross-tile links, root compaction, scan, bit packing ...); this returns the elapsed milliseconds between
+ * them for the most recent call (a profiling aid of bench.py; no reference counterpart). */
+int                 rc_profile_read_detail(rc_ctx *ctx, float *ms, int capacity);
 unsigned long long  rc_launch_count(const rc_ctx *ctx);
 /* Tell the context that several contexts keep batches in flight on this GPU (one stream each).  rc_reduce_compress
  * then runs everything after the streaming kernel on context-owned high-priority streams and labels puddles with a
@@ -104,7 +108,8 @@ int rc_make_threshold(rc_ctx *ctx, const rc_config *cfg, const void *d_dark, uin
  * rc_reduce: threshold + binary map (recode_writer.py:437,456) and, per level, the second stream:
  *   L1 packed (frame - thr) of foreground pixels (:440,:461-477); L2 packed per-puddle max/sum (:443-446);
  *   L3 nothing; L4 the map becomes the centroid map (:448-449).
- * d_maps: n_frames x rc_map_stride_words(P) uint32.  d_packed: n_frames x rc_packed_stride_bytes(cfg).
+ * d_maps: n_frames x rc_map_stride_words(P) uint32, 16-byte aligned (the labelling kernels fetch it with bulk async
+ * copies).  d_packed: n_frames x rc_packed_stride_bytes(cfg).
  * d_packed_bytes[i] = ceil(count*b/8).  d_counts as above. */
 int rc_reduce(rc_ctx *ctx, const rc_config *cfg, const void *d_frames, int n_frames, const void *d_thr,
               void *d_workspace, size_t workspace_bytes,

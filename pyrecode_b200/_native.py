@@ -37,6 +37,7 @@ _SIGNATURES = {
     'rc_sm_count': (ctypes.c_int, [_vp]),
     'rc_profile_enable': (ctypes.c_int, [_vp, ctypes.c_int]),
     'rc_profile_read': (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
+    'rc_profile_read_detail': (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
     'rc_launch_count': (ctypes.c_ulonglong, [_vp]),
     'rc_set_pipelined': (ctypes.c_int, [_vp, ctypes.c_int]),
     'rc_map_stride_words': (_sz, [_sz]),
@@ -146,11 +147,17 @@ class Context:
         self._check(self._lib.rc_set_pipelined(self._h, 1 if on else 0), 'rc_set_pipelined')
 
     def profile_enable(self, on=True):
-        self._check(self._lib.rc_profile_enable(self._h, 1 if on else 0), 'rc_profile_enable')
+        self._check(self._lib.rc_profile_enable(self._h, int(on)), 'rc_profile_enable')
 
     def profile_read(self):
         buf = (ctypes.c_float * 8)()
         n = self._lib.rc_profile_read(self._h, buf, 8)
+        return [float(buf[i]) for i in range(n)]
+
+    def profile_read_detail(self):
+        """per-kernel milliseconds of the reduction's second stage (after profile_enable(2))"""
+        buf = (ctypes.c_float * 16)()
+        n = self._lib.rc_profile_read_detail(self._h, buf, 16)
         return [float(buf[i]) for i in range(n)]
 
     def launch_count(self):

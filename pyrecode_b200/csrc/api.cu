@@ -150,7 +150,10 @@ extern "C" int rc_create(rc_ctx **out, int device)
 extern "C" void rc_destroy(rc_ctx *ctx)
 {
     if (!ctx) return;
-    if (ctx->profile) for (int i = 0; i < RC_MAX_MARKS; i++) cudaEventDestroy(ctx->marks[i]);
+    if (ctx->profile) {
+        for (int i = 0; i < RC_MAX_MARKS; i++) cudaEventDestroy(ctx->marks[i]);
+        for (int i = 0; i < RC_MAX_DMARKS; i++) cudaEventDestroy(ctx->dmarks[i]);
+    }
     if (ctx->kept_tables) cudaFree(ctx->kept_tables);
     if (ctx->side_ready) {
         cudaStreamDestroy(ctx->side);
@@ -171,13 +174,28 @@ extern "C" int rc_profile_enable(rc_ctx *ctx, int on)
     if (!ctx) return -1;
     if (on && !ctx->profile) {
         for (int i = 0; i < RC_MAX_MARKS; i++) RC_CUDA(ctx, cudaEventCreate(&ctx->marks[i]));
-        ctx->profile = 1;
+        for (int i = 0; i < RC_MAX_DMARKS; i++) RC_CUDA(ctx, cudaEventCreate(&ctx->dmarks[i]));
         ctx->n_marks = 0;
+        ctx->n_dmarks = 0;
     } else if (!on && ctx->profile) {
         for (int i = 0; i < RC_MAX_MARKS; i++) cudaEventDestroy(ctx->marks[i]);
-        ctx->profile = 0;
+        for (int i = 0; i < RC_MAX_DMARKS; i++) cudaEventDestroy(ctx->dmarks[i]);
     }
+    ctx->profile = on < 0 ? 0 : (on > 2 ? 2 : on);      // 2 = also the per-kernel marks of stage 2 (rc_profile_read_detail)
     return 0;
+}
+
+// profile level 2: elapsed ms between the per-kernel marks of the most recent rc_reduce_compress call's second stage:
+// L2: labelling | cross-tile links + folds | root compaction | scan | bit packing;  L4: clear | labelling | cross-tile |
+// open puddles | scan;  L1: scan | bit packing
+extern "C" int rc_profile_read_detail(rc_ctx *ctx, float *ms, int capacity)
+{
+    if (!ctx || ctx->profile < 2 || ctx->n_dmarks < 2) return 0;
+    RC_CUDA(ctx, cudaEventSynchronize(ctx->dmarks[ctx->n_dmarks - 1]));
+    int n = 0;
+    for (int i = 0; i + 1 < ctx->n_dmarks && n < capacity; i++, n++)
+        RC_CUDA(ctx, cudaEventElapsedTime(&ms[n], ctx->dmarks[i], ctx->dmarks[i + 1]));
+    return n;
 }
 
 extern "C" int rc_profile_read(rc_ctx *ctx, float *ms, int capacity)
@@ -284,9 +302,14 @@ static int reduce_stage2(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const
 {
     const int level = cfg->reduction_level, b = cfg->bit_depth, isz = cfg->itemsize;
     int rc;
+    ctx->n_dmarks = 0;
+    rc_dmark(ctx, 0, st);
     if (level == 1) {
         if ((rc = launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, packed_bytes, b, st))) return rc;
-        return launch_bitpack(ctx, g, isz, w.vals, w.tilepre, F, b, packed, packed_stride, st);
+        rc_dmark(ctx, 1, st);
+        rc = launch_bitpack(ctx, g, isz, w.vals, w.tilepre, F, b, packed, packed_stride, st);
+        rc_dmark(ctx, 2, st);
+        return rc;
     }
     if (level == 3) return launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, nullptr, 0, st);
     if (level == 2) {
@@ -294,24 +317,36 @@ static int reduce_stage2(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const
         if ((rc = launch_ccl_tiles(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf,
                                    w.xcount, w.xlinks, w.parent, w.acc, 0, nullptr, nullptr, nullptr, nullptr, F,
                                    st))) return rc;
+        rc_dmark(ctx, 1, st);
         if ((rc = launch_ccl_border(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, w.acc,
                                     F, st))) return rc;
+        rc_dmark(ctx, 2, st);
         if ((rc = launch_ccl_roots(ctx, g, 1, w.tilecnt, w.parent, w.acc, nullptr, w.rootcnt, nullptr, w.stats16,
                                    nullptr, F, st))) return rc;
+        rc_dmark(ctx, 3, st);
         if ((rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, packed_bytes, b, st))) return rc;
-        return launch_bitpack(ctx, g, 2, w.stats16, w.rootpre, F, b, packed, packed_stride, st);
+        rc_dmark(ctx, 4, st);
+        rc = launch_bitpack(ctx, g, 2, w.stats16, w.rootpre, F, b, packed, packed_stride, st);
+        rc_dmark(ctx, 5, st);
+        return rc;
     }
     // level 4: puddles inside one tile are finished by k_ccl_tiles, the ones that cross tiles by k_l4_open
     RC_CUDA(ctx, cudaMemsetAsync(maps, 0, (size_t)F * g.MS * sizeof(uint32_t), st));
+    rc_dmark(ctx, 1, st);
     if ((rc = launch_ccl_tiles(ctx, g, 3, w.map1, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf, w.xcount,
                                w.xlinks, w.parent, w.acc, cfg->l4_centroiding, w.bbox, maps, nullptr, w.rootcnt, F,
                                st))) return rc;
+    rc_dmark(ctx, 2, st);
     if ((rc = launch_ccl_border(ctx, g, 3, w.map1, w.wordpre, w.tileovf, w.xcount, w.xlinks, w.parent, w.bbox, F,
                                 st))) return rc;
+    rc_dmark(ctx, 3, st);
     if ((rc = launch_l4_open(ctx, g, cfg->l4_centroiding, w.map1, w.wordpre, w.tilecnt, w.tileovf, w.xcount, w.xlinks,
                              w.parent, w.acc, w.bbox, (const uint32_t *)w.vals, maps, nullptr, w.rootcnt, F, st)))
         return rc;
-    return launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, nullptr, 0, st);
+    rc_dmark(ctx, 4, st);
+    rc = launch_scan_tiles(ctx, g, w.rootcnt, F, w.rootpre, counts, nullptr, 0, st);
+    rc_dmark(ctx, 5, st);
+    return rc;
 }
 
 // one deflate group (F streams; group 0 = maps, 1 = values): descriptors, then encode (wrap = 1) or size
@@ -376,6 +411,7 @@ extern "C" int rc_reduce(rc_ctx *ctx, const rc_config *cfg, const void *d_frames
     if (check_cfg(ctx, cfg)) return -1;
     if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames %d exceeds max_frames %d", n_frames, cfg->max_frames);
     if (workspace_bytes < rc_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
+    if (((uintptr_t)d_maps | (uintptr_t)d_workspace) % 16) RC_FAIL(ctx, -1, "d_maps and d_workspace must be 16-byte aligned");
     const Geom g = make_geom(cfg->ny, cfg->nx);
     Carver c(d_workspace);
     const ReduceWs w = carve_reduce(c, cfg, g, 0);

@@ -110,25 +110,36 @@ __device__ __forceinline__ bool centroid_pixel(float fr, float fc, int ny, int n
 
 // FOLD: 1 = L2 max, 2 = L2 sum, 3 = L4: centroids of the puddles that lie entirely inside the tile ("closed");
 // puddles that continue in another tile ("open") get a bounding box and are finished by k_l4_open.
+// One tile's inputs as the bulk-copy engine delivers them (cp.async.bulk, 16-byte granules): the map words of the
+// tile preceded by a halo of CCL_HALO words, the per-word prefixes, the first CCL_VPS (value, position) words of the
+// tile's foreground pixels and, for L4, the first CCL_HALO map words of the next tile.
+constexpr int CCL_VPS = 1024;
+template <bool L4>
+struct __align__(128) CclStage {
+    uint32_t maskx[CCL_HALO + TILE_WORDS];
+    uint16_t wpre[TILE_WORDS];
+    uint32_t vp[CCL_VPS];
+    uint32_t bot[L4 ? CCL_HALO : 4];
+};
+
 template <int FOLD>
 __device__ __forceinline__ void
-ccl_tile(const int tile, const int f,
-         const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT,
-         const uint32_t *__restrict__ tilecnt, const uint32_t *__restrict__ vp_all, uint8_t *__restrict__ tileovf,
+ccl_tile(const int tile, const int f, CclStage<FOLD == 3> &S, const uint32_t total, int NT, size_t MS,
+         const uint32_t *__restrict__ vp_all, uint8_t *__restrict__ tileovf,
          uint32_t *__restrict__ xcount, uint2 *__restrict__ xlinks, uint32_t *__restrict__ parent_all,
          uint32_t *__restrict__ acc_all, int ny, int nx, int l4mode, uint32_t *__restrict__ bbox_all,
          uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all, uint32_t *__restrict__ rootcnt)
 {
     constexpr bool L4 = FOLD == 3;
-    // map words of the tile preceded by a halo: the CCL_HALO words before the tile (zeros before the frame),
-    // so that the W / NW / N / NE probes of every pixel are plain shared-memory reads
-    __shared__ __align__(16) uint32_t s_maskx[CCL_HALO + TILE_WORDS];
-    __shared__ __align__(16) uint16_t s_wpre[TILE_WORDS];
+    // S.maskx: map words of the tile preceded by a halo (zeros before the frame), so that the W / NW / N / NE probes
+    // of every pixel are plain shared-memory reads
+    uint32_t *s_maskx = S.maskx;
+    uint16_t *s_wpre = S.wpre;
+    const uint32_t *s_bot = S.bot;
     __shared__ uint32_t s_parent[CCL_CAP];
     __shared__ uint16_t s_pos[L4 ? CCL_CAP : 4];
     __shared__ uint32_t s_acc[CCL_CAP];                // L2: statistic per slot; L4: member-list heads
     __shared__ uint32_t s_links[CCL_LINKS];            // (a << 16) | b, tile-local slots
-    __shared__ __align__(16) uint32_t s_bot[L4 ? CCL_HALO : 4];     // first words of the next tile (zeros after the frame)
     __shared__ uint8_t s_open[L4 ? CCL_CAP : 4];       // pixel, then root: its puddle continues in another tile
     __shared__ uint32_t s_cmap[L4 ? TILE_WORDS : 4];   // centroid bits that fall inside the tile
     __shared__ uint32_t s_nlinks, s_nx, s_bad, s_nlist, s_nclosed;
@@ -137,19 +148,9 @@ ccl_tile(const int tile, const int f,
     const uint32_t base = (uint32_t)tile << TILE_LOG2;
     const size_t slots = (size_t)NT * TILE_PX;
     const size_t sbase = (size_t)f * slots + base;
-    const size_t wo = (size_t)f * MS + (size_t)tile * TILE_WORDS;
     uint32_t *parent = parent_all + sbase;
     const uint32_t *vp = vp_all + sbase;
     const uint32_t *s_mask = s_maskx + CCL_HALO;
-    // issue the tile's loads before the (dependent) per-pixel ones
-    uint4 r_map[CCL_MAPV];
-#pragma unroll
-    for (int u = 0; u < CCL_MAPV; u++) r_map[u] = reinterpret_cast<const uint4 *>(maps + wo)[t + u * CCL_THREADS];
-    uint4 r_wpre = make_uint4(0, 0, 0, 0), r_halo = make_uint4(0, 0, 0, 0), r_bot = make_uint4(0, 0, 0, 0);
-    if (t < TILE_WORDS / 8) r_wpre = reinterpret_cast<const uint4 *>(wordpre_all + wo)[t];
-    if (t < CCL_HALO / 4 && tile > 0) r_halo = reinterpret_cast<const uint4 *>(maps + wo - CCL_HALO)[t];
-    if (L4 && t < CCL_HALO / 4 && tile + 1 < NT) r_bot = reinterpret_cast<const uint4 *>(maps + wo + TILE_WORDS)[t];
-    const uint32_t total = tilecnt[ti];
     if (total == 0) {
         if (t == 0) { tileovf[ti] = 0; xcount[ti] = 0; if (L4) rootcnt[ti] = 0; }
         return;
@@ -160,13 +161,6 @@ ccl_tile(const int tile, const int f,
     const bool pow2 = (unx & (unx - 1u)) == 0;
     const uint32_t lg = 31 - __clz(unx);
     if (!overflow) {
-        // the first pixel values are requested before the barrier that publishes the map
-        uint32_t v_next = (uint32_t)t < total ? vp[t] : 0u;
-#pragma unroll
-        for (int u = 0; u < CCL_MAPV; u++) reinterpret_cast<uint4 *>(s_maskx + CCL_HALO)[t + u * CCL_THREADS] = r_map[u];
-        if (t < TILE_WORDS / 8) reinterpret_cast<uint4 *>(s_wpre)[t] = r_wpre;
-        if (t < CCL_HALO / 4) reinterpret_cast<uint4 *>(s_maskx)[t] = r_halo;
-        if (L4 && t < CCL_HALO / 4) reinterpret_cast<uint4 *>(s_bot)[t] = r_bot;
         if (L4) for (int i = t; i < TILE_WORDS; i += CCL_THREADS) s_cmap[i] = 0;
         if (t == 0) { s_nlinks = 0; s_nx = 0; s_bad = 0; s_nlist = 0; s_nclosed = 0; }
         __syncthreads();
@@ -176,8 +170,7 @@ ccl_tile(const int tile, const int f,
         constexpr uint32_t HP = CCL_HALO * 32;         // halo pixels
         constexpr uint32_t NONE = 0xffffffffu;
         for (uint32_t i = t; i < total; i += CCL_THREADS) {
-            const uint32_t v = v_next;
-            if (i + CCL_THREADS < total) v_next = vp[i + CCL_THREADS];
+            const uint32_t v = i < (uint32_t)CCL_VPS ? S.vp[i] : vp[i];
             const uint32_t p = v & 0xffffu;
             if (L4) { s_pos[i] = (uint16_t)p; s_open[i] = 0; }
             else s_acc[i] = v >> 16;
@@ -397,9 +390,11 @@ ccl_tile(const int tile, const int f,
     if (t == 0) rootcnt[ti] = s_nclosed;
 }
 
-// The grid is either one CTA per (tile, frame) or, when the launcher limits it to a few CTAs per SM, a
-// persistent one that walks the (tile, frame) pairs with a grid stride: the labelling then shares every SM with
-// the streaming kernel of the next batch (memory-bound next to issue-bound work) instead of displacing it.
+// Persistent grid: every CTA walks the (tile, frame) pairs with a grid stride.  The inputs of the NEXT pair are
+// brought into the other half of a two-stage shared-memory ring by bulk async copies (one elected thread, one
+// mbarrier per stage) while the current pair is labelled, so no thread ever waits for a dependent global load: the
+// kernel runs at the speed of its instruction stream instead of that of four DRAM round trips per tile.  With a few
+// CTAs per SM it shares every SM with the streaming kernel of the next batch (memory-bound next to issue-bound work).
 template <int FOLD>
 __global__ void __launch_bounds__(CCL_THREADS)
 k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT, int n_tiles_total,
@@ -408,11 +403,55 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
             uint32_t *__restrict__ acc_all, int ny, int nx, int l4mode, uint32_t *__restrict__ bbox_all,
             uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all, uint32_t *__restrict__ rootcnt)
 {
-    for (int gt = blockIdx.x; gt < n_tiles_total; gt += gridDim.x) {
+    constexpr bool L4 = FOLD == 3;
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    CclStage<L4> *stage = reinterpret_cast<CclStage<L4> *>(s_dyn);        // [2]
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const int t = threadIdx.x;
+    if (t < 2) mbar_init(smem_u32(&s_bar[t]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const size_t slots = (size_t)NT * TILE_PX;
+    auto issue = [&](int gt, int stg) {                 // thread 0: all copies of one (tile, frame) pair
         const int f = gt / NT, tile = gt - f * NT;
-        ccl_tile<FOLD>(tile, f, maps, MS, wordpre_all, NT, tilecnt, vp_all, tileovf, xcount, xlinks, parent_all, acc_all,
+        const size_t wo = (size_t)f * MS + (size_t)tile * TILE_WORDS;
+        const uint32_t bar = smem_u32(&s_bar[stg]);
+        CclStage<L4> &S = stage[stg];
+        const bool halo = tile > 0, bot = L4 && tile + 1 < NT;
+        mbar_expect_tx(bar, (uint32_t)(TILE_WORDS * 4 + TILE_WORDS * 2 + CCL_VPS * 4 + (halo ? CCL_HALO * 4 : 0) +
+                                       (bot ? CCL_HALO * 4 : 0)));
+        if (halo) bulk_g2s(smem_u32(S.maskx), maps + wo - CCL_HALO, CCL_HALO * 4, bar);
+        bulk_g2s(smem_u32(S.maskx + CCL_HALO), maps + wo, TILE_WORDS * 4, bar);
+        bulk_g2s(smem_u32(S.wpre), wordpre_all + wo, TILE_WORDS * 2, bar);
+        bulk_g2s(smem_u32(S.vp), vp_all + (size_t)f * slots + ((size_t)tile << TILE_LOG2), CCL_VPS * 4, bar);
+        if (bot) bulk_g2s(smem_u32(S.bot), maps + wo + TILE_WORDS, CCL_HALO * 4, bar);
+    };
+    int gt = blockIdx.x;
+    if (gt >= n_tiles_total) return;
+    if (t == 0) issue(gt, 0);
+    uint32_t total = tilecnt[gt];
+    for (int j = 0; gt < n_tiles_total; gt += gridDim.x, j++) {
+        const int stg = j & 1;
+        const int nxt = gt + (int)gridDim.x;
+        uint32_t total_next = 0;
+        if (nxt < n_tiles_total) {
+            // the other stage was consumed by the previous iteration (barrier at the end of the loop body)
+            if (t == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(nxt, stg ^ 1);
+            }
+            total_next = tilecnt[nxt];
+        }
+        const int f = gt / NT, tile = gt - f * NT;
+        mbar_wait(smem_u32(&s_bar[stg]), (uint32_t)(j >> 1) & 1u);
+        CclStage<L4> &S = stage[stg];
+        // rows before the frame / after it read as background
+        if (tile == 0 && t < CCL_HALO / 4) reinterpret_cast<uint4 *>(S.maskx)[t] = make_uint4(0, 0, 0, 0);
+        if (L4 && tile + 1 >= NT && t < CCL_HALO / 4) reinterpret_cast<uint4 *>(S.bot)[t] = make_uint4(0, 0, 0, 0);
+        ccl_tile<FOLD>(tile, f, S, total, NT, MS, vp_all, tileovf, xcount, xlinks, parent_all, acc_all,
                        ny, nx, l4mode, bbox_all, map2_all, cent_all, rootcnt);
         __syncthreads();                               // the next tile reuses the shared arrays
+        total = total_next;
     }
 }
 
@@ -733,17 +772,25 @@ int launch_ccl_tiles(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps,
 {
     if (F <= 0) return 0;
     const int nt = F * g.NT;
+    // CTAs per SM: RECODE_B200_CCL_CTAS, else few when several batches share the GPU (the rest of every SM is left to
+    // the streaming kernel of the next batch), else what fits
+    const int fit = fold == 3 ? 4 : 5;
+    int per_sm = ctx->ccl_ctas_per_sm > 0 ? ctx->ccl_ctas_per_sm
+                                          : ((ctx->use_priority == 0 || !ctx->pipelined) ? fit : (fold == 3 ? 3 : 2));
+    if (per_sm > fit) per_sm = fit;
     unsigned grid = (unsigned)nt;
-    const int per_sm = ctx->ccl_ctas_per_sm >= 0 ? ctx->ccl_ctas_per_sm
-                                                 : ((ctx->use_priority == 0 || !ctx->pipelined) ? 0 : (fold == 3 ? 3 : 2));
-    if (per_sm > 0 && (unsigned)(per_sm * ctx->sm_count) < grid) grid = (unsigned)(per_sm * ctx->sm_count);
+    if ((unsigned)(per_sm * ctx->sm_count) < grid) grid = (unsigned)(per_sm * ctx->sm_count);
 #define RC_CT(FO)                                                                                              \
-    k_ccl_tiles<FO><<<grid, CCL_THREADS, 0, st>>>(maps, g.MS, wordpre, g.NT, nt, tilecnt, vp, tileovf, xcount,   \
-                                                  (uint2 *)xlinks, parent, acc, g.ny, g.nx, l4mode, bbox, map2,  \
-                                                  cent, rootcnt)
-    if (fold == 1) RC_CT(1);
-    else if (fold == 2) RC_CT(2);
-    else RC_CT(3);
+    {                                                                                                          \
+        constexpr size_t dyn = 2 * sizeof(CclStage<FO == 3>);                                                  \
+        RC_CUDA(ctx, cudaFuncSetAttribute(k_ccl_tiles<FO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+        k_ccl_tiles<FO><<<grid, CCL_THREADS, dyn, st>>>(maps, g.MS, wordpre, g.NT, nt, tilecnt, vp, tileovf, xcount, \
+                                                        (uint2 *)xlinks, parent, acc, g.ny, g.nx, l4mode, bbox, map2, \
+                                                        cent, rootcnt);                                        \
+    }
+    if (fold == 1) RC_CT(1)
+    else if (fold == 2) RC_CT(2)
+    else RC_CT(3)
 #undef RC_CT
     RC_LAUNCH_CHECK(ctx, "k_ccl_tiles");
     return 0;

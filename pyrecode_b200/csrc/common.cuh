@@ -38,6 +38,7 @@ constexpr int SEGS_PER_TILE_LOG2 = TILE_LOG2 - 8;
 constexpr uint32_t UF_FLAG = 0x80000000u;
 
 constexpr int RC_MAX_MARKS = 8;
+constexpr int RC_MAX_DMARKS = 12;
 
 struct rc_ctx {
     int device;
@@ -47,6 +48,9 @@ struct rc_ctx {
     int profile;                       // when set, stage boundaries of rc_reduce_compress record events
     int n_marks;
     cudaEvent_t marks[RC_MAX_MARKS];
+    // profile == 2: additionally one event after every kernel (group) of the reduction's second stage
+    int n_dmarks;
+    cudaEvent_t dmarks[RC_MAX_DMARKS];
     bool deflate_attr_set, inflate_attr_set;
     // side stream: the map streams are deflated while the main stream still labels puddles / packs values
     cudaStream_t side;
@@ -79,6 +83,14 @@ static inline void rc_mark(rc_ctx *ctx, int idx, cudaStream_t st)
     if (ctx->profile && idx < RC_MAX_MARKS) {
         cudaEventRecord(ctx->marks[idx], st);
         if (idx + 1 > ctx->n_marks) ctx->n_marks = idx + 1;
+    }
+}
+
+static inline void rc_dmark(rc_ctx *ctx, int idx, cudaStream_t st)
+{
+    if (ctx->profile >= 2 && idx < RC_MAX_DMARKS) {
+        cudaEventRecord(ctx->dmarks[idx], st);
+        if (idx + 1 > ctx->n_dmarks) ctx->n_dmarks = idx + 1;
     }
 }
 
@@ -212,3 +224,34 @@ __device__ __forceinline__ uint32_t word_slot_base(const uint16_t *__restrict__ 
 {
     return ((w >> TILE_WORDS_LOG2) << TILE_LOG2) + wordpre[w];
 }
+
+// ---- bulk async copies (cp.async.bulk, the 1-D form of TMA) completing on a shared-memory mbarrier ---------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    // try_wait suspends the warp in hardware; the bound turns a programming error into a trap, not a hang
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); spin++)
+        if (spin > (1u << 26)) __trap();
+}
+

@@ -238,35 +238,6 @@ k_reduce_tiles(const T *__restrict__ frames, const T *__restrict__ thr, size_t P
 // refills a stage as soon as the warp has consumed it -- no registers are spent on covering DRAM latency, the
 // raw values need no second staging copy (the compaction reads them where the copy engine put them), and no
 // load instruction is issued for the frame at all.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    // try_wait suspends the warp in hardware; the bound turns a programming error into a trap, not a hang
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); spin++)
-        if (spin > (1u << 26)) __trap();
-}
-
 constexpr int BULK_STAGES = 2;                 // sub-tiles in flight per warp (ring)
 template <typename T>
 constexpr size_t bulk_smem_bytes(bool thr_bulk) { return (size_t)BULK_STAGES * SUB_PX * sizeof(T) * (thr_bulk ? 2 : 1); }

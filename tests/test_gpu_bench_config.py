@@ -114,7 +114,7 @@ def test_validation_frames_do_not_disturb_batches_in_flight(tmp_path, level):
         out[gap] = open(os.path.join(str(d), 'val.rc%d_part000' % level), 'rb').read()
         if gap > 0:
             assert len(m['run_dose_rates']) == nz
-            vf = open(os.path.join(str(d), 'val.rc%d_part000_validation_frames.bin' % level), 'rb').read()
+            vf = open(os.path.join(str(d), 'val_part000_validation_frames.bin'), 'rb').read()
             assert vf == frames.tobytes()
             # dose rate = puddles of the central 128 x 128 ROI / ROI area (recode_writer.py:402-415)
             thr = orc.make_threshold(dark, EPS)
