@@ -435,7 +435,7 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
     const uint32_t total_chunks = chunk_base[n_streams];
 
     while (true) {
-        if (t == 0) { s_ticket = atomicAdd(&counters[2], 1u); s_adler[0] = 0; s_adler[1] = 0; S.overflow = 0; }
+        if (t == 0) { s_ticket = atomicAdd(&counters[2], 1u); s_adler[0] = 0; s_adler[1] = 0; S.overflow = 0; S.e_bad = 0; }
         __syncthreads();
         const uint32_t gci = s_ticket;
         if (gci >= total_chunks) break;
@@ -468,13 +468,25 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
             if ((t & 31) == 0 && (a | b)) { atomicAdd(&s_adler[0], a % 65521u); atomicAdd(&s_adler[1], b % 65521u); }
         }
 
-        uint32_t body_bits = 0, my_bits = 0;
+        uint32_t body_bits = 0, my_bits = 0, my_off = 0, n_nz = 0;
+        bool sparse = false;
         if (!stored) {
             if (t == 0) S.header_bits = hb;
-            my_bits = df_encode_segment(S, t, clen);
+            // few non-zero bytes (a binary map): encode from their list -- work per non-zero byte, equal shares
+            if (shared_table && !S.e_bad) {
+                uint32_t nz[2];
+                const uint32_t cnt = df_nz_masks(S.io, t, df_seg_bytes(t, clen), nz);
+                const uint32_t base = block_excl_scan<8>(cnt, s_warp, &n_nz);
+                sparse = n_nz <= (uint32_t)DF_STAGE_WORDS;
+                if (sparse) df_nz_scatter(S.io, S.priv, t, base, nz);
+                __syncthreads();
+                if (sparse) my_bits = df_sparse_bits(S, S.priv, t, n_nz, clen);
+            }
+            if (!sparse) my_bits = df_encode_segment(S, t, clen);
             uint32_t tok_bits;
             const uint32_t e = block_excl_scan<8>(my_bits, s_warp, &tok_bits);     // two barriers: encode pass is over
             S.tbits[t] = e;
+            my_off = hb + e;
             body_bits = hb + tok_bits;
             stored = S.overflow || df_dynamic_bytes(body_bits, (int)(S.tbl[256] >> 24)) >= (uint32_t)clen + 10u;
         } else {
@@ -488,7 +500,8 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
             const int ow = (int)((df_dynamic_bytes(body_bits, (int)(S.tbl[256] >> 24)) + 3 + 4) >> 2);
             for (int i = t; i < ow && i < DF_STAGE_WORDS; i += DF_THREADS) S.io[i] = i < hw ? T.header[i] : 0;
             __syncthreads();
-            df_place_segment(S, t, my_bits);
+            if (sparse) df_sparse_emit(S, S.priv, t, n_nz, clen, my_off);
+            else df_place_segment(S, t, my_bits);
             __syncthreads();
             if (t == 0) df_phase_finish(S, body_bits);
             __syncthreads();

@@ -48,10 +48,12 @@ constexpr int DF_SEG_WORDS = DF_SEG / 4;            // 16
 constexpr int DF_SEG_STRIDE = DF_SEG_WORDS + 1;     // staging stride in words: 17 -> bank-conflict free per-thread access
 constexpr int DF_STAGE_WORDS = DF_THREADS * DF_SEG_STRIDE;   // 4352 words = 17408 bytes
 constexpr int DF_NSYM = 288;                        // literal/length alphabet (286 used)
-constexpr int DF_LEN_SYMS = 277;                    // symbols a chunk can produce: 0..255, 256, 257..276 (length <= 64)
+constexpr int DF_LEN_SYMS = 286;                    // symbols a chunk can produce: 0..255, 256, 257..285 (length <= 258)
+constexpr int DF_MAX_MATCH = 258;
+constexpr int DF_ZRUN = DF_MAX_MATCH + 1;           // zero bytes one composite run token covers: literal 0 + match(258)
 constexpr int DF_SLOT_BYTES = DF_CHUNK + 64;        // scratch slot per chunk (multiple of 16)
 constexpr int DF_HDR_WORDS = 136;                   // 17 + 57 + 288 * 14 bits worst case
-constexpr int DF_NTBL = DF_NSYM + DF_SEG + 1;       // token table: literals / EOB, then match lengths 0..64
+constexpr int DF_NTBL = DF_NSYM + DF_MAX_MATCH + 1; // token table: literals / EOB, then match lengths 0..258
 
 // per-stream (or per-group) code, built once by k_deflate_tables and read by every chunk that uses it
 struct DeflateTable {
@@ -450,9 +452,12 @@ struct DfEmitShared {
     uint32_t priv[DF_STAGE_WORDS];    // private code bits of thread t at [17 t, 17 t + 17): 544 bits
     uint32_t tbl[DF_NTBL];            // (bits << 24) | code: literals / EOB at [sym], matches of length L at [288 + L]
     uint32_t tbits[DF_THREADS];       // per-thread bit counts -> exclusive bit offsets
+    uint32_t ecode[DF_ZRUN + 1];      // sparse path: code bits of a run of g zero bytes, g = 0..259 (see df_load_table)
+    uint8_t elen[DF_ZRUN + 1];        // ... and their number
     uint32_t header_bits;
     uint32_t out_bytes;
     uint32_t overflow;                // a thread's code bits did not fit its private area: store the chunk
+    uint32_t e_bad;                   // a zero-run composite does not fit 32 bits / lacks a code: no sparse path
 };
 constexpr int DF_PRIV_BITS = DF_SEG_STRIDE * 32;
 
@@ -460,7 +465,7 @@ constexpr int DF_PRIV_BITS = DF_SEG_STRIDE * 32;
 DF_HD void df_load_table(DfEmitShared &S, const DeflateTable &T, int i, int nthreads)
 {
     for (int s = i; s < DF_NSYM; s += nthreads) S.tbl[s] = ((uint32_t)T.len[s] << 24) | T.code[s];
-    for (int L = i; L <= DF_SEG; L += nthreads) {
+    for (int L = i; L <= DF_MAX_MATCH; L += nthreads) {
         uint32_t e = 0;
         if (L >= 3) {
             int sym, eb, ev;
@@ -470,6 +475,29 @@ DF_HD void df_load_table(DfEmitShared &S, const DeflateTable &T, int i, int nthr
             e = ((l + eb + 1) << 24) | (uint32_t)T.code[sym] | ((uint32_t)ev << l);
         }
         S.tbl[DF_NSYM + L] = e;
+    }
+    // sparse path: a run of g zero bytes that follows a non-zero byte (or starts the chunk) is
+    //   g = 1..3: g literals 0x00;   g = 4..259: literal 0x00 + a distance-1 match of g - 1
+    // (what the tokenizer above produces for such a run), pre-merged into one code of at most 32 bits
+    const uint32_t l0 = T.len[0], c0 = T.code[0];
+    for (int g = i; g <= DF_ZRUN; g += nthreads) {
+        uint32_t code = 0, len = 0;
+        bool bad = l0 == 0;
+        if (g >= 1 && g <= 3) {
+            len = (uint32_t)g * l0;
+            bad = bad || len > 32;
+            if (!bad) for (int k = 0; k < g; k++) code |= c0 << (k * l0);
+        } else if (g >= 4) {
+            int sym, eb, ev;
+            df_len_code(g - 1, sym, eb, ev);
+            const uint32_t l = T.len[sym];
+            len = l0 + l + (uint32_t)eb + 1u;
+            bad = bad || l == 0 || len > 32;
+            if (!bad) code = c0 | ((uint32_t)T.code[sym] << l0) | ((uint32_t)ev << (l0 + l));
+        }
+        S.ecode[g] = code;
+        S.elen[g] = (uint8_t)len;
+        if (bad && g > 0) S.e_bad = 1;
     }
 }
 
@@ -526,6 +554,111 @@ DF_HD uint32_t df_encode_segment(DfEmitShared &S, int t, int clen)
     }
     if (w > (uint32_t)DF_SEG_STRIDE) S.overflow = 1;
     return total;
+}
+
+// ---- sparse chunks (binary maps: 85-99 % zero bytes) ---------------------------------------------------------
+// A chunk with few non-zero bytes is encoded from the LIST of its non-zero bytes instead of byte by byte: every list
+// entry is one literal preceded by the pre-merged code of the zero run in front of it (S.ecode), so the work is
+// proportional to the non-zero bytes, a thread's share is a contiguous range of the list (every lane equally busy),
+// and runs are not cut at 64-byte segments.  The tokens are a legal deflate stream for ANY input (a non-zero byte is
+// always sent as a literal); the kernel takes this path only when the list fits (DF_STAGE_WORDS entries, i.e. up to a
+// quarter of the bytes non-zero) and the code is the smoothed shared one (every length symbol has a code).
+//
+// bit i of nz[h] = byte 32 h + i of thread t's segment is non-zero
+DF_HD uint32_t df_nz_masks(const uint32_t *in32, int t, int nbytes, uint32_t (&nz)[2])
+{
+    nz[0] = nz[1] = 0;
+    if (nbytes <= 0) return 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < DF_SEG_WORDS; k++) {
+        const uint32_t x = in32[df_in_index(t, k)];                 // bytes past nbytes are staged as zeros
+        uint32_t z = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+        z = (z | x) & 0x80808080u;                                   // bit 7 of each non-zero byte
+        const uint32_t nib = ((z >> 7) * 0x00204081u >> 21) & 0xfu;
+        if (k < 8) nz[0] |= nib << (4 * k); else nz[1] |= nib << (4 * (k - 8));
+    }
+#ifdef __CUDA_ARCH__
+    return (uint32_t)(__popc(nz[0]) + __popc(nz[1]));
+#else
+    return (uint32_t)(__builtin_popcount(nz[0]) + __builtin_popcount(nz[1]));
+#endif
+}
+
+// list[base + k] = (position in the chunk << 8) | byte, in stream order
+DF_HD void df_nz_scatter(const uint32_t *in32, uint32_t *list, int t, uint32_t base, const uint32_t (&nz)[2])
+{
+    for (int h = 0; h < 2; h++) {
+        uint32_t m = nz[h];
+        while (m) {
+            const int pos = df_ctz32(m);
+            m &= m - 1;
+            list[base++] = ((uint32_t)(t * DF_SEG + 32 * h + pos) << 8) | df_byte_at(in32, t, 32 * h + pos);
+        }
+    }
+}
+
+// thread t's share of the n list entries: [lo, hi)
+DF_HD void df_sparse_range(int t, uint32_t n, uint32_t &lo, uint32_t &hi)
+{
+    lo = (uint32_t)(((uint64_t)n * (uint32_t)t) / DF_THREADS);
+    hi = (uint32_t)(((uint64_t)n * (uint32_t)(t + 1)) / DF_THREADS);
+}
+
+// code bits of thread t's entries; the zero bytes after the last entry of the chunk belong to the last thread
+DF_HD uint32_t df_sparse_bits(const DfEmitShared &S, const uint32_t *list, int t, uint32_t n, int clen)
+{
+    uint32_t lo, hi;
+    df_sparse_range(t, n, lo, hi);
+    uint32_t bits = 0;
+    uint32_t prev = lo ? (list[lo - 1] >> 8) + 1u : 0u;            // first byte not yet covered
+    const uint32_t l259 = S.elen[DF_ZRUN];
+    for (uint32_t k = lo; k < hi; k++) {
+        const uint32_t e = list[k];
+        const uint32_t g = (e >> 8) - prev;
+        prev = (e >> 8) + 1u;
+        const uint32_t rep = g / (uint32_t)DF_ZRUN;
+        bits += rep * l259 + S.elen[g - rep * (uint32_t)DF_ZRUN] + (S.tbl[e & 0xffu] >> 24);
+    }
+    if (t == DF_THREADS - 1) {
+        const uint32_t g = (uint32_t)clen - prev, rep = g / (uint32_t)DF_ZRUN;
+        bits += rep * l259 + S.elen[g - rep * (uint32_t)DF_ZRUN];
+    }
+    return bits;
+}
+
+DF_HD void df_or_bits(uint32_t *out, uint32_t &pos, uint32_t code, uint32_t n)
+{
+    if (!n) return;
+    const uint32_t w = pos >> 5, sh = pos & 31;
+    DF_ATOMIC_OR(&out[w], code << sh);
+    if (sh + n > 32) DF_ATOMIC_OR(&out[w + 1], code >> (32 - sh));
+    pos += n;
+}
+
+// ORs the codes of thread t's entries into the (zero-initialised) output bit stream from bit `pos`
+DF_HD void df_sparse_emit(DfEmitShared &S, const uint32_t *list, int t, uint32_t n, int clen, uint32_t pos)
+{
+    uint32_t lo, hi;
+    df_sparse_range(t, n, lo, hi);
+    uint32_t prev = lo ? (list[lo - 1] >> 8) + 1u : 0u;
+    for (uint32_t k = lo; k <= hi; k++) {
+        uint32_t g, lit = 0;
+        if (k < hi) {
+            const uint32_t e = list[k];
+            g = (e >> 8) - prev;
+            prev = (e >> 8) + 1u;
+            lit = S.tbl[e & 0xffu];
+        } else {
+            if (t != DF_THREADS - 1) break;
+            g = (uint32_t)clen - prev;                                // the zero bytes that end the chunk
+        }
+        for (; g > (uint32_t)DF_ZRUN; g -= DF_ZRUN) df_or_bits(S.io, pos, S.ecode[DF_ZRUN], S.elen[DF_ZRUN]);
+        if (g == (uint32_t)DF_ZRUN && S.elen[DF_ZRUN]) { df_or_bits(S.io, pos, S.ecode[DF_ZRUN], S.elen[DF_ZRUN]); g = 0; }
+        df_or_bits(S.io, pos, S.ecode[g], S.elen[g]);
+        df_or_bits(S.io, pos, lit & 0xffffffu, lit >> 24);
+    }
 }
 
 // ORs thread t's private bit string into the output stream at bit offset S.header_bits + S.tbits[t] (exclusive scan)

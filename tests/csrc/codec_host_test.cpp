@@ -80,13 +80,29 @@ extern "C" long host_deflate_stream(const uint8_t *in, uint32_t n, int level, ui
         }
         uint32_t body_bits = 0;
         bool stored = store_all;
+        bool sparse = false;
+        uint32_t n_nz = 0;
         const DeflateTable &T = B.tab;
         if (!stored) {
+            S.e_bad = 0;
             for (int i = 0; i < DF_THREADS; i++) df_load_table(S, T, i, DF_THREADS);
             S.header_bits = T.header_bits;
             S.overflow = 0;
             uint32_t run = 0;
-            for (int t = 0; t < DF_THREADS; t++) bits_of[t] = df_encode_segment(S, t, clen);
+            // sparse path (k_deflate_chunks: shared code, zero-run composites fit, list fits)
+            sparse = false;
+            if (shared_table && !S.e_bad) {
+                static uint32_t nzm[DF_THREADS][2];
+                n_nz = 0;
+                std::vector<uint32_t> base(DF_THREADS);
+                for (int t = 0; t < DF_THREADS; t++) { base[t] = n_nz; n_nz += df_nz_masks(S.io, t, df_seg_bytes(t, clen), nzm[t]); }
+                sparse = n_nz <= (uint32_t)DF_STAGE_WORDS;
+                if (sparse) {
+                    for (int t = 0; t < DF_THREADS; t++) df_nz_scatter(S.io, S.priv, t, base[t], nzm[t]);
+                    for (int t = 0; t < DF_THREADS; t++) bits_of[t] = df_sparse_bits(S, S.priv, t, n_nz, clen);
+                }
+            }
+            if (!sparse) for (int t = 0; t < DF_THREADS; t++) bits_of[t] = df_encode_segment(S, t, clen);
             for (int t = 0; t < DF_THREADS; t++) { S.tbits[t] = run; run += bits_of[t]; }
             body_bits = S.header_bits + run;
             stored = S.overflow || df_dynamic_bytes(body_bits, (int)(S.tbl[256] >> 24)) >= (uint32_t)clen + 10u;
@@ -95,7 +111,8 @@ extern "C" long host_deflate_stream(const uint8_t *in, uint32_t n, int level, ui
         if (!stored) {
             const int hw = (int)((T.header_bits + 31) >> 5);
             for (int i = 0; i < DF_STAGE_WORDS; i++) S.io[i] = i < hw ? T.header[i] : 0;
-            for (int t = 0; t < DF_THREADS; t++) df_place_segment(S, t, bits_of[t]);
+            if (sparse) for (int t = 0; t < DF_THREADS; t++) df_sparse_emit(S, S.priv, t, n_nz, clen, S.header_bits + S.tbits[t]);
+            else for (int t = 0; t < DF_THREADS; t++) df_place_segment(S, t, bits_of[t]);
             df_phase_finish(S, body_bits);
             piece.assign(reinterpret_cast<uint8_t *>(S.io), reinterpret_cast<uint8_t *>(S.io) + S.out_bytes);
         } else {
