@@ -301,21 +301,24 @@ class ReadEngine:
         self.t_dtype = _native.torch_dtype(itemsize)
         self.map_bytes = (self.P + 7) // 8
         self.ms = self.ctx.map_stride_words(self.P)
-        # one stride for both stream kinds so a single inflate call handles [maps..., vals...]
-        need = max(self.ms * 4, (self.P * self.bit_depth + 7) // 8 if self.level <= 2 else 0)
-        self.stride = (need + 15) // 16 * 16 + 16
+        # the streams are inflated where the unpack kernels read them: binary maps at the library's map stride (whole
+        # tiles of 1024 words per frame, the padding stays zero), value streams at their own stride -- no repacking
+        self.mstride = self.ms * 4
+        self.stride = ((self.P * self.bit_depth + 7) // 8 + 15) // 16 * 16 + 16 if self.level <= 2 else 16
         F = self.max_frames
         with torch.cuda.device(self.dev):
             self.ws = self.ctx.empty(self.ctx.read_workspace_bytes(self.cfg))
-            self.inflated = self.ctx.zeros(2 * F * self.stride + 64)
+            self.maps_buf = self.ctx.zeros(F * self.mstride + 64)
+            self.packed_buf = self.ctx.zeros(F * self.stride + 64)
             self.out_bytes = self.ctx.zeros(2 * F, torch.int32)
             self.status = self.ctx.zeros(2 * F, torch.int32)
             self.counts = self.ctx.zeros(F, torch.int32)
             self._inf_ws = None
+            self._inf_ws2 = None
             if self.mode == 1:
-                need = self.ctx._lib.rc_inflate_workspace_bytes(F, self.stride)
-                self._inf_ws = self.ctx.empty(need)
-                self._inf_ws2 = self.ctx.empty(need) if self.level <= 2 else None
+                self._inf_ws = self.ctx.empty(self.ctx._lib.rc_inflate_workspace_bytes(F, self.mstride))
+                if self.level <= 2:
+                    self._inf_ws2 = self.ctx.empty(self.ctx._lib.rc_inflate_workspace_bytes(F, self.stride))
 
     def load(self, map_streams, val_streams):
         """Stage n frames' streams (compressed when mode 1, raw when mode 0) -> device maps / packed values."""
@@ -329,29 +332,32 @@ class ReadEngine:
                 streams = list(map_streams) + (list(val_streams) if has_vals else [])
                 d_in, d_off, d_sz, staged = _stage_streams(self.ctx, streams)
                 ns = len(streams)
-                # maps occupy stream slots [0, n), values [F, F + n): issue as two calls so strides line up
-                self._inf_ws = self.ctx.inflate_zlib(d_in, d_off, d_sz, n, self.inflated, self.stride,
+                # maps occupy stream slots [0, n), values [F, F + n) of out_bytes / status
+                self._inf_ws = self.ctx.inflate_zlib(d_in, d_off, d_sz, n, self.maps_buf, self.mstride,
                                                      self.out_bytes, self.status, self._inf_ws)
                 if has_vals:
-                    self._inf_ws = self.ctx.inflate_zlib(d_in, d_off[n:], d_sz[n:], n,
-                                                         self.inflated[F * self.stride:], self.stride,
-                                                         self.out_bytes[F:], self.status[F:], self._inf_ws)
+                    self._inf_ws2 = self.ctx.inflate_zlib(d_in, d_off[n:], d_sz[n:], n, self.packed_buf, self.stride,
+                                                          self.out_bytes[F:], self.status[F:], self._inf_ws2)
                 self._keep = (d_in, d_off, d_sz)
                 h2d = staged + ns * 12
             else:
-                host = np.zeros((2 * F, self.stride), dtype=np.uint8)
+                hm = np.zeros((F, self.mstride), dtype=np.uint8)
+                hp = np.zeros((F, self.stride), dtype=np.uint8)
                 for f in range(n):
-                    host[f, :len(map_streams[f])] = np.frombuffer(map_streams[f], dtype=np.uint8)
+                    if len(map_streams[f]) > self.mstride or (has_vals and len(val_streams[f]) > self.stride):
+                        raise ValueError('stream of frame %d is longer than a frame can produce' % f)
+                    hm[f, :len(map_streams[f])] = np.frombuffer(map_streams[f], dtype=np.uint8)
                     if has_vals:
-                        host[F + f, :len(val_streams[f])] = np.frombuffer(val_streams[f], dtype=np.uint8)
-                self.inflated[:2 * F * self.stride].copy_(torch.from_numpy(host.reshape(-1)))
+                        hp[f, :len(val_streams[f])] = np.frombuffer(val_streams[f], dtype=np.uint8)
+                self.maps_buf[:F * self.mstride].copy_(torch.from_numpy(hm.reshape(-1)))
+                self.packed_buf[:F * self.stride].copy_(torch.from_numpy(hp.reshape(-1)))
                 self.status.zero_()
                 ob = np.zeros(2 * F, dtype=np.int32)
                 ob[:n] = [len(m) for m in map_streams]
                 if has_vals:
                     ob[F:F + n] = [len(v) for v in val_streams]
                 self.out_bytes.copy_(torch.from_numpy(ob))
-                h2d = host.nbytes
+                h2d = hm.nbytes + hp.nbytes
         self.n = n
         self.has_vals = has_vals
         return h2d
@@ -406,21 +412,14 @@ class ReadEngine:
             self._h2d_done.record()
             d_off = self._d_meta[:4 * F].view(torch.int64)
             d_sz = self._d_meta[4 * F:]
-            self._inf_ws = self.ctx.inflate_zlib(d_blk, d_off, d_sz, n, self.inflated, self.stride,
+            self._inf_ws = self.ctx.inflate_zlib(d_blk, d_off, d_sz, n, self.maps_buf, self.mstride,
                                                  self.out_bytes, self.status, self._inf_ws)
             if has_vals:
-                self._inf_ws2 = self.ctx.inflate_zlib(d_blk, d_off[F:], d_sz[F:], n, self.inflated[F * self.stride:],
-                                                      self.stride, self.out_bytes[F:], self.status[F:],
-                                                      getattr(self, '_inf_ws2', None))
+                self._inf_ws2 = self.ctx.inflate_zlib(d_blk, d_off[F:], d_sz[F:], n, self.packed_buf, self.stride,
+                                                      self.out_bytes[F:], self.status[F:], self._inf_ws2)
         self.n = n
         self.has_vals = has_vals
         return int(nbytes) + meta.numel() * 4
-
-    def _views(self):
-        F = self.max_frames
-        maps = self.inflated[:F * self.stride]
-        packed = self.inflated[F * self.stride:]
-        return maps, packed
 
     def check(self, packed_sizes=None):
         """Host-side validation after load(): stream status and sizes (raises ValueError like zlib.error would).
@@ -442,13 +441,10 @@ class ReadEngine:
     def sparse(self):
         """-> list of uint64 [n_fg, 3] (row, col, value) arrays, the c_recode.get_frame_sparse result."""
         n = self.n
-        maps, packed = self._views()
         with torch.cuda.device(self.dev):
-            # the map is strided by self.stride bytes here, not by the library's map stride: repack
-            m2 = self._maps_contig()
             cap = self.P
             tri = self.ctx.empty(n * cap * 3, torch.int64)
-            self.ctx.unpack_sparse(self.cfg, m2, packed, self.stride, n, self.ws, tri, cap, self.counts)
+            self.ctx.unpack_sparse(self.cfg, self.maps_buf, self.packed_buf, self.stride, n, self.ws, tri, cap, self.counts)
             torch.cuda.synchronize()
             k = self.counts[:n].cpu().numpy()
             out = []
@@ -461,7 +457,7 @@ class ReadEngine:
         """L2: unpack the per-puddle statistics of the loaded frames -> list of arrays of the target dtype
         (intent of recode_reader.py:473-481, count = bytes * 8 // bit_depth)."""
         F, n = self.max_frames, self.n
-        _, packed = self._views()
+        packed = self.packed_buf
         res = []
         with torch.cuda.device(self.dev):
             for f in range(n):
@@ -472,22 +468,15 @@ class ReadEngine:
                 res.append(out[:k].cpu().numpy().astype(self.np_dtype))
         return res
 
-    def _maps_contig(self):
-        F, n = self.max_frames, self.n
-        maps, _ = self._views()
-        v = maps.view(F, self.stride)[:n, :self.ms * 4]
-        m = v.contiguous().view(-1)
-        # zero the padding bits/bytes beyond the map (inflate wrote exactly map_bytes)
-        if self.ms * 4 > self.map_bytes:
-            m.view(n, self.ms * 4)[:, self.map_bytes:] = 0
-        return torch.cat([m, torch.zeros(64, dtype=torch.uint8, device=self.dev)])
-
-    def dense(self, total=None, want_dense=True):
-        """-> dense frames tensor [n, ny, nx] on the device (and/or accumulates into `total`, uint32 [ny*nx])."""
+    def dense(self, total=None, want_dense=True, out=None):
+        """-> dense frames [n, ny, nx] on the device (written into `out` when given: a preallocated tensor of the target
+        dtype with room for n frames) and/or accumulates into `total`, uint32 [ny*nx]."""
         n = self.n
-        _, packed = self._views()
         with torch.cuda.device(self.dev):
-            m2 = self._maps_contig()
-            dense = torch.empty((n, self.ny, self.nx), dtype=self.t_dtype, device=self.dev) if want_dense else None
-            self.ctx.unpack_dense(self.cfg, m2, packed, self.stride, n, self.ws, dense, total, self.counts)
+            dense = None
+            if want_dense:
+                dense = out[:n] if out is not None else torch.empty((n, self.ny, self.nx), dtype=self.t_dtype,
+                                                                    device=self.dev)
+            self.ctx.unpack_dense(self.cfg, self.maps_buf, self.packed_buf, self.stride, n, self.ws, dense, total,
+                                  self.counts)
         return dense

@@ -476,11 +476,24 @@ class ReCoDeReader:
         import torch
         if self._header['rc_operation_mode'] != 1:
             return self._read_frames_dense_serial(n)
-        out = []
-        ids = self._bulk_run(n, lambda eng: out.append(eng.dense()))
-        if not out:
+        # one output tensor for the whole request; every batch is unpacked straight into its slice
+        h = self._header
+        engs = self._bulk_engines()
+        left = min(n, max(h['nz'] - self._current_frame_index, 0)) if h['nz'] > 0 else n
+        out = torch.empty((max(left, 1), h['ny'], h['nx']), dtype=engs[0].t_dtype, device=engs[0].dev)
+        done = [0]
+
+        def consume(eng):
+            k = eng.n
+            if done[0] + k > out.shape[0]:
+                raise RuntimeError('more frames in the file than its header announces')
+            eng.dense(out=out[done[0]:done[0] + k])
+            done[0] += k
+
+        ids = self._bulk_run(min(n, out.shape[0]), consume)
+        if not ids:
             return ids, None
-        return ids, (out[0] if len(out) == 1 else torch.cat(out, 0))
+        return ids, out[:len(ids)]
 
     def sum_frames(self, n, total=None):
         """live view: adds the next n frames into `total` (uint32 CUDA tensor [ny*nx], created if None) without
