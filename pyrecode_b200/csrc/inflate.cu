@@ -423,19 +423,22 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         // Adler-32 partials of L copies of c in closed form
         s2 += (uint64_t)L * s1 + (uint64_t)(c * ((L * (L + 1)) >> 1));
         s1 += c * L;
-        if (c == 0) {
-            const uint32_t nn = n + L;
-            if ((n ^ nn) >> 2) {
-                if (w) out32[n >> 2] = w;
-                w = 0;
-            }
-            n = nn;
-        } else {
+        if (c != 0 && L > 1) {
+            // run of a non-zero byte: rare in binary maps
             for (uint32_t i = 0; i < L; i++) {
                 w |= c << ((n & 3u) * 8u);
                 n++;
                 if ((n & 3u) == 0) { out32[(n >> 2) - 1] = w; w = 0; }
             }
+        } else {
+            // a zero run of any length or ONE non-zero byte: the same few instructions for every lane of the warp
+            const uint32_t nn = n + L;
+            w |= c << ((n & 3u) * 8u);
+            if ((n ^ nn) >> 2) {
+                if (w) out32[n >> 2] = w;
+                w = 0;
+            }
+            n = nn;
         }
         last = c;
     }
@@ -565,6 +568,8 @@ int launch_inflate(rc_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const
     uint32_t *need_serial = c.take<uint32_t>((size_t)n_streams + 1);
     InfStreamTable *tabs = c.take<InfStreamTable>((size_t)n_streams);
 
+    ctx->n_dmarks = 0;                               // profile level 2: scan + tables | lanes | the rest
+    rc_dmark(ctx, 0, st);
     k_inflate_scan<<<n_streams, 256, 0, st>>>(in, in_off, in_bytes, cmax, cand, ncand, status);
     RC_LAUNCH_CHECK(ctx, "k_inflate_scan");
     k_scan_u32<<<1, 256, 0, st>>>(ncand, n_streams, cmax, task_base, counters);
@@ -581,9 +586,11 @@ int launch_inflate(rc_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const
             RC_CUDA(ctx, cudaFuncSetAttribute(k_inflate_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, lanes_smem));
             ctx->inflate_attr_set = true;
         }
+        rc_dmark(ctx, 1, st);
         k_inflate_lanes<<<grid, INF_LANES, lanes_smem, st>>>(in, in_off, in_bytes, cmax, cand, ncand, task_base, tabs, out,
                                                    out_stride, tasks);
         RC_LAUNCH_CHECK(ctx, "k_inflate_lanes");
+        rc_dmark(ctx, 2, st);
     }
     size_t blocks = ((size_t)n_streams * cmax + INF_WARPS - 1) / INF_WARPS;
     const size_t cap = (size_t)ctx->sm_count * 5;            // 5 CTAs of 43 KiB fit one SM
@@ -596,5 +603,6 @@ int launch_inflate(rc_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const
     RC_LAUNCH_CHECK(ctx, "k_inflate_validate");
     k_inflate_serial<<<n_streams, 32, 0, st>>>(in, in_off, in_bytes, need_serial, out, out_stride, out_bytes, status);
     RC_LAUNCH_CHECK(ctx, "k_inflate_serial");
+    rc_dmark(ctx, 3, st);
     return 0;
 }

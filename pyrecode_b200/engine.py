@@ -382,7 +382,7 @@ class ReadEngine:
         if ev is not None:
             ev.synchronize()
 
-    def load_block(self, nbytes, map_off, map_sz, val_off=None, val_sz=None):
+    def load_block(self, nbytes, map_off, map_sz, val_off=None, val_sz=None, maps_only=False):
         """Inflate n frames whose compressed streams lie in the pinned block (block_buffer) at the given byte
         offsets.  Everything is enqueued on the current CUDA stream; nothing synchronizes."""
         if self.mode != 1:
@@ -414,7 +414,7 @@ class ReadEngine:
             d_sz = self._d_meta[4 * F:]
             self._inf_ws = self.ctx.inflate_zlib(d_blk, d_off, d_sz, n, self.maps_buf, self.mstride,
                                                  self.out_bytes, self.status, self._inf_ws)
-            if has_vals:
+            if has_vals and not maps_only:
                 self._inf_ws2 = self.ctx.inflate_zlib(d_blk, d_off[F:], d_sz[F:], n, self.packed_buf, self.stride,
                                                       self.out_bytes[F:], self.status[F:], self._inf_ws2)
         self.n = n

@@ -21,13 +21,14 @@ from .structures import ReCoDeStructures
 
 class ReCoDeReader:
 
-    def __init__(self, file, is_intermediate=False, device=None, batch_frames=16, bulk_frames=64):
+    def __init__(self, file, is_intermediate=False, device=None, batch_frames=16, bulk_frames=64, bulk_inflight=6):
         self._source_filename = file
         self._current_frame_index = 0
         self._is_intermediate = 1 if is_intermediate else 0
         self._device = device
         self._batch_frames = batch_frames
         self._bulk_frames = bulk_frames          # frames per batch of read_frames_dense / sum_frames
+        self._bulk_inflight = max(1, int(bulk_inflight))   # ... and batches of them in flight (one engine + stream each)
         self._bulk = None
         self._ahead = []                         # decoded read-ahead frames of get_next_frame
         self._file_size = None
@@ -315,7 +316,7 @@ class ReCoDeReader:
     # batch of a merged file), copied to the device in one piece and inflated / unpacked asynchronously while the
     # host already stages the next batch.  (The serial inflate of a 16 KiB chunk takes milliseconds whatever the
     # batch size, so throughput comes from the number of chunks in flight.)
-    def _bulk_engines(self, n_inflight=3):
+    def _bulk_engines(self, n_inflight=None):
         if getattr(self, '_bulk', None) is None:
             from .engine import ReadEngine
             import torch
@@ -324,7 +325,9 @@ class ReCoDeReader:
                 raise NotImplementedError('only unsigned targets of 1..16 bits are supported on the GPU path')
             itemsize = 1 if h['target_bit_depth'] <= 8 else 2
             self._bulk = []
-            for _ in range(n_inflight):
+            # the lane-per-chunk inflate is a serial chain per lane (milliseconds per batch at a few per cent of the
+            # warp slots): throughput comes from the number of batches in flight
+            for _ in range(n_inflight or self._bulk_inflight):
                 e = ReadEngine(h['ny'], h['nx'], itemsize, h['target_bit_depth'], h['reduction_level'],
                                h['rc_operation_mode'], max_frames=self._bulk_frames, device=self._device)
                 e.stream = torch.cuda.Stream(device=e.dev)
@@ -402,7 +405,7 @@ class ReCoDeReader:
             voff = vsz = None
         return ids, pos, moff, msz, voff, vsz
 
-    def _pread_parallel(self, fd, buf, offset, nbytes, n_threads=4):
+    def _pread_parallel(self, fd, buf, offset, nbytes, n_threads=8):
         """file[offset : offset + nbytes] -> buf[:nbytes] (pinned), in slices read by a few threads (preadv releases
         the GIL; one thread copies out of the page cache at only a few GB/s)"""
         mv = memoryview(buf)
@@ -470,6 +473,53 @@ class ReCoDeReader:
             torch.cuda.current_stream(eng.dev).wait_stream(eng.stream)
         st['wait_s'] += time.perf_counter() - t0
         return ids
+
+    def decode_stage_ms(self, reps=3):
+        """Profiling aid (bench.py): one batch of the file decoded ALONE on one engine, timed with CUDA events.
+        -> dict: frames, map_inflate_ms (all inflate kernels of the map streams), lanes_ms (k_inflate_lanes of the map
+        streams alone), value_inflate_ms, unpack_dense_ms, unpack_sum_ms.  Leaves the reader rewound."""
+        import torch
+        engs = self._bulk_engines()
+        eng = engs[0]
+        self.rewind()
+        with torch.cuda.device(eng.dev):
+            torch.cuda.synchronize()
+            bi, nbytes, moff, msz, voff, vsz = self._read_block(eng.max_frames, eng)
+            n = len(bi)
+            out = {'frames': n}
+            if n == 0:
+                return out
+            dense = torch.empty((n, self._header['ny'], self._header['nx']), dtype=eng.t_dtype, device=eng.dev)
+            total = torch.zeros(self._header['ny'] * self._header['nx'], dtype=torch.int32, device=eng.dev)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            eng.ctx.profile_enable(2)
+            acc = {'map_inflate_ms': 0.0, 'lanes_ms': 0.0, 'value_inflate_ms': 0.0, 'unpack_dense_ms': 0.0,
+                   'unpack_sum_ms': 0.0}
+            for _ in range(reps + 1):
+                ev[0].record()
+                eng.load_block(nbytes, moff, msz, voff, vsz, maps_only=True)
+                ev[1].record()
+                torch.cuda.synchronize()
+                d = eng.ctx.profile_read_detail()
+                eng.load_block(nbytes, moff, msz, voff, vsz)
+                ev[2].record()
+                eng.dense(out=dense)
+                ev[3].record()
+                eng.dense(total=total, want_dense=False)
+                ev[4].record()
+                torch.cuda.synchronize()
+                if _ == 0:
+                    continue                           # warm-up
+                acc['map_inflate_ms'] += ev[0].elapsed_time(ev[1])
+                acc['lanes_ms'] += d[1] if len(d) > 1 else 0.0
+                acc['value_inflate_ms'] += max(ev[1].elapsed_time(ev[2]) - ev[0].elapsed_time(ev[1]), 0.0)
+                acc['unpack_dense_ms'] += ev[2].elapsed_time(ev[3])
+                acc['unpack_sum_ms'] += ev[3].elapsed_time(ev[4])
+            eng.ctx.profile_enable(0)
+            eng.check(eng.expect_packed if hasattr(eng, 'expect_packed') else None)
+            out.update({k: v / reps for k, v in acc.items()})
+        self.rewind()
+        return out
 
     def read_frames_dense(self, n):
         """next n frames -> (frame ids, CUDA tensor [k, ny, nx] of the target dtype); k <= n at EOF"""
