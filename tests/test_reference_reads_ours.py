@@ -1,5 +1,5 @@
 """CPU, build container only: files written by the GPU ReCoDeWriter (tests/golden/ours_*, produced on the B200 box by
-tests/make_ours_golden.py) are opened by the UNMODIFIED reference ReCoDeReader (pyrecode/recode_reader.py:39-61,
+tools/make_ours_golden.py) are opened by the UNMODIFIED reference ReCoDeReader (pyrecode/recode_reader.py:39-61,
 223-273, 188-221) and every frame is compared with the input -- the reverse direction of the on-disk contract
 (SURVEY Appendix A).  Skipped where /root/reference does not exist (the GPU box)."""
 import contextlib

@@ -3,7 +3,7 @@ brought back through gpurun_out/ours_golden/ and committed as tests/golden/ours_
 tests/test_reference_reads_ours.py can open them with the UNMODIFIED reference reader (reverse interop, SURVEY
 Appendix A).
 
-    python tests/make_ours_golden.py [out_dir]
+    python tools/make_ours_golden.py [out_dir]
 """
 import os
 import shutil
