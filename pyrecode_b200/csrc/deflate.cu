@@ -433,9 +433,17 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
     __shared__ uint32_t s_adler[2];
     const int t = threadIdx.x;
     const uint32_t total_chunks = chunk_base[n_streams];
+    // one code for all chunks (levels 1..5): its token tables are set up once per CTA, not once per chunk
+    bool table_loaded = false;
+    if (t == 0) S.e_bad = 0;
+    __syncthreads();
+    if (shared_table && level > 0 && tables[0].header_bits != 0xffffffffu) {
+        df_load_table(S, tables[0], t, DF_THREADS);
+        table_loaded = true;
+    }
 
     while (true) {
-        if (t == 0) { s_ticket = atomicAdd(&counters[2], 1u); s_adler[0] = 0; s_adler[1] = 0; S.overflow = 0; S.e_bad = 0; }
+        if (t == 0) { s_ticket = atomicAdd(&counters[2], 1u); s_adler[0] = 0; s_adler[1] = 0; S.overflow = 0; }
         __syncthreads();
         const uint32_t gci = s_ticket;
         if (gci >= total_chunks) break;
@@ -452,7 +460,7 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
             hb = T.header_bits;
             stored = hb == 0xffffffffu;
         }
-        if (!stored) df_load_table(S, T, t, DF_THREADS);
+        if (!stored && !table_loaded) df_load_table(S, T, t, DF_THREADS);     // per-stream codes (levels 6..9)
         __syncthreads();
 
         // Adler-32 partials of the chunk (warp shuffle reduction, one shared atomic per warp)
