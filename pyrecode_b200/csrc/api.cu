@@ -314,6 +314,13 @@ static int reduce_stage2(rc_ctx *ctx, const rc_config *cfg, const Geom &g, const
     if (level == 3) return launch_scan_tiles(ctx, g, w.tilecnt, F, w.tilepre, counts, nullptr, 0, st);
     if (level == 2) {
         const int sum = cfg->l2_statistics == 2;
+        // RC_ABLATE (timing experiments only, results are not valid records): bit 0 = no labelling stage at all
+        static const int ablate = getenv("RC_ABLATE") ? atoi(getenv("RC_ABLATE")) : 0;
+        if (ablate & 1) {
+            RC_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)F * sizeof(uint32_t), st));
+            RC_CUDA(ctx, cudaMemsetAsync(packed_bytes, 0, (size_t)F * sizeof(uint32_t), st));
+            return 0;
+        }
         if ((rc = launch_ccl_tiles(ctx, g, sum ? 2 : 1, maps, w.wordpre, w.tilecnt, (const uint32_t *)w.vals, w.tileovf,
                                    w.xcount, w.xlinks, w.parent, w.acc, 0, nullptr, nullptr, nullptr, nullptr, F,
                                    st))) return rc;

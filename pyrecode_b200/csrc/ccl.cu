@@ -46,9 +46,6 @@ constexpr int CCL_CAP = 2048;          // foreground pixels per tile handled in 
 constexpr int CCL_LINKS = 512;         // tile-local tree-joining links
 constexpr int CCL_XCAP = 256;          // cross-tile links per tile (global list)
 constexpr int CCL_HALO = 264;          // map words kept in front of the tile (multiple of 4): nx <= 8447
-constexpr int CCL_THREADS = 256;
-constexpr int CCL_WARPS = CCL_THREADS / 32;
-constexpr int CCL_MAPV = TILE_WORDS / 4 / CCL_THREADS;    // uint4 map loads per thread
 
 // shared-memory atomic add issued as is: around an atomicAdd() that only one lane executes the compiler still emits
 // its warp-aggregation sequence (vote, leader election, shuffle)
@@ -122,7 +119,7 @@ struct __align__(128) CclStage {
     uint32_t bot[L4 ? CCL_HALO : 4];
 };
 
-template <int FOLD>
+template <int FOLD, int CCL_THREADS>
 __device__ __forceinline__ void
 ccl_tile(const int tile, const int f, CclStage<FOLD == 3> &S, const uint32_t total, int NT, size_t MS,
          const uint32_t *__restrict__ vp_all, uint8_t *__restrict__ tileovf,
@@ -131,6 +128,7 @@ ccl_tile(const int tile, const int f, CclStage<FOLD == 3> &S, const uint32_t tot
          uint32_t *__restrict__ map2_all, uint64_t *__restrict__ cent_all, uint32_t *__restrict__ rootcnt)
 {
     constexpr bool L4 = FOLD == 3;
+    constexpr int CCL_WARPS = CCL_THREADS / 32;
     // S.maskx: map words of the tile preceded by a halo (zeros before the frame), so that the W / NW / N / NE probes
     // of every pixel are plain shared-memory reads
     uint32_t *s_maskx = S.maskx;
@@ -395,7 +393,7 @@ ccl_tile(const int tile, const int f, CclStage<FOLD == 3> &S, const uint32_t tot
 // mbarrier per stage) while the current pair is labelled, so no thread ever waits for a dependent global load: the
 // kernel runs at the speed of its instruction stream instead of that of four DRAM round trips per tile.  With a few
 // CTAs per SM it shares every SM with the streaming kernel of the next batch (memory-bound next to issue-bound work).
-template <int FOLD>
+template <int FOLD, int CCL_THREADS>
 __global__ void __launch_bounds__(CCL_THREADS)
 k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__restrict__ wordpre_all, int NT, int n_tiles_total,
             const uint32_t *__restrict__ tilecnt, const uint32_t *__restrict__ vp_all, uint8_t *__restrict__ tileovf,
@@ -430,6 +428,9 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
     if (gt >= n_tiles_total) return;
     if (t == 0) issue(gt, 0);
     uint32_t total = tilecnt[gt];
+    // (frame, tile) of gt, advanced by the grid stride without a division per tile
+    int f = gt / NT, tile = gt - f * NT;
+    const int step_f = (int)gridDim.x / NT, step_t = (int)gridDim.x - step_f * NT;
     for (int j = 0; gt < n_tiles_total; gt += gridDim.x, j++) {
         const int stg = j & 1;
         const int nxt = gt + (int)gridDim.x;
@@ -442,16 +443,18 @@ k_ccl_tiles(const uint32_t *__restrict__ maps, size_t MS, const uint16_t *__rest
             }
             total_next = tilecnt[nxt];
         }
-        const int f = gt / NT, tile = gt - f * NT;
         mbar_wait(smem_u32(&s_bar[stg]), (uint32_t)(j >> 1) & 1u);
         CclStage<L4> &S = stage[stg];
         // rows before the frame / after it read as background
         if (tile == 0 && t < CCL_HALO / 4) reinterpret_cast<uint4 *>(S.maskx)[t] = make_uint4(0, 0, 0, 0);
         if (L4 && tile + 1 >= NT && t < CCL_HALO / 4) reinterpret_cast<uint4 *>(S.bot)[t] = make_uint4(0, 0, 0, 0);
-        ccl_tile<FOLD>(tile, f, S, total, NT, MS, vp_all, tileovf, xcount, xlinks, parent_all, acc_all,
+        ccl_tile<FOLD, CCL_THREADS>(tile, f, S, total, NT, MS, vp_all, tileovf, xcount, xlinks, parent_all, acc_all,
                        ny, nx, l4mode, bbox_all, map2_all, cent_all, rootcnt);
         __syncthreads();                               // the next tile reuses the shared arrays
         total = total_next;
+        tile += step_t;
+        f += step_f;
+        if (tile >= NT) { tile -= NT; f++; }
     }
 }
 
@@ -780,17 +783,25 @@ int launch_ccl_tiles(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps,
     if (per_sm > fit) per_sm = fit;
     unsigned grid = (unsigned)nt;
     if ((unsigned)(per_sm * ctx->sm_count) < grid) grid = (unsigned)(per_sm * ctx->sm_count);
-#define RC_CT(FO)                                                                                              \
+#define RC_CT(FO, TPB)                                                                                         \
     {                                                                                                          \
         constexpr size_t dyn = 2 * sizeof(CclStage<FO == 3>);                                                  \
-        RC_CUDA(ctx, cudaFuncSetAttribute(k_ccl_tiles<FO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-        k_ccl_tiles<FO><<<grid, CCL_THREADS, dyn, st>>>(maps, g.MS, wordpre, g.NT, nt, tilecnt, vp, tileovf, xcount, \
-                                                        (uint2 *)xlinks, parent, acc, g.ny, g.nx, l4mode, bbox, map2, \
-                                                        cent, rootcnt);                                        \
+        RC_CUDA(ctx, cudaFuncSetAttribute(k_ccl_tiles<FO, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+        k_ccl_tiles<FO, TPB><<<grid, TPB, dyn, st>>>(maps, g.MS, wordpre, g.NT, nt, tilecnt, vp, tileovf, xcount, \
+                                                     (uint2 *)xlinks, parent, acc, g.ny, g.nx, l4mode, bbox, map2,  \
+                                                     cent, rootcnt);                                           \
     }
-    if (fold == 1) RC_CT(1)
-    else if (fold == 2) RC_CT(2)
-    else RC_CT(3)
+    // threads per CTA: 128 halves the per-tile fixed work and wastes fewer lanes on a tile's few hundred pixels
+    static const int tpb = getenv("RECODE_B200_CCL_TPB") ? atoi(getenv("RECODE_B200_CCL_TPB")) : 256;
+    if (tpb == 128) {
+        if (fold == 1) RC_CT(1, 128)
+        else if (fold == 2) RC_CT(2, 128)
+        else RC_CT(3, 128)
+    } else {
+        if (fold == 1) RC_CT(1, 256)
+        else if (fold == 2) RC_CT(2, 256)
+        else RC_CT(3, 256)
+    }
 #undef RC_CT
     RC_LAUNCH_CHECK(ctx, "k_ccl_tiles");
     return 0;

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "deflate_chunk.cuh"
+#include <stdlib.h>
 
 __global__ void __launch_bounds__(256)
 k_deflate_plan(const uint32_t *__restrict__ in_bytes, int n_streams, uint32_t *__restrict__ chunk_base,
@@ -549,30 +550,38 @@ k_stream_finalize(const uint32_t *__restrict__ in_bytes, const uint32_t *__restr
     __shared__ uint32_t s_warp[9];
     const int s = blockIdx.x, t = threadIdx.x;
     const uint32_t c0 = chunk_base[s], c1 = chunk_base[s + 1];
+    const uint32_t slen = in_bytes[s];
     uint32_t carry = 0;
+    // Adler-32 over the concatenated chunks from their (A_c, B_c, len_c) partials, all chunks in parallel:
+    //   s1 before chunk c = 1 + sum of A_k (k < c);   s2 = sum over c of (len_c * s1 before c + B_c)      (mod 65521)
+    uint32_t s1 = 1, s2 = 0;
     for (uint32_t i0 = c0; i0 < c1; i0 += 256) {
         const uint32_t i = i0 + t;
-        const uint32_t v = i < c1 ? chunk_bytes[i] : 0;
+        const bool in = i < c1;
+        const uint32_t v = in ? chunk_bytes[i] : 0;
+        const uint2 ab = (in && wrap) ? chunk_adler[i] : make_uint2(0, 0);
         uint32_t total;
         const uint32_t e = block_excl_scan<8>(v, s_warp, &total);
-        if (i < c1) chunk_rel[i] = carry + e;
+        if (in) chunk_rel[i] = carry + e;
         carry += total;
         __syncthreads();
+        if (wrap) {
+            uint32_t a_tot;
+            const uint32_t a_ex = block_excl_scan<8>(ab.x, s_warp, &a_tot);            // A_k < 65521: no overflow
+            __syncthreads();
+            const uint32_t s1b = (s1 + a_ex) % 65521u;
+            const uint32_t clen = in ? min((uint32_t)DF_CHUNK, slen - (i - c0) * DF_CHUNK) : 0u;
+            const uint32_t term = in ? (uint32_t)(((uint64_t)clen * s1b + ab.y) % 65521u) : 0u;
+            uint32_t t_tot;
+            block_excl_scan<8>(term, s_warp, &t_tot);
+            __syncthreads();
+            s2 = (s2 + t_tot % 65521u) % 65521u;
+            s1 = (s1 + a_tot % 65521u) % 65521u;
+        }
     }
     if (t == 0) {
         stream_bytes[s] = wrap ? carry + 8u : carry;
-        if (wrap) {
-            // Adler-32 over the concatenated chunks from (A_c, B_c, len_c) partials
-            uint32_t s1 = 1, s2 = 0;
-            const uint32_t slen = in_bytes[s];
-            for (uint32_t i = c0; i < c1; i++) {
-                const uint32_t clen = min((uint32_t)DF_CHUNK, slen - (i - c0) * DF_CHUNK);
-                const uint2 ab = chunk_adler[i];
-                s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)clen * s1 + ab.y) % 65521u);
-                s1 = (s1 + ab.x) % 65521u;
-            }
-            stream_adler[s] = (s2 << 16) | s1;
-        }
+        if (wrap) stream_adler[s] = (s2 << 16) | s1;
     }
 }
 
@@ -784,6 +793,12 @@ int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, int shared_table, v
         }
         want = w.max_chunks < (size_t)ctx->sm_count * 6 ? w.max_chunks : (size_t)ctx->sm_count * 6;
         if (want < 1) want = 1;
+        // RC_ABLATE bit 1 (timing experiments only): no chunk encoder, every piece is empty
+        static const int ablate = getenv("RC_ABLATE") ? atoi(getenv("RC_ABLATE")) : 0;
+        if (ablate & 2) {
+            cudaMemsetAsync(w.chunk_bytes, 0, (w.max_chunks + 1) * sizeof(uint32_t), st);
+            cudaMemsetAsync(w.chunk_adler, 0, (w.max_chunks + 1) * sizeof(uint2), st);
+        } else
         k_deflate_chunks<<<(unsigned)want, DF_THREADS, 0, st>>>(in, in_off, in_bytes, n_streams, w.chunk_base,
                                                                  w.counters, level, shared_table,
                                                                  tables, w.scratch,

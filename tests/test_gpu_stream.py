@@ -46,8 +46,9 @@ def test_stream_ingest_equals_batch(tmp_path, level, b):
             em_reader.write_seq(str(ram / ('chunk_%03d.seq' % i)), c, allocated_frames=len(c) + (3 if i == 2 else 0))
             time.sleep(0.05)
 
-    ip = make_params(ny, nx, -1, level=level, b=b, eps=eps)
-    ip._param_map['source_file_type'] = 2
+    ip = make_params(ny, nx, 1, level=level, b=b, eps=eps)
+    ip._param_map['source_file_type'] = 2          # SEQ chunks; the frame count comes from every chunk
+    ip._param_map['num_frames'] = -1
     assert ip.validate()
     w = ReCoDeWriter(str(ram / stream.NEXT_STREAM), dark_data=dark[None], output_directory=str(out), input_params=ip,
                      mode='stream', run_name='acq7', batch_frames=3, validation_frame_gap=4)
