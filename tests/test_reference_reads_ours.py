@@ -93,8 +93,29 @@ def test_reference_reads_our_part_files_l1(ref_reader, name):
 
 @pytest.mark.parametrize('name,inter', [('ours_l3.rc3_part000', True), ('ours_l3_mg.rc3', False)])
 def test_reference_reads_our_l3(ref_reader, name, inter):
+    """The reference's get_next_frame cannot decode ANY level-3 frame (it calls c_recode.get_frame_sparse with three
+    arguments, recode_reader.py:456 vs pyrecode.cpp:103 -- a SystemError on its own files too, asserted below), so the
+    level-3 contract is checked through the part of its reader that works: header, metadata walk and raw record
+    extraction (get_next_frame_raw, recode_reader.py:275-324), the payload inflated with stock zlib."""
+    import zlib
     data, thr = _inputs()
-    frames = _read_all(ref_reader, os.path.join(GOLD, name), inter)
-    assert sorted(frames) == list(range(data.shape[0]))
-    for z, d in frames.items():
-        assert np.array_equal(d != 0, data[z] > thr), 'frame %d' % z
+    with contextlib.redirect_stdout(io.StringIO()):
+        own = ref_reader(os.path.join(GOLD, 'gold_c_l3m1.rc3_part000'), is_intermediate=True)
+        own.open(print_header=False)
+        with pytest.raises(SystemError):
+            own.get_next_frame()
+        own.close()
+        r = ref_reader(os.path.join(GOLD, name), is_intermediate=inter)
+        r.open(print_header=False)
+        assert tuple(r.get_shape()) == data.shape
+        seen = []
+        for _ in range(data.shape[0]):
+            f = r.get_next_frame_raw()
+            z = int(list(f.keys())[0])
+            m = zlib.decompress(f[z]['data']['binary_map'])
+            bits = np.unpackbits(np.frombuffer(m, np.uint8), bitorder='little')[:data[z].size].reshape(data[z].shape)
+            assert np.array_equal(bits.astype(bool), data[z] > thr), 'frame %d' % z
+            assert int(f[z]['metadata']['bytes_in_compressed_binary_map']) == len(f[z]['data']['binary_map'])
+            seen.append(z)
+        r.close()
+    assert seen == list(range(data.shape[0]))
