@@ -128,9 +128,10 @@ class ReCoDeReader:
         raise NotImplementedError
 
     def close(self):
-        if getattr(self, '_pool', None) is not None:
-            self._pool.shutdown()
-            self._pool = None
+        for name in ('_io', '_pool'):
+            if getattr(self, name, None) is not None:
+                getattr(self, name).shutdown()
+                setattr(self, name, None)
         self._fp.close()
 
     def seek_to_frame_data(self):
@@ -336,31 +337,32 @@ class ReCoDeReader:
                 self._bulk.append(e)
         return self._bulk
 
-    def _read_block(self, n, eng):
-        """Reads the records of up to n frames into eng's pinned block.
-        -> (frame ids, nbytes, map_off, map_sz, val_off, val_sz); val_* are None for levels 3 / 4."""
+    def _plan_block(self, n):
+        """Locate the records of the next (up to) n frames without reading their payloads, and advance the reader
+        past them.  -> dict: ids, start (file offset of the byte range), nbytes, map_off / map_sz / val_off / val_sz
+        (offsets relative to start; val_* are None for levels 3 / 4), packed (bytes the value streams inflate to)."""
         self._drop_ahead()
         h = self._header
         level = h['reduction_level']
         two = level in (1, 2)
         vname = 'bytes_in_compressed_' + ('pixvals' if level == 1 else 'summary_stats')
         pname = 'bytes_in_packed_' + ('pixvals' if level == 1 else 'summary_stats')
-        self._block_packed = pk = []                  # bytes the value streams must inflate to (ReadEngine.check)
+        pk = []
         if self._current_frame_index == 0:
             self._fp.seek(self._frame_data_start_position, 0)
         ids, moff, msz, voff, vsz = [], [], [], [], []
-        pos = 0
+        start, pos = self._fp.tell(), 0
         fd = self._fp.fileno()
         if self._is_intermediate:
             # records are [frame_id][sizes...][map stream][value stream], back to back: walk the small headers with
-            # preads, then fetch the whole byte range of the batch at once (in parallel slices)
+            # preads; the whole byte range of the batch is fetched at once afterwards (in parallel slices)
             nf = len(self._sm)
             names = [f['name'] for f in self._sm]
             i_map = names.index('bytes_in_compressed_binary_map')
             i_val = names.index(vname) if two else -1
             i_pk = names.index(pname) if two else -1
             hlen = 4 + 4 * nf
-            start = fpos = self._fp.tell()
+            fpos = start
             while len(ids) < n:
                 hdr = os.pread(fd, hlen, fpos)
                 if len(hdr) < hlen:
@@ -378,7 +380,6 @@ class ReCoDeReader:
                 fpos += hlen + n_map + n_val
             pos = fpos - start
             if ids:
-                self._pread_parallel(fd, eng.block_buffer(pos + 16), start, pos)
                 self._fp.seek(fpos, 0)
                 self._current_frame_index += len(ids)
         else:
@@ -386,11 +387,11 @@ class ReCoDeReader:
             z1 = min(h['nz'], z0 + n)
             if z1 > z0:
                 sizes = self._seek_table[z0:z1, 0].astype(np.int64)
-                start = int(self._seek_table[z0, 1])
-                total = int(sizes.sum())
-                self._pread_parallel(fd, eng.block_buffer(total + 16), self._frame_data_start_position + start, total)
-                self._fp.seek(self._frame_data_start_position + start + total, 0)     # sequential reads continue here
-                rel = (self._seek_table[z0:z1, 1].astype(np.int64) - start)
+                rel0 = int(self._seek_table[z0, 1])
+                start = self._frame_data_start_position + rel0
+                pos = int(sizes.sum())
+                self._fp.seek(start + pos, 0)                                  # sequential reads continue here
+                rel = (self._seek_table[z0:z1, 1].astype(np.int64) - rel0)
                 for k, z in enumerate(range(z0, z1)):
                     md = self._frame_metadata[z]
                     n_map = int(md['bytes_in_compressed_binary_map'])
@@ -399,11 +400,20 @@ class ReCoDeReader:
                     if two:
                         voff.append(int(rel[k]) + n_map); vsz.append(int(md[vname]))
                         pk.append(int(md[pname]))
-                pos = total
                 self._current_frame_index = z1
         if not two:
             voff = vsz = None
-        return ids, pos, moff, msz, voff, vsz
+        return {'ids': ids, 'start': start, 'nbytes': pos, 'map_off': moff, 'map_sz': msz, 'val_off': voff,
+                'val_sz': vsz, 'packed': pk or None}
+
+    def _read_block(self, n, eng):
+        """Reads the records of up to n frames into eng's pinned block.
+        -> (frame ids, nbytes, map_off, map_sz, val_off, val_sz); val_* are None for levels 3 / 4."""
+        p = self._plan_block(n)
+        self._block_packed = p['packed']
+        if p['ids']:
+            self._pread_parallel(self._fp.fileno(), eng.block_buffer(p['nbytes'] + 16), p['start'], p['nbytes'])
+        return p['ids'], p['nbytes'], p['map_off'], p['map_sz'], p['val_off'], p['val_sz']
 
     def _pread_parallel(self, fd, buf, offset, nbytes, n_threads=8):
         """file[offset : offset + nbytes] -> buf[:nbytes] (pinned), in slices read by a few threads (preadv releases
@@ -431,41 +441,65 @@ class ReCoDeReader:
 
     def _bulk_run(self, n, consume):
         """Pipelined decode of the next n frames; consume(engine) enqueues the unpack of a loaded batch on the
-        engine's stream.  -> frame ids (in file order)"""
+        engine's stream.  The file read of batch k + 1 (an I/O thread, preadv releases the GIL) runs while batch k is
+        enqueued.  -> frame ids (in file order)"""
         import torch
         if self._header['rc_operation_mode'] != 1:
             raise ValueError('bulk decoding handles compressed files (rc_operation_mode 1) only')
         import time
         engs = self._bulk_engines()
+        if getattr(self, '_io', None) is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._io = ThreadPoolExecutor(1)
         pending = []                                   # engines whose batch has not been checked yet
         ids = []
-        k = 0
         st = self.bulk_stats = {'file_read_s': 0.0, 'enqueue_s': 0.0, 'wait_s': 0.0, 'bytes': 0}
-        while len(ids) < n:
-            eng = engs[k % len(engs)]
+        state = {'k': 0, 'planned': 0}
+        fd = self._fp.fileno()
+
+        def timed_read(buf, start, nbytes):
+            t = time.perf_counter()
+            self._pread_parallel(fd, buf, start, nbytes)
+            return time.perf_counter() - t
+
+        def start_read():
+            """plan the next batch and start reading it into the next engine's pinned block"""
+            if state['planned'] >= n:
+                return None
+            eng = engs[state['k'] % len(engs)]
             t0 = time.perf_counter()
             if eng in pending:                         # its previous batch: validate before reusing the buffers
                 eng.stream.synchronize()
                 eng.check(eng.expect_packed)
                 pending.remove(eng)
             eng.wait_block_free()
+            st['wait_s'] += time.perf_counter() - t0
+            plan = self._plan_block(min(eng.max_frames, n - state['planned']))
+            if not plan['ids']:
+                return None
+            fut = self._io.submit(timed_read, eng.block_buffer(plan['nbytes'] + 16), plan['start'], plan['nbytes'])
+            state['planned'] += len(plan['ids'])
+            state['k'] += 1
+            return eng, plan, fut
+
+        cur = start_read()
+        while cur is not None:
+            nxt = start_read()
+            eng, plan, fut = cur
+            t0 = time.perf_counter()
+            st['file_read_s'] += fut.result()          # time spent in the I/O thread (overlaps the enqueues)
             t1 = time.perf_counter()
-            bi, nbytes, moff, msz, voff, vsz = self._read_block(min(eng.max_frames, n - len(ids)), eng)
-            t2 = time.perf_counter()
             st['wait_s'] += t1 - t0
-            st['file_read_s'] += t2 - t1
-            if not bi:
-                break
-            eng.expect_packed = self._block_packed or None
+            eng.expect_packed = plan['packed']
             eng.stream.wait_stream(torch.cuda.current_stream(eng.dev))
             with torch.cuda.stream(eng.stream):
-                eng.load_block(nbytes, moff, msz, voff, vsz)
+                eng.load_block(plan['nbytes'], plan['map_off'], plan['map_sz'], plan['val_off'], plan['val_sz'])
                 consume(eng)
-            st['enqueue_s'] += time.perf_counter() - t2
-            st['bytes'] += nbytes
+            st['enqueue_s'] += time.perf_counter() - t1
+            st['bytes'] += plan['nbytes']
             pending.append(eng)
-            ids += bi
-            k += 1
+            ids += plan['ids']
+            cur = nxt
         t0 = time.perf_counter()
         for eng in pending:
             eng.stream.synchronize()
@@ -485,6 +519,7 @@ class ReCoDeReader:
         with torch.cuda.device(eng.dev):
             torch.cuda.synchronize()
             bi, nbytes, moff, msz, voff, vsz = self._read_block(eng.max_frames, eng)
+            eng.expect_packed = self._block_packed
             n = len(bi)
             out = {'frames': n}
             if n == 0:
@@ -516,7 +551,7 @@ class ReCoDeReader:
                 acc['unpack_dense_ms'] += ev[2].elapsed_time(ev[3])
                 acc['unpack_sum_ms'] += ev[3].elapsed_time(ev[4])
             eng.ctx.profile_enable(0)
-            eng.check(eng.expect_packed if hasattr(eng, 'expect_packed') else None)
+            eng.check(eng.expect_packed)
             out.update({k: v / reps for k, v in acc.items()})
         self.rewind()
         return out

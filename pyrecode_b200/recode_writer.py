@@ -176,6 +176,10 @@ class ReCoDeWriter:
             base_filename + '.rc' + str(self._input_params.reduction_level) +
             ('' if self._merged else '_part' + '{0:03d}'.format(self._node_id)))
         self._intermediate_file = open(self._intermediate_file_name, 'wb')
+        if self._rc_header.as_dict()['nz'] < 0:
+            # num_frames = -1 ("take the count from the source"): the reference cannot serialize that placeholder
+            # (recode_header.py:274 raises OverflowError); the true count is written by close() either way
+            self._rc_header.set('nz', 0)
         self._rc_header.serialize_to(self._intermediate_file)
         self._intermediate_file.flush()
         if self._init_params.validation_frame_gap > 0:
