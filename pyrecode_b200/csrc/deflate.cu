@@ -464,24 +464,14 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
         if (!stored && !table_loaded) df_load_table(S, T, t, DF_THREADS);     // per-stream codes (levels 6..9)
         __syncthreads();
 
-        // Adler-32 partials of the chunk (warp shuffle reduction, one shared atomic per warp)
-        {
-            uint32_t a, b;
-            df_adler_partial(S.io, t, clen, a, b);
-            a %= 65521u; b %= 65521u;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                a += __shfl_down_sync(0xffffffffu, a, d);
-                b += __shfl_down_sync(0xffffffffu, b, d);
-            }
-            if ((t & 31) == 0 && (a | b)) { atomicAdd(&s_adler[0], a % 65521u); atomicAdd(&s_adler[1], b % 65521u); }
-        }
-
+        // A chunk with few non-zero bytes (a binary map) is encoded from the list of those bytes -- work per non-zero
+        // byte, equal shares -- and its Adler-32 partials come from the same list; everything else is tokenized
+        // byte by byte.
         uint32_t body_bits = 0, my_bits = 0, my_off = 0, n_nz = 0;
+        uint32_t ad_a = 0, ad_b = 0;
         bool sparse = false;
         if (!stored) {
             if (t == 0) S.header_bits = hb;
-            // few non-zero bytes (a binary map): encode from their list -- work per non-zero byte, equal shares
             if (shared_table && !S.e_bad) {
                 uint32_t nz[2];
                 const uint32_t cnt = df_nz_masks(S.io, t, df_seg_bytes(t, clen), nz);
@@ -489,8 +479,21 @@ k_deflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
                 sparse = n_nz <= (uint32_t)DF_STAGE_WORDS;
                 if (sparse) df_nz_scatter(S.io, S.priv, t, base, nz);
                 __syncthreads();
-                if (sparse) my_bits = df_sparse_bits(S, S.priv, t, n_nz, clen);
+                if (sparse) my_bits = df_sparse_bits(S, S.priv, t, n_nz, clen, ad_a, ad_b);
             }
+        }
+        if (!sparse) df_adler_partial(S.io, t, clen, ad_a, ad_b);
+        {
+            // Adler-32 partials of the chunk (warp shuffle reduction, one shared atomic per warp)
+            uint32_t a = ad_a % 65521u, b = ad_b % 65521u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                a += __shfl_down_sync(0xffffffffu, a, d);
+                b += __shfl_down_sync(0xffffffffu, b, d);
+            }
+            if ((t & 31) == 0 && (a | b)) { atomicAdd(&s_adler[0], a % 65521u); atomicAdd(&s_adler[1], b % 65521u); }
+        }
+        if (!stored) {
             if (!sparse) my_bits = df_encode_segment(S, t, clen);
             uint32_t tok_bits;
             const uint32_t e = block_excl_scan<8>(my_bits, s_warp, &tok_bits);     // two barriers: encode pass is over

@@ -606,35 +606,52 @@ DF_HD void df_sparse_range(int t, uint32_t n, uint32_t &lo, uint32_t &hi)
     hi = (uint32_t)(((uint64_t)n * (uint32_t)(t + 1)) / DF_THREADS);
 }
 
-// code bits of thread t's entries; the zero bytes after the last entry of the chunk belong to the last thread
-DF_HD uint32_t df_sparse_bits(const DfEmitShared &S, const uint32_t *list, int t, uint32_t n, int clen)
+// code bits of a run of g zero bytes: whole composites of 259, then the composite of the rest
+DF_HD uint32_t df_zrun_bits(const DfEmitShared &S, uint32_t g)
+{
+    if (g <= (uint32_t)DF_ZRUN) return S.elen[g];                  // the common case: no division
+    const uint32_t rep = g / (uint32_t)DF_ZRUN;
+    return rep * S.elen[DF_ZRUN] + S.elen[g - rep * (uint32_t)DF_ZRUN];
+}
+
+// code bits of thread t's entries (the zero bytes after the last entry of the chunk belong to the last thread) and
+// the Adler-32 partials of its entries {sum b, sum (clen - i) b}: the zero bytes contribute nothing to either sum
+DF_HD uint32_t df_sparse_bits(const DfEmitShared &S, const uint32_t *list, int t, uint32_t n, int clen,
+                              uint32_t &adler_a, uint32_t &adler_b)
 {
     uint32_t lo, hi;
     df_sparse_range(t, n, lo, hi);
-    uint32_t bits = 0;
+    uint32_t bits = 0, a = 0, b = 0;
     uint32_t prev = lo ? (list[lo - 1] >> 8) + 1u : 0u;            // first byte not yet covered
-    const uint32_t l259 = S.elen[DF_ZRUN];
     for (uint32_t k = lo; k < hi; k++) {
         const uint32_t e = list[k];
-        const uint32_t g = (e >> 8) - prev;
-        prev = (e >> 8) + 1u;
-        const uint32_t rep = g / (uint32_t)DF_ZRUN;
-        bits += rep * l259 + S.elen[g - rep * (uint32_t)DF_ZRUN] + (S.tbl[e & 0xffu] >> 24);
+        const uint32_t pos = e >> 8, val = e & 0xffu;
+        bits += df_zrun_bits(S, pos - prev) + (S.tbl[val] >> 24);
+        prev = pos + 1u;
+        a += val;
+        b += ((uint32_t)clen - pos) * val;                          // <= 17 entries * 16384 * 255 < 2^32
     }
-    if (t == DF_THREADS - 1) {
-        const uint32_t g = (uint32_t)clen - prev, rep = g / (uint32_t)DF_ZRUN;
-        bits += rep * l259 + S.elen[g - rep * (uint32_t)DF_ZRUN];
-    }
+    if (t == DF_THREADS - 1) bits += df_zrun_bits(S, (uint32_t)clen - prev);
+    adler_a = a;
+    adler_b = b;
     return bits;
 }
 
-DF_HD void df_or_bits(uint32_t *out, uint32_t &pos, uint32_t code, uint32_t n)
+// ORs `n` (<= 47) code bits into the output stream at bit `pos`: at most three words
+DF_HD void df_or_bits64(uint32_t *out, uint32_t &pos, uint32_t lo, uint32_t hi, uint32_t n)
 {
-    if (!n) return;
     const uint32_t w = pos >> 5, sh = pos & 31;
-    DF_ATOMIC_OR(&out[w], code << sh);
-    if (sh + n > 32) DF_ATOMIC_OR(&out[w + 1], code >> (32 - sh));
     pos += n;
+    uint32_t x0 = lo << sh, x1, x2 = 0;
+    if (sh) {
+        x1 = (lo >> (32 - sh)) | (hi << sh);
+        x2 = hi >> (32 - sh);
+    } else {
+        x1 = hi;
+    }
+    if (x0) DF_ATOMIC_OR(&out[w], x0);
+    if (x1) DF_ATOMIC_OR(&out[w + 1], x1);
+    if (x2) DF_ATOMIC_OR(&out[w + 2], x2);
 }
 
 // ORs the codes of thread t's entries into the (zero-initialised) output bit stream from bit `pos`
@@ -654,10 +671,13 @@ DF_HD void df_sparse_emit(DfEmitShared &S, const uint32_t *list, int t, uint32_t
             if (t != DF_THREADS - 1) break;
             g = (uint32_t)clen - prev;                                // the zero bytes that end the chunk
         }
-        for (; g > (uint32_t)DF_ZRUN; g -= DF_ZRUN) df_or_bits(S.io, pos, S.ecode[DF_ZRUN], S.elen[DF_ZRUN]);
-        if (g == (uint32_t)DF_ZRUN && S.elen[DF_ZRUN]) { df_or_bits(S.io, pos, S.ecode[DF_ZRUN], S.elen[DF_ZRUN]); g = 0; }
-        df_or_bits(S.io, pos, S.ecode[g], S.elen[g]);
-        df_or_bits(S.io, pos, lit & 0xffffffu, lit >> 24);
+        for (; g > (uint32_t)DF_ZRUN; g -= DF_ZRUN) df_or_bits64(S.io, pos, S.ecode[DF_ZRUN], 0u, S.elen[DF_ZRUN]);
+        // the run's composite (<= 32 bits) and the literal (<= 15 bits) as one bit string
+        const uint32_t el = S.elen[g], ec = S.ecode[g], lc = lit & 0xffffffu, ll = lit >> 24;
+        uint32_t c_lo = ec, c_hi = 0;
+        if (el < 32) { c_lo |= lc << el; c_hi = el ? lc >> (32 - el) : 0u; }
+        else c_hi = lc;
+        df_or_bits64(S.io, pos, c_lo, c_hi, el + ll);
     }
 }
 

@@ -99,7 +99,14 @@ extern "C" long host_deflate_stream(const uint8_t *in, uint32_t n, int level, ui
                 sparse = n_nz <= (uint32_t)DF_STAGE_WORDS;
                 if (sparse) {
                     for (int t = 0; t < DF_THREADS; t++) df_nz_scatter(S.io, S.priv, t, base[t], nzm[t]);
-                    for (int t = 0; t < DF_THREADS; t++) bits_of[t] = df_sparse_bits(S, S.priv, t, n_nz, clen);
+                    // the Adler-32 partials of a sparse chunk come from its list: must equal the byte-wise ones
+                    uint32_t la = 0, lb = 0;
+                    for (int t = 0; t < DF_THREADS; t++) {
+                        uint32_t a, b;
+                        bits_of[t] = df_sparse_bits(S, S.priv, t, n_nz, clen, a, b);
+                        la = (la + a % 65521u) % 65521u; lb = (lb + b % 65521u) % 65521u;
+                    }
+                    if (la != ca || lb != cb) return -7;
                 }
             }
             if (!sparse) for (int t = 0; t < DF_THREADS; t++) bits_of[t] = df_encode_segment(S, t, clen);
