@@ -251,7 +251,8 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
     tmp = tempfile.mkdtemp(prefix='recode_bench_', dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
     try:
         ip = InputParams()
-        for k, v in dict(l4_centroiding=0, source_file_type=0, num_frames=nz, source_header_length=0,
+        nz = max(256, nz // 256 * 256)
+        for k, v in dict(l4_centroiding=0, source_file_type=0, num_frames=256, source_header_length=0,
                          calibration_frame_offset=0, compression_scheme=0, calibration_file_type=0, compression_level=1,
                          l2_statistics=0, calibration_threshold_epsilon=eps_of(), frame_offset=0, num_threads=1,
                          rc_operation_mode=1, num_calibration_frames=1, reduction_level=2, keep_calibration_data=1,
@@ -261,9 +262,12 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
         w = ReCoDeWriter('rb', dark_data=dark[None], output_directory=tmp, input_params=ip, mode='batch', node_id=0,
                          device=local_rank)
         w.start()
-        w.run(np.stack([frames[i % len(frames)] for i in range(nz)]))
+        per_run = ip._param_map['num_frames']
+        chunk = np.stack([frames[i % len(frames)] for i in range(per_run)])
+        for _ in range(nz // per_run):                # the part file grows by one chunk of frames per run()
+            w.run(chunk)
         w.close()
-        del w
+        del w, chunk
         path = os.path.join(tmp, 'rb.rc2_part000')
         fsize = os.path.getsize(path)
 
@@ -290,7 +294,7 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
                 ar1.record()
                 out = int(total[:1024].sum().item())          # device -> host read of the result
             else:
-                ids, dense = r.read_frames_dense(min(nz, 128))
+                ids, dense = r.read_frames_dense(min(nz, 256))
                 out = int(dense[0, 0, :8].sum().item())
                 del dense
             return len(ids), dict(r.bulk_stats)
@@ -389,10 +393,10 @@ def main():
     ap.add_argument('--mode', default='write', choices=['write', 'read'],
                     help="read: only BASELINE config 5 -- an L2 part file per GPU -> live-view sum (+ NCCL all-reduce) and "
                          "dense frames through ReCoDeReader's bulk calls")
-    ap.add_argument('--read-frames', type=int, default=256, help='frames in the part file of the read leg')
+    ap.add_argument('--read-frames', type=int, default=1024, help='frames in the part file of the read leg (a multiple of 256)')
     ap.add_argument('--read-steps', type=int, default=5)
-    ap.add_argument('--read-batch', type=int, default=32, help='frames per decode batch of the read leg')
-    ap.add_argument('--read-inflight', type=int, default=8, help='decode batches in flight')
+    ap.add_argument('--read-batch', type=int, default=64, help='frames per decode batch of the read leg')
+    ap.add_argument('--read-inflight', type=int, default=6, help='decode batches in flight')
     args = ap.parse_args()
     global BIT_DEPTH
     BIT_DEPTH = args.bit_depth

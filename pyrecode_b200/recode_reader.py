@@ -415,7 +415,7 @@ class ReCoDeReader:
             self._pread_parallel(self._fp.fileno(), eng.block_buffer(p['nbytes'] + 16), p['start'], p['nbytes'])
         return p['ids'], p['nbytes'], p['map_off'], p['map_sz'], p['val_off'], p['val_sz']
 
-    def _pread_parallel(self, fd, buf, offset, nbytes, n_threads=8):
+    def _pread_parallel(self, fd, buf, offset, nbytes, n_threads=None):
         """file[offset : offset + nbytes] -> buf[:nbytes] (pinned), in slices read by a few threads (preadv releases
         the GIL; one thread copies out of the page cache at only a few GB/s)"""
         mv = memoryview(buf)
@@ -430,6 +430,12 @@ class ReCoDeReader:
         if nbytes < (8 << 20):
             rd(0, nbytes)
             return
+        if n_threads is None:
+            # copying out of the page cache is memory-bound per thread: use what this process may run on, up to 16
+            try:
+                n_threads = max(4, min(16, len(os.sched_getaffinity(0))))
+            except AttributeError:
+                n_threads = 8
         if getattr(self, '_pool', None) is None:
             from concurrent.futures import ThreadPoolExecutor
             self._pool = ThreadPoolExecutor(n_threads)
