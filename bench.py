@@ -323,6 +323,20 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             res[what] = (world * n / float(t[0]), float(t[0]) / steps, st)
         gpu = r.decode_stage_ms()
+        # the per-frame API (get_next_frame -> scipy COO + summary statistics), as a user loop would call it
+        seq_fps = None
+        if rank == 0:
+            rr = ReCoDeReader(path, is_intermediate=True, device=local_rank)
+            rr.open(print_header=False)
+            rr.get_next_frame()
+            t0 = time.perf_counter()
+            k = 0
+            for _ in range(48):
+                if rr.get_next_frame() is None:
+                    break
+                k += 1
+            seq_fps = k / (time.perf_counter() - t0)
+            rr.close()
         # records for the CPU baseline before the file goes away
         recs = None
         if want_cpu and rank == 0:
@@ -343,7 +357,8 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
                'live_view_frames_per_s': res['sum'][0], 'ms_per_view': 1e3 * res['sum'][1],
                'allreduce_ms': float(np.median(ar_ms)) if ar_ms else None,
                'dense_frames_per_s': res['dense'][0], 'dense_output_gb_s': res['dense'][0] * frame_bytes / 1e9,
-               'file_bytes': fsize, 'steps': steps,
+               'file_bytes': fsize, 'steps': steps, 'frames_per_view': nz,
+               'get_next_frame_fps': seq_fps,
                'host_time_split_ms_last_view': {k: (1e3 * v if k.endswith('_s') else v) for k, v in res['sum'][2].items()},
                'e2e': {'value': res['sum'][0], 'unit': 'frames/s', 'h2d_bytes_per_step': fsize, 'd2h_bytes_per_step': 8}}
         if gpu and gpu.get('frames'):
@@ -389,6 +404,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-read', action='store_true', help='skip the read-path sub-record (BASELINE config 5)')
     ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--also-levels', default='1,4', help='other reduction levels timed briefly beside the headline one')
     ap.add_argument('--bit-depth', type=int, default=12, help='source / target bit depth (SURVEY 8d: 8, 12, 16)')
     ap.add_argument('--mode', default='write', choices=['write', 'read'],
                     help="read: only BASELINE config 5 -- an L2 part file per GPU -> live-view sum (+ NCCL all-reduce) and "
@@ -611,11 +627,55 @@ def main():
                'cpu_affinity': cpus}
 
     del d_frames
+    eng = None
+    torch.cuda.empty_cache()
+
+    # ---- the other reduction levels of BASELINE.json's configs (L1: config 2, L4: config 4), same harness, short
+    others = {}
+    for lv in [int(x) for x in args.also_levels.split(',') if x.strip()]:
+        if lv == level:
+            continue
+        dk, fr = make_inputs(lv, args.distinct, seed=1234 + rank)
+        e2 = WriteEngine(NY, NX, isz, BIT_DEPTH, lv, 1, 0, 0, 1, max_frames=F, device=local_rank,
+                         records_capacity=F * (frame_bytes // 4), n_slots=args.slots)
+        e2.set_threshold(dk, eps_of())
+        for i in range(F):
+            hv[i] = fr[i % len(fr)]
+        d2 = host.to(dev)
+        ids2 = [None] * len(e2.slots)
+
+        def steps2(n_steps, id0):
+            for sl in e2.slots:
+                sl.stream.wait_stream(cur)
+            for q in range(n_steps * M):
+                sl = e2.slots[q % len(e2.slots)]
+                with torch.cuda.stream(sl.stream):
+                    e2.launch(d2, F, id0 + q * F, q % len(e2.slots))
+                ids2[q % len(e2.slots)] = id0 + q * F
+            for sl in e2.slots:
+                cur.wait_stream(sl.stream)
+
+        steps2(2, 0)
+        barrier()
+        e0.record()
+        steps2(5, 7000)
+        e1.record()
+        barrier()
+        t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        v2 = world * F * M * 5 / (float(t2[0]) / 1e3)
+        par2 = parity_check(e2, lv, dk, fr, F, ids2) if (rank == 0 and not args.no_parity) else None
+        others['L%d' % lv] = {'value': v2, 'unit': 'frames/s', 'steps': 5, 'ms_per_launch': float(t2[0]) / (5 * M),
+                              'input_gb_s': v2 * frame_bytes / 1e9,
+                              'hbm_roofline_frac_whole_path': v2 / world * frame_bytes / 1e9 / measured_peak()[0],
+                              'parity_checked': bool(par2[0]) if par2 else False,
+                              'workload': 'L%d reduce + deflate, synthetic %s frames, same geometry / batching' % (lv, KIND[lv])}
+        del e2, d2
+        torch.cuda.empty_cache()
+
     rd = None
     if not args.no_read:
-        # free the write engine's workspaces before the reader allocates its own
-        del eng
-        torch.cuda.empty_cache()
         dark2, frames2 = (dark, frames) if level == 2 else make_inputs(2, args.distinct, seed=1234 + rank)
         rd = read_leg(args, rank, world, local_rank, dev, dark2, frames2, not args.no_cpu)
 
@@ -643,6 +703,8 @@ def main():
                                             [float(x) for x in stage_ms])),
             'stage2_kernel_ms_per_launch': detail,
             'record_bytes_per_frame': rec_bytes / F, 'status': st}
+    if others:
+        line['other_levels'] = others
     if rd is not None:
         line['read'] = rd
     if not args.no_cpu:

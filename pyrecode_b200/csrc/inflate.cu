@@ -513,13 +513,19 @@ k_inflate_serial(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
                  uint8_t *__restrict__ out, size_t out_stride, uint32_t *__restrict__ out_bytes,
                  uint32_t *__restrict__ status)
 {
+    // A stream that is not a chain of our own chunks (a file written by the reference: one block sequence per stream,
+    // matches at any distance) is decoded by one lane through a 32 KiB shared-memory history ring and a 2 KiB input
+    // window: match copies and input bytes never wait for global memory.
     __shared__ IfTables s_tab;
+    __shared__ __align__(16) uint8_t s_ring[IF_RING_BYTES];
+    __shared__ __align__(16) uint32_t s_win[IF_WIN_BYTES / 4];
     const int s = blockIdx.x;
     if (!need_serial[s] || threadIdx.x != 0) return;
     IfOut O;
-    O.init(out + (size_t)s * out_stride, out_stride);
+    O.init_ring(out + (size_t)s * out_stride, out_stride, s_ring);
     uint64_t end = 0;
-    const int code = if_inflate(in + in_off[s], in_bytes[s], 2, O, s_tab, false, &end);
+    const int code = if_inflate(in + in_off[s], in_bytes[s], 2, O, s_tab, false, &end, s_win);
+    O.flush(O.n);
     uint32_t st = RC_STATUS_OK;
     if (code == IF_ERR_OUT) st = RC_STATUS_OUT_OVERFLOW;
     else if (code != IF_END_FINAL || end + 4 > in_bytes[s]) st = RC_STATUS_BAD_STREAM;

@@ -197,23 +197,63 @@ IF_HD int if_decode(IfBits &B, const IfTable &T)
     return -1;
 }
 
+constexpr uint32_t IF_RING_BYTES = 32768;   // ring mode: deflate's whole history window (a power of two)
+constexpr uint32_t IF_FLUSH_BYTES = 4096;   // ... written back to global memory in segments of this size
+
 struct IfOut {
     uint8_t *out;
     uint64_t cap;
     uint64_t n;          // bytes produced
     uint32_t s1, s2;     // Adler-32 partials, started from (0, 0), of the bytes produced at index >= sh_cap
-    // Device: the first sh_cap bytes (a whole chunk of our own encoder) are produced in a shared-memory buffer,
-    // zero-filled beforehand, that the warp copies out -- and checksums -- together afterwards.  Runs of 0x00, most of
-    // a binary map, then need no stores at all, and the byte before a run is read back from shared memory.
+                         // (ring mode: of all bytes)
+    // Device, own chunks: the first sh_cap bytes (a whole chunk of our own encoder) are produced in a shared-memory
+    // buffer, zero-filled beforehand, that the warp copies out -- and checksums -- together afterwards.  Runs of 0x00,
+    // most of a binary map, then need no stores at all, and the byte before a run is read back from shared memory.
     uint8_t *sh;
     uint32_t sh_cap;
+    // Ring mode (foreign streams: one block sequence of megabytes with matches at any distance up to 32 KiB): `sh` is
+    // a circular window of IF_RING_BYTES over ALL the output, so a match copies shared memory to shared memory
+    // instead of paying a global store -> load round trip per byte; finished IF_FLUSH_BYTES segments go to `out`
+    // with 128-bit stores.
+    bool ring;
+    uint64_t flushed;
     IF_HD void init(uint8_t *o, uint64_t capacity, uint8_t *shared = nullptr, uint32_t shared_cap = 0)
     {
-        out = o; cap = capacity; n = 0; s1 = 0; s2 = 0; sh = shared; sh_cap = shared_cap;
+        out = o; cap = capacity; n = 0; s1 = 0; s2 = 0; sh = shared; sh_cap = shared_cap; ring = false; flushed = 0;
     }
-    IF_HD uint8_t at(uint64_t i) const { return i < sh_cap ? sh[i] : out[i]; }
+    IF_HD void init_ring(uint8_t *o, uint64_t capacity, uint8_t *ring_buf)
+    {
+        out = o; cap = capacity; n = 0; s1 = 0; s2 = 0; sh = ring_buf; sh_cap = 0; ring = true; flushed = 0;
+    }
+    IF_HD uint8_t at(uint64_t i) const
+    {
+        if (ring) return sh[(uint32_t)i & (IF_RING_BYTES - 1)];
+        return i < sh_cap ? sh[i] : out[i];
+    }
+    // ring mode: copy [flushed, upto) to global memory; upto = n at the end of the stream, else a segment boundary
+    IF_HD void flush(uint64_t upto)
+    {
+        uint64_t i = flushed;
+#ifdef __CUDA_ARCH__
+        if ((((uintptr_t)out) & 15) == 0)
+            for (; i + 16 <= upto; i += 16)
+                *reinterpret_cast<uint4 *>(out + i) = *reinterpret_cast<const uint4 *>(sh + ((uint32_t)i & (IF_RING_BYTES - 1)));
+#endif
+        for (; i < upto; i++) out[i] = sh[(uint32_t)i & (IF_RING_BYTES - 1)];
+        flushed = upto;
+    }
     IF_HD void put(uint8_t c)
     {
+        if (ring) {
+            sh[(uint32_t)n & (IF_RING_BYTES - 1)] = c;
+            n++;
+            s1 += c; s2 += s1;
+            if ((n & 2047) == 0) {
+                s1 %= 65521u; s2 %= 65521u;
+                if ((n & (IF_FLUSH_BYTES - 1)) == 0) flush(n);
+            }
+            return;
+        }
         if (n < sh_cap) { sh[n++] = c; return; }
         out[n++] = c;
         s1 += c; s2 += s1;
@@ -223,6 +263,16 @@ struct IfOut {
     // s2' = s2 + len s1 + c len (len + 1) / 2
     IF_HD void put_run(uint8_t c, uint32_t len)
     {
+        if (ring) {
+            for (uint32_t i = 0; i < len; i++) sh[(uint32_t)(n + i) & (IF_RING_BYTES - 1)] = c;
+            n += len;
+            s1 %= 65521u;
+            s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)len * s1 + (uint64_t)c * (len * (len + 1) / 2)) % 65521u);
+            s1 = (s1 + len * (uint32_t)c) % 65521u;
+            const uint64_t seg = n & ~(uint64_t)(IF_FLUSH_BYTES - 1);
+            if (seg > flushed) flush(seg);
+            return;
+        }
         if (n < sh_cap) {
             const uint32_t k = (uint64_t)len < sh_cap - n ? len : (uint32_t)(sh_cap - n);
             if (c != 0)

@@ -148,10 +148,13 @@ extern "C" long host_inflate_stream(const uint8_t *in, uint32_t n, uint8_t *out,
     if (n < 8) return -1;
     if ((in[0] & 0x0f) != 8 || ((in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) return -1;
     if (serial) {
+        // serial = 1: plain output; serial = 2: through the 32 KiB history ring (k_inflate_serial)
+        static uint8_t ring[IF_RING_BYTES];
         IfOut O;
-        O.init(out, cap);
+        if (serial == 2) O.init_ring(out, cap, ring); else O.init(out, cap);
         uint64_t end = 0;
         const int code = if_inflate(in, n, 2, O, T, false, &end);
+        if (serial == 2) O.flush(O.n);
         if (code != IF_END_FINAL || end + 4 > n) return code == IF_ERR_OUT ? -2 : -1;
         const uint32_t a = (1u + O.s1 % 65521u) % 65521u;
         const uint32_t b = (uint32_t)(((uint64_t)O.n + O.s2) % 65521u);

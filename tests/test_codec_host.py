@@ -76,6 +76,8 @@ def test_decoder_reads_stock_zlib_and_own_streams(codec):
         for c in streams:
             n, o = inflate(codec, c, len(d), 1)
             assert n == len(d) and o == d, name
+            n, o = inflate(codec, c, len(d), 2)                         # through the 32 KiB history ring
+            assert n == len(d) and o == d, name
             n, o = inflate(codec, c, len(d), 0)                         # chunk-parallel path or its fallback signal
             assert (n == len(d) and o == d) or n == -100, name
     # own streams without marker look-alikes take the parallel path
