@@ -230,7 +230,19 @@ class ReCoDeWriter:
 
     def run(self, data=None):
         """Process this node's share of a chunk of frames (recode_writer.py:292-428).  `data` is
-        [nz, ny, nx]: a numpy array, or a CUDA torch tensor of the source dtype (no host round trip)."""
+        [nz, ny, nx]: a numpy array, or a CUDA torch tensor of the source dtype (no host round trip); None reads the
+        source file (raw binary, or the SEQ chunk of a streaming session).
+
+        run_metrics keeps the reference's keys, but the GPU path has other stage boundaries (rc_profile_read), summed
+        over the run's batches as GPU time:
+          frame_thresholding_and_counting_time   threshold compare + binary-map packing + value compaction (one kernel)
+          frame_binary_image_packing_time        0 (fused into the kernel above)
+          frame_pixel_intensity_packing_time     the rest of the reduction: puddle labelling, statistics / centroids,
+                                                 bit packing
+          frame_binary_image_compression_time    deflate of BOTH streams (maps and values run as two groups of one stage)
+          frame_pixel_intensity_compression_time 0 (included above)
+          frame_time                             their sum (+ record assembly)
+        With two batches in flight the stages of different batches overlap, so the sum can exceed run_time."""
         import torch
         run_metrics = {}
         self._do_sanity_checks(data)
