@@ -337,6 +337,24 @@ def payload_cases():
     return cases
 
 
+@pytest.mark.parametrize('level', [1, 9])
+def test_deflate_long_streams(ctx, level):
+    """streams of more than 256 chunks (the per-stream prefix / Adler-32 combine loops in tiles of 256 chunks) and a
+    very sparse one (zero runs far beyond one composite run token); stock zlib verifies payload and checksum"""
+    from pyrecode_b200.engine import deflate_batch, inflate_batch
+    rng = np.random.default_rng(77)
+    big = np.packbits(rng.random(5 * (1 << 23) + 1000) < 0.03, bitorder='little').tobytes()        # 5.2 MB: 321 chunks
+    sparse = np.packbits(rng.random(1 << 25) < 0.00002, bitorder='little').tobytes()               # 4 MB, ~80 set bits
+    mixed = big[:700001] + bytes(300000) + rng.integers(0, 256, 123457, dtype=np.uint8).tobytes() + sparse[:2000001]
+    payloads = [big, sparse, mixed]
+    comp = deflate_batch(ctx, payloads, level)
+    for c, d in zip(comp, payloads):
+        assert zlib.decompress(c) == d
+    assert len(comp[1]) < 40000
+    back, st = inflate_batch(ctx, comp, max(len(p) for p in payloads))
+    assert not st.any() and all(b == d for b, d in zip(back, payloads))
+
+
 @pytest.mark.parametrize('level', [1, 0, 9])
 def test_deflate_inflates_with_stock_zlib(ctx, level):
     from pyrecode_b200.engine import deflate_batch
