@@ -70,11 +70,13 @@ def make_inputs(level, n_distinct, seed=1234):
     from pyrecode_b200.synth import synth_dark, synth_frames
     dt, _ = src_dtype()
     dark = synth_dark(NY, NX)
-    frames = synth_frames(KIND[level], n_distinct, NY, NX, dark, seed=seed, bit_depth=BIT_DEPTH)
     if dt == np.uint8:
-        # an 8-bit detector: dark level and amplitudes scaled to the depth (synth scales the amplitudes)
-        dark = (dark // 16).astype(np.uint8)
-        frames = np.clip(frames.astype(np.int64) - 100 + 6, 0, 255).astype(np.uint8)
+        # an 8-bit detector: the 12-bit model (dark level, read noise, event amplitudes) seen through a converter that
+        # drops the 4 low bits -- the same events and the same occupancy, one byte per pixel (eps_of() scales too)
+        frames = synth_frames(KIND[level], n_distinct, NY, NX, dark, seed=seed, bit_depth=12)
+        sh = 12 - min(BIT_DEPTH, 8)
+        return (dark >> 4).astype(np.uint8), ((frames >> 4) >> (4 - sh if sh > 4 else 0)).astype(np.uint8)
+    frames = synth_frames(KIND[level], n_distinct, NY, NX, dark, seed=seed, bit_depth=BIT_DEPTH)
     return dark, frames
 
 

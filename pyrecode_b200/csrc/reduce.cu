@@ -557,10 +557,59 @@ k_bitpack(const T *__restrict__ vals, const uint32_t *__restrict__ tilepre, int 
     }
 }
 
+// Same result, organised by tile: one warp per (tile, frame) packs the output words whose FIRST bit belongs to one of
+// the tile's values -- words [ceil(pre[tile] b / 32), ceil(pre[tile + 1] b / 32)) -- so every word is still written by
+// exactly one thread (no atomics, no zero-initialised output), but nobody searches the prefix table: a word's
+// values start in the warp's own tile and at most spill into the following ones.  (k_bitpack spent 350 instructions per
+// output word, most of them in the binary search.)  For frames of fewer than 2^32 value bits.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bitpack_tiles(const T *__restrict__ vals, const uint32_t *__restrict__ tilepre, int NT, int n_tiles_total, int b,
+                uint8_t *__restrict__ packed, size_t packed_stride)
+{
+    const int gt = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (gt >= n_tiles_total) return;
+    const int lane = threadIdx.x & 31;
+    const int f = gt / NT, tile = gt - f * NT;
+    const uint32_t *pre = tilepre + (size_t)f * (NT + 1);
+    const uint32_t j0 = pre[tile], j1 = pre[tile + 1];
+    if (j1 == j0) return;
+    const uint32_t n = pre[NT], ub = (uint32_t)b;
+    const T *v = vals + (size_t)f * ((size_t)NT * TILE_PX);
+    uint32_t *out = reinterpret_cast<uint32_t *>(packed + (size_t)f * packed_stride);
+    const uint32_t vmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+    const uint32_t w_lo = (j0 * ub + 31u) >> 5, w_hi = (j1 * ub + 31u) >> 5;
+    for (uint32_t w = w_lo + lane; w < w_hi; w += 32) {
+        const uint32_t bit0 = w << 5;
+        uint32_t j = bit0 / ub;                                   // >= j0: the word's first bit is one of this tile's
+        uint32_t jl = (bit0 + 31u) / ub;
+        if (jl >= n) jl = n - 1;
+        int tt = tile;
+        uint32_t acc = 0;
+        int sh = (int)(j * ub) - (int)bit0;                       // bit position of value j relative to the word: (-b, 32)
+        for (; j <= jl; j++, sh += b) {
+            while (pre[tt + 1] <= j) tt++;
+            const uint32_t val = (uint32_t)v[(size_t)tt * TILE_PX + (j - pre[tt])] & vmask;
+            acc |= sh >= 0 ? (val << sh) : (val >> (-sh));
+        }
+        out[w] = acc;
+    }
+}
+
 int launch_bitpack(rc_ctx *ctx, const Geom &g, int val_itemsize, const void *vals, const uint32_t *tilepre, int F,
                    int b, uint8_t *packed, size_t packed_stride, cudaStream_t st)
 {
     if (F <= 0) return 0;
+    if ((uint64_t)g.P * (uint64_t)b < 0xffffffe0ull) {
+        const int nt = F * g.NT;
+        const unsigned blocks = (unsigned)((nt + 7) / 8);
+        if (val_itemsize == 2)
+            k_bitpack_tiles<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t *)vals, tilepre, g.NT, nt, b, packed, packed_stride);
+        else
+            k_bitpack_tiles<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t *)vals, tilepre, g.NT, nt, b, packed, packed_stride);
+        RC_LAUNCH_CHECK(ctx, "k_bitpack_tiles");
+        return 0;
+    }
     dim3 grid(128, F);
     if (val_itemsize == 2)
         k_bitpack<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)vals, tilepre, g.NT, b, packed, packed_stride);
