@@ -634,7 +634,7 @@ def main():
 
     # ---- the other reduction levels of BASELINE.json's configs (L1: config 2, L4: config 4), same harness, short
     others = {}
-    for lv in [int(x) for x in args.also_levels.split(',') if x.strip()]:
+    for lv in [int(x) for x in args.also_levels.replace("'", '').replace('"', '').split(',') if x.strip()]:
         if lv == level:
             continue
         dk, fr = make_inputs(lv, args.distinct, seed=1234 + rank)

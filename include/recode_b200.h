@@ -77,6 +77,7 @@ int                 rc_set_pipelined(rc_ctx *ctx, int on);
 size_t rc_map_stride_words(size_t n_pixels);                 /* uint32 words per frame map on device      */
 size_t rc_packed_stride_bytes(const rc_config *cfg);         /* bytes per frame of packed values (worst)  */
 size_t rc_workspace_bytes(const rc_config *cfg);             /* device workspace for rc_reduce_compress   */
+size_t rc_stage_workspace_bytes(const rc_config *cfg);       /* ... for rc_ccl_label / rc_l4_centroids    */
 size_t rc_records_capacity(const rc_config *cfg);            /* worst-case record bytes for max_frames    */
 size_t rc_read_workspace_bytes(const rc_config *cfg);             /* device workspace for rc_unpack_*          */
 

@@ -43,6 +43,7 @@ _SIGNATURES = {
     'rc_map_stride_words': (_sz, [_sz]),
     'rc_packed_stride_bytes': (_sz, [_cfgp]),
     'rc_workspace_bytes': (_sz, [_cfgp]),
+    'rc_stage_workspace_bytes': (_sz, [_cfgp]),
     'rc_records_capacity': (_sz, [_cfgp]),
     'rc_read_workspace_bytes': (_sz, [_cfgp]),
     'rc_reduce_compress': (ctypes.c_int, [_vp, _cfgp, _vp, ctypes.c_int, _vp, ctypes.c_uint32, _vp, _sz, _vp, _sz,
@@ -175,6 +176,9 @@ class Context:
 
     def records_capacity(self, cfg):
         return self._lib.rc_records_capacity(ctypes.byref(cfg))
+
+    def stage_workspace_bytes(self, cfg):
+        return self._lib.rc_stage_workspace_bytes(ctypes.byref(cfg))
 
     def read_workspace_bytes(self, cfg):
         return self._lib.rc_read_workspace_bytes(ctypes.byref(cfg))

@@ -28,7 +28,10 @@ static size_t packed_stride_of(const rc_config *c)
 {
     const size_t P = (size_t)c->ny * c->nx;
     if (c->reduction_level == 3 || c->reduction_level == 4) return 16;
-    return round_up((P * (size_t)c->bit_depth + 7) / 8, 16) + 16;
+    // level 2 packs one value per puddle: at most ceil(ny / 2) * ceil(nx / 2) puddles are pairwise non-adjacent under
+    // 8-connectivity
+    const size_t n = c->reduction_level == 2 ? ((size_t)c->ny + 1) / 2 * (((size_t)c->nx + 1) / 2) : P;
+    return round_up((n * (size_t)c->bit_depth + 7) / 8, 16) + 16;
 }
 
 struct ReduceWs {
@@ -68,7 +71,9 @@ static ReduceWs carve_reduce(Carver &c, const rc_config *cfg, const Geom &g, int
     }
     if (what == 0 && level == 2) {
         w.acc = c.take<uint32_t>(F * g.slots);
-        w.stats16 = c.take<uint16_t>(F * g.slots);
+        // the compacted statistics reuse the (value, position) words: nothing reads those after the tile labelling, and
+        // k_ccl_roots only reads parent / acc while it writes here
+        w.stats16 = (uint16_t *)w.vals;
     }
     if ((what == 0 && level == 4) || what == 2) w.acc = c.take<uint32_t>(F * g.slots);    // L4: claim flags
     if ((what == 0 && level == 4) || what == 2) {
@@ -237,12 +242,22 @@ extern "C" size_t rc_workspace_bytes(const rc_config *cfg)
 {
     const Geom g = make_geom(cfg->ny, cfg->nx);
     rc_config c2 = *cfg;
-    // the stage APIs share one workspace: size it for the largest user
+    Carver cc(nullptr);
+    carve_reduce(cc, &c2, g, 0);
+    carve_compress(cc, &c2, g);
+    return cc.used() + 256;
+}
+
+// rc_ccl_label / rc_l4_centroids (label images, centroid lists: per-slot ordinals, 64-bit centroids, boxes) need more
+// than the write path does; they take their own workspace so that the hot path's stays small
+extern "C" size_t rc_stage_workspace_bytes(const rc_config *cfg)
+{
+    const Geom g = make_geom(cfg->ny, cfg->nx);
+    rc_config c2 = *cfg;
     size_t best = 0;
-    for (int what = 0; what < 3; what++) {
+    for (int what = 1; what < 3; what++) {
         Carver cc(nullptr);
         carve_reduce(cc, &c2, g, what);
-        if (what == 0) carve_compress(cc, &c2, g);
         if (cc.used() > best) best = cc.used();
     }
     return best + 256;
@@ -502,7 +517,7 @@ extern "C" int rc_ccl_label(rc_ctx *ctx, const rc_config *cfg, const uint32_t *d
     if (!ctx) return -1;
     if (check_cfg(ctx, cfg)) return -1;
     if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames exceeds max_frames");
-    if (workspace_bytes < rc_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
+    if (workspace_bytes < rc_stage_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small (rc_stage_workspace_bytes)");
     cudaStream_t st = (cudaStream_t)stream;
     const Geom g = make_geom(cfg->ny, cfg->nx);
     Carver c(d_workspace);
@@ -526,7 +541,7 @@ extern "C" int rc_l4_centroids(rc_ctx *ctx, const rc_config *cfg, const void *d_
     if (!ctx) return -1;
     if (check_cfg(ctx, cfg)) return -1;
     if (n_frames < 0 || n_frames > cfg->max_frames) RC_FAIL(ctx, -1, "n_frames exceeds max_frames");
-    if (workspace_bytes < rc_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small");
+    if (workspace_bytes < rc_stage_workspace_bytes(cfg)) RC_FAIL(ctx, -1, "workspace too small (rc_stage_workspace_bytes)");
     cudaStream_t st = (cudaStream_t)stream;
     const Geom g = make_geom(cfg->ny, cfg->nx);
     Carver c(d_workspace);

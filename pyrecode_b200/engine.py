@@ -191,6 +191,12 @@ class WriteEngine:
             out_p = [ph[f * ps:f * ps + int(pb[f])].tobytes() for f in range(n)]
             return out_m, out_p, counts.cpu().numpy()
 
+    def _stage_workspace(self):
+        """workspace of the stage entry points rc_ccl_label / rc_l4_centroids (larger than the write path's)"""
+        if getattr(self, '_stage_ws', None) is None:
+            self._stage_ws = self.ctx.empty(self.ctx.stage_workspace_bytes(self.cfg))
+        return self._stage_ws
+
     def labels(self, maps_bytes):
         """8-connected labels of packed binary maps -> (int32 [n, ny, nx], k[n]) through rc_ccl_label."""
         n = len(maps_bytes)
@@ -202,7 +208,7 @@ class WriteEngine:
             maps = torch.from_numpy(host.view(np.int32).reshape(-1)).to(self.dev)
             labels = self.ctx.empty(n * self.P, torch.int32)
             counts = self.ctx.zeros(n, torch.int32)
-            self.ctx.ccl_label(self.cfg, maps, n, self.ws, labels, counts)
+            self.ctx.ccl_label(self.cfg, maps, n, self._stage_workspace(), labels, counts)
             torch.cuda.synchronize()
             return labels.cpu().numpy().reshape(n, self.ny, self.nx), counts.cpu().numpy()
 
@@ -214,7 +220,7 @@ class WriteEngine:
             fd, _ = self._to_device(frames)
             cent = self.ctx.zeros(n * cap * 2, torch.float32)
             counts = self.ctx.zeros(n, torch.int32)
-            self.ctx.l4_centroids(self.cfg, fd, n, self.thr, self.ws, cent, cap, counts)
+            self.ctx.l4_centroids(self.cfg, fd, n, self.thr, self._stage_workspace(), cent, cap, counts)
             torch.cuda.synchronize()
             c = cent.cpu().numpy().reshape(n, cap, 2)
             k = counts.cpu().numpy()
