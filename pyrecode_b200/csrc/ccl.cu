@@ -293,11 +293,12 @@ ccl_tile(const int tile, const int f, CclStage<FOLD == 3> &S, const uint32_t tot
     }
     if (!L4) return;
 
-    // ---- phase 5 (L4): one thread per root.  Single-pixel puddles are finished at once; the others go to a
-    // dense list first so that every lane of the second loop has a puddle to replay.  Members are visited in
-    // slot order = raster order.
+    // ---- phase 5 (L4): one thread per root.  The roots go to a dense list first, so that the warps that replay
+    // puddles have every lane busy and the others skip the (long, inlined) replay code altogether: the path is bound
+    // by instruction issue, and a warp pays for the whole body however few of its lanes have a puddle.  Members are
+    // visited in slot order = raster order.
     uint32_t *cmap_g = map2_all ? map2_all + (size_t)f * MS : nullptr;
-    uint16_t *s_list = s_wpre;                        // the per-word prefixes are no longer needed
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(S.vp);   // up to CCL_CAP roots; the staged (value, position) words are consumed
     uint32_t nclosed = 0;
     auto finish_root = [&](uint32_t i, bool open, const CentAcc &ca, uint4 box) {
         if (open) {
@@ -319,24 +320,16 @@ ccl_tile(const int tile, const int f, CclStage<FOLD == 3> &S, const uint32_t tot
     for (uint32_t i0 = 0; i0 < total; i0 += CCL_THREADS) {
         const uint32_t i = i0 + t;
         const bool root = i < total && s_parent[i] == i;
-        const bool multi = root && s_head[i] != NIL;
-        if (root && !multi) {
-            const uint32_t gp = base + s_pos[i];
-            const uint32_t r = pow2 ? gp >> lg : gp / unx, c = gp - r * unx;
-            CentAcc ca;
-            ca.add(l4mode, r, c, vp[i] >> 16);
-            finish_root(i, s_open[i], ca, make_uint4(r, r, c, c));
-        }
-        const uint32_t bm = __ballot_sync(0xffffffffu, multi);
+        const uint32_t bm = __ballot_sync(0xffffffffu, root);
         uint32_t wbase = 0;
         if (lane == 0 && bm) wbase = atom_add_shared(&s_nlist, __popc(bm));
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (multi) s_list[wbase + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)i;
+        if (root) s_list[wbase + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)i;
     }
     __syncthreads();
     const uint32_t nlist = s_nlist;
-    // list entry k -> warp k % CCL_WARPS, lane k / CCL_WARPS: every warp gets its share of the replays
-    for (uint32_t k = (uint32_t)(t >> 5) + (uint32_t)CCL_WARPS * (uint32_t)lane; k < nlist; k += CCL_THREADS) {
+    // list entry k -> thread k: the first warps are full, the rest have nothing to do
+    for (uint32_t k = (uint32_t)t; k < nlist; k += CCL_THREADS) {
         const uint32_t i = s_list[k];
         const bool open = s_open[i];
         CentAcc ca;
