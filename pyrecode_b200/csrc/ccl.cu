@@ -111,6 +111,7 @@ __device__ __forceinline__ bool centroid_pixel(float fr, float fc, int ny, int n
 // tile preceded by a halo of CCL_HALO words, the per-word prefixes, the first CCL_VPS (value, position) words of the
 // tile's foreground pixels and, for L4, the first CCL_HALO map words of the next tile.
 constexpr int CCL_VPS = 1024;
+static_assert(CCL_VPS * 2 >= CCL_CAP, "the staged (value, position) words double as the L4 root list (uint16 per root)");
 template <bool L4>
 struct __align__(128) CclStage {
     uint32_t maskx[CCL_HALO + TILE_WORDS];
