@@ -579,15 +579,19 @@ k_bitpack_tiles(const T *__restrict__ vals, const uint32_t *__restrict__ tilepre
     uint32_t *out = reinterpret_cast<uint32_t *>(packed + (size_t)f * packed_stride);
     const uint32_t vmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
     const uint32_t w_lo = (j0 * ub + 31u) >> 5, w_hi = (j1 * ub + 31u) >> 5;
+    // floor(x / b) for x < 2^32 without a division: umulhi by ceil(2^32 / b) is exact or one too large
+    const uint32_t magic = ub > 1 ? (uint32_t)((0x100000000ull + ub - 1) / ub) : 0u;
     for (uint32_t w = w_lo + lane; w < w_hi; w += 32) {
         const uint32_t bit0 = w << 5;
-        uint32_t j = bit0 / ub;                                   // >= j0: the word's first bit is one of this tile's
-        uint32_t jl = (bit0 + 31u) / ub;
-        if (jl >= n) jl = n - 1;
+        uint32_t j = bit0;                                        // >= j0: the word's first bit is one of this tile's
+        if (ub > 1) {
+            j = __umulhi(bit0, magic);
+            if (j * ub > bit0) j--;
+        }
         int tt = tile;
         uint32_t acc = 0;
         int sh = (int)(j * ub) - (int)bit0;                       // bit position of value j relative to the word: (-b, 32)
-        for (; j <= jl; j++, sh += b) {
+        for (; j < n && sh < 32; j++, sh += b) {                  // every value that starts before the word ends
             while (pre[tt + 1] <= j) tt++;
             const uint32_t val = (uint32_t)v[(size_t)tt * TILE_PX + (j - pre[tt])] & vmask;
             acc |= sh >= 0 ? (val << sh) : (val >> (-sh));
