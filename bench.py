@@ -324,6 +324,16 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             res[what] = (world * n / float(t[0]), float(t[0]) / steps, st)
+        # the collective alone: all ranks enter together (inside a view its events also hold the wait for the slowest rank)
+        ar_iso = []
+        if world > 1:
+            for _ in range(6):
+                barrier()
+                ar0.record()
+                rcd.allreduce_view(view)
+                ar1.record()
+                torch.cuda.synchronize()
+                ar_iso.append(ar0.elapsed_time(ar1))
         gpu = r.decode_stage_ms()
         # the per-frame API (get_next_frame -> scipy COO + summary statistics), as a user loop would call it
         seq_fps = None
@@ -358,6 +368,7 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
                            'inside the timed region; live-view sum all-reduced (NCCL, 64 MiB int32) once per view' % (nz, BIT_DEPTH),
                'live_view_frames_per_s': res['sum'][0], 'ms_per_view': 1e3 * res['sum'][1],
                'allreduce_ms': float(np.median(ar_ms)) if ar_ms else None,
+               'allreduce_ms_isolated': float(np.median(ar_iso[1:])) if len(ar_iso) > 1 else None,
                'dense_frames_per_s': res['dense'][0], 'dense_output_gb_s': res['dense'][0] * frame_bytes / 1e9,
                'file_bytes': fsize, 'steps': steps, 'frames_per_view': nz,
                'get_next_frame_fps': seq_fps,

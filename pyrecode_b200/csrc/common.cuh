@@ -161,11 +161,14 @@ struct Carver {
 // ---- warp / block primitives -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
 {
-    const int lane = threadIdx.x & 31;
+    // shfl.up hands back its own predicate "the source lane exists": a predicated add instead of a lane compare and a
+    // select per step (two instructions a step instead of four)
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += n;
+        asm volatile("{\n.reg .u32 r0;\n.reg .pred p;\n"
+                     "shfl.sync.up.b32 r0|p, %0, %1, 0, 0xffffffff;\n"
+                     "@p add.u32 %0, %0, r0;\n}"
+                     : "+r"(v) : "r"(d));
     }
     return v;
 }
