@@ -581,6 +581,7 @@ k_bitpack_tiles(const T *__restrict__ vals, const uint32_t *__restrict__ tilepre
     const uint32_t w_lo = (j0 * ub + 31u) >> 5, w_hi = (j1 * ub + 31u) >> 5;
     // floor(x / b) for x < 2^32 without a division: umulhi by ceil(2^32 / b) is exact or one too large
     const uint32_t magic = ub > 1 ? (uint32_t)((0x100000000ull + ub - 1) / ub) : 0u;
+    const uint32_t max_cnt = (32u + ub - 1u) / ub + 1u;           // values that can start before a word ends
     for (uint32_t w = w_lo + lane; w < w_hi; w += 32) {
         const uint32_t bit0 = w << 5;
         uint32_t j = bit0;                                        // >= j0: the word's first bit is one of this tile's
@@ -588,13 +589,23 @@ k_bitpack_tiles(const T *__restrict__ vals, const uint32_t *__restrict__ tilepre
             j = __umulhi(bit0, magic);
             if (j * ub > bit0) j--;
         }
-        int tt = tile;
         uint32_t acc = 0;
         int sh = (int)(j * ub) - (int)bit0;                       // bit position of value j relative to the word: (-b, 32)
-        for (; j < n && sh < 32; j++, sh += b) {                  // every value that starts before the word ends
-            while (pre[tt + 1] <= j) tt++;
-            const uint32_t val = (uint32_t)v[(size_t)tt * TILE_PX + (j - pre[tt])] & vmask;
-            acc |= sh >= 0 ? (val << sh) : (val >> (-sh));
+        if (j + max_cnt <= j1) {
+            // every value that starts before the word ends is this tile's (all words but the tile's last ones):
+            // consecutive loads, no prefix lookups
+            const T *vt = v + (size_t)tile * TILE_PX + (j - j0);
+            for (; sh < 32; sh += b) {
+                const uint32_t val = (uint32_t)(*vt++) & vmask;
+                acc |= sh >= 0 ? (val << sh) : (val >> (-sh));
+            }
+        } else {
+            int tt = tile;
+            for (; j < n && sh < 32; j++, sh += b) {
+                while (pre[tt + 1] <= j) tt++;
+                const uint32_t val = (uint32_t)v[(size_t)tt * TILE_PX + (j - pre[tt])] & vmask;
+                acc |= sh >= 0 ? (val << sh) : (val >> (-sh));
+            }
         }
         out[w] = acc;
     }
