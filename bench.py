@@ -363,6 +363,28 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
         r.close()
         if rank != 0:
             return None
+        # reference-written files hold ONE block sequence per stream (stock zlib, matches at any distance): no chunk
+        # parallelism, one decoding lane per stream through a 32 KiB shared-memory history ring
+        foreign = None
+        if recs:
+            import zlib
+            from pyrecode_b200._native import Context
+            from pyrecode_b200.engine import inflate_batch
+            maps = [zlib.decompress(cm) for cm, _ in recs]
+            streams = [zlib.compress(maps[i % len(maps)], 1) for i in range(32)]
+            t0 = time.perf_counter()
+            for st_ in streams:
+                zlib.decompress(st_)
+            cpu_ms = 1e3 * (time.perf_counter() - t0)
+            fctx = Context(local_rank)
+            inflate_batch(fctx, streams[:2], len(maps[0]))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            back, fst = inflate_batch(fctx, streams, len(maps[0]))
+            gpu_ms = 1e3 * (time.perf_counter() - t0)
+            foreign = {'streams': len(streams), 'inflated_bytes_each': len(maps[0]), 'gpu_ms_incl_copies': gpu_ms,
+                       'stock_zlib_one_core_ms': cpu_ms, 'ok': bool(not fst.any() and back[0] == maps[0] and back[-1] == maps[(len(streams) - 1) % len(maps)])}
+            fctx.close()
         peak, peak_src = measured_peak()
         out = {'workload': 'read path (BASELINE config 5): %d-frame L2 part file per GPU on tmpfs, %d-bit, file reads '
                            'inside the timed region; live-view sum all-reduced (NCCL, 64 MiB int32) once per view' % (nz, BIT_DEPTH),
@@ -371,7 +393,7 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
                'allreduce_ms_isolated': float(np.median(ar_iso[1:])) if len(ar_iso) > 1 else None,
                'dense_frames_per_s': res['dense'][0], 'dense_output_gb_s': res['dense'][0] * frame_bytes / 1e9,
                'file_bytes': fsize, 'steps': steps, 'frames_per_view': nz,
-               'get_next_frame_fps': seq_fps,
+               'get_next_frame_fps': seq_fps, 'foreign_zlib_streams': foreign,
                'host_time_split_ms_last_view': {k: (1e3 * v if k.endswith('_s') else v) for k, v in res['sum'][2].items()},
                'e2e': {'value': res['sum'][0], 'unit': 'frames/s', 'h2d_bytes_per_step': fsize, 'd2h_bytes_per_step': 8}}
         if gpu and gpu.get('frames'):
