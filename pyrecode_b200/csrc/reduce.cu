@@ -321,17 +321,11 @@ k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, siz
         const uint32_t incl = warp_incl_scan(pc);
         if (lane == 31) s_wsum[sub & 1][warp] = incl;
         __syncthreads();
-        uint32_t before = 0, total = 0;
-        {
-            const uint4 a = *reinterpret_cast<const uint4 *>(&s_wsum[sub & 1][0]);
-            const uint4 b = *reinterpret_cast<const uint4 *>(&s_wsum[sub & 1][4]);
-            const uint32_t ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (i < warp) before += ws[i];
-                total += ws[i];
-            }
-        }
+        // foreground pixels of the warps before this one / of all eight: two warp-wide integer reductions (REDUX) over
+        // the eight sums instead of eight selects and adds per thread
+        const uint32_t wsv = s_wsum[sub & 1][lane & 7];
+        const uint32_t before = __reduce_add_sync(0xffffffffu, lane < warp ? wsv : 0u);
+        const uint32_t total = __reduce_add_sync(0xffffffffu, lane < 8 ? wsv : 0u);
         const uint32_t rank = run + before + incl - pc;
         s_wpre[sub * SUB_WORDS + t] = (uint16_t)rank;
         if (VALMODE) {
