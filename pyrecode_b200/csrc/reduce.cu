@@ -339,12 +339,17 @@ k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, siz
                     *o++ = src[k];
                 }
             } else {
-                uint32_t *o = reinterpret_cast<uint32_t *>(vals_out) + sbase + rank;
+                // one 64-bit multiply-add per store from a 32-bit index (the compiler otherwise carries a 64-bit
+                // pointer through the loop: four instructions per pixel)
+                uint32_t *const ob = reinterpret_cast<uint32_t *>(vals_out) + sbase;
+                uint32_t idx = rank;
                 const uint32_t posbase = (uint32_t)(sub * SUB_PX + t * 32);
                 while (bits) {
                     const uint32_t k = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    *o++ = ((uint32_t)src[k] << 16) | posbase | k;
+                    asm volatile("" : "+r"(idx));
+                    ob[idx] = ((uint32_t)src[k] << 16) | posbase | k;
+                    idx++;
                 }
             }
         }
