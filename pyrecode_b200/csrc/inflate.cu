@@ -186,7 +186,10 @@ k_inflate_chunks(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
         int code = 0;
         if (lane == 0) {
             IfOut O;
-            O.init(dst, cap, W.out, (uint32_t)INF_CHUNK);
+            // a piece of our own encoder never exceeds one chunk; anything longer (a foreign stream: one block sequence
+            // of megabytes) stops here with IF_ERR_OUT, fails validation and is decoded by k_inflate_serial through its
+            // shared-memory history ring instead of byte by byte through global memory
+            O.init(dst, cap < (uint64_t)INF_CHUNK ? cap : (uint64_t)INF_CHUNK, W.out, (uint32_t)INF_CHUNK);
             uint64_t end = 0;
             code = if_inflate(in + in_off[s], in_bytes[s], cand[(size_t)s * cmax + j], O, W.tab, true, &end, W.win);
             o_n = (uint32_t)O.n; o_s1 = O.s1 % 65521u; o_s2 = O.s2 % 65521u; o_end = (uint32_t)end;
