@@ -672,8 +672,10 @@ __device__ __forceinline__ void copy_bytes_shifted(uint8_t *__restrict__ dst, co
     const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
     const uint32_t sh = head * 8;     // source byte offset of the first aligned destination word is `head`
     if (sh == 0) {
+#pragma unroll 4
         for (uint32_t i = t; i < nw; i += nt) d32[i] = s32[i];
     } else {
+#pragma unroll 4
         for (uint32_t i = t; i < nw; i += nt) d32[i] = __funnelshift_r(s32[i], s32[i + 1], sh);
     }
     const uint32_t done = head + nw * 4;
@@ -689,8 +691,9 @@ k_copy_pieces(const uint8_t *__restrict__ raw_in, const uint64_t *__restrict__ i
               uint8_t *__restrict__ out, size_t capacity, uint32_t *__restrict__ counters,
               uint32_t *__restrict__ status)
 {
-    __shared__ uint32_t s_ticket;
-    const int t = threadIdx.x;
+    // one piece per WARP and ticket: a piece is a few KiB, so a whole CTA per piece spends most of its instructions on
+    // the ticket, the stream search and the head / tail bytes rather than on the copy
+    const int t = threadIdx.x, lane = t & 31;
     const uint32_t total_chunks = chunk_base[n_streams];
     // empty streams have no chunk: their wrapper is written by the first CTA
     if (wrap && blockIdx.x == 0) {
@@ -702,25 +705,24 @@ k_copy_pieces(const uint8_t *__restrict__ raw_in, const uint64_t *__restrict__ i
         }
     }
     while (true) {
-        if (t == 0) s_ticket = atomicAdd(&counters[1], 1u);
-        __syncthreads();
-        const uint32_t gci = s_ticket;
-        __syncthreads();
+        uint32_t gci = 0;
+        if (lane == 0) gci = atomicAdd(&counters[1], 1u);
+        gci = __shfl_sync(0xffffffffu, gci, 0);
         if (gci >= total_chunks) break;
         const int s = find_stream(chunk_base, n_streams, gci);
         const uint32_t ci = gci - chunk_base[s];
         const uint64_t sd = stream_dst[s];
         const uint32_t sb = stream_bytes[s];
         if (sd + sb > capacity) {
-            if (t == 0) atomicOr(status, RC_STATUS_RECORDS_OVERFLOW);
+            if (lane == 0) atomicOr(status, RC_STATUS_RECORDS_OVERFLOW);
             continue;
         }
         const uint32_t nb = chunk_bytes[gci];
         uint8_t *dst = out + sd + (wrap ? 2 : 0) + chunk_rel[gci];
         const uint8_t *src = wrap ? scratch + (size_t)gci * DF_SLOT_BYTES
                                   : raw_in + in_off[s] + (size_t)ci * DF_CHUNK;
-        copy_bytes_shifted(dst, src, nb, t, 256);
-        if (wrap && t == 0) {
+        copy_bytes_shifted(dst, src, nb, lane, 32);
+        if (wrap && lane == 0) {
             if (ci == 0) { out[sd] = 0x78; out[sd + 1] = 0x01; }
             if (gci + 1 == chunk_base[s + 1]) {
                 uint8_t *tr = out + sd + sb - 6;
@@ -840,7 +842,8 @@ int launch_copy_pieces(rc_ctx *ctx, const DeflateWs &w, int wrap, const uint8_t 
                        const uint32_t *in_bytes, int n_streams, uint8_t *out, size_t capacity, uint32_t *status,
                        cudaStream_t st)
 {
-    size_t want = w.max_chunks < (size_t)ctx->sm_count * 8 ? w.max_chunks : (size_t)ctx->sm_count * 8;
+    size_t want = (w.max_chunks + 7) / 8;                    // 8 warps per CTA, one piece per warp and ticket
+    if (want > (size_t)ctx->sm_count * 4) want = (size_t)ctx->sm_count * 4;
     if (want < 1) want = 1;
     k_copy_pieces<<<(unsigned)want, 256, 0, st>>>(raw_in, in_off, in_bytes, n_streams, w.chunk_base, w.scratch,
                                                   w.chunk_bytes, w.chunk_rel, w.stream_bytes, w.stream_adler,

@@ -205,7 +205,7 @@ struct IfOut {
     uint64_t cap;
     uint64_t n;          // bytes produced
     uint32_t s1, s2;     // Adler-32 partials, started from (0, 0), of the bytes produced at index >= sh_cap
-                         // (ring mode: of all bytes)
+                         // (ring mode: of the bytes flushed so far, reduced mod 65521 -- all of them after flush(n))
     // Device, own chunks: the first sh_cap bytes (a whole chunk of our own encoder) are produced in a shared-memory
     // buffer, zero-filled beforehand, that the warp copies out -- and checksums -- together afterwards.  Runs of 0x00,
     // most of a binary map, then need no stores at all, and the byte before a run is read back from shared memory.
@@ -230,28 +230,47 @@ struct IfOut {
         if (ring) return sh[(uint32_t)i & (IF_RING_BYTES - 1)];
         return i < sh_cap ? sh[i] : out[i];
     }
-    // ring mode: copy [flushed, upto) to global memory; upto = n at the end of the stream, else a segment boundary
+    // ring mode: copy [flushed, upto) to global memory and fold those bytes into the Adler-32 partials (nothing is
+    // summed per byte while decoding); upto = n at the end of the stream, else a segment boundary.  Pieces of at most
+    // IF_FLUSH_BYTES: with L bytes c_0.. after state (s1, s2), s1' = s1 + sum c_i, s2' = s2 + L s1 + sum (L - i) c_i,
+    // and the last sum stays below 255 * 4096 * 4097 / 2 < 2^32.
     IF_HD void flush(uint64_t upto)
     {
-        uint64_t i = flushed;
+        while (flushed < upto) {
+            const uint64_t lim = upto - flushed > IF_FLUSH_BYTES ? flushed + IF_FLUSH_BYTES : upto;
+            const uint32_t L = (uint32_t)(lim - flushed);
+            uint32_t A = 0, W = 0;
+            uint64_t i = flushed;
 #ifdef __CUDA_ARCH__
-        if ((((uintptr_t)out) & 15) == 0)
-            for (; i + 16 <= upto; i += 16)
-                *reinterpret_cast<uint4 *>(out + i) = *reinterpret_cast<const uint4 *>(sh + ((uint32_t)i & (IF_RING_BYTES - 1)));
+            if (((((uintptr_t)out) | (uintptr_t)flushed) & 15) == 0)
+                for (; i + 16 <= lim; i += 16) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(sh + ((uint32_t)i & (IF_RING_BYTES - 1)));
+                    *reinterpret_cast<uint4 *>(out + i) = v;
+                    const uint32_t a = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u,
+                                       __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
+                    const uint32_t w = __dp4a(v.x, 0x03020100u, __dp4a(v.y, 0x07060504u,
+                                       __dp4a(v.z, 0x0b0a0908u, __dp4a(v.w, 0x0f0e0d0cu, 0u))));
+                    A += a;
+                    W += (uint32_t)(lim - i) * a - w;
+                }
 #endif
-        for (; i < upto; i++) out[i] = sh[(uint32_t)i & (IF_RING_BYTES - 1)];
-        flushed = upto;
+            for (; i < lim; i++) {
+                const uint32_t c = sh[(uint32_t)i & (IF_RING_BYTES - 1)];
+                out[i] = (uint8_t)c;
+                A += c;
+                W += (uint32_t)(lim - i) * c;
+            }
+            s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)L * s1 + W) % 65521u);
+            s1 = (s1 + A) % 65521u;
+            flushed = lim;
+        }
     }
     IF_HD void put(uint8_t c)
     {
         if (ring) {
             sh[(uint32_t)n & (IF_RING_BYTES - 1)] = c;
             n++;
-            s1 += c; s2 += s1;
-            if ((n & 2047) == 0) {
-                s1 %= 65521u; s2 %= 65521u;
-                if ((n & (IF_FLUSH_BYTES - 1)) == 0) flush(n);
-            }
+            if (((uint32_t)n & (IF_FLUSH_BYTES - 1)) == 0) flush(n);
             return;
         }
         if (n < sh_cap) { sh[n++] = c; return; }
@@ -264,13 +283,10 @@ struct IfOut {
     IF_HD void put_run(uint8_t c, uint32_t len)
     {
         if (ring) {
-            for (uint32_t i = 0; i < len; i++) sh[(uint32_t)(n + i) & (IF_RING_BYTES - 1)] = c;
+            const uint32_t at0 = (uint32_t)n;
+            for (uint32_t i = 0; i < len; i++) sh[(at0 + i) & (IF_RING_BYTES - 1)] = c;
             n += len;
-            s1 %= 65521u;
-            s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)len * s1 + (uint64_t)c * (len * (len + 1) / 2)) % 65521u);
-            s1 = (s1 + len * (uint32_t)c) % 65521u;
-            const uint64_t seg = n & ~(uint64_t)(IF_FLUSH_BYTES - 1);
-            if (seg > flushed) flush(seg);
+            if ((at0 ^ (uint32_t)n) & ~(IF_FLUSH_BYTES - 1)) flush(n & ~(uint64_t)(IF_FLUSH_BYTES - 1));
             return;
         }
         if (n < sh_cap) {
@@ -287,7 +303,48 @@ struct IfOut {
         s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)len * s1 + (uint64_t)c * (len * (len + 1) / 2)) % 65521u);
         s1 = (s1 + len * (uint32_t)c) % 65521u;
     }
+    // a match at distance >= 2 (1 <= dist <= n, len <= 258).  Ring mode copies min(dist, 8) bytes per round: the
+    // source bytes of a round lie entirely before its destination, so the loads are independent of each other and of
+    // the round's stores -- one shared-memory round trip per 8 bytes instead of one per byte (stock zlib's matches on
+    // a binary map are short, 8.6 bytes on average, and almost never at distance 1).
+    IF_HD void copy_match(uint32_t dist, uint32_t len)
+    {
+        if (ring) {
+            const uint32_t M = IF_RING_BYTES - 1, d0 = (uint32_t)n;
+            uint32_t d = d0, s = d0 - dist;
+            n += len;
+            const uint32_t step = dist < 8u ? dist : 8u;
+            while (len) {
+                const uint32_t k = len < step ? len : step;
+                uint8_t b[8];
+                for (uint32_t j = 0; j < 8; j++)
+                    if (j < k) b[j] = sh[(s + j) & M];
+                for (uint32_t j = 0; j < 8; j++)
+                    if (j < k) sh[(d + j) & M] = b[j];
+                s += k; d += k; len -= k;
+            }
+            if ((d0 ^ (uint32_t)n) & ~(IF_FLUSH_BYTES - 1)) flush(n & ~(uint64_t)(IF_FLUSH_BYTES - 1));
+            return;
+        }
+        for (uint32_t i = 0; i < len; i++) put(at(n - dist));
+    }
 };
+
+// RFC 1951 3.2.5 in closed form (no table in local memory on the device): length symbol 257 + li -> base length and
+// extra bits; distance symbol ds -> base distance and extra bits
+IF_HD uint32_t if_len_base(int li, int &ext)
+{
+    if (li < 8) { ext = 0; return 3u + (uint32_t)li; }
+    if (li == 28) { ext = 0; return 258u; }
+    ext = (li >> 2) - 1;
+    return 3u + ((4u + ((uint32_t)li & 3u)) << ext);
+}
+IF_HD uint32_t if_dist_base(int ds, int &ext)
+{
+    if (ds < 4) { ext = 0; return 1u + (uint32_t)ds; }
+    ext = (ds >> 1) - 1;
+    return 1u + ((2u + ((uint32_t)ds & 1u)) << ext);
+}
 
 // Reads the code description of a dynamic block (RFC 1951 3.2.7) that follows the 3 block-header bits:
 // lens[0..nlen_codes) literal/length code lengths, lens[288..288 + ndist_codes) distance code lengths.
@@ -336,11 +393,6 @@ IF_HD int if_dynamic_lengths(IfBits &B, IfTables &T, uint8_t *lens, int &nlen_co
 IF_HD int if_inflate(const uint8_t *in, uint64_t nbytes, uint64_t start, IfOut &O, IfTables &T, bool stop_at_sync,
                      uint64_t *end_byte, uint32_t *window = nullptr)
 {
-    const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-    const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-    const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-    const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-
     IfBits B;
     B.init(in, nbytes, start, window);
     while (true) {
@@ -384,10 +436,13 @@ IF_HD int if_inflate(const uint8_t *in, uint64_t nbytes, uint64_t start, IfOut &
                 } else {
                     const int li = sym - 257;
                     if (li >= 29) return IF_ERR_DATA;
-                    const uint32_t len = lbase[li] + B.get(lext[li]);
+                    int ext;
+                    uint32_t len = if_len_base(li, ext);
+                    if (ext) len += B.get(ext);
                     const int ds = if_decode(B, T.d);
                     if (ds < 0 || ds >= 30) return IF_ERR_DATA;
-                    const uint32_t dist = dbase[ds] + B.get(dext[ds]);
+                    uint32_t dist = if_dist_base(ds, ext);
+                    if (ext) dist += B.get(ext);
                     if (dist > O.n) return IF_ERR_DATA;          // reaches before this range's own output
                     if (O.n + len > O.cap) return IF_ERR_OUT;
                     if (dist == 1) {
@@ -395,10 +450,10 @@ IF_HD int if_inflate(const uint8_t *in, uint64_t nbytes, uint64_t start, IfOut &
                         // stores only -- no store -> load round trip through memory per byte
                         O.put_run(O.at(O.n - 1), len);
                     } else {
-                        for (uint32_t i = 0; i < len; i++) O.put(O.at(O.n - dist));
+                        O.copy_match(dist, len);
                     }
                 }
-                if (B.overrun()) return IF_ERR_IN;
+                if (B.pos > B.nbytes && B.overrun()) return IF_ERR_IN;    // overrun implies pos > nbytes
             }
         } else {
             return IF_ERR_DATA;

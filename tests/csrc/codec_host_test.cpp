@@ -209,3 +209,21 @@ extern "C" int host_huffman_check(const uint32_t *freq, int n, int maxbits)
     }
     return kraft == (1ull << maxbits) ? 0 : -3;
 }
+
+// closed-form length / distance bases of inflate_core.cuh against the tables of RFC 1951 3.2.5; returns 0 when equal
+extern "C" int host_base_tables_check()
+{
+    static const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    for (int i = 0; i < 29; i++) {
+        int e = -1;
+        if (if_len_base(i, e) != lbase[i] || e != lext[i]) return 1 + i;
+    }
+    for (int i = 0; i < 30; i++) {
+        int e = -1;
+        if (if_dist_base(i, e) != dbase[i] || e != dext[i]) return 100 + i;
+    }
+    return 0;
+}

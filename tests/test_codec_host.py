@@ -87,6 +87,27 @@ def test_decoder_reads_stock_zlib_and_own_streams(codec):
         assert n == len(d) and o == d
 
 
+def test_closed_form_length_and_distance_bases(codec):
+    assert codec.host_base_tables_check() == 0
+
+
+def test_decoder_reads_long_and_overlapping_matches_through_the_ring(codec):
+    """matches of every period 1..40 and of distances up to the 32 KiB window, lengths up to 258, across the 4 KiB
+    flush boundaries of the ring decoder"""
+    rng = np.random.default_rng(7)
+    parts = []
+    for period in list(range(1, 41)) + [255, 256, 257, 4095, 4096, 4097, 32767, 32768]:
+        unit = rng.integers(0, 256, period, dtype=np.uint8).tobytes()
+        parts.append(unit * max(2, 700 // period))
+    parts.append(parts[3] + parts[10] + parts[-1])
+    d = b''.join(parts)
+    for lvl in (1, 6, 9):
+        c = zlib.compress(d, lvl)
+        for serial in (1, 2):
+            n, o = inflate(codec, c, len(d), serial)
+            assert n == len(d) and o == d, (lvl, serial)
+
+
 def test_decoder_rejects_bad_input(codec):
     d = cases()['map0.02']
     c = bytearray(zlib.compress(d, 1))
