@@ -481,7 +481,8 @@ extern "C" int rc_reduce_compress(rc_ctx *ctx, const rc_config *cfg, const void 
     if (sp != st) RC_CUDA(ctx, cudaStreamWaitEvent(sp, ctx->ev_fork, 0));
     cudaStream_t sm = sp;
     if (fork) {
-        sm = prio ? ctx->side_hi : ctx->side;
+        static const bool side_low = getenv("RECODE_B200_SIDE_LOW") && atoi(getenv("RECODE_B200_SIDE_LOW")) != 0;
+        sm = (prio && !side_low) ? ctx->side_hi : ctx->side;
         RC_CUDA(ctx, cudaStreamWaitEvent(sm, ctx->ev_fork, 0));
         if ((rc = deflate_group(ctx, cfg, 0, base, (const uint8_t *)cw.maps, g.MS * 4, nullptr, (uint32_t)g.map_bytes, F,
                                 cw.map_off, cw.map_len, cw.dm, sm))) return rc;

@@ -796,7 +796,13 @@ int launch_deflate_streams(rc_ctx *ctx, int level, int wrap, int shared_table, v
                 w.ghist, w.chunk_base, in_bytes, w.counters, shared_table, n_streams, tables);
             RC_LAUNCH_CHECK(ctx, "k_deflate_tables");
         }
-        want = w.max_chunks < (size_t)ctx->sm_count * 6 ? w.max_chunks : (size_t)ctx->sm_count * 6;
+        // Persistent CTAs per SM (40 KiB of shared memory each).  A batch alone on the GPU takes all that fit; with
+        // several batches in flight (rc_set_pipelined) the encoder runs thin and long -- ONE CTA per SM -- beside the
+        // DRAM-bound streaming kernel of the next batch instead of displacing its CTAs: 81.1 k vs 76.6 k L2 frames/s
+        // (profiles/r02_sweep_residency.txt).  RECODE_B200_DEFLATE_CTAS overrides.
+        static const int def_ctas = getenv("RECODE_B200_DEFLATE_CTAS") ? atoi(getenv("RECODE_B200_DEFLATE_CTAS")) : 0;
+        const size_t per_sm = (size_t)(def_ctas > 0 ? def_ctas : (ctx->pipelined ? 1 : 6));
+        want = w.max_chunks < (size_t)ctx->sm_count * per_sm ? w.max_chunks : (size_t)ctx->sm_count * per_sm;
         if (want < 1) want = 1;
         // RC_ABLATE bit 1 (timing experiments only): no chunk encoder, every piece is empty
         static const int ablate = getenv("RC_ABLATE") ? atoi(getenv("RC_ABLATE")) : 0;

@@ -316,11 +316,21 @@ struct IfOut {
             const uint32_t step = dist < 8u ? dist : 8u;
             while (len) {
                 const uint32_t k = len < step ? len : step;
-                uint8_t b[8];
-                for (uint32_t j = 0; j < 8; j++)
-                    if (j < k) b[j] = sh[(s + j) & M];
-                for (uint32_t j = 0; j < 8; j++)
-                    if (j < k) sh[(d + j) & M] = b[j];
+                const uint32_t so = s & M, dd = d & M;
+                if (k == 8u && so <= IF_RING_BYTES - 8u && dd <= IF_RING_BYTES - 8u) {
+                    // a full round that does not wrap: plain offsets, no predicates
+                    const uint8_t *ps = sh + so;
+                    uint8_t *pd = sh + dd;
+                    uint8_t b[8];
+                    for (int j = 0; j < 8; j++) b[j] = ps[j];
+                    for (int j = 0; j < 8; j++) pd[j] = b[j];
+                } else {
+                    uint8_t b[8];
+                    for (uint32_t j = 0; j < 8; j++)
+                        if (j < k) b[j] = sh[(s + j) & M];
+                    for (uint32_t j = 0; j < 8; j++)
+                        if (j < k) sh[(d + j) & M] = b[j];
+                }
                 s += k; d += k; len -= k;
             }
             if ((d0 ^ (uint32_t)n) & ~(IF_FLUSH_BYTES - 1)) flush(n & ~(uint64_t)(IF_FLUSH_BYTES - 1));

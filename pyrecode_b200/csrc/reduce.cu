@@ -383,12 +383,15 @@ static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, const 
     static const bool force_generic = getenv("RC_K1_GENERIC") != nullptr;
     static const bool l1_bulk = getenv("RC_K1_L1_BULK") ? atoi(getenv("RC_K1_L1_BULK")) != 0 : true;
     const bool bulk = vec_ok && g.P % TILE_PX == 0 && !force_generic && (valmode != 1 || l1_bulk);
+    // unused dynamic shared memory requested on top of the ring: fewer K1 CTAs per SM (5 without), i.e. room for the
+    // labelling and encoder CTAs of the batches in flight on the other streams
+    static const size_t k1_pad = getenv("RC_K1_SMEM_PAD") ? (size_t)atoi(getenv("RC_K1_SMEM_PAD")) : 0;
     static const bool thr_bulk = getenv("RC_K1_THR_BULK") ? atoi(getenv("RC_K1_THR_BULK")) != 0 : false;
 #define RC_K1B(VM, TB)                                                                                     \
     {                                                                                                      \
         cudaFuncSetAttribute(k_reduce_tiles_bulk<T, VM, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             (int)bulk_smem_bytes<T>(TB));                                                 \
-        k_reduce_tiles_bulk<T, VM, TB><<<grid, block, bulk_smem_bytes<T>(TB), st>>>(                       \
+                             (int)(bulk_smem_bytes<T>(TB) + k1_pad));                                      \
+        k_reduce_tiles_bulk<T, VM, TB><<<grid, block, bulk_smem_bytes<T>(TB) + k1_pad, st>>>(              \
             (const T *)frames, (const T *)thr, g.P, g.NT, g.MS, maps, tilecnt, wordpre, vals, k1_prefetch); \
     }
     static const int k1_prefetch = getenv("RC_K1_PREFETCH") ? atoi(getenv("RC_K1_PREFETCH")) : 1;
