@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(32)
 k_inflate_serial(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                  const uint32_t *__restrict__ in_bytes, const uint32_t *__restrict__ need_serial,
                  uint8_t *__restrict__ out, size_t out_stride, uint32_t *__restrict__ out_bytes,
-                 uint32_t *__restrict__ status, int fast8)
+                 uint32_t *__restrict__ status)
 {
     // A stream that is not a chain of our own chunks (a file written by the reference: one block sequence per stream,
     // matches at any distance) is decoded by one lane through a 32 KiB shared-memory history ring and a 2 KiB input
@@ -526,7 +526,6 @@ k_inflate_serial(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in
     if (!need_serial[s] || threadIdx.x != 0) return;
     IfOut O;
     O.init_ring(out + (size_t)s * out_stride, out_stride, s_ring);
-    O.fast8 = fast8 != 0;
     uint64_t end = 0;
     const int code = if_inflate(in + in_off[s], in_bytes[s], 2, O, s_tab, false, &end, s_win);
     O.flush(O.n);
@@ -611,9 +610,7 @@ int launch_inflate(rc_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const
     k_inflate_validate<<<(n_streams + 127) / 128, 128, 0, st>>>(in, in_off, in_bytes, n_streams, cmax, cand, ncand,
                                                                task_base, tasks, out_bytes, status, need_serial);
     RC_LAUNCH_CHECK(ctx, "k_inflate_validate");
-    static const int ring_fast8 = getenv("RECODE_B200_RING_FAST8") ? atoi(getenv("RECODE_B200_RING_FAST8")) : 1;
-    k_inflate_serial<<<n_streams, 32, 0, st>>>(in, in_off, in_bytes, need_serial, out, out_stride, out_bytes, status,
-                                               ring_fast8);
+    k_inflate_serial<<<n_streams, 32, 0, st>>>(in, in_off, in_bytes, need_serial, out, out_stride, out_bytes, status);
     RC_LAUNCH_CHECK(ctx, "k_inflate_serial");
     rc_dmark(ctx, 3, st);
     return 0;

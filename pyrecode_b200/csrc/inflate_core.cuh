@@ -216,15 +216,14 @@ struct IfOut {
     // instead of paying a global store -> load round trip per byte; finished IF_FLUSH_BYTES segments go to `out`
     // with 128-bit stores.
     bool ring;
-    bool fast8;          // ring mode: full, non-wrapping copy rounds take the unpredicated path
     uint64_t flushed;
     IF_HD void init(uint8_t *o, uint64_t capacity, uint8_t *shared = nullptr, uint32_t shared_cap = 0)
     {
-        out = o; cap = capacity; n = 0; s1 = 0; s2 = 0; sh = shared; sh_cap = shared_cap; ring = false; fast8 = true; flushed = 0;
+        out = o; cap = capacity; n = 0; s1 = 0; s2 = 0; sh = shared; sh_cap = shared_cap; ring = false; flushed = 0;
     }
     IF_HD void init_ring(uint8_t *o, uint64_t capacity, uint8_t *ring_buf)
     {
-        out = o; cap = capacity; n = 0; s1 = 0; s2 = 0; sh = ring_buf; sh_cap = 0; ring = true; fast8 = true; flushed = 0;
+        out = o; cap = capacity; n = 0; s1 = 0; s2 = 0; sh = ring_buf; sh_cap = 0; ring = true; flushed = 0;
     }
     IF_HD uint8_t at(uint64_t i) const
     {
@@ -317,21 +316,11 @@ struct IfOut {
             const uint32_t step = dist < 8u ? dist : 8u;
             while (len) {
                 const uint32_t k = len < step ? len : step;
-                const uint32_t so = s & M, dd = d & M;
-                if (fast8 && k == 8u && so <= IF_RING_BYTES - 8u && dd <= IF_RING_BYTES - 8u) {
-                    // a full round that does not wrap: plain offsets, no predicates
-                    const uint8_t *ps = sh + so;
-                    uint8_t *pd = sh + dd;
-                    uint8_t b[8];
-                    for (int j = 0; j < 8; j++) b[j] = ps[j];
-                    for (int j = 0; j < 8; j++) pd[j] = b[j];
-                } else {
-                    uint8_t b[8];
-                    for (uint32_t j = 0; j < 8; j++)
-                        if (j < k) b[j] = sh[(s + j) & M];
-                    for (uint32_t j = 0; j < 8; j++)
-                        if (j < k) sh[(d + j) & M] = b[j];
-                }
+                uint8_t b[8];
+                for (uint32_t j = 0; j < 8; j++)
+                    if (j < k) b[j] = sh[(s + j) & M];
+                for (uint32_t j = 0; j < 8; j++)
+                    if (j < k) sh[(d + j) & M] = b[j];
                 s += k; d += k; len -= k;
             }
             if ((d0 ^ (uint32_t)n) & ~(IF_FLUSH_BYTES - 1)) flush(n & ~(uint64_t)(IF_FLUSH_BYTES - 1));
