@@ -459,19 +459,59 @@ class ReadEngine:
                 out.append(t)
             return out
 
+    def sparse_coo(self):
+        """-> list of (rows int32, cols int32, values of the target dtype), one triple of numpy arrays per loaded frame:
+        the arrays scipy's coo_matrix keeps.  Same kernel as sparse(); the uint64 triples are narrowed on the device, so
+        10 instead of 24 bytes per foreground pixel cross PCIe, in three copies per batch instead of one per frame."""
+        n = self.n
+        with torch.cuda.device(self.dev):
+            cap = self.P
+            tri = self.ctx.empty(n * cap * 3, torch.int64)
+            self.ctx.unpack_sparse(self.cfg, self.maps_buf, self.packed_buf, self.stride, n, self.ws, tri, cap, self.counts)
+            k = self.counts[:n].cpu().numpy().astype(np.int64)
+            total = int(k.sum())
+            vt = torch.int16 if self.itemsize == 2 else torch.uint8       # int16: the bits of the uint16 values
+            rows_d = torch.empty(max(total, 1), dtype=torch.int32, device=self.dev)
+            cols_d = torch.empty(max(total, 1), dtype=torch.int32, device=self.dev)
+            vals_d = torch.empty(max(total, 1), dtype=vt, device=self.dev)
+            off = 0
+            for f in range(n):
+                kf = int(k[f])
+                if kf:
+                    t = tri[f * cap * 3:f * cap * 3 + kf * 3].view(kf, 3)
+                    rows_d[off:off + kf].copy_(t[:, 0])
+                    cols_d[off:off + kf].copy_(t[:, 1])
+                    vals_d[off:off + kf].copy_(t[:, 2])
+                off += kf
+            rows = rows_d.cpu().numpy()
+            cols = cols_d.cpu().numpy()
+            vals = vals_d.cpu().numpy().view(self.np_dtype)
+        out, off = [], 0
+        for f in range(n):
+            kf = int(k[f])
+            out.append((rows[off:off + kf], cols[off:off + kf], vals[off:off + kf]))
+            off += kf
+        return out
+
     def summary_stats(self, out_bytes):
         """L2: unpack the per-puddle statistics of the loaded frames -> list of arrays of the target dtype
         (intent of recode_reader.py:473-481, count = bytes * 8 // bit_depth)."""
         F, n = self.max_frames, self.n
         packed = self.packed_buf
-        res = []
+        ks = [int(out_bytes[F + f]) * 8 // self.bit_depth for f in range(n)]
+        total = sum(ks)
         with torch.cuda.device(self.dev):
-            for f in range(n):
-                k = int(out_bytes[F + f]) * 8 // self.bit_depth
-                out = self.ctx.zeros(max(k, 1), torch.int64)
-                if k:
-                    self.ctx.bit_unpack(self.bit_depth, packed[f * self.stride:], k, out)
-                res.append(out[:k].cpu().numpy().astype(self.np_dtype))
+            out = self.ctx.zeros(max(total, 1), torch.int64)
+            off = 0
+            for f in range(n):                      # one launch per frame, one copy to the host for the batch
+                if ks[f]:
+                    self.ctx.bit_unpack(self.bit_depth, packed[f * self.stride:], ks[f], out[off:])
+                off += ks[f]
+            host = out.cpu().numpy().astype(self.np_dtype)
+        res, off = [], 0
+        for f in range(n):
+            res.append(host[off:off + ks[f]])
+            off += ks[f]
         return res
 
     def dense(self, total=None, want_dense=True, out=None):

@@ -206,14 +206,14 @@ class ReCoDeReader:
                 name = 'bytes_in_packed_' + ('pixvals' if level == 1 else 'summary_stats')
                 pk = [int(mds[i0 + j][name]) for j in range(len(part))]
             sizes = eng.check(pk)
-            tri = eng.sparse()
+            tri = eng.sparse_coo()
             stats = eng.summary_stats(sizes) if level == 2 else [None] * len(part)
-            for j, t in enumerate(tri):
+            for j, (rows, cols, vals) in enumerate(tri):
                 if level == 1:
                     npk = int(mds[i0 + j]['bytes_in_packed_pixvals'])
-                    if (t.shape[0] * b + 7) // 8 != npk:
-                        raise ValueError('frame has %d foreground pixels but %d packed bytes' % (t.shape[0], npk))
-                coo = coo_matrix((t[:, 2], (t[:, 0], t[:, 1])), shape=(h['ny'], h['nx']), dtype=self._numpy_dtype)
+                    if (rows.shape[0] * b + 7) // 8 != npk:
+                        raise ValueError('frame has %d foreground pixels but %d packed bytes' % (rows.shape[0], npk))
+                coo = coo_matrix((vals, (rows, cols)), shape=(h['ny'], h['nx']), dtype=self._numpy_dtype, copy=False)
                 out.append((coo, stats[j]))
         return out
 
