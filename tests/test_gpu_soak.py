@@ -1,0 +1,16 @@
+"""A short soak of the pipelined write path (tools/soak.py): random geometries (full-tile and ragged), levels, bit depths,
+occupancies up to the tile-overflow path, thresholds down to two sigma of the noise, 3-4 batches in flight with slot
+reuse; every record of every slot compared with the CPU oracle.  compute-sanitizer is not available on the GPU pool:
+this and tests/test_gpu_bench_config.py are the race checks that run."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_soak_pipelined_write_path():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tools'))
+    import soak
+    soak.main(iters=8, seed=11)
