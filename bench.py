@@ -334,6 +334,35 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
                 ar1.record()
                 torch.cuda.synchronize()
                 ar_iso.append(ar0.elapsed_time(ar1))
+        # parity of the read leg (outside the timed regions; the oracle is the checker): this rank's live-view sum before
+        # the all-reduce, and the first dense frames, against stock zlib + the oracle's unpack of the file's own records
+        read_parity, read_parity_err = None, None
+        if rank == 0 and not args.no_parity:
+            try:
+                import zlib
+                from oracle import oracle as orc
+                r.rewind()
+                view.zero_()
+                r.sum_frames(nz, total=view)
+                got = view.cpu().numpy().astype(np.int64).reshape(NY, NX)
+                r.rewind()
+                _, dn = r.read_frames_dense(len(frames))
+                dn = dn.cpu().numpy()
+                rr = ReCoDeReader(path, is_intermediate=True, device=local_rank)
+                rr.open(print_header=False)
+                want = np.zeros((NY, NX), dtype=np.int64)
+                ok = nz % len(frames) == 0 and per_run % len(frames) == 0
+                for j in range(len(frames)):                       # the file cycles through the distinct frames
+                    fr = next(iter(rr.get_next_frame_raw().values()))['data']
+                    d = orc.unpack_dense(NY, NX, BIT_DEPTH, zlib.decompress(bytes(fr['binary_map'])),
+                                         zlib.decompress(bytes(fr['pixvals'])), 2)
+                    ok = ok and np.array_equal(dn[j], d)
+                    want += d.astype(np.int64) * (nz // len(frames))
+                rr.close()
+                read_parity = bool(ok and np.array_equal(got, want))
+                del dn
+            except Exception as e:                              # a checker problem must not lose the bench line
+                read_parity, read_parity_err = False, repr(e)[:200]
         gpu = r.decode_stage_ms()
         # the per-frame API (get_next_frame -> scipy COO + summary statistics), as a user loop would call it
         seq_fps = None
@@ -416,7 +445,7 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
                'allreduce_ms_isolated': float(np.median(ar_iso[1:])) if len(ar_iso) > 1 else None,
                'dense_frames_per_s': res['dense'][0], 'dense_output_gb_s': res['dense'][0] * frame_bytes / 1e9,
                'file_bytes': fsize, 'steps': steps, 'frames_per_view': nz,
-               'get_next_frame_fps': seq_fps, 'foreign_zlib_streams': foreign,
+               'get_next_frame_fps': seq_fps, 'foreign_zlib_streams': foreign, 'parity_checked': read_parity, 'parity_error': read_parity_err,
                'host_time_split_ms_last_view': {k: (1e3 * v if k.endswith('_s') else v) for k, v in res['sum'][2].items()},
                'e2e': {'value': res['sum'][0], 'unit': 'frames/s', 'h2d_bytes_per_step': fsize, 'd2h_bytes_per_step': 8}}
         if gpu and gpu.get('frames'):
