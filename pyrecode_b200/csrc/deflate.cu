@@ -13,7 +13,7 @@
 //   k_stream_finalize   1 CTA per stream: prefix of piece sizes, Adler-32 combine, total stream size
 //   k_layout_*          destination offset of every stream (fixed stride, or ReCoDe records incl. the
 //                       [frame_id][sizes...] header and the exclusive scan of record sizes)
-//   k_copy_pieces       persistent CTAs copy pieces to their final byte offsets (funnel-shifted 32-bit
+//   k_copy_pieces       one warp per piece and ticket copies it to its final byte offset (funnel-shifted 32-bit
 //                       words) and write the zlib header / final block / Adler-32 trailer
 // Only compact records cross PCIe afterwards.
 #include "common.cuh"
