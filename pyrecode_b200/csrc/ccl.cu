@@ -773,7 +773,7 @@ int launch_ccl_tiles(rc_ctx *ctx, const Geom &g, int fold, const uint32_t *maps,
     // the streaming kernel of the next batch), else what fits
     const int fit = fold == 3 ? 4 : 5;
     int per_sm = ctx->ccl_ctas_per_sm > 0 ? ctx->ccl_ctas_per_sm
-                                          : ((ctx->use_priority == 0 || !ctx->pipelined) ? fit : (fold == 3 ? 3 : 2));
+                                          : ((ctx->use_priority == 0 || !ctx->pipelined) ? fit : 2);
     if (per_sm > fit) per_sm = fit;
     unsigned grid = (unsigned)nt;
     if ((unsigned)(per_sm * ctx->sm_count) < grid) grid = (unsigned)(per_sm * ctx->sm_count);
