@@ -296,7 +296,7 @@ def read_leg(args, rank, world, local_rank, dev, dark, frames, want_cpu):
                 ar1.record()
                 out = int(total[:1024].sum().item())          # device -> host read of the result
             else:
-                ids, dense = r.read_frames_dense(min(nz, 256))
+                ids, dense = r.read_frames_dense(min(nz, args.read_dense_frames))
                 out = int(dense[0, 0, :8].sum().item())
                 del dense
             return len(ids), dict(r.bulk_stats)
@@ -498,6 +498,8 @@ def main():
                          "dense frames through ReCoDeReader's bulk calls")
     ap.add_argument('--read-frames', type=int, default=1024, help='frames in the part file of the read leg (a multiple of 256)')
     ap.add_argument('--read-steps', type=int, default=5)
+    ap.add_argument('--read-dense-frames', type=int, default=1024,
+                    help='frames per dense read (32 MiB of device memory each at 4096 x 4096 x 16 bit)')
     ap.add_argument('--read-batch', type=int, default=64, help='frames per decode batch of the read leg')
     ap.add_argument('--read-inflight', type=int, default=6, help='decode batches in flight')
     args = ap.parse_args()
