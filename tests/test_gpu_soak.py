@@ -14,3 +14,11 @@ def test_soak_pipelined_write_path():
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tools'))
     import soak
     soak.main(iters=8, seed=11)
+
+
+def test_soak_read_path():
+    """tools/soak_read.py: random files written by ReCoDeWriter (several parts, merged), read back through the bulk
+    pipeline, get_next_frame and get_frame; every frame against the oracle"""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tools'))
+    import soak_read
+    soak_read.main(iters=5, seed=5)
