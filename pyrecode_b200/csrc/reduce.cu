@@ -295,7 +295,7 @@ k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, siz
             for (int j = 0; j < 4; j++) Px<T>::load_cached(th + wpx0 + j * 256 + lane * 8, tw[j]);
             // the threshold pixels of the NEXT sub-tile: one 128-byte line per lane into L1, so that the loads above
             // find them there one iteration later instead of waiting for L2
-            if (k1_prefetch && sub + 1 < NSUB && lane * (128 / (int)sizeof(T)) < 1024)
+            if ((k1_prefetch & 1) && sub + 1 < NSUB && lane * (128 / (int)sizeof(T)) < 1024)
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(th + wpx0 + SUB_PX + lane * (128 / (int)sizeof(T))));
         }
         const int stg = sub % BULK_STAGES;
@@ -318,7 +318,22 @@ k_reduce_tiles_bulk(const T *__restrict__ frames, const T *__restrict__ thr, siz
         __syncwarp();
         const uint32_t word = s_mask[sub * SUB_WORDS + t];
         const uint32_t pc = __popc(word);
-        const uint32_t incl = warp_incl_scan(pc);
+        // inclusive prefix of the 32 counts.  Bit-sliced with ballots (k1_prefetch bit 1, the default; RC_K1_BALLOT_SCAN=0
+        // selects the shuffle scan; L1 +1.9 %, L2 +0.4 % frames/s): the three low bits of the counts
+        // cost three INDEPENDENT vote + popc pairs (the shuffle scan is five dependent round trips); counts of 8 or more in
+        // any lane (rare at a few per cent occupancy) add the three high bits.
+        uint32_t incl;
+        if (k1_prefetch & 2) {
+            const uint32_t le = 0xffffffffu >> (31 - lane);
+            incl = __popc(__ballot_sync(0xffffffffu, pc & 1u) & le) + (__popc(__ballot_sync(0xffffffffu, pc & 2u) & le) << 1) +
+                   (__popc(__ballot_sync(0xffffffffu, pc & 4u) & le) << 2);
+            if (__any_sync(0xffffffffu, pc >> 3))
+                incl += (__popc(__ballot_sync(0xffffffffu, pc & 8u) & le) << 3) +
+                        (__popc(__ballot_sync(0xffffffffu, pc & 16u) & le) << 4) +
+                        (__popc(__ballot_sync(0xffffffffu, pc & 32u) & le) << 5);
+        } else {
+            incl = warp_incl_scan(pc);
+        }
         if (lane == 31) s_wsum[sub & 1][warp] = incl;
         __syncthreads();
         // foreground pixels of the warps before this one / of all eight: two warp-wide integer reductions (REDUX) over
@@ -394,14 +409,15 @@ static int launch_reduce_tiles_t(rc_ctx *ctx, const Geom &g, int valmode, const 
         k_reduce_tiles_bulk<T, VM, TB><<<grid, block, bulk_smem_bytes<T>(TB) + k1_pad, st>>>(              \
             (const T *)frames, (const T *)thr, g.P, g.NT, g.MS, maps, tilecnt, wordpre, vals, k1_prefetch); \
     }
-    static const int k1_prefetch = getenv("RC_K1_PREFETCH") ? atoi(getenv("RC_K1_PREFETCH")) : 1;
+    static const int k1_prefetch = (getenv("RC_K1_PREFETCH") ? (atoi(getenv("RC_K1_PREFETCH")) & 1) : 1) |
+                                   ((getenv("RC_K1_BALLOT_SCAN") ? atoi(getenv("RC_K1_BALLOT_SCAN")) != 0 : true) ? 2 : 0);
 #define RC_K1(VM)                                                                                          \
     if (bulk) {                                                                                            \
         if (thr_bulk) RC_K1B(VM, true) else RC_K1B(VM, false)                                              \
     } else {                                                                                               \
         k_reduce_tiles<T, VM><<<grid, block, 0, st>>>((const T *)frames, (const T *)thr, g.P, g.NT, g.MS,  \
                                                       maps, tilecnt, wordpre, vals,                        \
-                                                      vec_ok ? (k1_prefetch ? 2 : 1) : 0);                 \
+                                                      vec_ok ? ((k1_prefetch & 1) ? 2 : 1) : 0);           \
     }
     if (valmode == 0) { RC_K1(0) }
     else if (valmode == 1) { RC_K1(1) }
